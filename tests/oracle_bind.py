@@ -1,0 +1,231 @@
+"""ctypes binding of the CPU oracle (oracle/liborc_parity.so). TEST INFRASTRUCTURE ONLY:
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg — never by
+fast_livo2_b200/."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+STATE_PACK = 386
+
+_libs = {}
+
+
+def build_oracle():
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
+
+
+def load(kind="parity"):
+    if kind in _libs:
+        return _libs[kind]
+    path = os.path.join(ORACLE_DIR, f"liborc_{kind}.so")
+    if not os.path.exists(path):
+        build_oracle()
+    lib = C.CDLL(path)
+    vp, dp, fp, ip, i64p, u8p = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_uint8)
+    lib.orc_lio_create.restype = vp
+    lib.orc_lio_create.argtypes = [dp, dp, dp, C.c_int]
+    lib.orc_lio_destroy.argtypes = [vp]
+    lib.orc_lio_set_map_flat.argtypes = [vp, i64p, ip, ip, C.c_int, vp, C.c_int]
+    lib.orc_lio_build_map.argtypes = [vp, fp, fp, C.c_int, dp]
+    lib.orc_lio_update_map.argtypes = [vp, dp, dp, C.c_int]
+    lib.orc_lio_flatten.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), i64p, ip, ip, vp]
+    lib.orc_lio_state_estimation.restype = C.c_double
+    lib.orc_lio_state_estimation.argtypes = [vp, fp, C.c_int, dp, dp, dp, ip, ip, fp, dp, dp, dp]
+    lib.orc_lio_single_pass.argtypes = [vp, fp, C.c_int, dp, dp, ip, fp, dp, dp, dp, dp]
+    lib.orc_vio_create.restype = vp
+    lib.orc_vio_create.argtypes = [dp, dp, dp, dp, dp, dp, C.c_int]
+    lib.orc_vio_destroy.argtypes = [vp]
+    lib.orc_vio_update.restype = C.c_double
+    lib.orc_vio_update.argtypes = [vp, u8p, C.c_int, dp, fp, ip, dp, dp, dp, dp, fp, dp]
+    lib.orc_vio_get_image_patch.argtypes = [vp, u8p, dp, C.c_int, fp]
+    lib.orc_vio_warp_affine.argtypes = [vp, u8p, C.c_int, C.c_int, dp, dp, C.c_int, fp]
+    lib.orc_vio_warp_matrix.restype = C.c_int
+    lib.orc_vio_warp_matrix.argtypes = [vp, dp, dp, dp, dp, dp, dp, dp, dp]
+    lib.orc_cam_world2cam.argtypes = [vp, dp, dp]
+    lib.orc_cam_cam2world.argtypes = [vp, dp, dp]
+    for name in ("orc_boxplus", "orc_boxminus"):
+        getattr(lib, name).argtypes = [dp, dp, dp]
+    lib.orc_exp.argtypes = [dp, dp]
+    lib.orc_log.argtypes = [dp, dp]
+    lib.orc_inverse19.argtypes = [dp, dp]
+    lib.orc_calc_body_cov.argtypes = [dp, C.c_float, C.c_float, dp, dp]
+    lib.orc_default_state.argtypes = [dp]
+    lib.orc_max_threads.restype = C.c_int
+    _libs[kind] = lib
+    return lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def dptr(a):
+    return _p(a, C.c_double)
+
+
+def fptr(a):
+    return _p(a, C.c_float)
+
+
+def iptr(a):
+    return _p(a, C.c_int32)
+
+
+def c64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class OracleLIO:
+    def __init__(self, lio_cfg, ext, threads=1, kind="parity"):
+        self.lib = load(kind)
+        self.cfg = lio_cfg
+        self.h = self.lib.orc_lio_create(dptr(lio_cfg.as_array()), dptr(c64(ext.extR)), dptr(c64(ext.extT)), threads)
+
+    def __del__(self):
+        try:
+            self.lib.orc_lio_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_map(self, vmap):
+        self._map = vmap  # keep alive
+        k, f, c, p = vmap["keys"], vmap["first"], vmap["count"], vmap["planes"]
+        self.lib.orc_lio_set_map_flat(self.h, _p(k, C.c_int64), iptr(f), iptr(c), len(f), p.ctypes.data, len(p))
+
+    def build_map(self, pts_world_f32, pts_body_f32, state):
+        pw = np.ascontiguousarray(pts_world_f32, dtype=np.float32)
+        pb = np.ascontiguousarray(pts_body_f32, dtype=np.float32)
+        self.lib.orc_lio_build_map(self.h, fptr(pw), fptr(pb), len(pw), dptr(c64(state)))
+
+    def flatten(self):
+        from fast_livo2_b200.synthetic import PLANE_DTYPE
+
+        nr, npl = C.c_int(0), C.c_int(0)
+        self.lib.orc_lio_flatten(self.h, C.byref(nr), C.byref(npl), None, None, None, None)
+        keys = np.zeros((nr.value, 3), np.int64)
+        first = np.zeros(nr.value, np.int32)
+        count = np.zeros(nr.value, np.int32)
+        planes = np.zeros(npl.value, PLANE_DTYPE)
+        self.lib.orc_lio_flatten(self.h, C.byref(nr), C.byref(npl), _p(keys, C.c_int64), iptr(first), iptr(count), planes.ctypes.data)
+        return dict(keys=keys, first=first, count=count, planes=planes)
+
+    def state_estimation(self, pts, state_in, state_prop):
+        pts = np.ascontiguousarray(pts, dtype=np.float32)
+        n = len(pts)
+        out = np.zeros(STATE_PACK)
+        match = np.zeros(n, np.int32)
+        normal = np.zeros(n, np.int32)
+        dis = np.zeros(n, np.float32)
+        stats = np.zeros(520)
+        secs = self.lib.orc_lio_state_estimation(self.h, fptr(pts), n, dptr(c64(state_in)), dptr(c64(state_prop)), dptr(out), iptr(match),
+                                                 iptr(normal), fptr(dis), dptr(stats), None, None)
+        iters = int(stats[0])
+        return dict(state=out, match_plane=match, normal_plane=normal, dis_to_plane=dis, iters=iters, M=stats[1:9].astype(int)[:iters],
+                    total_residual=stats[9:17][:iters], HTH=stats[17:305].reshape(8, 6, 6)[:iters], HTz=stats[305:353].reshape(8, 6)[:iters],
+                    solution=stats[353:505].reshape(8, 19)[:iters], converged=stats[505:513].astype(int)[:iters], secs=secs)
+
+    def single_pass(self, pts, state_cur, state_prop):
+        pts = np.ascontiguousarray(pts, dtype=np.float32)
+        n = len(pts)
+        plane = np.zeros(n, np.int32)
+        dis = np.zeros(n, np.float32)
+        H = np.zeros((n, 6))
+        rinv = np.zeros(n)
+        pw = np.zeros((n, 3))
+        var = np.zeros((n, 3, 3))
+        self.lib.orc_lio_single_pass(self.h, fptr(pts), n, dptr(c64(state_cur)), dptr(c64(state_prop)), iptr(plane), fptr(dis), dptr(H),
+                                     dptr(rinv), dptr(pw), dptr(var))
+        return dict(plane=plane, dis=dis, H=H, R_inv=rinv, point_w=pw, var=var)
+
+
+class OracleVIO:
+    def __init__(self, cam_cfg, ext, vio_cfg, threads=1, kind="parity"):
+        self.lib = load(kind)
+        self.cam, self.cfg = cam_cfg, vio_cfg
+        self.h = self.lib.orc_vio_create(dptr(cam_cfg.as_array()), dptr(c64(ext.extR)), dptr(c64(ext.extT)), dptr(c64(ext.Rcl)),
+                                         dptr(c64(ext.Pcl)), dptr(vio_cfg.as_array()), threads)
+
+    def __del__(self):
+        try:
+            self.lib.orc_vio_destroy(self.h)
+        except Exception:
+            pass
+
+    def update(self, img, pos, warp_patch, search_levels, inv_expo, state_in, state_prop):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        pos = c64(pos)
+        n = len(pos)
+        wp = np.ascontiguousarray(warp_patch, dtype=np.float32)
+        sl = np.ascontiguousarray(search_levels, dtype=np.int32)
+        ie = c64(inv_expo)
+        out = np.zeros(STATE_PACK)
+        err = np.zeros(n, np.float32)
+        stats = np.zeros(4881)
+        secs = self.lib.orc_vio_update(self.h, _p(img, C.c_uint8), n, dptr(pos), fptr(wp), iptr(sl), dptr(ie), dptr(c64(state_in)),
+                                       dptr(c64(state_prop)), dptr(out), fptr(err), dptr(stats))
+        return dict(state=out, errors=err, total_iters=int(stats[0]), iters_per_level=stats[1:9].astype(int),
+                    accepted_per_level=stats[9:17].astype(int), error_trace=stats[17:81].reshape(8, 8),
+                    HTH=stats[81:3217].reshape(8, 8, 7, 7), HTz=stats[3217:3665].reshape(8, 8, 7), solution=stats[3665:4881].reshape(8, 8, 19),
+                    secs=secs)
+
+    def get_image_patch(self, img, pc, level):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        out = np.zeros(64 * self.cfg.levels, np.float32)
+        self.lib.orc_vio_get_image_patch(self.h, _p(img, C.c_uint8), dptr(c64(pc)), level, fptr(out))
+        return out[64 * level: 64 * level + 64].copy()
+
+    def warp_affine(self, img_ref, A_cur_ref, px_ref, search_level):
+        img_ref = np.ascontiguousarray(img_ref, dtype=np.uint8)
+        out = np.zeros(64 * self.cfg.levels, np.float32)
+        self.lib.orc_vio_warp_affine(self.h, _p(img_ref, C.c_uint8), img_ref.shape[1], img_ref.shape[0], dptr(c64(A_cur_ref)), dptr(c64(px_ref)),
+                                     int(search_level), fptr(out))
+        return out
+
+    def warp_matrix(self, px_ref, pos_w, normal_w, T_ref, T_cur):
+        A = np.zeros(4)
+        sl = self.lib.orc_vio_warp_matrix(self.h, dptr(c64(px_ref)), dptr(c64(pos_w)), dptr(c64(normal_w)), dptr(c64(T_ref[0])),
+                                          dptr(c64(T_ref[1])), dptr(c64(T_cur[0])), dptr(c64(T_cur[1])), dptr(A))
+        return A.reshape(2, 2), sl
+
+    def world2cam(self, xyz):
+        px = np.zeros(2)
+        self.lib.orc_cam_world2cam(self.h, dptr(c64(xyz)), dptr(px))
+        return px
+
+    def cam2world(self, px):
+        f = np.zeros(3)
+        self.lib.orc_cam_cam2world(self.h, dptr(c64(px)), dptr(f))
+        return f
+
+
+def oracle_warp_patches(frame, state_for_cur_pose, threads=1):
+    """Build the VIO inputs (A_cur_ref, search_level, warp_patch) with the oracle's
+    getWarpMatrixAffineHomography / warpAffine. The 'current frame pose' used for the warp
+    is the one implied by `state_for_cur_pose` (vio.cpp:1800 updateFrameState before retrieve)."""
+    from fast_livo2_b200.synthetic import camera_pose, unpack_state
+
+    vio = OracleVIO(frame["cam_cfg"], frame["ext"], frame["vio_cfg"], threads)
+    st = unpack_state(state_for_cur_pose)
+    T_cur = camera_pose(frame["ext"], st["R"], st["p"])
+    n = len(frame["vis_pos"])
+    L = frame["vio_cfg"].levels
+    wp = np.zeros((n, L * 64), np.float32)
+    sl = np.zeros(n, np.int32)
+    A_all = np.zeros((n, 2, 2))
+    for i in range(n):
+        A, s = vio.warp_matrix(frame["px_ref"][i], frame["vis_pos"][i], frame["vis_normal"][i], frame["T_ref"], T_cur)
+        A_all[i], sl[i] = A, s
+        wp[i] = vio.warp_affine(frame["img_ref"], A, frame["px_ref"][i], s)
+    return dict(warp_patch=wp, search_levels=sl, A_cur_ref=A_all)
+
+
+def rot_err(Ra, Rb):
+    v = np.zeros(3)
+    load().orc_log(dptr(c64(Ra.T @ Rb)), dptr(v))
+    return float(np.linalg.norm(v))
