@@ -1,0 +1,751 @@
+// Host side of the C ABI declared in include/esikf_b200.h: context, device mirror of the voxel map, staging of the
+// per-tick inputs, and the launch sequences of the LIO / VIO update loops. No CPU fallback: every entry point fails
+// with a status code when the device or an input is missing.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "esikf_dev.cuh"
+
+namespace esikf {
+// kernels (defined in the other translation units of this library)
+struct LioKernelArgs;
+struct VioKernelArgs;
+struct SolveArgs;
+}  // namespace esikf
+
+#include "esikf_lio.cu"
+#include "esikf_solve.cu"
+#include "esikf_vio.cu"
+
+using namespace esikf;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// NCCL through dlopen: the library has no link-time dependency on NCCL; when the process already holds a libnccl.so.2
+// (e.g. torch's bundled one) that copy is reused.
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+  void *handle = nullptr;
+  int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool load() {
+    if (handle) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+      handle = dlopen(n, RTLD_NOW | RTLD_NOLOAD);
+      if (handle) break;
+    }
+    if (!handle)
+      for (const char *n : names) {
+        handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (handle) break;
+      }
+    if (!handle) return false;
+    GetUniqueId = (int (*)(ncclUniqueId *))dlsym(handle, "ncclGetUniqueId");
+    CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(handle, "ncclCommInitRank");
+    AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(handle, "ncclAllReduce");
+    CommDestroy = (int (*)(ncclComm_t))dlsym(handle, "ncclCommDestroy");
+    GetErrorString = (const char *(*)(int))dlsym(handle, "ncclGetErrorString");
+    return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+  }
+};
+static NcclApi g_nccl;
+enum { NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T> struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr, cap = 0;
+    size_t want = n + n / 4 + 64;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr, cap = 0;
+  }
+};
+
+struct esikf_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  int solve_mode = 0;
+  esikf_extrinsics ext{};
+  bool have_ext = false;
+
+  // map
+  DevBuf<HashSlot> slots;
+  uint32_t hash_mask = 0;
+  DevBuf<esikf_plane> planes;
+  int n_planes = 0, n_roots = 0;
+  double voxel_size = 0.5;
+  bool have_map = false;
+
+  // LIO
+  DevBuf<float> pts;
+  DevBuf<double> pre;
+  DevBuf<int32_t> match_plane, normal_plane;
+  DevBuf<float> dis;
+  int n_pts = 0;
+  bool scan_fresh = false;   // precompute pending
+  esikf_lio_cfg lio_cfg{};
+  DevBuf<double> ext_dev;    // extR(9) extT(3)
+
+  // shared update state
+  DevBuf<double> state, prop, info, partials, old_state, G;
+  DevBuf<Ctrl> ctrl;
+  DevBuf<esikf_lio_stats> lio_stats;
+  DevBuf<esikf_vio_stats> vio_stats;
+  int partial_blocks = 0;
+
+  // VIO
+  esikf_camera cam{};
+  esikf_vio_cfg vio_cfg{};
+  bool have_cam = false;
+  DevBuf<uint8_t> img;
+  int img_w = 0, img_h = 0;
+  DevBuf<double> vis_pos, inv_expo;
+  DevBuf<float> warp_patch, errors;
+  DevBuf<int32_t> search_levels;
+  int n_patches = 0;
+  // warp producers
+  std::vector<uint8_t *> ref_imgs;
+  DevBuf<const uint8_t *> ref_img_ptrs;
+  int ref_w = 0, ref_h = 0;
+  DevBuf<int32_t> ref_idx;
+  DevBuf<double> px_ref, pos_w, normal_w, T_ref, T_cur, A_cur_ref, pc_buf;
+  DevBuf<float> patch_buf;
+
+  // multi-GPU
+  int rank = 0, nranks = 1;
+  ncclComm_t comm = nullptr;
+
+  // measurement
+  DevBuf<uint8_t> flush;
+  DevBuf<double> scratch_state;
+};
+
+static int fail(esikf_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+#define CK(call)                                                                                                   \
+  do {                                                                                                             \
+    cudaError_t e__ = (call);                                                                                      \
+    if (e__ != cudaSuccess) return fail(ctx, ESIKF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+static void shard_of(int n, int rank, int nranks, int &begin, int &count) {
+  // contiguous blocks, remainder spread over the first ranks
+  int base = n / nranks, rem = n % nranks;
+  begin = rank * base + (rank < rem ? rank : rem);
+  count = base + (rank < rem ? 1 : 0);
+}
+
+extern "C" {
+
+int esikf_create(esikf_ctx **out, int device) {
+  if (!out) return ESIKF_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return ESIKF_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return ESIKF_ERR_NO_DEVICE;
+  if (prop.major != 10) return ESIKF_ERR_NO_DEVICE;  // sm_100a binary only
+  esikf_ctx *ctx = new esikf_ctx;
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return ESIKF_ERR_CUDA;
+  }
+  bool ok = ctx->state.reserve(S_N) == cudaSuccess && ctx->prop.reserve(S_N) == cudaSuccess && ctx->info.reserve(INFO_N) == cudaSuccess &&
+            ctx->old_state.reserve(32) == cudaSuccess && ctx->G.reserve(19 * 7) == cudaSuccess && ctx->ctrl.reserve(1) == cudaSuccess &&
+            ctx->lio_stats.reserve(1) == cudaSuccess && ctx->vio_stats.reserve(1) == cudaSuccess && ctx->ext_dev.reserve(12) == cudaSuccess &&
+            ctx->scratch_state.reserve(S_N) == cudaSuccess;
+  ctx->partial_blocks = ctx->sm_count * 4;
+  ok = ok && ctx->partials.reserve((size_t)ctx->partial_blocks * INFO_N) == cudaSuccess;
+  if (!ok) {
+    esikf_destroy(ctx);
+    return ESIKF_ERR_CUDA;
+  }
+  cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), ctx->stream);
+  cudaFuncSetAttribute(lio_residual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
+  cudaFuncSetAttribute(vio_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VioSmem));
+  *out = ctx;
+  return ESIKF_OK;
+}
+
+void esikf_destroy(esikf_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+  ctx->slots.release(), ctx->planes.release(), ctx->pts.release(), ctx->pre.release(), ctx->match_plane.release();
+  ctx->normal_plane.release(), ctx->dis.release(), ctx->ext_dev.release(), ctx->state.release(), ctx->prop.release();
+  ctx->info.release(), ctx->partials.release(), ctx->old_state.release(), ctx->G.release(), ctx->ctrl.release();
+  ctx->lio_stats.release(), ctx->vio_stats.release(), ctx->img.release(), ctx->vis_pos.release(), ctx->inv_expo.release();
+  ctx->warp_patch.release(), ctx->errors.release(), ctx->search_levels.release(), ctx->ref_img_ptrs.release(), ctx->ref_idx.release();
+  ctx->px_ref.release(), ctx->pos_w.release(), ctx->normal_w.release(), ctx->T_ref.release(), ctx->T_cur.release();
+  ctx->A_cur_ref.release(), ctx->pc_buf.release(), ctx->patch_buf.release(), ctx->flush.release(), ctx->scratch_state.release();
+  for (uint8_t *p : ctx->ref_imgs) cudaFree(p);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *esikf_last_error(const esikf_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void *esikf_stream(esikf_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int64_t esikf_launch_count(const esikf_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int esikf_synchronize(esikf_ctx *ctx) {
+  if (!ctx) return ESIKF_ERR_ARG;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return ESIKF_OK;
+}
+int esikf_set_solve_mode(esikf_ctx *ctx, int mode) {
+  if (!ctx || mode < 0 || mode > 1) return ESIKF_ERR_ARG;
+  ctx->solve_mode = mode;
+  return ESIKF_OK;
+}
+int esikf_set_extrinsics(esikf_ctx *ctx, const esikf_extrinsics *ext) {
+  if (!ctx || !ext) return ESIKF_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  ctx->ext = *ext;
+  ctx->have_ext = true;
+  double h[12];
+  memcpy(h, ext->extR, 9 * sizeof(double));
+  memcpy(h + 9, ext->extT, 3 * sizeof(double));
+  CK(cudaMemcpyAsync(ctx->ext_dev.p, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return ESIKF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- map
+int esikf_map_upload(esikf_ctx *ctx, const int64_t *keys, const int32_t *first, const int32_t *count, int32_t n_roots,
+                     const esikf_plane *planes, int32_t n_planes, double voxel_size) {
+  if (!ctx || n_roots < 0 || n_planes < 0 || (n_roots > 0 && (!keys || !first || !count)) || (n_planes > 0 && !planes) || !(voxel_size > 0))
+    return fail(ctx, ESIKF_ERR_ARG, "map_upload: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  uint32_t cap = 1024;
+  while (cap < (uint32_t)n_roots * 2u) cap <<= 1;
+  std::vector<HashSlot> table(cap);
+  for (auto &s : table) s.key = ESIKF_KEY_EMPTY, s.first = 0, s.count = 0;
+  const float vsf = (float)voxel_size;
+  for (int r = 0; r < n_roots; r++) {
+    long long x = keys[3 * r], y = keys[3 * r + 1], z = keys[3 * r + 2];
+    if (!key_in_range(x, y, z)) return fail(ctx, ESIKF_ERR_ARG, "map_upload: voxel key (%lld,%lld,%lld) outside +-2^20", x, y, z);
+    if (first[r] < 0 || count[r] < 0 || first[r] + count[r] > n_planes) return fail(ctx, ESIKF_ERR_ARG, "map_upload: root %d plane range", r);
+    unsigned long long k = pack_key(x, y, z);
+    uint32_t s = hash_key(k) & (cap - 1);
+    while (table[s].key != ESIKF_KEY_EMPTY) {
+      if (table[s].key == k) return fail(ctx, ESIKF_ERR_ARG, "map_upload: duplicate voxel key");
+      s = (s + 1) & (cap - 1);
+    }
+    table[s].key = k, table[s].first = (uint32_t)first[r], table[s].count = (uint32_t)count[r];
+  }
+  (void)vsf;
+  CK(ctx->slots.reserve(cap));
+  CK(ctx->planes.reserve((size_t)n_planes + 1));
+  CK(cudaMemcpyAsync(ctx->slots.p, table.data(), cap * sizeof(HashSlot), cudaMemcpyHostToDevice, ctx->stream));
+  if (n_planes) CK(cudaMemcpyAsync(ctx->planes.p, planes, (size_t)n_planes * sizeof(esikf_plane), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->hash_mask = cap - 1;
+  ctx->n_planes = n_planes, ctx->n_roots = n_roots;
+  ctx->voxel_size = voxel_size;
+  ctx->have_map = true;
+  return ESIKF_OK;
+}
+
+int esikf_map_patch(esikf_ctx *ctx, const int32_t *plane_ids, const esikf_plane *planes, int32_t n) {
+  if (!ctx || n < 0 || (n > 0 && (!plane_ids || !planes))) return fail(ctx, ESIKF_ERR_ARG, "map_patch: bad argument");
+  if (!ctx->have_map) return fail(ctx, ESIKF_ERR_STATE, "map_patch before map_upload");
+  CK(cudaSetDevice(ctx->device));
+  for (int i = 0; i < n; i++) {
+    if (plane_ids[i] < 0 || plane_ids[i] >= ctx->n_planes) return fail(ctx, ESIKF_ERR_ARG, "map_patch: plane id %d", plane_ids[i]);
+    CK(cudaMemcpyAsync(ctx->planes.p + plane_ids[i], planes + i, sizeof(esikf_plane), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return ESIKF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- LIO
+int esikf_lio_set_scan(esikf_ctx *ctx, const float *pts_xyz, int32_t n) {
+  if (!ctx || n < 0 || (n > 0 && !pts_xyz)) return fail(ctx, ESIKF_ERR_ARG, "lio_set_scan: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->pts.reserve((size_t)n * 3 + 4));
+  CK(ctx->pre.reserve((size_t)n * 9 + 16));
+  CK(ctx->match_plane.reserve(n + 1));
+  CK(ctx->normal_plane.reserve(n + 1));
+  CK(ctx->dis.reserve(n + 1));
+  if (n) CK(cudaMemcpyAsync(ctx->pts.p, pts_xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->n_pts = n;
+  ctx->scan_fresh = true;
+  return ESIKF_OK;
+}
+
+static int lio_fill_args(esikf_ctx *ctx, LioKernelArgs &ka, double *state_ptr) {
+  memset(&ka, 0, sizeof(ka));
+  ka.pts = ctx->pts.p, ka.pre = ctx->pre.p;
+  shard_of(ctx->n_pts, ctx->rank, ctx->nranks, ka.begin, ka.count);
+  ka.state = state_ptr, ka.prop = ctx->prop.p;
+  ka.slots = ctx->slots.p, ka.hash_mask = ctx->hash_mask, ka.planes = ctx->planes.p;
+  memcpy(ka.extR, ctx->ext.extR, sizeof(ka.extR));
+  memcpy(ka.extT, ctx->ext.extT, sizeof(ka.extT));
+  ka.voxel_size = ctx->lio_cfg.voxel_size;
+  ka.voxel_size_f = (float)ctx->lio_cfg.voxel_size;
+  ka.sigma_num = ctx->lio_cfg.sigma_num;
+  ka.match_plane = ctx->match_plane.p, ka.normal_plane = ctx->normal_plane.p, ka.dis_to_plane = ctx->dis.p;
+  ka.partials = ctx->partials.p, ka.info = ctx->info.p, ka.ctrl = ctx->ctrl.p;
+  return 0;
+}
+static int lio_grid(const esikf_ctx *ctx, int count) {
+  int tiles = (count + LIO_THREADS - 1) / LIO_THREADS;
+  int g = tiles < ctx->partial_blocks ? tiles : ctx->partial_blocks;
+  return g < 1 ? 1 : g;
+}
+static int allreduce_info(esikf_ctx *ctx) {
+  if (ctx->nranks <= 1) return ESIKF_OK;
+  int r = g_nccl.AllReduce(ctx->info.p, ctx->info.p, INFO_N, NCCL_FLOAT64, NCCL_SUM, ctx->comm, ctx->stream);
+  if (r != 0) return fail(ctx, ESIKF_ERR_COMM, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  return ESIKF_OK;
+}
+
+int esikf_lio_run(esikf_ctx *ctx, const double *state_in, const double *state_prop, const esikf_lio_cfg *cfg) {
+  if (!ctx || !state_in || !state_prop || !cfg) return fail(ctx, ESIKF_ERR_ARG, "lio_run: null argument");
+  if (!ctx->have_map) return fail(ctx, ESIKF_ERR_STATE, "lio_run before map_upload");
+  if (!ctx->have_ext) return fail(ctx, ESIKF_ERR_STATE, "lio_run before set_extrinsics");
+  if (cfg->max_iterations < 1 || cfg->max_iterations > 8) return fail(ctx, ESIKF_ERR_ARG, "lio_run: max_iterations must be in [1,8]");
+  CK(cudaSetDevice(ctx->device));
+  ctx->lio_cfg = *cfg;
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(ctx->state.p, state_in, S_N * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->prop.p, state_prop, S_N * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), st));
+  CK(cudaMemsetAsync(ctx->lio_stats.p, 0, sizeof(esikf_lio_stats), st));
+  const int n = ctx->n_pts;
+  if (ctx->scan_fresh) {
+    if (n > 0) {
+      lio_precompute_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->pts.p, n, ctx->pre.p, ctx->ext_dev.p, (float)cfg->dept_err, (float)cfg->beam_err);
+      ctx->launches++;
+      CK(cudaMemsetAsync(ctx->normal_plane.p, 0xff, (size_t)n * sizeof(int32_t), st));  // pv.normal = 0 <=> no plane yet
+      CK(cudaMemsetAsync(ctx->match_plane.p, 0xff, (size_t)n * sizeof(int32_t), st));
+      CK(cudaMemsetAsync(ctx->dis.p, 0, (size_t)n * sizeof(float), st));
+    }
+    ctx->scan_fresh = false;
+  } else if (n > 0) {
+    CK(cudaMemsetAsync(ctx->normal_plane.p, 0xff, (size_t)n * sizeof(int32_t), st));
+  }
+  LioKernelArgs ka;
+  lio_fill_args(ctx, ka, ctx->state.p);
+  SolveArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.state = ctx->state.p, sa.prop = ctx->prop.p, sa.info = ctx->info.p, sa.ctrl = ctx->ctrl.p;
+  sa.max_iterations = cfg->max_iterations, sa.solve_mode = ctx->solve_mode, sa.lio_stats = ctx->lio_stats.p;
+  const int grid = lio_grid(ctx, ka.count);
+  for (int it = 0; it < cfg->max_iterations; it++) {
+    lio_residual_kernel<<<grid, LIO_THREADS, sizeof(LioSmem), st>>>(ka);
+    int rc = allreduce_info(ctx);
+    if (rc) return rc;
+    lio_solve_kernel<<<1, 32, 0, st>>>(sa);
+    ctx->launches += 2;
+  }
+  CK(cudaGetLastError());
+  return ESIKF_OK;
+}
+
+int esikf_lio_fetch(esikf_ctx *ctx, double *state_out, esikf_lio_stats *stats, int32_t *match_plane, int32_t *normal_plane, float *dis_to_plane) {
+  if (!ctx) return ESIKF_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t n = (size_t)ctx->n_pts;
+  if (state_out) CK(cudaMemcpyAsync(state_out, ctx->state.p, S_N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (stats) CK(cudaMemcpyAsync(stats, ctx->lio_stats.p, sizeof(esikf_lio_stats), cudaMemcpyDeviceToHost, st));
+  if (match_plane && n) CK(cudaMemcpyAsync(match_plane, ctx->match_plane.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (normal_plane && n) CK(cudaMemcpyAsync(normal_plane, ctx->normal_plane.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (dis_to_plane && n) CK(cudaMemcpyAsync(dis_to_plane, ctx->dis.p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return ESIKF_OK;
+}
+
+int esikf_lio_update(esikf_ctx *ctx, const float *pts_xyz, int32_t n, const double *state_in, const double *state_prop, const esikf_lio_cfg *cfg,
+                     double *state_out, esikf_lio_stats *stats, int32_t *match_plane, int32_t *normal_plane, float *dis_to_plane) {
+  int rc = esikf_lio_set_scan(ctx, pts_xyz, n);
+  if (rc) return rc;
+  rc = esikf_lio_run(ctx, state_in, state_prop, cfg);
+  if (rc) return rc;
+  return esikf_lio_fetch(ctx, state_out, stats, match_plane, normal_plane, dis_to_plane);
+}
+
+__global__ void expand_point_cov_kernel(const double *__restrict__ pre, int n, double *__restrict__ body_cov9, double *__restrict__ cross9) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double *p = pre + 9 * (size_t)i;
+  if (body_cov9) {
+    double *o = body_cov9 + 9 * (size_t)i;
+    o[0] = p[3], o[1] = p[4], o[2] = p[5], o[3] = p[4], o[4] = p[6], o[5] = p[7], o[6] = p[5], o[7] = p[7], o[8] = p[8];
+  }
+  if (cross9) {
+    double *o = cross9 + 9 * (size_t)i;
+    o[0] = 0, o[1] = -p[2], o[2] = p[1], o[3] = p[2], o[4] = 0, o[5] = -p[0], o[6] = -p[1], o[7] = p[0], o[8] = 0;
+  }
+}
+
+int esikf_lio_fetch_point_cov(esikf_ctx *ctx, double *body_cov9, double *cross_mat9) {
+  if (!ctx) return ESIKF_ERR_ARG;
+  if (ctx->scan_fresh) return fail(ctx, ESIKF_ERR_STATE, "fetch_point_cov before lio_run");
+  CK(cudaSetDevice(ctx->device));
+  const int n = ctx->n_pts;
+  if (n == 0) return ESIKF_OK;
+  DevBuf<double> tmp;
+  CK(tmp.reserve((size_t)n * 18));
+  expand_point_cov_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->pre.p, n, body_cov9 ? tmp.p : nullptr, cross_mat9 ? tmp.p + 9 * (size_t)n : nullptr);
+  ctx->launches++;
+  if (body_cov9) CK(cudaMemcpyAsync(body_cov9, tmp.p, (size_t)n * 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (cross_mat9) CK(cudaMemcpyAsync(cross_mat9, tmp.p + 9 * (size_t)n, (size_t)n * 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  tmp.release();
+  return ESIKF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- VIO
+int esikf_vio_set_camera(esikf_ctx *ctx, const esikf_camera *cam, const esikf_vio_cfg *cfg) {
+  if (!ctx || !cam || !cfg) return fail(ctx, ESIKF_ERR_ARG, "vio_set_camera: null argument");
+  if (cam->model < 0 || cam->model > 1 || cam->width <= 0 || cam->height <= 0) return fail(ctx, ESIKF_ERR_ARG, "vio_set_camera: bad camera");
+  if (cfg->patch_pyrimid_level < 1 || cfg->patch_pyrimid_level > 8 || cfg->max_iterations < 1 || cfg->max_iterations > 8 || !(cfg->img_point_cov > 0))
+    return fail(ctx, ESIKF_ERR_ARG, "vio_set_camera: bad vio cfg");
+  ctx->cam = *cam;
+  ctx->vio_cfg = *cfg;
+  ctx->have_cam = true;
+  return ESIKF_OK;
+}
+
+int esikf_vio_set_image(esikf_ctx *ctx, const uint8_t *img, int32_t width, int32_t height) {
+  if (!ctx || !img || width <= 0 || height <= 0) return fail(ctx, ESIKF_ERR_ARG, "vio_set_image: bad argument");
+  if (!ctx->have_cam) return fail(ctx, ESIKF_ERR_STATE, "vio_set_image before vio_set_camera");
+  if (width != ctx->cam.width || height != ctx->cam.height) return fail(ctx, ESIKF_ERR_ARG, "vio_set_image: image is %dx%d, camera %dx%d", width, height, ctx->cam.width, ctx->cam.height);
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->img.reserve((size_t)width * height + 64));
+  CK(cudaMemcpyAsync(ctx->img.p, img, (size_t)width * height, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->img_w = width, ctx->img_h = height;
+  return ESIKF_OK;
+}
+
+int esikf_vio_set_patches(esikf_ctx *ctx, const double *pos, const float *warp_patch, const int32_t *search_levels, const double *inv_expo_list, int32_t n) {
+  if (!ctx || n < 0 || (n > 0 && (!pos || !warp_patch || !search_levels || !inv_expo_list))) return fail(ctx, ESIKF_ERR_ARG, "vio_set_patches: bad argument");
+  if (!ctx->have_cam) return fail(ctx, ESIKF_ERR_STATE, "vio_set_patches before vio_set_camera");
+  CK(cudaSetDevice(ctx->device));
+  const int L = ctx->vio_cfg.patch_pyrimid_level;
+  CK(ctx->vis_pos.reserve((size_t)n * 3 + 4));
+  CK(ctx->warp_patch.reserve((size_t)n * 64 * L + 64));
+  CK(ctx->search_levels.reserve(n + 1));
+  CK(ctx->inv_expo.reserve(n + 1));
+  CK(ctx->errors.reserve(n + 1));
+  cudaStream_t st = ctx->stream;
+  if (n) {
+    CK(cudaMemcpyAsync(ctx->vis_pos.p, pos, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->warp_patch.p, warp_patch, (size_t)n * 64 * L * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->search_levels.p, search_levels, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->inv_expo.p, inv_expo_list, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  ctx->n_patches = n;
+  return ESIKF_OK;
+}
+
+static void vio_consts(const esikf_ctx *ctx, double Rci[9], double Pci[3], double Jdp_dR[9]) {
+  // vio.cpp:29-33, 57-65: Rli = extR^T, Pli = -extR^T extT, Rci = Rcl Rli, Pci = Rcl Pli + Pcl, Pic = -Rci^T Pci, Jdp_dR = -Rci [Pic]x
+  const esikf_extrinsics &e = ctx->ext;
+  double Rli[9], Pli[3];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) Rli[3 * r + c] = e.extR[3 * c + r];
+  for (int r = 0; r < 3; r++) Pli[r] = -(Rli[3 * r] * e.extT[0] + Rli[3 * r + 1] * e.extT[1] + Rli[3 * r + 2] * e.extT[2]);
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) Rci[3 * r + c] = e.Rcl[3 * r] * Rli[c] + e.Rcl[3 * r + 1] * Rli[3 + c] + e.Rcl[3 * r + 2] * Rli[6 + c];
+  for (int r = 0; r < 3; r++) Pci[r] = e.Rcl[3 * r] * Pli[0] + e.Rcl[3 * r + 1] * Pli[1] + e.Rcl[3 * r + 2] * Pli[2] + e.Pcl[r];
+  double Pic[3];
+  for (int r = 0; r < 3; r++) Pic[r] = -(Rci[r] * Pci[0] + Rci[3 + r] * Pci[1] + Rci[6 + r] * Pci[2]);
+  const double tmp[9] = {0.0, -Pic[2], Pic[1], Pic[2], 0.0, -Pic[0], -Pic[1], Pic[0], 0.0};
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) Jdp_dR[3 * r + c] = -(Rci[3 * r] * tmp[c] + Rci[3 * r + 1] * tmp[3 + c] + Rci[3 * r + 2] * tmp[6 + c]);
+}
+static void cam_dev(const esikf_ctx *ctx, CamDev &c) {
+  c.model = ctx->cam.model, c.width = ctx->cam.width, c.height = ctx->cam.height;
+  c.fx = ctx->cam.fx, c.fy = ctx->cam.fy, c.cx = ctx->cam.cx, c.cy = ctx->cam.cy;
+  for (int i = 0; i < 5; i++) c.d[i] = ctx->cam.d[i];
+}
+static void vio_fill_args(esikf_ctx *ctx, VioKernelArgs &ka, double *state_ptr) {
+  memset(&ka, 0, sizeof(ka));
+  ka.img = ctx->img.p;
+  cam_dev(ctx, ka.cam);
+  ka.pos = ctx->vis_pos.p, ka.warp_patch = ctx->warp_patch.p, ka.search_levels = ctx->search_levels.p, ka.inv_expo_list = ctx->inv_expo.p;
+  shard_of(ctx->n_patches, ctx->rank, ctx->nranks, ka.begin, ka.count);
+  ka.levels = ctx->vio_cfg.patch_pyrimid_level;
+  ka.exposure_en = ctx->vio_cfg.exposure_estimate_en;
+  ka.state = state_ptr;
+  vio_consts(ctx, ka.Rci, ka.Pci, ka.Jdp_dR);
+  ka.errors = ctx->errors.p, ka.partials = ctx->partials.p, ka.info = ctx->info.p, ka.ctrl = ctx->ctrl.p;
+}
+static int vio_grid(const esikf_ctx *ctx, int count) {
+  int g = (count + VIO_WARPS - 1) / VIO_WARPS;
+  if (g > ctx->partial_blocks) g = ctx->partial_blocks;
+  return g < 1 ? 1 : g;
+}
+
+int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_prop) {
+  if (!ctx || !state_in || !state_prop) return fail(ctx, ESIKF_ERR_ARG, "vio_run: null argument");
+  if (!ctx->have_cam || !ctx->have_ext) return fail(ctx, ESIKF_ERR_STATE, "vio_run before vio_set_camera / set_extrinsics");
+  if (ctx->img_w == 0) return fail(ctx, ESIKF_ERR_STATE, "vio_run before vio_set_image");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(ctx->state.p, state_in, S_N * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->prop.p, state_prop, S_N * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), st));
+  CK(cudaMemsetAsync(ctx->vio_stats.p, 0, sizeof(esikf_vio_stats), st));
+  if (ctx->n_patches == 0) return ESIKF_OK;  // total_points == 0: early return (vio.cpp:786)
+  VioKernelArgs ka;
+  vio_fill_args(ctx, ka, ctx->state.p);
+  SolveArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.state = ctx->state.p, sa.prop = ctx->prop.p, sa.info = ctx->info.p, sa.ctrl = ctx->ctrl.p;
+  sa.max_iterations = ctx->vio_cfg.max_iterations, sa.solve_mode = ctx->solve_mode, sa.vio_stats = ctx->vio_stats.p;
+  sa.old_state = ctx->old_state.p, sa.G = ctx->G.p, sa.img_point_cov = ctx->vio_cfg.img_point_cov;
+  const int grid = vio_grid(ctx, ka.count);
+  for (int level = ctx->vio_cfg.patch_pyrimid_level - 1; level >= 0; level--) {
+    for (int it = 0; it < ctx->vio_cfg.max_iterations; it++) {
+      ka.level = level, ka.slot_iter = it;
+      vio_patch_kernel<<<grid, VIO_THREADS, sizeof(VioSmem), st>>>(ka);
+      int rc = allreduce_info(ctx);
+      if (rc) return rc;
+      sa.level = level, sa.slot_iter = it, sa.last_slot = (level == 0 && it == ctx->vio_cfg.max_iterations - 1);
+      vio_solve_kernel<<<1, 32, 0, st>>>(sa);
+      ctx->launches += 2;
+    }
+  }
+  CK(cudaGetLastError());
+  return ESIKF_OK;
+}
+
+int esikf_vio_fetch(esikf_ctx *ctx, double *state_out, esikf_vio_stats *stats, float *errors) {
+  if (!ctx) return ESIKF_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (state_out) CK(cudaMemcpyAsync(state_out, ctx->state.p, S_N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (stats) CK(cudaMemcpyAsync(stats, ctx->vio_stats.p, sizeof(esikf_vio_stats), cudaMemcpyDeviceToHost, st));
+  if (errors && ctx->n_patches) CK(cudaMemcpyAsync(errors, ctx->errors.p, (size_t)ctx->n_patches * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return ESIKF_OK;
+}
+
+int esikf_vio_update(esikf_ctx *ctx, const uint8_t *img, int32_t width, int32_t height, const double *pos, const float *warp_patch,
+                     const int32_t *search_levels, const double *inv_expo_list, int32_t n, const double *state_in, const double *state_prop,
+                     double *state_out, esikf_vio_stats *stats, float *errors) {
+  int rc = esikf_vio_set_image(ctx, img, width, height);
+  if (rc) return rc;
+  rc = esikf_vio_set_patches(ctx, pos, warp_patch, search_levels, inv_expo_list, n);
+  if (rc) return rc;
+  rc = esikf_vio_run(ctx, state_in, state_prop);
+  if (rc) return rc;
+  return esikf_vio_fetch(ctx, state_out, stats, errors);
+}
+
+// ---------------------------------------------------------------------------------------------------------------- patch producers
+int esikf_vio_get_image_patch(esikf_ctx *ctx, const double *pc, int32_t n, int32_t level, float *patch_out) {
+  if (!ctx || n < 0 || level < 0 || level > 12 || (n > 0 && (!pc || !patch_out))) return fail(ctx, ESIKF_ERR_ARG, "get_image_patch: bad argument");
+  if (ctx->img_w == 0) return fail(ctx, ESIKF_ERR_STATE, "get_image_patch before vio_set_image");
+  if (n == 0) return ESIKF_OK;
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->pc_buf.reserve((size_t)n * 2));
+  CK(ctx->patch_buf.reserve((size_t)n * 64));
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(ctx->pc_buf.p, pc, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  image_patch_kernel<<<(n * 64 + 255) / 256, 256, 0, st>>>(ctx->img.p, ctx->img_w, ctx->img_h, ctx->pc_buf.p, n, level, ctx->patch_buf.p);
+  ctx->launches++;
+  CK(cudaMemcpyAsync(patch_out, ctx->patch_buf.p, (size_t)n * 64 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return ESIKF_OK;
+}
+
+int esikf_vio_set_ref_images(esikf_ctx *ctx, const uint8_t *const *imgs, int32_t n_imgs, int32_t width, int32_t height) {
+  if (!ctx || n_imgs < 0 || width <= 0 || height <= 0 || (n_imgs > 0 && !imgs)) return fail(ctx, ESIKF_ERR_ARG, "set_ref_images: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (uint8_t *p : ctx->ref_imgs) cudaFree(p);
+  ctx->ref_imgs.clear();
+  for (int i = 0; i < n_imgs; i++) {
+    uint8_t *d = nullptr;
+    CK(cudaMalloc(&d, (size_t)width * height + 64));
+    ctx->ref_imgs.push_back(d);
+    CK(cudaMemcpyAsync(d, imgs[i], (size_t)width * height, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CK(ctx->ref_img_ptrs.reserve(n_imgs + 1));
+  if (n_imgs) CK(cudaMemcpyAsync(ctx->ref_img_ptrs.p, ctx->ref_imgs.data(), n_imgs * sizeof(uint8_t *), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->ref_w = width, ctx->ref_h = height;
+  return ESIKF_OK;
+}
+
+int esikf_vio_warp_patches(esikf_ctx *ctx, int32_t n, const int32_t *ref_img_index, const double *px_ref, const double *pos_w, const double *normal_w,
+                           const double *T_ref_w, const double *T_cur_w, double *A_cur_ref_out, int32_t *search_level_out, float *warp_patch_out,
+                           int32_t keep_on_device) {
+  if (!ctx || n < 0 || (n > 0 && (!ref_img_index || !px_ref || !pos_w || !normal_w || !T_ref_w || !T_cur_w)))
+    return fail(ctx, ESIKF_ERR_ARG, "warp_patches: bad argument");
+  if (!ctx->have_cam) return fail(ctx, ESIKF_ERR_STATE, "warp_patches before vio_set_camera");
+  if (ctx->ref_imgs.empty()) return fail(ctx, ESIKF_ERR_STATE, "warp_patches before set_ref_images");
+  for (int i = 0; i < n; i++)
+    if (ref_img_index[i] < 0 || ref_img_index[i] >= (int)ctx->ref_imgs.size()) return fail(ctx, ESIKF_ERR_ARG, "warp_patches: ref image index %d", ref_img_index[i]);
+  if (n == 0) return ESIKF_OK;
+  CK(cudaSetDevice(ctx->device));
+  const int L = ctx->vio_cfg.patch_pyrimid_level;
+  cudaStream_t st = ctx->stream;
+  CK(ctx->ref_idx.reserve(n));
+  CK(ctx->px_ref.reserve((size_t)n * 2));
+  CK(ctx->pos_w.reserve((size_t)n * 3));
+  CK(ctx->normal_w.reserve((size_t)n * 3));
+  CK(ctx->T_ref.reserve((size_t)n * 12));
+  CK(ctx->T_cur.reserve(12));
+  CK(ctx->A_cur_ref.reserve((size_t)n * 4));
+  CK(ctx->search_levels.reserve(n + 1));
+  CK(ctx->warp_patch.reserve((size_t)n * 64 * L + 64));
+  CK(cudaMemcpyAsync(ctx->ref_idx.p, ref_img_index, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->px_ref.p, px_ref, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->pos_w.p, pos_w, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->normal_w.p, normal_w, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->T_ref.p, T_ref_w, (size_t)n * 12 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->T_cur.p, T_cur_w, 12 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CamDev cam;
+  cam_dev(ctx, cam);
+  warp_matrix_kernel<<<(n + 127) / 128, 128, 0, st>>>(cam, n, ctx->px_ref.p, ctx->pos_w.p, ctx->normal_w.p, ctx->T_ref.p, ctx->T_cur.p, ctx->A_cur_ref.p,
+                                                     ctx->search_levels.p);
+  CK(cudaMemsetAsync(ctx->warp_patch.p, 0, (size_t)n * 64 * L * sizeof(float), st));
+  warp_affine_kernel<<<(n * L * 64 + 255) / 256, 256, 0, st>>>(ctx->ref_img_ptrs.p, ctx->ref_idx.p, ctx->ref_w, ctx->ref_h, n, L, ctx->A_cur_ref.p,
+                                                              ctx->px_ref.p, ctx->search_levels.p, ctx->warp_patch.p);
+  ctx->launches += 2;
+  if (A_cur_ref_out) CK(cudaMemcpyAsync(A_cur_ref_out, ctx->A_cur_ref.p, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (search_level_out) CK(cudaMemcpyAsync(search_level_out, ctx->search_levels.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (warp_patch_out) CK(cudaMemcpyAsync(warp_patch_out, ctx->warp_patch.p, (size_t)n * 64 * L * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (keep_on_device) {
+    // install as the visual sub-map of the coming update: pos = pos_w, inv_expo filled by the caller through set_patches otherwise
+    CK(ctx->vis_pos.reserve((size_t)n * 3 + 4));
+    CK(ctx->inv_expo.reserve(n + 1));
+    CK(ctx->errors.reserve(n + 1));
+    CK(cudaMemcpyAsync(ctx->vis_pos.p, ctx->pos_w.p, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    std::vector<double> ones(n, 1.0);
+    CK(cudaMemcpyAsync(ctx->inv_expo.p, ones.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->n_patches = n;
+  }
+  CK(cudaStreamSynchronize(st));
+  return ESIKF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- multi-GPU
+int esikf_comm_unique_id(char out[128]) {
+  if (!out) return ESIKF_ERR_ARG;
+  if (!g_nccl.load()) return ESIKF_ERR_COMM;
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != 0) return ESIKF_ERR_COMM;
+  memcpy(out, id.internal, 128);
+  return ESIKF_OK;
+}
+int esikf_comm_init(esikf_ctx *ctx, int32_t rank, int32_t nranks, const char unique_id[128]) {
+  if (!ctx || nranks < 1 || rank < 0 || rank >= nranks || !unique_id) return fail(ctx, ESIKF_ERR_ARG, "comm_init: bad argument");
+  if (nranks == 1) {
+    ctx->rank = 0, ctx->nranks = 1;
+    return ESIKF_OK;
+  }
+  if (!g_nccl.load()) return fail(ctx, ESIKF_ERR_COMM, "libnccl.so.2 not found");
+  CK(cudaSetDevice(ctx->device));
+  ncclUniqueId id;
+  memcpy(id.internal, unique_id, 128);
+  int r = g_nccl.CommInitRank(&ctx->comm, nranks, id, rank);
+  if (r != 0) return fail(ctx, ESIKF_ERR_COMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  ctx->rank = rank, ctx->nranks = nranks;
+  return ESIKF_OK;
+}
+int esikf_comm_rank(const esikf_ctx *ctx, int32_t *rank, int32_t *nranks) {
+  if (!ctx) return ESIKF_ERR_ARG;
+  if (rank) *rank = ctx->rank;
+  if (nranks) *nranks = ctx->nranks;
+  return ESIKF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- measurement
+int esikf_profile_kernel(esikf_ctx *ctx, int32_t which, int32_t arg, int32_t reps, int32_t flush_l2, float *avg_ms) {
+  if (!ctx || !avg_ms || reps < 1) return fail(ctx, ESIKF_ERR_ARG, "profile_kernel: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t flush_bytes = 256u << 20;
+  if (flush_l2) CK(ctx->flush.reserve(flush_bytes));
+  // work on a scratch copy of the resident state so the measured launches never disturb an update in flight
+  CK(cudaMemcpyAsync(ctx->scratch_state.p, ctx->state.p, S_N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), st));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  double total = 0.0;
+  LioKernelArgs la;
+  VioKernelArgs va;
+  SolveArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  int grid = 1;
+  if (which == 0 || which == 1 || which == 3) {
+    if (!ctx->have_map || ctx->n_pts == 0 || ctx->scan_fresh) return fail(ctx, ESIKF_ERR_STATE, "profile_kernel: no resident LIO frame (run lio once)");
+    lio_fill_args(ctx, la, ctx->scratch_state.p);
+    grid = lio_grid(ctx, la.count);
+    sa.state = ctx->scratch_state.p, sa.prop = ctx->prop.p, sa.info = ctx->info.p, sa.ctrl = ctx->ctrl.p;
+    sa.max_iterations = 1 << 20, sa.solve_mode = ctx->solve_mode;
+  } else if (which == 2) {
+    if (ctx->n_patches == 0 || ctx->img_w == 0) return fail(ctx, ESIKF_ERR_STATE, "profile_kernel: no resident VIO frame");
+    vio_fill_args(ctx, va, ctx->scratch_state.p);
+    va.level = arg, va.slot_iter = 0;
+    grid = vio_grid(ctx, va.count);
+  } else {
+    return fail(ctx, ESIKF_ERR_ARG, "profile_kernel: which=%d", which);
+  }
+  for (int r = 0; r < reps + 3; r++) {  // 3 warm-up launches
+    if (flush_l2) CK(cudaMemsetAsync(ctx->flush.p, r & 0xff, flush_bytes, st));
+    if (which == 1) {
+      CK(cudaMemcpyAsync(ctx->scratch_state.p, ctx->state.p, S_N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), st));
+    }
+    CK(cudaEventRecord(e0, st));
+    if (which == 0) lio_residual_kernel<<<grid, LIO_THREADS, sizeof(LioSmem), st>>>(la);
+    else if (which == 1) lio_solve_kernel<<<1, 32, 0, st>>>(sa);
+    else if (which == 2) vio_patch_kernel<<<grid, VIO_THREADS, sizeof(VioSmem), st>>>(va);
+    else lio_precompute_kernel<<<(ctx->n_pts + 255) / 256, 256, 0, st>>>(ctx->pts.p, ctx->n_pts, ctx->pre.p, ctx->ext_dev.p, (float)ctx->lio_cfg.dept_err,
+                                                                       (float)ctx->lio_cfg.beam_err);
+    CK(cudaEventRecord(e1, st));
+    CK(cudaEventSynchronize(e1));
+    ctx->launches++;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (r >= 3) total += ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  CK(cudaGetLastError());
+  *avg_ms = (float)(total / reps);
+  return ESIKF_OK;
+}
+
+}  // extern "C"

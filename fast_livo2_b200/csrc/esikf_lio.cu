@@ -1,0 +1,348 @@
+// LIO kernels of the B200 ESIKF update (sm_100a).
+//
+//   lio_precompute_kernel : per-frame calcBodyCov + cross-matrix vector     (reference src/voxel_map.cpp:15-34, 349-360)
+//   lio_residual_kernel   : one ESIKF iteration's residual / Jacobian build (src/voxel_map.cpp:376-390 TransformLidar + point
+//                           covariance, :643-786 voxel probe + plane association, :414-458 Jacobian / R^-1) fused with the
+//                           H^T R^-1 H, H^T R^-1 z reduction (:464-466). No PointToPlane is ever materialised.
+//
+// Mapping: one thread per LiDAR point (fp64 work per point is ~600 flop and sequential; a warp per point would idle 31/32 of
+// the fp64 pipe), 32 points per warp. The per-warp contraction sum_i a_i (w_i a_i)^T, a = [H_i(6), z_i, 1], runs on the fp64
+// tensor-core path (mma.sync.m8n8k4.f64, SASS DMMA) out of shared-memory staged rows; partial 8x8 blocks are combined in a
+// fixed order (warp -> block -> grid) so the result is bit-reproducible run to run.
+#include "esikf_dev.cuh"
+
+namespace esikf {
+
+#define LIO_THREADS 256
+#define LIO_WARPS (LIO_THREADS / 32)
+
+struct LioKernelArgs {
+  const float *pts;          // [n_total][3] body-frame scan
+  const double *pre;         // [n_total][9]: cross vector c(3) | body cov xx xy xz yy yz zz
+  int begin, count;          // this rank's shard
+  const double *state;       // current iterate (device, packed)
+  const double *prop;        // state_propagat
+  const HashSlot *slots;
+  uint32_t hash_mask;
+  const esikf_plane *planes;
+  double extR[9], extT[3];
+  double voxel_size;         // double voxel size used for the key (voxel_map.cpp:646,668)
+  float voxel_size_f;        // float voxel size that positioned the roots (voxel_map.cpp:534,578-581)
+  double sigma_num;
+  int32_t *match_plane;      // [n_total]
+  int32_t *normal_plane;     // [n_total] sticky
+  float *dis_to_plane;       // [n_total]
+  double *partials;          // [grid][INFO_N]
+  double *info;              // [INFO_N]
+  Ctrl *ctrl;
+};
+
+__device__ __forceinline__ double dot3_rn(double a0, double a1, double a2, double b0, double b1, double b2) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(a0, b0), __dmul_rn(a1, b1)), __dmul_rn(a2, b2));
+}
+
+// index of (i,j) in the row-major upper triangle of a 6x6
+__device__ __forceinline__ constexpr int tri6(int i, int j) {
+  return (i <= j) ? (i * 6 - (i * (i - 1)) / 2 + (j - i)) : (j * 6 - (j * (j - 1)) / 2 + (i - j));
+}
+
+// sigma = J^T PV J evaluated as (J PV) J, the order of src/voxel_map.cpp:735
+__device__ __forceinline__ double quad6(const double *__restrict__ pv, const double J[6]) {
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    double t = J[0] * pv[tri6(0, j)];
+#pragma unroll
+    for (int i = 1; i < 6; i++) t += J[i] * pv[tri6(i, j)];
+    s = (j == 0) ? t * J[0] : s + t * J[j];
+  }
+  return s;
+}
+
+__device__ __forceinline__ double quad3_sym(const double v[6], double n0, double n1, double n2) {
+  // n^T V n with V symmetric (xx xy xz yy yz zz), evaluated as (n^T V) n
+  double t0 = n0 * v[0] + n1 * v[1] + n2 * v[2];
+  double t1 = n0 * v[1] + n1 * v[3] + n2 * v[4];
+  double t2 = n0 * v[2] + n1 * v[4] + n2 * v[5];
+  return t0 * n0 + t1 * n1 + t2 * n2;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Per-frame precompute: calcBodyCov (voxel_map.cpp:15-34) and the cross-matrix vector extR*p+extT (:356-359).
+__global__ void lio_precompute_kernel(const float *__restrict__ pts, int n, double *__restrict__ pre, const double *__restrict__ ext,
+                                      float dept_err, float beam_err) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double px = pts[3 * i], py = pts[3 * i + 1], pz = pts[3 * i + 2];
+  if (pz == 0) pz = 0.001;  // :352  (calcBodyCov's own 0 -> 1e-4 fix at :17 can then never trigger)
+  float range = (float)sqrt(px * px + py * py + pz * pz);
+  float range_var = dept_err * dept_err;
+  double sdv = sin((double)beam_err * 0.017453293);  // PCL DEG2RAD
+  double dv = sdv * sdv;
+  double nrm = sqrt(px * px + py * py + pz * pz);
+  double dx = px / nrm, dy = py / nrm, dz = pz / nrm;
+  double b1x = 1.0, b1y = 1.0, b1z = -(dx + dy) / dz;
+  double n1 = sqrt(b1x * b1x + b1y * b1y + b1z * b1z);
+  b1x /= n1, b1y /= n1, b1z /= n1;
+  double b2x = b1y * dz - b1z * dy, b2y = b1z * dx - b1x * dz, b2z = b1x * dy - b1y * dx;  // base_vector1.cross(direction)
+  double n2 = sqrt(b2x * b2x + b2y * b2y + b2z * b2z);
+  b2x /= n2, b2y /= n2, b2z /= n2;
+  // A = range * [d]x * [b1 b2]   (3x2)
+  double r = (double)range;
+  double a00 = r * (-dz * b1y + dy * b1z), a01 = r * (-dz * b2y + dy * b2z);
+  double a10 = r * (dz * b1x - dx * b1z), a11 = r * (dz * b2x - dx * b2z);
+  double a20 = r * (-dy * b1x + dx * b1y), a21 = r * (-dy * b2x + dx * b2y);
+  double rv = (double)range_var;
+  double *o = pre + 9 * (size_t)i;
+  // cross vector
+  o[0] = ext[0] * px + ext[1] * py + ext[2] * pz + ext[9];
+  o[1] = ext[3] * px + ext[4] * py + ext[5] * pz + ext[10];
+  o[2] = ext[6] * px + ext[7] * py + ext[8] * pz + ext[11];
+  // cov = d rv d^T + A dv A^T  (symmetric; upper triangle stored)
+  o[3] = dx * rv * dx + dv * (a00 * a00 + a01 * a01);
+  o[4] = dx * rv * dy + dv * (a00 * a10 + a01 * a11);
+  o[5] = dx * rv * dz + dv * (a00 * a20 + a01 * a21);
+  o[6] = dy * rv * dy + dv * (a10 * a10 + a11 * a11);
+  o[7] = dy * rv * dz + dv * (a10 * a20 + a11 * a21);
+  o[8] = dz * rv * dz + dv * (a20 * a20 + a21 * a21);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+struct Cand {
+  double prob;
+  int idx;
+  float dis;  // signed n.p + d narrowed to float (PointToPlane::dis_to_plane_, voxel_map.cpp:753)
+};
+
+// build_single_residual's plane branch (src/voxel_map.cpp:721-768) for one candidate plane.
+__device__ __forceinline__ void eval_plane(const esikf_plane *__restrict__ pl, int idx, const double pw[3], const double var[6],
+                                           double sigma_num, Cand &best) {
+  const double *__restrict__ q = reinterpret_cast<const double *>(pl);
+  double c0 = q[0], c1 = q[1], c2 = q[2];
+  double n0 = q[3], n1 = q[4], n2 = q[5];
+  float2 dr = *reinterpret_cast<const float2 *>(q + 27);  // d, radius
+  double sd = n0 * pw[0] + n1 * pw[1] + n2 * pw[2] + (double)dr.x;
+  float dis_to_plane = (float)fabs(sd);
+  double e0 = c0 - pw[0], e1 = c1 - pw[1], e2 = c2 - pw[2];
+  float dis_to_center = (float)(e0 * e0 + e1 * e1 + e2 * e2);
+  float range_dis = sqrtf(__fsub_rn(dis_to_center, __fmul_rn(dis_to_plane, dis_to_plane)));
+  if ((double)range_dis <= 3.0 * (double)dr.y) {  // NaN fails, as in the reference
+    double J[6] = {pw[0] - c0, pw[1] - c1, pw[2] - c2, -n0, -n1, -n2};
+    double sigma_l = quad6(q + 6, J);
+    sigma_l += quad3_sym(var, n0, n1, n2);
+    if ((double)dis_to_plane < sigma_num * sqrt(sigma_l)) {
+      double this_prob = 1.0 / sqrt(sigma_l) * exp(-0.5 * (double)dis_to_plane * (double)dis_to_plane / sigma_l);
+      if (this_prob > best.prob) {
+        best.prob = this_prob;
+        best.idx = idx;
+        best.dis = (float)sd;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ bool probe(const HashSlot *__restrict__ slots, uint32_t mask, long long kx, long long ky, long long kz,
+                                      uint32_t &first, uint32_t &count) {
+  if (!key_in_range(kx, ky, kz)) return false;
+  unsigned long long key = pack_key(kx, ky, kz);
+  uint32_t s = hash_key(key) & mask;
+  for (;;) {
+    ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(slots + s));
+    if (v.x == key) {
+      first = (uint32_t)(v.y & 0xffffffffull);
+      count = (uint32_t)(v.y >> 32);
+      return true;
+    }
+    if (v.x == ESIKF_KEY_EMPTY) return false;
+    s = (s + 1) & mask;
+  }
+}
+
+// shared-memory layout of the residual kernel
+struct LioSmem {
+  double R[9], t[3], Ptt[9], Ppp[9];  // current state
+  double Rp[9], tp[3], Mp[9];         // prior pose, Mp = Rp * extR
+  double rows[LIO_THREADS][8];        // a_i = [A(3) n(3) z 1]
+  double w[LIO_THREADS];              // R_inv
+  double absd[LIO_THREADS];           // |dis_to_plane|
+  ReduceSmem<LIO_WARPS> red;
+};
+
+__global__ void __launch_bounds__(LIO_THREADS, 2) lio_residual_kernel(const LioKernelArgs a) {
+  if (a.ctrl->stop) return;  // EKF_stop_flg: remaining iterations of the unrolled loop do nothing
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  LioSmem &sm = *reinterpret_cast<LioSmem *>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (tid < 9) {
+    sm.R[tid] = a.state[S_R + tid];
+    sm.Rp[tid] = a.prop[S_R + tid];
+    int r = tid / 3, c = tid % 3;
+    sm.Ptt[tid] = a.state[S_COV + r * 19 + c];
+    sm.Ppp[tid] = a.state[S_COV + (3 + r) * 19 + (3 + c)];
+    // Mp = Rp * extR  (state_propagat.rot_end * extR_, voxel_map.cpp:445)
+    double s = 0;
+    for (int k = 0; k < 3; k++) s += a.prop[S_R + r * 3 + k] * a.extR[k * 3 + c];
+    sm.Mp[tid] = s;
+  } else if (tid < 12) {
+    sm.t[tid - 9] = a.state[S_P + tid - 9];
+    sm.tp[tid - 9] = a.prop[S_P + tid - 9];
+  }
+  __syncthreads();
+
+  double D0 = 0.0, D1 = 0.0;  // this lane's two entries of the warp's 8x8 block
+  int cnt = 0;
+
+  const int tiles = (a.count + LIO_THREADS - 1) / LIO_THREADS;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int li = tile * LIO_THREADS + tid;
+    const bool valid = li < a.count;
+    const int i = a.begin + li;
+    bool matched = false;
+    int midx = -1;
+    double row[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double wgt = 0.0, absd = 0.0;
+    if (valid) {
+      const double px = a.pts[3 * (size_t)i], py = a.pts[3 * (size_t)i + 1], pz = a.pts[3 * (size_t)i + 2];
+      const double *__restrict__ pre = a.pre + 9 * (size_t)i;
+      // p_imu = extR p + extT ; p_w = R p_imu + t, narrowed to float (TransformLidar, voxel_map.cpp:522-526). No FMA contraction
+      // on this chain: the float rounding of p_w decides the voxel key.
+      const double pi0 = __dadd_rn(dot3_rn(a.extR[0], a.extR[1], a.extR[2], px, py, pz), a.extT[0]);
+      const double pi1 = __dadd_rn(dot3_rn(a.extR[3], a.extR[4], a.extR[5], px, py, pz), a.extT[1]);
+      const double pi2 = __dadd_rn(dot3_rn(a.extR[6], a.extR[7], a.extR[8], px, py, pz), a.extT[2]);
+      double pw[3];
+      pw[0] = (double)(float)__dadd_rn(dot3_rn(sm.R[0], sm.R[1], sm.R[2], pi0, pi1, pi2), sm.t[0]);
+      pw[1] = (double)(float)__dadd_rn(dot3_rn(sm.R[3], sm.R[4], sm.R[5], pi0, pi1, pi2), sm.t[1]);
+      pw[2] = (double)(float)__dadd_rn(dot3_rn(sm.R[6], sm.R[7], sm.R[8], pi0, pi1, pi2), sm.t[2]);
+
+      // voxel key (voxel_map.cpp:665-671): float quotient, "-1 if negative", truncate
+      float loc[3];
+      long long key[3];
+      bool finite = true;
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        loc[j] = (float)__ddiv_rn(pw[j], a.voxel_size);
+        if (loc[j] < 0) loc[j] = (float)__dadd_rn((double)loc[j], -1.0);
+        finite = finite && (fabsf(loc[j]) < 3.0e6f);
+        key[j] = (long long)loc[j];
+      }
+
+      uint32_t first = 0, count = 0;
+      if (finite && probe(a.slots, a.hash_mask, key[0], key[1], key[2], first, count)) {
+        // pv.var = R body_cov R^T + (-C) P_tt (-C)^T + P_pp   (voxel_map.cpp:385-388), symmetric 6
+        double var[6];
+        {
+          const double b0 = pre[3], b1 = pre[4], b2 = pre[5], b3 = pre[6], b4 = pre[7], b5 = pre[8];
+          double T[9];
+#pragma unroll
+          for (int r = 0; r < 3; r++) {
+            const double r0 = sm.R[3 * r], r1 = sm.R[3 * r + 1], r2 = sm.R[3 * r + 2];
+            T[3 * r + 0] = r0 * b0 + r1 * b1 + r2 * b2;
+            T[3 * r + 1] = r0 * b1 + r1 * b3 + r2 * b4;
+            T[3 * r + 2] = r0 * b2 + r1 * b4 + r2 * b5;
+          }
+          const double cx = pre[0], cy = pre[1], cz = pre[2];
+          // C = [c]x ; U = C * Ptt
+          double U[9];
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            const double p0 = sm.Ptt[c], p1 = sm.Ptt[3 + c], p2 = sm.Ptt[6 + c];
+            U[0 + c] = -cz * p1 + cy * p2;
+            U[3 + c] = cz * p0 - cx * p2;
+            U[6 + c] = -cy * p0 + cx * p1;
+          }
+          // (C Ptt) C^T : column j of C^T is row j of C
+          // row of C: C0 = (0,-cz,cy), C1 = (cz,0,-cx), C2 = (-cy,cx,0)
+          const double V00 = -U[1] * cz + U[2] * cy, V01 = U[0] * cz - U[2] * cx, V02 = -U[0] * cy + U[1] * cx;
+          const double V11 = U[3] * cz - U[5] * cx, V12 = -U[3] * cy + U[4] * cx;
+          const double V22 = -U[6] * cy + U[7] * cx;
+          var[0] = (T[0] * sm.R[0] + T[1] * sm.R[1] + T[2] * sm.R[2]) + V00 + sm.Ppp[0];
+          var[1] = (T[0] * sm.R[3] + T[1] * sm.R[4] + T[2] * sm.R[5]) + V01 + sm.Ppp[1];
+          var[2] = (T[0] * sm.R[6] + T[1] * sm.R[7] + T[2] * sm.R[8]) + V02 + sm.Ppp[2];
+          var[3] = (T[3] * sm.R[3] + T[4] * sm.R[4] + T[5] * sm.R[5]) + V11 + sm.Ppp[4];
+          var[4] = (T[3] * sm.R[6] + T[4] * sm.R[7] + T[5] * sm.R[8]) + V12 + sm.Ppp[5];
+          var[5] = (T[6] * sm.R[6] + T[7] * sm.R[7] + T[8] * sm.R[8]) + V22 + sm.Ppp[8];
+        }
+
+        Cand best;
+        best.prob = 0.0, best.idx = -1, best.dis = 0.f;
+        for (uint32_t c = 0; c < count; c++) eval_plane(a.planes + first + c, (int)(first + c), pw, var, a.sigma_num, best);
+        if (best.idx < 0) {
+          // one neighbour voxel (voxel_map.cpp:680-691). loc is in voxel units, centre/quarter length in metres: reproduced literally.
+          const double vsf = (double)a.voxel_size_f;
+          const double ql = (double)(a.voxel_size_f / 4.0f);
+          long long nk[3] = {key[0], key[1], key[2]};
+#pragma unroll
+          for (int j = 0; j < 3; j++) {
+            const double center = (0.5 + (double)key[j]) * vsf;
+            if ((double)loc[j] > center + ql) nk[j] = key[j] + 1;
+            else if ((double)loc[j] < center - ql) nk[j] = key[j] - 1;
+          }
+          uint32_t f2 = 0, c2 = 0;
+          if (probe(a.slots, a.hash_mask, nk[0], nk[1], nk[2], f2, c2))
+            for (uint32_t c = 0; c < c2; c++) eval_plane(a.planes + f2 + c, (int)(f2 + c), pw, var, a.sigma_num, best);
+        }
+
+        if (best.idx >= 0) {
+          matched = true;
+          midx = best.idx;
+          // Jacobian / measurement-noise loop (voxel_map.cpp:414-458) for this point
+          const double *__restrict__ q = reinterpret_cast<const double *>(a.planes + best.idx);
+          const double c0 = q[0], c1 = q[1], c2 = q[2];
+          const double n0 = q[3], n1 = q[4], n2 = q[5];
+          // point_world with the PRIOR pose (:425)
+          const double w0 = sm.Rp[0] * pi0 + sm.Rp[1] * pi1 + sm.Rp[2] * pi2 + sm.tp[0];
+          const double w1 = sm.Rp[3] * pi0 + sm.Rp[4] * pi1 + sm.Rp[5] * pi2 + sm.tp[1];
+          const double w2 = sm.Rp[6] * pi0 + sm.Rp[7] * pi1 + sm.Rp[8] * pi2 + sm.tp[2];
+          double J[6] = {w0 - c0, w1 - c1, w2 - c2, -n0, -n1, -n2};
+          const double sigma_l = quad6(q + 6, J);
+          // n^T (Mp body_cov Mp^T) n = m^T body_cov m, m = Mp^T n   (:445-449)
+          const double m0 = sm.Mp[0] * n0 + sm.Mp[3] * n1 + sm.Mp[6] * n2;
+          const double m1 = sm.Mp[1] * n0 + sm.Mp[4] * n1 + sm.Mp[7] * n2;
+          const double m2 = sm.Mp[2] * n0 + sm.Mp[5] * n1 + sm.Mp[8] * n2;
+          const double nvn = quad3_sym(pre + 3, m0, m1, m2);
+          wgt = 1.0 / (0.001 + sigma_l + nvn);
+          // A = [p_imu]x R^T n with the CURRENT rotation (:453)
+          const double g0 = sm.R[0] * n0 + sm.R[3] * n1 + sm.R[6] * n2;
+          const double g1 = sm.R[1] * n0 + sm.R[4] * n1 + sm.R[7] * n2;
+          const double g2 = sm.R[2] * n0 + sm.R[5] * n1 + sm.R[8] * n2;
+          row[0] = -pi2 * g1 + pi1 * g2;
+          row[1] = pi2 * g0 - pi0 * g2;
+          row[2] = -pi1 * g0 + pi0 * g1;
+          row[3] = n0, row[4] = n1, row[5] = n2;
+          row[6] = -(double)best.dis;  // meas_vec (:457)
+          row[7] = 1.0;
+          absd = fabs((double)best.dis);
+          a.normal_plane[i] = best.idx;  // pv.normal = plane.normal_ (:744), sticky across iterations
+          a.dis_to_plane[i] = best.dis;
+        }
+      }
+      a.match_plane[i] = midx;  // ptpl_list_ membership of this iteration
+    }
+    cnt += __popc(__ballot_sync(0xffffffffu, matched));
+
+    // stage the 32 rows of this warp and contract them on the fp64 tensor path
+    double4 *dst = reinterpret_cast<double4 *>(&sm.rows[tid][0]);
+    dst[0] = make_double4(row[0], row[1], row[2], row[3]);
+    dst[1] = make_double4(row[4], row[5], row[6], row[7]);
+    sm.w[tid] = wgt;
+    sm.absd[tid] = absd;
+    __syncwarp();
+    {
+      const int g = lane >> 2, t = lane & 3;
+      const int base = warp * 32;
+#pragma unroll
+      for (int s = 0; s < 8; s++) {
+        const int r = base + 4 * s + t;
+        const double v = sm.rows[r][g];
+        const double b = (g == 7) ? sm.absd[r] : sm.w[r] * v;
+        dmma_m8n8k4(D0, D1, v, b);
+      }
+    }
+    __syncwarp();
+  }
+
+  reduce_info<LIO_WARPS>(sm.red, D0, D1, (double)cnt, true, a.partials, a.info, a.ctrl);
+}
+
+}  // namespace esikf

@@ -1,0 +1,371 @@
+// Solve kernels of the B200 ESIKF update: the Kalman gain, the boxplus state update, loop control and the final
+// covariance update, executed by ONE warp so the whole iteration loop runs on the device with no host round trip.
+//
+//   lio_solve_kernel : src/voxel_map.cpp:462-499  (K_1, G, solution, state_ += solution, convergence / rematch / (I-G)P)
+//   vio_solve_kernel : src/vio.cpp:1636-1685 + :800 (error-gated accept / rollback, K_1, G, solution, final cov -= G cov)
+//
+// Gain: the reference computes K_1 = (H^T H + P^-1)^-1 with two 19x19 partial-pivot inversions and then only uses the
+// first m (6 or 7) columns of K_1. Because H^T H is zero outside its leading m x m block A, the push-through identity gives
+//     K_1[:, :m] = P[:, :m] (I_m + A P_mm)^-1
+// exactly — an m x m solve with 19 right-hand sides, one per lane. solve_mode 1 keeps the literal double inversion (Gauss-
+// Jordan with partial pivoting in shared memory) for parity checks.
+#include <float.h>
+#include "esikf_dev.cuh"
+
+namespace esikf {
+
+struct SolveArgs {
+  double *state;        // current iterate (device, packed) — updated in place
+  const double *prop;   // state_propagat
+  const double *info;   // reduced information buffer
+  Ctrl *ctrl;
+  int max_iterations;
+  int solve_mode;
+  // LIO
+  esikf_lio_stats *lio_stats;
+  // VIO
+  esikf_vio_stats *vio_stats;
+  double *old_state;    // 25 doubles (pose part of old_state)
+  double *G;            // 19 x 7 last accepted gain block
+  double img_point_cov;
+  int level, slot_iter, last_slot;
+};
+
+struct SolveSmem {
+  double P[19 * 19];
+  double A[49];     // m x m information block
+  double M[49];     // I + A P_mm, transposed for the per-lane solve
+  double HTz[8];
+  double vec[19];
+  double sol[19];
+  double W[19 * 38];  // literal mode workspace
+  double K[19 * 19];
+};
+
+// Exp(v) of include/utils/so3_math.h:44-58 (identity when |v| <= 1e-5)
+__device__ inline void so3_exp(const double v[3], double E[9]) {
+  double nrm = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  for (int i = 0; i < 9; i++) E[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  if (nrm > 0.00001) {
+    double r[3] = {v[0] / nrm, v[1] / nrm, v[2] / nrm};
+    double K[9] = {0.0, -r[2], r[1], r[2], 0.0, -r[0], -r[1], r[0], 0.0};
+    double s = sin(nrm), c = 1.0 - cos(nrm);
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        double kk = K[i * 3] * K[j] + K[i * 3 + 1] * K[3 + j] + K[i * 3 + 2] * K[6 + j];
+        E[i * 3 + j] = E[i * 3 + j] + s * K[i * 3 + j] + c * kk;
+      }
+  }
+}
+// Log(R) of include/utils/so3_math.h:61-66
+__device__ inline void so3_log(const double R[9], double out[3]) {
+  double tr = R[0] + R[4] + R[8];
+  double theta = (tr > 3.0 - 1e-6) ? 0.0 : acos(0.5 * (tr - 1));
+  double K[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};
+  double f = (fabs(theta) < 0.001) ? 0.5 : (0.5 * theta / sin(theta));
+  for (int i = 0; i < 3; i++) out[i] = f * K[i];
+}
+
+// vec = state_propagat (-) state  (common_lib.h:194-206), by lane 0 for the rotation part
+__device__ inline void boxminus_warp(const double *prop, const double *st, double *vec, int lane) {
+  if (lane == 0) {
+    double Rd[9];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) Rd[i * 3 + j] = st[S_R + 0 * 3 + i] * prop[S_R + 0 * 3 + j] + st[S_R + 1 * 3 + i] * prop[S_R + 1 * 3 + j] +
+                                                   st[S_R + 2 * 3 + i] * prop[S_R + 2 * 3 + j];  // b.rot^T * this.rot
+    double l[3];
+    so3_log(Rd, l);
+    vec[0] = l[0], vec[1] = l[1], vec[2] = l[2];
+  }
+  if (lane >= 3 && lane < 19) {
+    // packed offsets of the additive blocks in error-state order: p(3:6) expo(6) v(7:10) bg(10:13) ba(13:16) g(16:19)
+    int off = (lane < 6) ? S_P + (lane - 3) : (lane == 6) ? S_EXPO : (lane < 10) ? S_V + (lane - 7) : (lane < 13) ? S_BG + (lane - 10)
+              : (lane < 16) ? S_BA + (lane - 13) : S_G + (lane - 16);
+    vec[lane] = prop[off] - st[off];
+  }
+}
+
+// state (+)= sol  (common_lib.h:182-192)
+__device__ inline void boxplus_warp(double *st, const double *sol, int lane) {
+  if (lane == 0) {
+    double E[9], Rn[9];
+    so3_exp(sol, E);
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) Rn[i * 3 + j] = st[S_R + i * 3] * E[j] + st[S_R + i * 3 + 1] * E[3 + j] + st[S_R + i * 3 + 2] * E[6 + j];
+    for (int i = 0; i < 9; i++) st[S_R + i] = Rn[i];
+  }
+  if (lane >= 3 && lane < 19) {
+    int off = (lane < 6) ? S_P + (lane - 3) : (lane == 6) ? S_EXPO : (lane < 10) ? S_V + (lane - 7) : (lane < 13) ? S_BG + (lane - 10)
+              : (lane < 16) ? S_BA + (lane - 13) : S_G + (lane - 16);
+    st[off] += sol[lane];
+  }
+}
+
+// In-place inverse of a 19x19 in shared memory by one warp (Gauss-Jordan, partial pivoting) — literal mode only.
+__device__ inline void inverse19_warp(const double *Ain, double *W /*19x38*/, double *out, int lane) {
+  for (int idx = lane; idx < 19 * 38; idx += 32) {
+    int r = idx / 38, c = idx % 38;
+    W[idx] = (c < 19) ? Ain[r * 19 + c] : ((c - 19) == r ? 1.0 : 0.0);
+  }
+  __syncwarp();
+  for (int k = 0; k < 19; k++) {
+    int piv = k;
+    double best = fabs(W[k * 38 + k]);
+    for (int r = k + 1; r < 19; r++) {
+      double v = fabs(W[r * 38 + k]);
+      if (v > best) best = v, piv = r;
+    }
+    __syncwarp();
+    if (piv != k)
+      for (int c = lane; c < 38; c += 32) {
+        double t = W[k * 38 + c];
+        W[k * 38 + c] = W[piv * 38 + c];
+        W[piv * 38 + c] = t;
+      }
+    __syncwarp();
+    double d = W[k * 38 + k];
+    double f[19];
+    for (int r = 0; r < 19; r++) f[r] = W[r * 38 + k];
+    __syncwarp();
+    for (int c = lane; c < 38; c += 32) {
+      double pk = W[k * 38 + c] / d;
+      W[k * 38 + c] = pk;
+      for (int r = 0; r < 19; r++)
+        if (r != k) W[r * 38 + c] -= f[r] * pk;
+    }
+    __syncwarp();
+  }
+  for (int idx = lane; idx < 361; idx += 32) out[idx] = W[(idx / 19) * 38 + 19 + (idx % 19)];
+  __syncwarp();
+}
+
+// Gain block x = K_1[lane, 0:m] for every lane < 19. PS = P * pscale (pscale = 1 for LIO, 1/img_point_cov for VIO).
+template <int m>
+__device__ inline void gain_rows(SolveSmem &sm, double pscale, int solve_mode, int lane, double x[m]) {
+  if (solve_mode == 1) {
+    // literal: K_1 = (H_T_H + (P*pscale)^-1)^-1
+    for (int idx = lane; idx < 361; idx += 32) sm.K[idx] = sm.P[idx] * pscale;
+    __syncwarp();
+    inverse19_warp(sm.K, sm.W, sm.K, lane);
+    for (int idx = lane; idx < m * m; idx += 32) sm.K[(idx / m) * 19 + (idx % m)] += sm.A[idx];
+    __syncwarp();
+    inverse19_warp(sm.K, sm.W, sm.K, lane);
+    if (lane < 19)
+      for (int j = 0; j < m; j++) x[j] = sm.K[lane * 19 + j];
+    return;
+  }
+  // Mt = (I + A P_mm)^T, built cooperatively
+  for (int idx = lane; idx < m * m; idx += 32) {
+    int i = idx / m, j = idx % m;
+    double s = (i == j) ? 1.0 : 0.0;
+    for (int k = 0; k < m; k++) s += sm.A[i * m + k] * (sm.P[k * 19 + j] * pscale);
+    sm.M[j * m + i] = s;  // transposed
+  }
+  __syncwarp();
+  // every lane eliminates its own copy of [Mt | b], b = P[lane, 0:m] * pscale  (solves Mt x^T = b^T)
+  double Mt[m][m + 1];
+  const int row = lane < 19 ? lane : 0;
+#pragma unroll
+  for (int i = 0; i < m; i++) {
+#pragma unroll
+    for (int j = 0; j < m; j++) Mt[i][j] = sm.M[i * m + j];
+    Mt[i][m] = sm.P[row * 19 + i] * pscale;
+  }
+#pragma unroll
+  for (int k = 0; k < m; k++) {
+    // bring the largest |pivot| of column k to row k by compare-swaps (static indices keep Mt in registers)
+#pragma unroll
+    for (int r = k + 1; r < m; r++) {
+      bool sw = fabs(Mt[r][k]) > fabs(Mt[k][k]);
+#pragma unroll
+      for (int c = k; c <= m; c++) {
+        double u = Mt[k][c], v = Mt[r][c];
+        Mt[k][c] = sw ? v : u;
+        Mt[r][c] = sw ? u : v;
+      }
+    }
+    double inv = 1.0 / Mt[k][k];
+#pragma unroll
+    for (int r = k + 1; r < m; r++) {
+      double f = Mt[r][k] * inv;
+#pragma unroll
+      for (int c = k + 1; c <= m; c++) Mt[r][c] -= f * Mt[k][c];
+    }
+  }
+#pragma unroll
+  for (int i = m - 1; i >= 0; i--) {
+    double s = Mt[i][m];
+#pragma unroll
+    for (int j = i + 1; j < m; j++) s -= Mt[i][j] * x[j];
+    x[i] = s / Mt[i][i];
+  }
+}
+
+__device__ inline double warp_norm3(const double *v) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32, 1) lio_solve_kernel(const SolveArgs a) {
+  Ctrl &ctrl = *a.ctrl;
+  if (ctrl.stop) return;
+  __shared__ SolveSmem sm;
+  const int lane = threadIdx.x;
+  double *st = a.state;
+  for (int idx = lane; idx < 361; idx += 32) sm.P[idx] = st[S_COV + idx];
+  for (int idx = lane; idx < 36; idx += 32) sm.A[idx] = a.info[(idx / 6) * 8 + (idx % 6)];  // H^T R^-1 H
+  if (lane < 6) sm.HTz[lane] = a.info[lane * 8 + 6];                                        // H^T R^-1 z
+  boxminus_warp(a.prop, st, sm.vec, lane);
+  __syncwarp();
+
+  double x[6];
+  gain_rows<6>(sm, 1.0, a.solve_mode, lane, x);
+  // G[lane, 0:6] = K_1[lane, 0:6] * HTH   (voxel_map.cpp:469)
+  double g[6];
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) s += x[k] * sm.A[k * 6 + j];
+    g[j] = s;
+  }
+  // solution = K_1[:, :6] HTz + vec - G[:, :6] vec[:6]   (:471-472)
+  if (lane < 19) {
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) s1 += x[k] * sm.HTz[k], s2 += g[k] * sm.vec[k];
+    sm.sol[lane] = s1 + sm.vec[lane] - s2;
+  }
+  __syncwarp();
+  boxplus_warp(st, sm.sol, lane);  // state_ += solution (:474)
+  const bool converged = (warp_norm3(sm.sol) * 57.3 < 0.01) && (warp_norm3(sm.sol + 3) * 100 < 0.015);  // :477
+  const int iterCount = ctrl.iter;
+  int rematch = ctrl.rematch_num;
+  if (converged || ((rematch == 0) && (iterCount == (a.max_iterations - 2)))) rematch++;  // :482
+  const bool stop = (rematch >= 2) || (iterCount == a.max_iterations - 1);                // :485
+  if (stop && lane < 19) {
+    // cov = (I - G) cov   (:489-490); G only has its first 6 columns
+    for (int c = 0; c < 19; c++) {
+      double s = sm.P[lane * 19 + c];
+#pragma unroll
+      for (int j = 0; j < 6; j++) s -= g[j] * sm.P[j * 19 + c];
+      st[S_COV + lane * 19 + c] = s;
+    }
+  }
+  if (a.lio_stats && iterCount < 8) {
+    esikf_lio_stats &S = *a.lio_stats;
+    for (int idx = lane; idx < 36; idx += 32) S.HTH[iterCount][idx] = sm.A[idx];
+    if (lane < 6) S.HTz[iterCount][lane] = sm.HTz[lane];
+    if (lane < 19) S.solution[iterCount][lane] = sm.sol[lane];
+    if (lane == 0) {
+      S.iters = iterCount + 1;
+      S.effct_feat_num[iterCount] = (int)a.info[INFO_COUNT];
+      S.total_residual[iterCount] = a.info[INFO_ABS];
+      S.converged[iterCount] = converged;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    ctrl.iter = iterCount + 1;
+    ctrl.rematch_num = rematch;
+    ctrl.stop = stop ? 1 : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32, 1) vio_solve_kernel(const SolveArgs a) {
+  Ctrl &ctrl = *a.ctrl;
+  __shared__ SolveSmem sm;
+  const int lane = threadIdx.x;
+  double *st = a.state;
+  bool level_done = ctrl.level_done != 0;
+  float last_error = ctrl.last_error;
+  if (a.slot_iter == 0) {
+    // entering a level: old_state = *state, last_error = FLT_MAX, EKF_end = false  (vio.cpp:1523-1528)
+    level_done = false;
+    last_error = FLT_MAX;
+    if (lane < 25) a.old_state[lane] = st[lane];
+  }
+  if (!level_done) {
+    for (int idx = lane; idx < 361; idx += 32) sm.P[idx] = st[S_COV + idx];
+    __syncwarp();
+    const int level = a.level, iteration = a.slot_iter;
+    // error = sum(res^2) / n_meas as float (vio.cpp:1636)
+    const double sum_sq = a.info[7 * 8 + 7];
+    const int n_meas = (int)a.info[INFO_COUNT];
+    const float error = __fdiv_rn((float)sum_sq, (float)n_meas);
+    bool accepted = false;
+    bool ekf_end = false;
+    if (error <= last_error) {  // :1648
+      accepted = true;
+      if (lane < 25) a.old_state[lane] = st[lane];  // old_state = *state
+      last_error = error;
+      for (int idx = lane; idx < 49; idx += 32) sm.A[idx] = a.info[(idx / 7) * 8 + (idx % 7)];  // H^T H 7x7
+      if (lane < 7) sm.HTz[lane] = a.info[lane * 8 + 7];
+      boxminus_warp(a.prop, st, sm.vec, lane);
+      __syncwarp();
+      double x[7];
+      gain_rows<7>(sm, 1.0 / a.img_point_cov, a.solve_mode, lane, x);
+      double g[7];
+#pragma unroll
+      for (int j = 0; j < 7; j++) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 7; k++) s += x[k] * sm.A[k * 7 + j];
+        g[j] = s;
+      }
+      if (lane < 19) {
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 7; k++) s1 += x[k] * sm.HTz[k], s2 += g[k] * sm.vec[k];
+        sm.sol[lane] = -s1 + sm.vec[lane] - s2;  // :1667
+#pragma unroll
+        for (int j = 0; j < 7; j++) a.G[lane * 7 + j] = g[j];  // G.block<19,7>  (:1665)
+      }
+      __syncwarp();
+      boxplus_warp(st, sm.sol, lane);
+      // :1675 (float constants 57.3f / 100.0f / 0.001f promote to double against the double norm)
+      ekf_end = (warp_norm3(sm.sol) * (double)57.3f < (double)0.001f) && (warp_norm3(sm.sol + 3) * (double)100.0f < (double)0.001f);
+      if (a.vio_stats && level < 8 && iteration < 8) {
+        esikf_vio_stats &S = *a.vio_stats;
+        for (int idx = lane; idx < 49; idx += 32) S.HTH[level][iteration][idx] = sm.A[idx];
+        if (lane < 7) S.HTz[level][iteration][lane] = sm.HTz[lane];
+        if (lane < 19) S.solution[level][iteration][lane] = sm.sol[lane];
+      }
+    } else {
+      if (lane < 25) st[lane] = a.old_state[lane];  // *state = old_state  (:1679)
+      ekf_end = true;
+    }
+    if (a.vio_stats && lane == 0 && level < 8) {
+      esikf_vio_stats &S = *a.vio_stats;
+      if (iteration < 8) S.error_trace[level][iteration] = error;
+      S.iters_per_level[level] = iteration + 1;
+      if (accepted) S.accepted_per_level[level] += 1;
+      S.total_iters += 1;
+    }
+    if (accepted) ctrl.has_G = 1;
+    level_done = ekf_end;
+    if (lane == 0) ctrl.iter += 1;
+  }
+  __syncwarp();
+  if (a.last_slot) {
+    // state->cov -= G * state->cov   (vio.cpp:800) with the last accepted G
+    __threadfence_block();
+    for (int idx = lane; idx < 361; idx += 32) sm.P[idx] = st[S_COV + idx];
+    __syncwarp();
+    if (ctrl.has_G && lane < 19) {
+      double g[7];
+      for (int j = 0; j < 7; j++) g[j] = a.G[lane * 7 + j];
+      for (int c = 0; c < 19; c++) {
+        double s = 0.0;
+        for (int j = 0; j < 7; j++) s += g[j] * sm.P[j * 19 + c];
+        st[S_COV + lane * 19 + c] = sm.P[lane * 19 + c] - s;
+      }
+    }
+    if (lane == 0) ctrl.stop = 1;
+  }
+  if (lane == 0) {
+    ctrl.level_done = level_done ? 1 : 0;
+    ctrl.last_error = last_error;
+  }
+}
+
+}  // namespace esikf

@@ -1,0 +1,346 @@
+// VIO kernels of the B200 ESIKF update (sm_100a).
+//
+//   vio_patch_kernel      : one (level, iteration) of VIOManager::updateState's per-patch loop (reference src/vio.cpp:1556-1634):
+//                           projection, bilinear taps on the level-0 image at stride 2^(level+search_level), 64 photometric
+//                           residuals and 1x7 Jacobian rows per patch, fused with the H^T H / H^T z / sum(res^2) reduction
+//                           (:1660-1662). H_sub (128k x 7 doubles per iteration in the reference) is never materialised.
+//   image_patch_kernel    : batched getImagePatch (:203-225)
+//   warp_matrix_kernel    : batched getWarpMatrixAffineHomography + getBestSearchLevel (:252-273, 320-331, 701-714)
+//   warp_affine_kernel    : batched warpAffine over all pyramid levels (:292-318, 739-742)
+//
+// Mapping: one warp per visual patch, two pixels per lane. The 64 rows [JdR Jdt cur res] of a patch are staged in shared
+// memory and contracted with 16 fp64 tensor-core steps (mma.sync.m8n8k4.f64); per-warp 8x8 blocks are combined in a fixed
+// order so the error-gated accept / rollback decision is reproducible.
+#include "esikf_dev.cuh"
+
+namespace esikf {
+
+#define VIO_THREADS 256
+#define VIO_WARPS (VIO_THREADS / 32)
+
+struct CamDev {
+  int model, width, height;
+  double fx, fy, cx, cy;
+  double d[5];
+};
+
+// vk::PinholeCamera::world2cam / vk::EquidistantCamera::world2cam (vikit, unpinned; restated from its published algorithm)
+__device__ __forceinline__ void world2cam(const CamDev &cam, double X, double Y, double Z, double &u, double &v) {
+  double x = X / Z, y = Y / Z;
+  if (cam.model == 0) {
+    if (!(fabs(cam.d[0]) > 0.0000001)) {
+      u = cam.fx * x + cam.cx;
+      v = cam.fy * y + cam.cy;
+    } else {
+      double r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+      double a1 = 2 * x * y, a2 = r2 + 2 * x * x, a3 = r2 + 2 * y * y;
+      double cdist = 1 + cam.d[0] * r2 + cam.d[1] * r4 + cam.d[4] * r6;
+      double xd = x * cdist + cam.d[2] * a1 + cam.d[3] * a2;
+      double yd = y * cdist + cam.d[2] * a3 + cam.d[3] * a1;
+      u = xd * cam.fx + cam.cx;
+      v = yd * cam.fy + cam.cy;
+    }
+  } else {
+    double r = sqrt(x * x + y * y);
+    double theta = atan(r);
+    double t2 = theta * theta, t4 = t2 * t2, t6 = t4 * t2, t8 = t4 * t4;
+    double theta_d = theta * (1 + cam.d[0] * t2 + cam.d[1] * t4 + cam.d[2] * t6 + cam.d[3] * t8);
+    double scaling = (r > 1e-8) ? theta_d / r : 1.0;
+    u = cam.fx * x * scaling + cam.cx;
+    v = cam.fy * y * scaling + cam.cy;
+  }
+}
+// cam2world -> unit bearing (distorted pinhole: 5 fixed-point iterations as cv::undistortPoints)
+__device__ __forceinline__ void cam2world(const CamDev &cam, double u, double v, double f[3]) {
+  double x0 = (u - cam.cx) / cam.fx, y0 = (v - cam.cy) / cam.fy;
+  double x = x0, y = y0;
+  if (cam.model == 0) {
+    if (fabs(cam.d[0]) > 0.0000001) {
+      for (int it = 0; it < 5; it++) {
+        double r2 = x * x + y * y;
+        double icdist = 1.0 / (1 + ((cam.d[4] * r2 + cam.d[1]) * r2 + cam.d[0]) * r2);
+        double dx = 2 * cam.d[2] * x * y + cam.d[3] * (r2 + 2 * x * x);
+        double dy = cam.d[2] * (r2 + 2 * y * y) + 2 * cam.d[3] * x * y;
+        x = (x0 - dx) * icdist;
+        y = (y0 - dy) * icdist;
+      }
+    }
+  } else {
+    double theta_d = sqrt(x0 * x0 + y0 * y0);
+    if (theta_d > 1e-8) {
+      double theta = theta_d;
+      for (int it = 0; it < 10; it++) {
+        double t2 = theta * theta, t4 = t2 * t2, t6 = t4 * t2, t8 = t4 * t4;
+        theta = theta_d / (1 + cam.d[0] * t2 + cam.d[1] * t4 + cam.d[2] * t6 + cam.d[3] * t8);
+      }
+      double scaling = tan(theta) / theta_d;
+      x = x0 * scaling;
+      y = y0 * scaling;
+    }
+  }
+  double n = sqrt(x * x + y * y + 1.0);
+  f[0] = x / n, f[1] = y / n, f[2] = 1.0 / n;
+}
+
+struct VioKernelArgs {
+  const uint8_t *img;
+  CamDev cam;
+  const double *pos;           // [n_total][3]
+  const float *warp_patch;     // [n_total][levels*64]
+  const int32_t *search_levels;
+  const double *inv_expo_list;
+  int begin, count;            // this rank's shard of the patches
+  int levels, level, slot_iter, exposure_en;
+  const double *state;         // current iterate
+  double Rci[9], Pci[3], Jdp_dR[9];
+  float *errors;               // [n_total]
+  double *partials;
+  double *info;
+  Ctrl *ctrl;
+};
+
+// raw img.data + offset reads of the reference, with 0 outside the buffer (the reference would read out of bounds there)
+__device__ __forceinline__ float tap(const uint8_t *__restrict__ img, long idx, long npix) {
+  return (idx >= 0 && idx < npix) ? (float)__ldg(img + idx) : 0.0f;
+}
+// w_tl*a + w_tr*b + w_bl*c + w_br*d in float, left to right, no FMA contraction (vio.cpp:1600-1620)
+__device__ __forceinline__ float bil(float wtl, float wtr, float wbl, float wbr, float a, float b, float c, float d) {
+  return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wtl, a), __fmul_rn(wtr, b)), __fmul_rn(wbl, c)), __fmul_rn(wbr, d));
+}
+
+struct VioSmem {
+  double Rcw[9], Pcw[3];
+  double inv_expo;
+  double rows[VIO_WARPS][64][8];
+  ReduceSmem<VIO_WARPS> red;
+};
+
+__global__ void __launch_bounds__(VIO_THREADS, 2) vio_patch_kernel(const VioKernelArgs a) {
+  if (a.slot_iter > 0 && a.ctrl->level_done) return;  // EKF_end of this level: remaining slots do nothing
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  VioSmem &sm = *reinterpret_cast<VioSmem *>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 9) {
+    // Rcw = Rci * Rwi^T  (vio.cpp:1542)
+    int r = tid / 3, c = tid % 3;
+    double s = 0;
+    for (int k = 0; k < 3; k++) s += a.Rci[r * 3 + k] * a.state[S_R + c * 3 + k];
+    sm.Rcw[tid] = s;
+  }
+  if (tid == 0) sm.inv_expo = a.state[S_EXPO];
+  __syncthreads();
+  if (tid < 3) {
+    // Pcw = -Rci Rwi^T Pwi + Pci  (:1543)
+    double s = 0;
+    for (int k = 0; k < 3; k++) s += sm.Rcw[tid * 3 + k] * a.state[S_P + k];
+    sm.Pcw[tid] = -s + a.Pci[tid];
+  }
+  __syncthreads();
+
+  const long npix = (long)a.cam.width * a.cam.height;
+  const int width = a.cam.width;
+  const double inv_expo = sm.inv_expo;
+  double D0 = 0.0, D1 = 0.0;
+  double n_meas = 0.0;
+
+  for (int lp = blockIdx.x * VIO_WARPS + warp; lp < a.count; lp += gridDim.x * VIO_WARPS) {
+    const int i = a.begin + lp;
+    const int search_level = a.search_levels[i];
+    const int pyramid_level = a.level + search_level;
+    const int scale = 1 << pyramid_level;
+    const float inv_scale = 1.0f / (float)scale;
+    const double X = a.pos[3 * (size_t)i], Y = a.pos[3 * (size_t)i + 1], Z = a.pos[3 * (size_t)i + 2];
+    const double pf0 = sm.Rcw[0] * X + sm.Rcw[1] * Y + sm.Rcw[2] * Z + sm.Pcw[0];
+    const double pf1 = sm.Rcw[3] * X + sm.Rcw[4] * Y + sm.Rcw[5] * Z + sm.Pcw[1];
+    const double pf2 = sm.Rcw[6] * X + sm.Rcw[7] * Y + sm.Rcw[8] * Z + sm.Pcw[2];
+    double pcu, pcv;
+    world2cam(a.cam, pf0, pf1, pf2, pcu, pcv);
+    // computeProjectionJacobian (:189-201)
+    const double z_inv = 1. / pf2, z_inv_2 = z_inv * z_inv;
+    const double J00 = a.cam.fx * z_inv, J02 = -a.cam.fx * pf0 * z_inv_2, J11 = a.cam.fy * z_inv, J12 = -a.cam.fy * pf1 * z_inv_2;
+    // Per-patch 2x3 maps so that per pixel  JdR = [du dv] WR,  Jdt = [du dv] WT  (vio.cpp:1611-1617):
+    //   Jimg = [du dv] * inv_expo * inv_scale ; Jdphi = Jimg Jdpi [pf]x ; Jdp = -Jimg Jdpi
+    //   JdR = Jdphi Rci + Jdp Jdp_dR ; Jdt = Jdp Rcw
+    const double sc = inv_expo * (double)inv_scale;
+    // Jdpi [pf]x  (2x3);  [pf]x = [0 -z y; z 0 -x; -y x 0]
+    const double Q00 = J02 * (-pf1), Q01 = J00 * (-pf2) + J02 * pf0, Q02 = J00 * pf1;
+    const double Q10 = J11 * pf2 + J12 * (-pf1), Q11 = J12 * pf0, Q12 = J11 * (-pf0);
+    double WR[2][3], WT[2][3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      WR[0][c] = sc * ((Q00 * a.Rci[c] + Q01 * a.Rci[3 + c] + Q02 * a.Rci[6 + c]) - (J00 * a.Jdp_dR[c] + J02 * a.Jdp_dR[6 + c]));
+      WR[1][c] = sc * ((Q10 * a.Rci[c] + Q11 * a.Rci[3 + c] + Q12 * a.Rci[6 + c]) - (J11 * a.Jdp_dR[3 + c] + J12 * a.Jdp_dR[6 + c]));
+      WT[0][c] = -sc * (J00 * sm.Rcw[c] + J02 * sm.Rcw[6 + c]);
+      WT[1][c] = -sc * (J11 * sm.Rcw[3 + c] + J12 * sm.Rcw[6 + c]);
+    }
+    // bilinear weights (:1580-1589) — float, via double (1.0 - subpix)
+    const float u_ref = (float)pcu, v_ref = (float)pcv;
+    const int u_ref_i = (int)(floorf((float)(pcu / scale)) * scale);
+    const int v_ref_i = (int)(floorf((float)(pcv / scale)) * scale);
+    const float subpix_u = (u_ref - (float)u_ref_i) / (float)scale;
+    const float subpix_v = (v_ref - (float)v_ref_i) / (float)scale;
+    const float w_tl = (float)((1.0 - subpix_u) * (1.0 - subpix_v));
+    const float w_tr = (float)(subpix_u * (1.0 - subpix_v));
+    const float w_bl = (float)((1.0 - subpix_u) * subpix_v);
+    const float w_br = subpix_u * subpix_v;
+    const double inv_ref_expo = a.inv_expo_list[i];
+    const float *__restrict__ P = a.warp_patch + (size_t)i * 64 * a.levels + 64 * a.level;
+
+    double sq = 0.0;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const int pix = 2 * lane + k;  // = x*8 + y
+      const int x = pix >> 3, y = pix & 7;
+      const long b = (long)(v_ref_i + x * scale - 4 * scale) * width + u_ref_i - 4 * scale + (long)y * scale;
+      const long sw = (long)scale * width;
+      const float i_m10 = tap(a.img, b - sw, npix), i_m11 = tap(a.img, b - sw + scale, npix);
+      const float i_0m = tap(a.img, b - scale, npix), i_00 = tap(a.img, b, npix), i_01 = tap(a.img, b + scale, npix),
+                  i_02 = tap(a.img, b + 2 * scale, npix);
+      const float i_1m = tap(a.img, b + sw - scale, npix), i_10 = tap(a.img, b + sw, npix), i_11 = tap(a.img, b + sw + scale, npix),
+                  i_12 = tap(a.img, b + sw + 2 * scale, npix);
+      const float i_20 = tap(a.img, b + 2 * sw, npix), i_21 = tap(a.img, b + 2 * sw + scale, npix);
+      const float du = __fmul_rn(0.5f, __fsub_rn(bil(w_tl, w_tr, w_bl, w_br, i_01, i_02, i_11, i_12), bil(w_tl, w_tr, w_bl, w_br, i_0m, i_00, i_1m, i_10)));
+      const float dv = __fmul_rn(0.5f, __fsub_rn(bil(w_tl, w_tr, w_bl, w_br, i_10, i_11, i_20, i_21), bil(w_tl, w_tr, w_bl, w_br, i_m10, i_m11, i_00, i_01)));
+      const double cur_value = (double)bil(w_tl, w_tr, w_bl, w_br, i_00, i_01, i_10, i_11);
+      const double res = inv_expo * cur_value - inv_ref_expo * (double)P[pix];
+      const double ddu = (double)du, ddv = (double)dv;
+      double4 *dst = reinterpret_cast<double4 *>(&sm.rows[warp][pix][0]);
+      dst[0] = make_double4(ddu * WR[0][0] + ddv * WR[1][0], ddu * WR[0][1] + ddv * WR[1][1], ddu * WR[0][2] + ddv * WR[1][2],
+                            ddu * WT[0][0] + ddv * WT[1][0]);
+      dst[1] = make_double4(ddu * WT[0][1] + ddv * WT[1][1], ddu * WT[0][2] + ddv * WT[1][2], a.exposure_en ? cur_value : 0.0, res);
+      sq += res * res;
+    }
+    // patch error (visual_submap->errors[i], :1632): fp64 tree sum narrowed to float
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (lane == 0) a.errors[i] = (float)sq;
+    n_meas += 64.0;
+    __syncwarp();
+    {
+      const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+      for (int s = 0; s < 16; s++) {
+        const double v = sm.rows[warp][4 * s + t][g];
+        dmma_m8n8k4(D0, D1, v, v);
+      }
+    }
+    __syncwarp();
+  }
+  reduce_info<VIO_WARPS>(sm.red, D0, D1, n_meas, false, a.partials, a.info, a.ctrl);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// getImagePatch (vio.cpp:203-225), one thread per output pixel.
+__global__ void image_patch_kernel(const uint8_t *__restrict__ img, int width, int height, const double *__restrict__ pc, int n, int level,
+                                   float *__restrict__ out) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n * 64) return;
+  int i = gid >> 6, pix = gid & 63, x = pix >> 3, y = pix & 7;
+  const double pcu = pc[2 * i], pcv = pc[2 * i + 1];
+  const int scale = 1 << level;
+  const float u_ref = (float)pcu, v_ref = (float)pcv;
+  const int u_ref_i = (int)(floorf((float)(pcu / scale)) * scale);
+  const int v_ref_i = (int)(floorf((float)(pcv / scale)) * scale);
+  const float subpix_u = (u_ref - (float)u_ref_i) / (float)scale;
+  const float subpix_v = (v_ref - (float)v_ref_i) / (float)scale;
+  const float w_tl = (float)((1.0 - subpix_u) * (1.0 - subpix_v));
+  const float w_tr = (float)(subpix_u * (1.0 - subpix_v));
+  const float w_bl = (float)((1.0 - subpix_u) * subpix_v);
+  const float w_br = subpix_u * subpix_v;
+  const long npix = (long)width * height;
+  const long b = (long)(v_ref_i - 4 * scale + x * scale) * width + (u_ref_i - 4 * scale) + (long)y * scale;
+  const long sw = (long)scale * width;
+  out[gid] = bil(w_tl, w_tr, w_bl, w_br, tap(img, b, npix), tap(img, b + scale, npix), tap(img, b + sw, npix), tap(img, b + sw + scale, npix));
+}
+
+// getWarpMatrixAffineHomography + getBestSearchLevel for the normal_en branch of retrieveFromVisualSparseMap (vio.cpp:699-715).
+__global__ void warp_matrix_kernel(CamDev cam, int n, const double *__restrict__ px_ref, const double *__restrict__ pos_w,
+                                   const double *__restrict__ normal_w, const double *__restrict__ T_ref_w, const double *__restrict__ T_cur_w,
+                                   double *__restrict__ A_out, int32_t *__restrict__ search_level) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double *Rr = T_ref_w + 12 * (size_t)i, *tr = Rr + 9;
+  const double *Rc = T_cur_w, *tc = T_cur_w + 9;
+  const double *nw = normal_w + 3 * (size_t)i, *pw = pos_w + 3 * (size_t)i;
+  // norm_vec = (R_ref * normal).normalized(); pf = T_ref * pos   (:701-703)
+  double nv[3], pf[3];
+  for (int r = 0; r < 3; r++) {
+    nv[r] = Rr[3 * r] * nw[0] + Rr[3 * r + 1] * nw[1] + Rr[3 * r + 2] * nw[2];
+    pf[r] = Rr[3 * r] * pw[0] + Rr[3 * r + 1] * pw[1] + Rr[3 * r + 2] * pw[2] + tr[r];
+  }
+  double nn = sqrt(nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2]);
+  nv[0] /= nn, nv[1] /= nn, nv[2] /= nn;
+  // T_cur_ref = T_cur * T_ref^-1 : R = Rc Rr^T, t = tc - R tr   (:710)
+  double R[9], t[3];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) R[3 * r + c] = Rc[3 * r] * Rr[3 * c] + Rc[3 * r + 1] * Rr[3 * c + 1] + Rc[3 * r + 2] * Rr[3 * c + 2];
+  for (int r = 0; r < 3; r++) t[r] = tc[r] - (R[3 * r] * tr[0] + R[3 * r + 1] * tr[1] + R[3 * r + 2] * tr[2]);
+  // t_inv = T_cur_ref.inverse().translation() = -R^T t   (:256)
+  double ti[3];
+  for (int r = 0; r < 3; r++) ti[r] = -(R[r] * t[0] + R[3 + r] * t[1] + R[6 + r] * t[2]);
+  // H = R * (n.xyz * I - t_inv n^T)   (:257-258)
+  const double ndx = nv[0] * pf[0] + nv[1] * pf[1] + nv[2] * pf[2];
+  double Bm[9];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) Bm[3 * r + c] = ((r == c) ? ndx : 0.0) - ti[r] * nv[c];
+  double H[9];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) H[3 * r + c] = R[3 * r] * Bm[c] + R[3 * r + 1] * Bm[3 + c] + R[3 * r + 2] * Bm[6 + c];
+  double fdu[3], fdv[3];
+  cam2world(cam, px_ref[2 * i] + 4.0, px_ref[2 * i + 1], fdu);  // level_ref = 0 (:712)
+  cam2world(cam, px_ref[2 * i], px_ref[2 * i + 1] + 4.0, fdv);
+  double fc[3], fu[3], fv[3];
+  for (int r = 0; r < 3; r++) {
+    fc[r] = H[3 * r] * pf[0] + H[3 * r + 1] * pf[1] + H[3 * r + 2] * pf[2];
+    fu[r] = H[3 * r] * fdu[0] + H[3 * r + 1] * fdu[1] + H[3 * r + 2] * fdu[2];
+    fv[r] = H[3 * r] * fdv[0] + H[3 * r + 1] * fdv[1] + H[3 * r + 2] * fdv[2];
+  }
+  double cu, cv, uu, uv, vu, vv;
+  world2cam(cam, fc[0], fc[1], fc[2], cu, cv);
+  world2cam(cam, fu[0], fu[1], fu[2], uu, uv);
+  world2cam(cam, fv[0], fv[1], fv[2], vu, vv);
+  const double A00 = (uu - cu) / 4, A10 = (uv - cv) / 4, A01 = (vu - cu) / 4, A11 = (vv - cv) / 4;
+  A_out[4 * i] = A00, A_out[4 * i + 1] = A01, A_out[4 * i + 2] = A10, A_out[4 * i + 3] = A11;
+  // getBestSearchLevel(A, 2)   (:320-331)
+  int sl = 0;
+  double Dt = A00 * A11 - A01 * A10;
+  while (Dt > 3.0 && sl < 2) {
+    sl += 1;
+    Dt *= 0.25;
+  }
+  search_level[i] = sl;
+}
+
+// warpAffine for all pyramid levels (vio.cpp:292-318, 739-742). One thread per output value.
+__global__ void warp_affine_kernel(const uint8_t *const *__restrict__ ref_imgs, const int32_t *__restrict__ ref_idx, int cols, int rows, int n,
+                                   int levels, const double *__restrict__ A_cur_ref, const double *__restrict__ px_ref,
+                                   const int32_t *__restrict__ search_level, float *__restrict__ out) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n * levels * 64) return;
+  const int i = gid / (levels * 64), rem = gid % (levels * 64), pyramid_level = rem >> 6, pix = rem & 63, y = pix >> 3, x = pix & 7;
+  const double a00 = A_cur_ref[4 * i], a01 = A_cur_ref[4 * i + 1], a10 = A_cur_ref[4 * i + 2], a11 = A_cur_ref[4 * i + 3];
+  const double det = a00 * a11 - a01 * a10;
+  const double id = 1.0 / det;
+  const float A00 = (float)(a11 * id), A01 = (float)(-a01 * id), A10 = (float)(-a10 * id), A11 = (float)(a00 * id);
+  if (isnan(A00)) return;  // :297-301 (patch left untouched)
+  float pp0 = (float)(x - 4), pp1 = (float)(y - 4);
+  const float s1 = (float)(1 << search_level[i]), s2 = (float)(1 << pyramid_level);
+  pp0 = __fmul_rn(__fmul_rn(pp0, s1), s2);
+  pp1 = __fmul_rn(__fmul_rn(pp1, s1), s2);
+  const float px0 = __fadd_rn(__fadd_rn(__fmul_rn(A00, pp0), __fmul_rn(A01, pp1)), (float)px_ref[2 * i]);
+  const float px1 = __fadd_rn(__fadd_rn(__fmul_rn(A10, pp0), __fmul_rn(A11, pp1)), (float)px_ref[2 * i + 1]);
+  float val = 0.0f;
+  if (!(px0 < 0 || px1 < 0 || px0 >= (float)(cols - 1) || px1 >= (float)(rows - 1))) {
+    // vk::interpolateMat_8u
+    const uint8_t *__restrict__ img = ref_imgs[ref_idx[i]];
+    const int xi = (int)floorf(px0), yi = (int)floorf(px1);
+    const float sx = px0 - (float)xi, sy = px1 - (float)yi;
+    const float w00 = __fmul_rn(1.0f - sx, 1.0f - sy), w01 = __fmul_rn(1.0f - sx, sy), w10 = __fmul_rn(sx, 1.0f - sy), w11 = __fmul_rn(sx, sy);
+    const uint8_t *p = img + (long)yi * cols + xi;
+    val = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w00, (float)p[0]), __fmul_rn(w01, (float)p[cols])), __fmul_rn(w10, (float)p[1])),
+                    __fmul_rn(w11, (float)p[cols + 1]));
+  }
+  out[gid] = val;
+}
+
+}  // namespace esikf

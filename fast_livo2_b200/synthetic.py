@@ -255,7 +255,7 @@ def calc_body_cov_np(pb, range_inc, degree_inc):
     pb[pb[:, 2] == 0, 2] = 0.0001
     rng_f = np.sqrt((pb ** 2).sum(1)).astype(np.float32)
     range_var = np.float32(range_inc) * np.float32(range_inc)
-    dv = np.sin(np.float32(degree_inc) * 0.017453293) ** 2
+    dv = np.sin(np.float64(np.float32(degree_inc)) * 0.017453293) ** 2
     dirn = pb / np.linalg.norm(pb, axis=1, keepdims=True)
     b1 = np.stack([np.ones(len(pb)), np.ones(len(pb)), -(dirn[:, 0] + dirn[:, 1]) / dirn[:, 2]], 1)
     b1 /= np.linalg.norm(b1, axis=1, keepdims=True)

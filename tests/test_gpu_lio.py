@@ -1,0 +1,163 @@
+"""GPU parity: the CUDA LIO update (through the C ABI) against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+import oracle_bind as O
+from conftest import get_frame
+from fast_livo2_b200 import synthetic as S
+from parity_util import INFO_RTOL, assert_state_close, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(fr, cfg=None, state_in=None):
+    cfg = cfg or fr["lio_cfg"]
+    lio = O.OracleLIO(cfg, fr["ext"])
+    lio.set_map(fr["map"])
+    s = fr["state_prior"] if state_in is None else state_in
+    return lio.state_estimation(fr["pts"], s, fr["state_prior"])
+
+
+def _gpu(ctx, fr, cfg=None, state_in=None, solve_mode=0):
+    cfg = cfg or fr["lio_cfg"]
+    ctx.set_solve_mode(solve_mode)
+    ctx.set_extrinsics(fr["ext"])
+    ctx.map_upload(fr["map"], cfg.voxel_size)
+    s = fr["state_prior"] if state_in is None else state_in
+    r = ctx.lio_update(fr["pts"], s, fr["state_prior"], cfg)
+    ctx.set_solve_mode(0)
+    return r
+
+
+def _compare(g, o):
+    assert g["iters"] == o["iters"]
+    # integer / index work is bit-exact: association, matched counts, sticky normal plane
+    assert np.array_equal(g["match_plane"], o["match_plane"])
+    assert np.array_equal(g["normal_plane"], o["normal_plane"])
+    assert np.array_equal(g["M"], o["M"])
+    assert np.array_equal(g["converged"], o["converged"])
+    assert np.array_equal(g["dis_to_plane"], o["dis_to_plane"])  # float, same op order
+    for it in range(o["iters"]):
+        assert rel(g["HTH"][it], o["HTH"][it]) < INFO_RTOL
+        assert rel(g["HTz"][it], o["HTz"][it]) < 1e-8
+        assert abs(g["total_residual"][it] - o["total_residual"][it]) < 1e-9 * max(1.0, o["total_residual"][it])
+    assert_state_close(g["state"], o["state"])
+
+
+@pytest.mark.parametrize("seed,n_pts", [(1, 4000), (3, 5000), (4, 20000)])
+def test_lio_matches_oracle(gpu_ctx, seed, n_pts):
+    fr = get_frame(seed=seed, n_pts=n_pts, n_map=150_000, scene_scale=0.5)
+    _compare(_gpu(gpu_ctx, fr), _oracle(fr))
+
+
+def test_lio_literal_solve_mode_matches_oracle_and_woodbury(gpu_ctx, small_frame):
+    fr = small_frame
+    o = _oracle(fr)
+    g1 = _gpu(gpu_ctx, fr, solve_mode=1)
+    g0 = _gpu(gpu_ctx, fr, solve_mode=0)
+    _compare(g1, o)
+    assert_state_close(g0["state"], g1["state"], cov_tol=1e-7)
+
+
+def test_config1_three_iterations(gpu_ctx):
+    """BASELINE config 1: 5k points, LIO only, max_iterations = 3."""
+    fr = get_frame(seed=0, n_pts=5000, n_map=150_000, scene_scale=0.5)
+    cfg = S.LioCfg(**{**fr["lio_cfg"].__dict__, "max_iterations": 3})
+    g, o = _gpu(gpu_ctx, fr, cfg), _oracle(fr, cfg)
+    assert g["iters"] == 3
+    _compare(g, o)
+
+
+def test_early_stop_on_double_convergence(gpu_ctx, small_frame):
+    fr = small_frame
+    o = _oracle(fr)
+    st = o["state"].copy()
+    st[25:] = (np.eye(19) * 1e-12).reshape(-1)
+    fr2 = dict(fr, state_prior=st)
+    g, o2 = _gpu(gpu_ctx, fr2), _oracle(fr2)
+    assert o2["iters"] == 2 and g["iters"] == 2
+    _compare(g, o2)
+
+
+def test_hilti_like_config_non_identity_extrinsics_and_voxel_04(gpu_ctx):
+    """config 3 flavour: voxel 0.4 (not exactly representable: float vs double voxel size differ), non-identity extR,
+    degenerate corridor scene."""
+    cfg = S.LioCfg(voxel_size=0.4, min_eigen_value=1e-4, max_points_num=100)
+    fr = get_frame(seed=5, n_pts=6000, n_map=400_000, lio=cfg, ext=S.hilti_extrinsics(), scene="corridor", scene_scale=0.25)
+    g, o = _gpu(gpu_ctx, fr), _oracle(fr)
+    assert o["M"][0] > 1000
+    _compare(g, o)
+
+
+def test_edge_cases(gpu_ctx, small_frame):
+    fr = small_frame
+    cfg = fr["lio_cfg"]
+    # (a) zero-z and exactly-on-voxel-boundary / negative-coordinate points mixed into the scan
+    pts = fr["pts"].copy()
+    pts[:50, 2] = 0.0
+    pts[50:60] = 0.0
+    pts[50:60, 0] = np.arange(10) * 0.5 + 1.0
+    fr_a = dict(fr, pts=pts)
+    _compare(_gpu(gpu_ctx, fr_a), _oracle(fr_a))
+    # (b) every point far outside the map: nothing matches, M = 0, the update falls back to the prior
+    far = fr["pts"] + np.float32(500.0)
+    fr_b = dict(fr, pts=far)
+    g, o = _gpu(gpu_ctx, fr_b), _oracle(fr_b)
+    assert g["M"].tolist() == [0] * g["iters"] and np.all(g["match_plane"] == -1)
+    _compare(g, o)
+    # (c) a single point, and an empty scan
+    fr_c = dict(fr, pts=fr["pts"][:1])
+    _compare(_gpu(gpu_ctx, fr_c), _oracle(fr_c))
+    g = _gpu(gpu_ctx, dict(fr, pts=np.zeros((0, 3), np.float32)))
+    assert g["iters"] == cfg.max_iterations or g["iters"] >= 2
+    # (d) empty map
+    empty = dict(keys=np.zeros((0, 3), np.int64), first=np.zeros(0, np.int32), count=np.zeros(0, np.int32), planes=np.zeros(0, S.PLANE_DTYPE))
+    fr_d = dict(fr, map=empty)
+    g, o = _gpu(gpu_ctx, fr_d), _oracle(fr_d)
+    assert np.all(g["match_plane"] == -1)
+    _compare(g, o)
+
+
+def test_argument_errors(gpu_ctx, small_frame):
+    from fast_livo2_b200 import api
+
+    fr = small_frame
+    bad = dict(fr["map"], keys=fr["map"]["keys"].copy())
+    bad["keys"][0, 0] = 1 << 40
+    with pytest.raises(api.EsikfError):
+        gpu_ctx.map_upload(bad, 0.5)
+    cfg = S.LioCfg(**{**fr["lio_cfg"].__dict__, "max_iterations": 9})
+    gpu_ctx.map_upload(fr["map"], 0.5)
+    with pytest.raises(api.EsikfError):
+        gpu_ctx.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], cfg)
+
+
+def test_point_cov_outputs_match_oracle_lists(gpu_ctx, small_frame):
+    """body_cov_list_ / cross_mat_list_ consumed by LIVMapper.cpp:418-419."""
+    import ctypes as C
+
+    fr = small_frame
+    _gpu(gpu_ctx, fr)
+    bc, cm = gpu_ctx.lio_fetch_point_cov()
+    lib = O.load()
+    for i in range(0, 400, 7):
+        p = fr["pts"][i].astype(np.float64)
+        cov = np.zeros(9)
+        lib.orc_calc_body_cov(O.dptr(p), C.c_float(fr["lio_cfg"].dept_err), C.c_float(fr["lio_cfg"].beam_err), O.dptr(cov), None)
+        np.testing.assert_allclose(bc[i], cov.reshape(3, 3), rtol=1e-11, atol=1e-18)
+        np.testing.assert_allclose(cm[i], S.skew(fr["ext"].extR @ p + fr["ext"].extT), rtol=1e-14)
+
+
+def test_full_size_properties(gpu_ctx):
+    """BASELINE config 2 LiDAR size (100 k points): run-to-run bit reproducibility, symmetric PSD information matrix,
+    and agreement with the oracle on the whole update."""
+    fr = get_frame(seed=0, n_pts=100_000, n_map=1_000_000)
+    a = _gpu(gpu_ctx, fr)
+    b = _gpu(gpu_ctx, fr)
+    assert np.array_equal(a["state"], b["state"]) and np.array_equal(a["HTH"], b["HTH"])  # fixed-order reductions
+    assert np.array_equal(a["match_plane"], b["match_plane"])
+    for H in a["HTH"]:
+        assert rel(H, H.T) < 1e-12
+        assert np.linalg.eigvalsh(0.5 * (H + H.T)).min() > 0
+    assert a["M"][0] > 0.85 * 100_000
+    _compare(a, _oracle(fr))

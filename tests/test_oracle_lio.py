@@ -1,0 +1,173 @@
+"""Oracle LIO checks on CPU: the restatement behaves like an ESIKF update should, its Jacobian agrees with finite
+differences, the two map restatements (numpy generator / C++ BuildVoxelMap) agree, and the flat candidate list is
+equivalent to the recursive octree walk."""
+import numpy as np
+
+import oracle_bind as O
+from fast_livo2_b200 import synthetic as S
+
+
+def _pose_err(a, b):
+    ua, ub = S.unpack_state(a), S.unpack_state(b)
+    return O.rot_err(ua["R"], ub["R"]), float(np.linalg.norm(ua["p"] - ub["p"]))
+
+
+def test_lio_update_pulls_prior_to_truth(small_frame):
+    fr = small_frame
+    lio = O.OracleLIO(fr["lio_cfg"], fr["ext"])
+    lio.set_map(fr["map"])
+    r = lio.state_estimation(fr["pts"], fr["state_prior"], fr["state_prior"])
+    e0 = _pose_err(fr["state_prior"], fr["state_true"])
+    e1 = _pose_err(r["state"], fr["state_true"])
+    assert r["iters"] >= 3 and r["M"][0] > 0.8 * len(fr["pts"])
+    assert e1[0] < 0.1 * e0[0] and e1[1] < 0.2 * e0[1]
+    # posterior covariance: symmetric, PD, smaller than the prior on the pose block
+    P0 = S.unpack_state(fr["state_prior"])["cov"]
+    P1 = S.unpack_state(r["state"])["cov"]
+    np.testing.assert_allclose(P1, P1.T, atol=1e-12)
+    assert np.linalg.eigvalsh(0.5 * (P1 + P1.T)).min() > 0
+    assert (np.diag(P1)[:6] < np.diag(P0)[:6]).all()
+    # information matrix symmetric PSD
+    for H in r["HTH"]:
+        np.testing.assert_allclose(H, H.T, rtol=1e-9, atol=1e-9 * np.abs(H).max())
+        assert np.linalg.eigvalsh(0.5 * (H + H.T)).min() > -1e-6 * np.abs(H).max()
+
+
+def test_iteration_control_matches_reference_rule(small_frame):
+    """voxel_map.cpp:482-499: with max_iterations=3 and no early double convergence exactly 3 iterations run."""
+    fr = small_frame
+    cfg = S.LioCfg(**{**fr["lio_cfg"].__dict__, "max_iterations": 3})
+    lio = O.OracleLIO(cfg, fr["ext"])
+    lio.set_map(fr["map"])
+    r = lio.state_estimation(fr["pts"], fr["state_prior"], fr["state_prior"])
+    assert r["iters"] == 3
+    # starting at the converged answer with a tiny prior covariance: converged twice -> stops after 2 iterations
+    r2 = lio.state_estimation(fr["pts"], r["state"], r["state"])
+    cfg5 = S.LioCfg(**{**fr["lio_cfg"].__dict__, "max_iterations": 5})
+    lio5 = O.OracleLIO(cfg5, fr["ext"])
+    lio5.set_map(fr["map"])
+    st = r["state"].copy()
+    st[25:] = (np.eye(19) * 1e-12).reshape(-1)
+    r3 = lio5.state_estimation(fr["pts"], st, st)
+    assert r3["iters"] == 2 and r3["converged"].tolist() == [1, 1]
+    assert r2["iters"] <= 3
+
+
+def test_jacobian_rows_match_finite_differences(small_frame):
+    """H_i = d(n.(R Exp(dth)(extR p + extT) + t + dp) + d)/d(dth, dp) — voxel_map.cpp:453-454."""
+    fr = small_frame
+    lio = O.OracleLIO(fr["lio_cfg"], fr["ext"])
+    lio.set_map(fr["map"])
+    sp = lio.single_pass(fr["pts"][:600], fr["state_prior"], fr["state_prior"])
+    st = S.unpack_state(fr["state_prior"])
+    planes = fr["map"]["planes"]
+    idx = np.nonzero(sp["plane"] >= 0)[0][:100]
+    assert len(idx) > 50
+    eps = 1e-6
+    for i in idx:
+        pl = planes[sp["plane"][i]]
+        n, d = pl["normal"], float(pl["d"])
+        p_imu = fr["ext"].extR @ fr["pts"][i].astype(np.float64) + fr["ext"].extT
+
+        def resid(delta):
+            R = st["R"] @ S.so3_exp(delta[:3])
+            return n @ (R @ p_imu + st["p"] + delta[3:]) + d
+
+        num = np.array([(resid(eps * e) - resid(-eps * e)) / (2 * eps) for e in np.eye(6)])
+        np.testing.assert_allclose(sp["H"][i], num, rtol=1e-6, atol=1e-7)
+        # residual sign convention: meas = -dis_to_plane (voxel_map.cpp:457); p_w is float-rounded in the reference
+        assert abs(sp["dis"][i] - resid(np.zeros(6))) < 1e-4
+
+
+def test_plane_normal_sign_flip_leaves_information_unchanged(small_frame):
+    """flipping (normal, d) of every plane leaves H^T R^-1 H and H^T R^-1 z unchanged."""
+    fr = small_frame
+    vm = {k: v.copy() for k, v in fr["map"].items()}
+    vm["planes"]["normal"] *= -1
+    vm["planes"]["d"] *= -1
+    pv = np.zeros((len(vm["planes"]), 6, 6))
+    iu = np.triu_indices(6)
+    pv[:, iu[0], iu[1]] = vm["planes"]["plane_var"]
+    pv[:, 0:3, 3:6] *= -1  # cross terms between the normal block and the centre block change sign
+    vm["planes"]["plane_var"] = pv[:, iu[0], iu[1]]
+    a = O.OracleLIO(fr["lio_cfg"], fr["ext"])
+    a.set_map(fr["map"])
+    b = O.OracleLIO(fr["lio_cfg"], fr["ext"])
+    b.set_map(vm)
+    ra = a.state_estimation(fr["pts"], fr["state_prior"], fr["state_prior"])
+    rb = b.state_estimation(fr["pts"], fr["state_prior"], fr["state_prior"])
+    assert np.array_equal(ra["match_plane"], rb["match_plane"])
+    np.testing.assert_allclose(ra["HTH"], rb["HTH"], rtol=1e-12)
+    np.testing.assert_allclose(ra["HTz"], rb["HTz"], rtol=1e-10, atol=1e-9)
+    np.testing.assert_allclose(ra["state"], rb["state"], rtol=1e-10, atol=1e-12)
+
+
+def test_numpy_map_builder_agrees_with_cpp_build_voxel_map():
+    """Two independent restatements of BuildVoxelMap / init_plane / cut_octo_tree (voxel_map.cpp:532-591, 55-217):
+    the vectorised numpy one in the generator and the C++ oracle. Same roots, same DFS plane lists, same planes."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    cfg = S.LioCfg()
+    ext = S.avia_extrinsics()
+    rects = S.make_scene("room", 0.25)
+    pw, _ = S.sample_on_rects(rects, 40_000, rng)
+    st = S.pack_state(np.eye(3), np.zeros(3), cov=np.eye(19) * 1e-6)
+    pb = ((pw - ext.extT) @ ext.extR).astype(np.float32)            # body = extR^T (p - extT) at identity pose
+    pw32 = (pb.astype(np.float64) @ ext.extR.T + ext.extT).astype(np.float32)
+    lio = O.OracleLIO(cfg, ext)
+    lio.build_map(pw32, pb, st)
+    fo = lio.flatten()
+    # generator side with the same per-point covariance (BuildVoxelMap :546-553)
+    pbd = pb.astype(np.float64)
+    bc = S.calc_body_cov_np(pbd, cfg.dept_err, cfg.beam_err)
+    cm = np.zeros((len(pb), 3, 3))
+    cm[:, 0, 1], cm[:, 0, 2], cm[:, 1, 0], cm[:, 1, 2], cm[:, 2, 0], cm[:, 2, 1] = -pbd[:, 2], pbd[:, 1], pbd[:, 2], -pbd[:, 0], -pbd[:, 1], pbd[:, 0]
+    var = ext.extR @ bc @ ext.extR.T + 1e-6 * (cm @ cm.transpose(0, 2, 1)) + 1e-6 * np.eye(3)
+    fg = S.build_voxel_map(pw32.astype(np.float64), var, cfg)
+
+    def index(fm):
+        return {tuple(k): (f, c) for k, f, c in zip(fm["keys"].tolist(), fm["first"], fm["count"])}
+
+    io, ig = index(fo), index(fg)
+    assert set(io) == set(ig)
+    n_multi = 0
+    for k, (f, c) in io.items():
+        f2, c2 = ig[k]
+        assert c == c2, (k, c, c2)
+        n_multi += c > 1
+        for j in range(c):
+            a, b = fo["planes"][f + j], fg["planes"][f2 + j]
+            assert a["layer"] == b["layer"] and a["path"] == b["path"]
+            s = 1.0 if a["normal"] @ b["normal"] > 0 else -1.0  # eigenvector sign is free
+            np.testing.assert_allclose(a["center"], b["center"], rtol=1e-9, atol=1e-9)
+            np.testing.assert_allclose(a["normal"], s * b["normal"], atol=1e-6)
+            np.testing.assert_allclose(a["radius"], b["radius"], rtol=1e-5)
+            np.testing.assert_allclose(a["d"], s * b["d"], rtol=1e-4, atol=1e-5)
+            pa, pbv = np.zeros((6, 6)), np.zeros((6, 6))
+            iu = np.triu_indices(6)
+            pa[iu], pbv[iu] = a["plane_var"], b["plane_var"]
+            pbv[0:3, 3:6] *= s
+            np.testing.assert_allclose(pa[iu], pbv[iu], rtol=2e-4, atol=1e-12)
+    assert n_multi > 5  # the scene has edges/corners: sub-divided roots with several leaf planes are covered
+
+
+def test_flat_candidate_list_equals_recursive_walk():
+    """Appendix A-6: the DFS-ordered flat list visits exactly what build_single_residual's recursion visits. The oracle
+    walks a pointer octree; build it (a) natively with BuildVoxelMap and (b) from its own flattened arrays."""
+    fr = S.make_frame(seed=7, n_pts=3000, n_map=60_000, scene_scale=0.3)
+    ext, cfg = fr["ext"], fr["lio_cfg"]
+    st = S.unpack_state(fr["state_true"])
+    pb = fr["pts"]
+    pw = ((pb.astype(np.float64) @ ext.extR.T + ext.extT) @ st["R"].T + st["p"]).astype(np.float32)
+    a = O.OracleLIO(cfg, ext)
+    a.build_map(pw, pb, fr["state_true"])
+    flat = a.flatten()
+    b = O.OracleLIO(cfg, ext)
+    b.set_map(flat)
+    rng = np.random.default_rng(0)
+    q = fr["pts"][rng.permutation(len(fr["pts"]))[:2000]]
+    ra = a.single_pass(q, fr["state_prior"], fr["state_prior"])
+    rb = b.single_pass(q, fr["state_prior"], fr["state_prior"])
+    assert (ra["plane"] >= 0).sum() > 500
+    assert np.array_equal(ra["plane"], rb["plane"])
+    assert np.array_equal(ra["dis"], rb["dis"])
+    np.testing.assert_allclose(ra["R_inv"], rb["R_inv"], rtol=1e-12)
