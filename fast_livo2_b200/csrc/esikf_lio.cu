@@ -121,10 +121,11 @@ __device__ __forceinline__ void eval_plane(const esikf_plane *__restrict__ pl, i
   double c0 = q[0], c1 = q[1], c2 = q[2];
   double n0 = q[3], n1 = q[4], n2 = q[5];
   float2 dr = *reinterpret_cast<const float2 *>(q + 27);  // d, radius
-  double sd = n0 * pw[0] + n1 * pw[1] + n2 * pw[2] + (double)dr.x;
+  // float-rounded quantities that gate the association: evaluated without FMA contraction, left to right, like the oracle
+  double sd = __dadd_rn(dot3_rn(n0, n1, n2, pw[0], pw[1], pw[2]), (double)dr.x);
   float dis_to_plane = (float)fabs(sd);
   double e0 = c0 - pw[0], e1 = c1 - pw[1], e2 = c2 - pw[2];
-  float dis_to_center = (float)(e0 * e0 + e1 * e1 + e2 * e2);
+  float dis_to_center = (float)dot3_rn(e0, e1, e2, e0, e1, e2);
   float range_dis = sqrtf(__fsub_rn(dis_to_center, __fmul_rn(dis_to_plane, dis_to_plane)));
   if ((double)range_dis <= 3.0 * (double)dr.y) {  // NaN fails, as in the reference
     double J[6] = {pw[0] - c0, pw[1] - c1, pw[2] - c2, -n0, -n1, -n2};
@@ -159,10 +160,10 @@ __device__ __forceinline__ bool probe(const HashSlot *__restrict__ slots, uint32
 }
 
 // shared-memory layout of the residual kernel
-struct LioSmem {
+struct __align__(128) LioSmem {
+  double rows[LIO_THREADS][8];        // a_i = [A(3) n(3) z 1]   (first: double4 stores need 32-byte alignment)
   double R[9], t[3], Ptt[9], Ppp[9];  // current state
   double Rp[9], tp[3], Mp[9];         // prior pose, Mp = Rp * extR
-  double rows[LIO_THREADS][8];        // a_i = [A(3) n(3) z 1]
   double w[LIO_THREADS];              // R_inv
   double absd[LIO_THREADS];           // |dis_to_plane|
   ReduceSmem<LIO_WARPS> red;
@@ -170,7 +171,7 @@ struct LioSmem {
 
 __global__ void __launch_bounds__(LIO_THREADS, 2) lio_residual_kernel(const LioKernelArgs a) {
   if (a.ctrl->stop) return;  // EKF_stop_flg: remaining iterations of the unrolled loop do nothing
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   LioSmem &sm = *reinterpret_cast<LioSmem *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -314,10 +315,10 @@ __global__ void __launch_bounds__(LIO_THREADS, 2) lio_residual_kernel(const LioK
           row[7] = 1.0;
           absd = fabs((double)best.dis);
           a.normal_plane[i] = best.idx;  // pv.normal = plane.normal_ (:744), sticky across iterations
-          a.dis_to_plane[i] = best.dis;
         }
       }
       a.match_plane[i] = midx;  // ptpl_list_ membership of this iteration
+      a.dis_to_plane[i] = (float)(-row[6]);  // PointToPlane::dis_to_plane_ of this iteration (0 when unmatched)
     }
     cnt += __popc(__ballot_sync(0xffffffffu, matched));
 

@@ -108,16 +108,16 @@ __device__ __forceinline__ float bil(float wtl, float wtr, float wbl, float wbr,
   return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wtl, a), __fmul_rn(wtr, b)), __fmul_rn(wbl, c)), __fmul_rn(wbr, d));
 }
 
-struct VioSmem {
+struct __align__(128) VioSmem {
+  double rows[VIO_WARPS][64][8];  // first: double4 stores need 32-byte alignment
   double Rcw[9], Pcw[3];
   double inv_expo;
-  double rows[VIO_WARPS][64][8];
   ReduceSmem<VIO_WARPS> red;
 };
 
 __global__ void __launch_bounds__(VIO_THREADS, 2) vio_patch_kernel(const VioKernelArgs a) {
   if (a.slot_iter > 0 && a.ctrl->level_done) return;  // EKF_end of this level: remaining slots do nothing
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   VioSmem &sm = *reinterpret_cast<VioSmem *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < 9) {
