@@ -95,6 +95,8 @@ def load_library():
     lib.esikf_comm_init.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p]
     lib.esikf_comm_rank.argtypes = [vp, ip, ip]
     lib.esikf_profile_kernel.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, fp]
+    lib.esikf_set_kernel_timing.argtypes = [vp, C.c_int32]
+    lib.esikf_get_kernel_timing.argtypes = [vp, fp, fp, fp, fp]
     _lib = lib
     return lib
 
@@ -104,7 +106,7 @@ EXPORTED_SYMBOLS = [
     "esikf_set_extrinsics", "esikf_map_upload", "esikf_map_patch", "esikf_lio_set_scan", "esikf_lio_run", "esikf_lio_fetch",
     "esikf_lio_update", "esikf_lio_fetch_point_cov", "esikf_vio_set_camera", "esikf_vio_set_image", "esikf_vio_set_patches",
     "esikf_vio_run", "esikf_vio_fetch", "esikf_vio_update", "esikf_vio_get_image_patch", "esikf_vio_set_ref_images",
-    "esikf_vio_warp_patches", "esikf_comm_unique_id", "esikf_comm_init", "esikf_comm_rank", "esikf_profile_kernel",
+    "esikf_vio_warp_patches", "esikf_comm_unique_id", "esikf_comm_init", "esikf_comm_rank", "esikf_profile_kernel", "esikf_set_kernel_timing", "esikf_get_kernel_timing",
 ]
 
 
@@ -198,13 +200,15 @@ class Context:
         self._cfg_keep = lio_cfg_c(cfg) if not isinstance(cfg, LioCfgC) else cfg
         self._ck(self.lib.esikf_lio_run(self.h, _addr(state_in), _addr(state_prop), C.byref(self._cfg_keep)))
 
-    def lio_fetch(self, per_point=True, state_out=None):
+    def lio_fetch(self, per_point=True, state_out=None, match=None, normal=None, dis=None):
+        """Outputs may be caller-provided (e.g. pinned torch tensors); otherwise numpy arrays are allocated."""
         out = np.zeros(STATE_DOUBLES) if state_out is None else state_out
         st = LioStatsC()
         n = self.n_pts
-        match = np.zeros(n, np.int32) if per_point else None
-        normal = np.zeros(n, np.int32) if per_point else None
-        dis = np.zeros(n, np.float32) if per_point else None
+        if per_point:
+            match = np.zeros(n, np.int32) if match is None else match
+            normal = np.zeros(n, np.int32) if normal is None else normal
+            dis = np.zeros(n, np.float32) if dis is None else dis
         self._ck(self.lib.esikf_lio_fetch(self.h, _addr(out), C.byref(st), _addr(match), _addr(normal), _addr(dis)))
         return self._lio_result(out, st, match, normal, dis)
 
@@ -256,10 +260,11 @@ class Context:
     def vio_run(self, state_in, state_prop):
         self._ck(self.lib.esikf_vio_run(self.h, _addr(state_in), _addr(state_prop)))
 
-    def vio_fetch(self, errors=True, state_out=None):
+    def vio_fetch(self, errors=True, state_out=None, err=None):
         out = np.zeros(STATE_DOUBLES) if state_out is None else state_out
         st = VioStatsC()
-        err = np.zeros(self.n_patches, np.float32) if errors else None
+        if errors and err is None:
+            err = np.zeros(self.n_patches, np.float32)
         self._ck(self.lib.esikf_vio_fetch(self.h, _addr(out), C.byref(st), _addr(err)))
         return self._vio_result(out, st, err)
 
@@ -315,6 +320,15 @@ class Context:
     # ------------------------------------------------------------------ multi-GPU / measurement
     def comm_init(self, rank, nranks, unique_id: bytes):
         self._ck(self.lib.esikf_comm_init(self.h, rank, nranks, unique_id))
+
+    def set_kernel_timing(self, enable):
+        self._ck(self.lib.esikf_set_kernel_timing(self.h, int(enable)))
+
+    def get_kernel_timing(self):
+        a, b, c, d = (np.zeros(8, np.float32), np.zeros(8, np.float32), np.zeros(64, np.float32), np.zeros(64, np.float32))
+        f = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
+        self._ck(self.lib.esikf_get_kernel_timing(self.h, f(a), f(b), f(c), f(d)))
+        return dict(lio_residual_ms=a, lio_solve_ms=b, vio_patch_ms=c, vio_solve_ms=d)
 
     def profile_kernel(self, which, arg=0, reps=20, flush_l2=True):
         ms = C.c_float(0)

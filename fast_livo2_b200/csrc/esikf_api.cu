@@ -137,6 +137,10 @@ struct esikf_ctx {
   ncclComm_t comm = nullptr;
 
   // measurement
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;      // 3 per slot: before residual, after residual, after solve
+  int lio_slots = 0, vio_slots = 0;
+  bool lio_timed = false, vio_timed = false;
   DevBuf<uint8_t> flush;
   DevBuf<double> scratch_state;
 };
@@ -155,6 +159,17 @@ static int fail(esikf_ctx *c, int code, const char *fmt, ...) {
     cudaError_t e__ = (call);                                                                                      \
     if (e__ != cudaSuccess) return fail(ctx, ESIKF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
+
+static cudaEvent_t *timing_events(esikf_ctx *ctx, int base, int slot) {
+  size_t need = (size_t)(base + slot + 1) * 3;
+  while (ctx->ev.size() < need) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    ctx->ev.push_back(e);
+  }
+  return &ctx->ev[(size_t)(base + slot) * 3];
+}
+enum { EV_LIO_BASE = 0, EV_VIO_BASE = 8 };
 
 static void shard_of(int n, int rank, int nranks, int &begin, int &count) {
   // contiguous blocks, remainder spread over the first ranks
@@ -210,6 +225,7 @@ void esikf_destroy(esikf_ctx *ctx) {
   ctx->px_ref.release(), ctx->pos_w.release(), ctx->normal_w.release(), ctx->T_ref.release(), ctx->T_cur.release();
   ctx->A_cur_ref.release(), ctx->pc_buf.release(), ctx->patch_buf.release(), ctx->flush.release(), ctx->scratch_state.release();
   for (uint8_t *p : ctx->ref_imgs) cudaFree(p);
+  for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -363,11 +379,17 @@ int esikf_lio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   sa.state = ctx->state.p, sa.prop = ctx->prop.p, sa.info = ctx->info.p, sa.ctrl = ctx->ctrl.p;
   sa.max_iterations = cfg->max_iterations, sa.solve_mode = ctx->solve_mode, sa.lio_stats = ctx->lio_stats.p;
   const int grid = lio_grid(ctx, ka.count);
+  ctx->lio_timed = ctx->timing;
+  ctx->lio_slots = cfg->max_iterations;
   for (int it = 0; it < cfg->max_iterations; it++) {
+    cudaEvent_t *e = ctx->timing ? timing_events(ctx, EV_LIO_BASE, it) : nullptr;
+    if (e) cudaEventRecord(e[0], st);
     lio_residual_kernel<<<grid, LIO_THREADS, sizeof(LioSmem), st>>>(ka);
+    if (e) cudaEventRecord(e[1], st);
     int rc = allreduce_info(ctx);
     if (rc) return rc;
     lio_solve_kernel<<<1, 32, 0, st>>>(sa);
+    if (e) cudaEventRecord(e[2], st);
     ctx->launches += 2;
   }
   CK(cudaGetLastError());
@@ -530,14 +552,21 @@ int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   sa.max_iterations = ctx->vio_cfg.max_iterations, sa.solve_mode = ctx->solve_mode, sa.vio_stats = ctx->vio_stats.p;
   sa.old_state = ctx->old_state.p, sa.G = ctx->G.p, sa.img_point_cov = ctx->vio_cfg.img_point_cov;
   const int grid = vio_grid(ctx, ka.count);
+  ctx->vio_timed = ctx->timing;
+  ctx->vio_slots = ctx->vio_cfg.patch_pyrimid_level * ctx->vio_cfg.max_iterations;
+  int slot = 0;
   for (int level = ctx->vio_cfg.patch_pyrimid_level - 1; level >= 0; level--) {
-    for (int it = 0; it < ctx->vio_cfg.max_iterations; it++) {
+    for (int it = 0; it < ctx->vio_cfg.max_iterations; it++, slot++) {
       ka.level = level, ka.slot_iter = it;
+      cudaEvent_t *e = ctx->timing ? timing_events(ctx, EV_VIO_BASE, slot) : nullptr;
+      if (e) cudaEventRecord(e[0], st);
       vio_patch_kernel<<<grid, VIO_THREADS, sizeof(VioSmem), st>>>(ka);
+      if (e) cudaEventRecord(e[1], st);
       int rc = allreduce_info(ctx);
       if (rc) return rc;
       sa.level = level, sa.slot_iter = it, sa.last_slot = (level == 0 && it == ctx->vio_cfg.max_iterations - 1);
       vio_solve_kernel<<<1, 32, 0, st>>>(sa);
+      if (e) cudaEventRecord(e[2], st);
       ctx->launches += 2;
     }
   }
@@ -745,6 +774,35 @@ int esikf_profile_kernel(esikf_ctx *ctx, int32_t which, int32_t arg, int32_t rep
   cudaEventDestroy(e1);
   CK(cudaGetLastError());
   *avg_ms = (float)(total / reps);
+  return ESIKF_OK;
+}
+
+int esikf_set_kernel_timing(esikf_ctx *ctx, int32_t enable) {
+  if (!ctx) return ESIKF_ERR_ARG;
+  ctx->timing = enable != 0;
+  return ESIKF_OK;
+}
+
+int esikf_get_kernel_timing(esikf_ctx *ctx, float *lio_residual_ms, float *lio_solve_ms, float *vio_patch_ms, float *vio_solve_ms) {
+  if (!ctx) return ESIKF_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int pass = 0; pass < 2; pass++) {
+    const bool timed = pass == 0 ? ctx->lio_timed : ctx->vio_timed;
+    const int slots = pass == 0 ? ctx->lio_slots : ctx->vio_slots, base = pass == 0 ? EV_LIO_BASE : EV_VIO_BASE, cap = pass == 0 ? 8 : 64;
+    float *a = pass == 0 ? lio_residual_ms : vio_patch_ms, *b = pass == 0 ? lio_solve_ms : vio_solve_ms;
+    for (int i = 0; i < cap; i++) {
+      if (a) a[i] = 0.f;
+      if (b) b[i] = 0.f;
+    }
+    if (!timed) continue;
+    for (int i = 0; i < slots && i < cap; i++) {
+      cudaEvent_t *e = &ctx->ev[(size_t)(base + i) * 3];
+      float ms = 0.f;
+      if (a && cudaEventElapsedTime(&ms, e[0], e[1]) == cudaSuccess) a[i] = ms;
+      if (b && cudaEventElapsedTime(&ms, e[1], e[2]) == cudaSuccess) b[i] = ms;
+    }
+  }
   return ESIKF_OK;
 }
 

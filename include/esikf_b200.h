@@ -204,6 +204,14 @@ int esikf_comm_rank(const esikf_ctx *ctx, int32_t *rank, int32_t *nranks);
  * (excluded from the timing). */
 int esikf_profile_kernel(esikf_ctx *ctx, int32_t which, int32_t arg, int32_t reps, int32_t flush_l2, float *avg_ms);
 
+/* Per-launch device times of the update loops. enable != 0 brackets every residual / patch / solve launch of the
+ * following lio_run / vio_run calls with CUDA events on esikf_stream (adds sub-microsecond gaps: use a separate,
+ * untimed pass). get: ms of the launches of the LAST run, in launch order; LIO: residual[8], solve[8];
+ * VIO: patch[64], solve[64] indexed (levels-1-level)*max_iterations + iteration. Unlaunched slots are 0. */
+int esikf_set_kernel_timing(esikf_ctx *ctx, int32_t enable);
+int esikf_get_kernel_timing(esikf_ctx *ctx, float *lio_residual_ms /* 8 */, float *lio_solve_ms /* 8 */,
+                            float *vio_patch_ms /* 64 */, float *vio_solve_ms /* 64 */);
+
 #ifdef __cplusplus
 }
 #endif
