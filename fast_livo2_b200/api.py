@@ -74,6 +74,7 @@ def load_library():
     lib.esikf_launch_count.argtypes = [vp]
     lib.esikf_launch_count.restype = C.c_int64
     lib.esikf_set_solve_mode.argtypes = [vp, C.c_int]
+    lib.esikf_set_loop_mode.argtypes = [vp, C.c_int]
     lib.esikf_set_extrinsics.argtypes = [vp, C.POINTER(ExtrinsicsC)]
     lib.esikf_map_upload.argtypes = [vp, i64p, ip, ip, C.c_int32, vp, C.c_int32, C.c_double]
     lib.esikf_map_patch.argtypes = [vp, ip, vp, C.c_int32]
@@ -96,17 +97,19 @@ def load_library():
     lib.esikf_comm_rank.argtypes = [vp, ip, ip]
     lib.esikf_profile_kernel.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, fp]
     lib.esikf_set_kernel_timing.argtypes = [vp, C.c_int32]
+    lib.esikf_set_phase_stamps.argtypes = [vp, C.c_int32]
+    lib.esikf_get_phase_stamps.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.esikf_get_kernel_timing.argtypes = [vp, fp, fp, fp, fp]
     _lib = lib
     return lib
 
 
 EXPORTED_SYMBOLS = [
-    "esikf_create", "esikf_destroy", "esikf_last_error", "esikf_stream", "esikf_synchronize", "esikf_launch_count", "esikf_set_solve_mode",
+    "esikf_create", "esikf_destroy", "esikf_last_error", "esikf_stream", "esikf_synchronize", "esikf_launch_count", "esikf_set_solve_mode", "esikf_set_loop_mode",
     "esikf_set_extrinsics", "esikf_map_upload", "esikf_map_patch", "esikf_lio_set_scan", "esikf_lio_run", "esikf_lio_fetch",
     "esikf_lio_update", "esikf_lio_fetch_point_cov", "esikf_vio_set_camera", "esikf_vio_set_image", "esikf_vio_set_patches",
     "esikf_vio_run", "esikf_vio_fetch", "esikf_vio_update", "esikf_vio_get_image_patch", "esikf_vio_set_ref_images",
-    "esikf_vio_warp_patches", "esikf_comm_unique_id", "esikf_comm_init", "esikf_comm_rank", "esikf_profile_kernel", "esikf_set_kernel_timing", "esikf_get_kernel_timing",
+    "esikf_vio_warp_patches", "esikf_comm_unique_id", "esikf_comm_init", "esikf_comm_rank", "esikf_profile_kernel", "esikf_set_kernel_timing", "esikf_get_kernel_timing", "esikf_set_phase_stamps", "esikf_get_phase_stamps",
 ]
 
 
@@ -168,6 +171,9 @@ class Context:
 
     def set_solve_mode(self, mode):
         self._ck(self.lib.esikf_set_solve_mode(self.h, mode))
+
+    def set_loop_mode(self, mode):
+        self._ck(self.lib.esikf_set_loop_mode(self.h, mode))
 
     def set_extrinsics(self, ext):
         e = ExtrinsicsC()
@@ -320,6 +326,14 @@ class Context:
     # ------------------------------------------------------------------ multi-GPU / measurement
     def comm_init(self, rank, nranks, unique_id: bytes):
         self._ck(self.lib.esikf_comm_init(self.h, rank, nranks, unique_id))
+
+    def set_phase_stamps(self, enable):
+        self._ck(self.lib.esikf_set_phase_stamps(self.h, int(enable)))
+
+    def get_phase_stamps(self):
+        out = np.zeros(576, np.uint64)
+        self._ck(self.lib.esikf_get_phase_stamps(self.h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out.reshape(72, 8)
 
     def set_kernel_timing(self, enable):
         self._ck(self.lib.esikf_set_kernel_timing(self.h, int(enable)))

@@ -21,6 +21,7 @@ struct SolveArgs;
 #include "esikf_lio.cu"
 #include "esikf_solve.cu"
 #include "esikf_vio.cu"
+#include "esikf_fused.cu"
 
 using namespace esikf;
 
@@ -86,6 +87,11 @@ struct esikf_ctx {
   std::string err;
   int64_t launches = 0;
   int solve_mode = 0;
+  int loop_mode = 1;      // 1: persistent cooperative kernel per update (single GPU), 0: one residual + one solve launch per iteration
+  int coop_ok = 0;
+  DevBuf<unsigned int> barrier;
+  DevBuf<unsigned long long> stamps;  // 8 per slot: 8 LIO slots then 64 VIO slots
+  bool want_stamps = false;
   esikf_extrinsics ext{};
   bool have_ext = false;
 
@@ -103,6 +109,7 @@ struct esikf_ctx {
   DevBuf<int32_t> match_plane, normal_plane;
   DevBuf<float> dis;
   int n_pts = 0;
+  int pre_stride = 0;
   bool scan_fresh = false;   // precompute pending
   esikf_lio_cfg lio_cfg{};
   DevBuf<double> ext_dev;    // extR(9) extT(3)
@@ -199,8 +206,9 @@ int esikf_create(esikf_ctx **out, int device) {
             ctx->old_state.reserve(32) == cudaSuccess && ctx->G.reserve(19 * 7) == cudaSuccess && ctx->ctrl.reserve(1) == cudaSuccess &&
             ctx->lio_stats.reserve(1) == cudaSuccess && ctx->vio_stats.reserve(1) == cudaSuccess && ctx->ext_dev.reserve(12) == cudaSuccess &&
             ctx->scratch_state.reserve(S_N) == cudaSuccess;
-  ctx->partial_blocks = ctx->sm_count * 4;
-  ok = ok && ctx->partials.reserve((size_t)ctx->partial_blocks * INFO_N) == cudaSuccess;
+  ctx->partial_blocks = ctx->sm_count * 2;  // residual kernels are persistent: 2 resident CTAs per SM
+  ok = ok && ctx->partials.reserve((size_t)ctx->partial_blocks * INFO_N) == cudaSuccess && ctx->barrier.reserve(4) == cudaSuccess && ctx->stamps.reserve(8 * 72) == cudaSuccess;
+  cudaDeviceGetAttribute(&ctx->coop_ok, cudaDevAttrCooperativeLaunch, device);
   if (!ok) {
     esikf_destroy(ctx);
     return ESIKF_ERR_CUDA;
@@ -208,6 +216,8 @@ int esikf_create(esikf_ctx **out, int device) {
   cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), ctx->stream);
   cudaFuncSetAttribute(lio_residual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
   cudaFuncSetAttribute(vio_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VioSmem));
+  cudaFuncSetAttribute(lio_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
+  cudaFuncSetAttribute(vio_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VioSmem));
   *out = ctx;
   return ESIKF_OK;
 }
@@ -220,7 +230,7 @@ void esikf_destroy(esikf_ctx *ctx) {
   ctx->slots.release(), ctx->planes.release(), ctx->pts.release(), ctx->pre.release(), ctx->match_plane.release();
   ctx->normal_plane.release(), ctx->dis.release(), ctx->ext_dev.release(), ctx->state.release(), ctx->prop.release();
   ctx->info.release(), ctx->partials.release(), ctx->old_state.release(), ctx->G.release(), ctx->ctrl.release();
-  ctx->lio_stats.release(), ctx->vio_stats.release(), ctx->img.release(), ctx->vis_pos.release(), ctx->inv_expo.release();
+  ctx->barrier.release(), ctx->stamps.release(), ctx->lio_stats.release(), ctx->vio_stats.release(), ctx->img.release(), ctx->vis_pos.release(), ctx->inv_expo.release();
   ctx->warp_patch.release(), ctx->errors.release(), ctx->search_levels.release(), ctx->ref_img_ptrs.release(), ctx->ref_idx.release();
   ctx->px_ref.release(), ctx->pos_w.release(), ctx->normal_w.release(), ctx->T_ref.release(), ctx->T_cur.release();
   ctx->A_cur_ref.release(), ctx->pc_buf.release(), ctx->patch_buf.release(), ctx->flush.release(), ctx->scratch_state.release();
@@ -242,6 +252,11 @@ int esikf_synchronize(esikf_ctx *ctx) {
 int esikf_set_solve_mode(esikf_ctx *ctx, int mode) {
   if (!ctx || mode < 0 || mode > 1) return ESIKF_ERR_ARG;
   ctx->solve_mode = mode;
+  return ESIKF_OK;
+}
+int esikf_set_loop_mode(esikf_ctx *ctx, int mode) {
+  if (!ctx || mode < 0 || mode > 1) return ESIKF_ERR_ARG;
+  ctx->loop_mode = mode;
   return ESIKF_OK;
 }
 int esikf_set_extrinsics(esikf_ctx *ctx, const esikf_extrinsics *ext) {
@@ -310,7 +325,8 @@ int esikf_lio_set_scan(esikf_ctx *ctx, const float *pts_xyz, int32_t n) {
   if (!ctx || n < 0 || (n > 0 && !pts_xyz)) return fail(ctx, ESIKF_ERR_ARG, "lio_set_scan: bad argument");
   CK(cudaSetDevice(ctx->device));
   CK(ctx->pts.reserve((size_t)n * 3 + 4));
-  CK(ctx->pre.reserve((size_t)n * 9 + 16));
+  ctx->pre_stride = (n + 31) & ~31;
+  CK(ctx->pre.reserve((size_t)ctx->pre_stride * 9 + 16));
   CK(ctx->match_plane.reserve(n + 1));
   CK(ctx->normal_plane.reserve(n + 1));
   CK(ctx->dis.reserve(n + 1));
@@ -323,12 +339,19 @@ int esikf_lio_set_scan(esikf_ctx *ctx, const float *pts_xyz, int32_t n) {
 static int lio_fill_args(esikf_ctx *ctx, LioKernelArgs &ka, double *state_ptr) {
   memset(&ka, 0, sizeof(ka));
   ka.pts = ctx->pts.p, ka.pre = ctx->pre.p;
+  ka.pre_stride = ctx->pre_stride;
+  ka.partial_stride = ctx->partial_blocks;
   shard_of(ctx->n_pts, ctx->rank, ctx->nranks, ka.begin, ka.count);
   ka.state = state_ptr, ka.prop = ctx->prop.p;
   ka.slots = ctx->slots.p, ka.hash_mask = ctx->hash_mask, ka.planes = ctx->planes.p;
   memcpy(ka.extR, ctx->ext.extR, sizeof(ka.extR));
   memcpy(ka.extT, ctx->ext.extT, sizeof(ka.extT));
   ka.voxel_size = ctx->lio_cfg.voxel_size;
+  ka.inv_voxel_size = 1.0 / ctx->lio_cfg.voxel_size;
+  {
+    int ex = 0;
+    ka.inv_voxel_exact = (frexp(ctx->lio_cfg.voxel_size, &ex) == 0.5) ? 1 : 0;  // power of two: the reciprocal is exact
+  }
   ka.voxel_size_f = (float)ctx->lio_cfg.voxel_size;
   ka.sigma_num = ctx->lio_cfg.sigma_num;
   ka.match_plane = ctx->match_plane.p, ka.normal_plane = ctx->normal_plane.p, ka.dis_to_plane = ctx->dis.p;
@@ -337,7 +360,7 @@ static int lio_fill_args(esikf_ctx *ctx, LioKernelArgs &ka, double *state_ptr) {
 }
 static int lio_grid(const esikf_ctx *ctx, int count) {
   int tiles = (count + LIO_THREADS - 1) / LIO_THREADS;
-  int g = tiles < ctx->partial_blocks ? tiles : ctx->partial_blocks;
+  int g = tiles < ctx->partial_blocks ? tiles : ctx->partial_blocks;  // persistent: <= 2 CTAs per SM, equal slices
   return g < 1 ? 1 : g;
 }
 static int allreduce_info(esikf_ctx *ctx) {
@@ -362,7 +385,7 @@ int esikf_lio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   const int n = ctx->n_pts;
   if (ctx->scan_fresh) {
     if (n > 0) {
-      lio_precompute_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->pts.p, n, ctx->pre.p, ctx->ext_dev.p, (float)cfg->dept_err, (float)cfg->beam_err);
+      lio_precompute_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->pts.p, n, ctx->pre.p, ctx->pre_stride, ctx->ext_dev.p, (float)cfg->dept_err, (float)cfg->beam_err);
       ctx->launches++;
       CK(cudaMemsetAsync(ctx->normal_plane.p, 0xff, (size_t)n * sizeof(int32_t), st));  // pv.normal = 0 <=> no plane yet
       CK(cudaMemsetAsync(ctx->match_plane.p, 0xff, (size_t)n * sizeof(int32_t), st));
@@ -379,6 +402,17 @@ int esikf_lio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   sa.state = ctx->state.p, sa.prop = ctx->prop.p, sa.info = ctx->info.p, sa.ctrl = ctx->ctrl.p;
   sa.max_iterations = cfg->max_iterations, sa.solve_mode = ctx->solve_mode, sa.lio_stats = ctx->lio_stats.p;
   const int grid = lio_grid(ctx, ka.count);
+  if (ctx->loop_mode == 1 && ctx->nranks == 1 && ctx->coop_ok && !ctx->timing) {
+    CK(cudaMemsetAsync(ctx->barrier.p, 0, sizeof(unsigned int), st));
+    unsigned int *bar = ctx->barrier.p;
+    unsigned long long *stamps = ctx->want_stamps ? ctx->stamps.p : nullptr;
+    if (stamps) CK(cudaMemsetAsync(stamps, 0, 64 * sizeof(unsigned long long), st));
+    void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&stamps};
+    CK(cudaLaunchCooperativeKernel((const void *)lio_update_kernel, dim3(grid), dim3(LIO_THREADS), kargs, sizeof(LioSmem), st));
+    ctx->launches += 1;
+    ctx->lio_timed = false;
+    return ESIKF_OK;
+  }
   ctx->lio_timed = ctx->timing;
   ctx->lio_slots = cfg->max_iterations;
   for (int it = 0; it < cfg->max_iterations; it++) {
@@ -388,7 +422,7 @@ int esikf_lio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
     if (e) cudaEventRecord(e[1], st);
     int rc = allreduce_info(ctx);
     if (rc) return rc;
-    lio_solve_kernel<<<1, 32, 0, st>>>(sa);
+    lio_solve_kernel<<<1, SOLVE_THREADS, 0, st>>>(sa);
     if (e) cudaEventRecord(e[2], st);
     ctx->launches += 2;
   }
@@ -419,10 +453,11 @@ int esikf_lio_update(esikf_ctx *ctx, const float *pts_xyz, int32_t n, const doub
   return esikf_lio_fetch(ctx, state_out, stats, match_plane, normal_plane, dis_to_plane);
 }
 
-__global__ void expand_point_cov_kernel(const double *__restrict__ pre, int n, double *__restrict__ body_cov9, double *__restrict__ cross9) {
+__global__ void expand_point_cov_kernel(const double *__restrict__ pre, int pre_stride, int n, double *__restrict__ body_cov9, double *__restrict__ cross9) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const double *p = pre + 9 * (size_t)i;
+  double p[9];
+  for (int k = 0; k < 9; k++) p[k] = pre[(size_t)k * pre_stride + i];
   if (body_cov9) {
     double *o = body_cov9 + 9 * (size_t)i;
     o[0] = p[3], o[1] = p[4], o[2] = p[5], o[3] = p[4], o[4] = p[6], o[5] = p[7], o[6] = p[5], o[7] = p[7], o[8] = p[8];
@@ -441,7 +476,7 @@ int esikf_lio_fetch_point_cov(esikf_ctx *ctx, double *body_cov9, double *cross_m
   if (n == 0) return ESIKF_OK;
   DevBuf<double> tmp;
   CK(tmp.reserve((size_t)n * 18));
-  expand_point_cov_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->pre.p, n, body_cov9 ? tmp.p : nullptr, cross_mat9 ? tmp.p + 9 * (size_t)n : nullptr);
+  expand_point_cov_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->pre.p, ctx->pre_stride, n, body_cov9 ? tmp.p : nullptr, cross_mat9 ? tmp.p + 9 * (size_t)n : nullptr);
   ctx->launches++;
   if (body_cov9) CK(cudaMemcpyAsync(body_cov9, tmp.p, (size_t)n * 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (cross_mat9) CK(cudaMemcpyAsync(cross_mat9, tmp.p + 9 * (size_t)n, (size_t)n * 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -526,6 +561,7 @@ static void vio_fill_args(esikf_ctx *ctx, VioKernelArgs &ka, double *state_ptr) 
   ka.state = state_ptr;
   vio_consts(ctx, ka.Rci, ka.Pci, ka.Jdp_dR);
   ka.errors = ctx->errors.p, ka.partials = ctx->partials.p, ka.info = ctx->info.p, ka.ctrl = ctx->ctrl.p;
+  ka.partial_stride = ctx->partial_blocks;
 }
 static int vio_grid(const esikf_ctx *ctx, int count) {
   int g = (count + VIO_WARPS - 1) / VIO_WARPS;
@@ -552,6 +588,17 @@ int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   sa.max_iterations = ctx->vio_cfg.max_iterations, sa.solve_mode = ctx->solve_mode, sa.vio_stats = ctx->vio_stats.p;
   sa.old_state = ctx->old_state.p, sa.G = ctx->G.p, sa.img_point_cov = ctx->vio_cfg.img_point_cov;
   const int grid = vio_grid(ctx, ka.count);
+  if (ctx->loop_mode == 1 && ctx->nranks == 1 && ctx->coop_ok && !ctx->timing) {
+    CK(cudaMemsetAsync(ctx->barrier.p, 0, sizeof(unsigned int), st));
+    unsigned int *bar = ctx->barrier.p;
+    unsigned long long *stamps = ctx->want_stamps ? ctx->stamps.p + 64 : nullptr;
+    if (stamps) CK(cudaMemsetAsync(stamps, 0, 512 * sizeof(unsigned long long), st));
+    void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&stamps};
+    CK(cudaLaunchCooperativeKernel((const void *)vio_update_kernel, dim3(grid), dim3(VIO_THREADS), kargs, sizeof(VioSmem), st));
+    ctx->launches += 1;
+    ctx->vio_timed = false;
+    return ESIKF_OK;
+  }
   ctx->vio_timed = ctx->timing;
   ctx->vio_slots = ctx->vio_cfg.patch_pyrimid_level * ctx->vio_cfg.max_iterations;
   int slot = 0;
@@ -565,7 +612,7 @@ int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
       int rc = allreduce_info(ctx);
       if (rc) return rc;
       sa.level = level, sa.slot_iter = it, sa.last_slot = (level == 0 && it == ctx->vio_cfg.max_iterations - 1);
-      vio_solve_kernel<<<1, 32, 0, st>>>(sa);
+      vio_solve_kernel<<<1, SOLVE_THREADS, 0, st>>>(sa);
       if (e) cudaEventRecord(e[2], st);
       ctx->launches += 2;
     }
@@ -759,9 +806,9 @@ int esikf_profile_kernel(esikf_ctx *ctx, int32_t which, int32_t arg, int32_t rep
     }
     CK(cudaEventRecord(e0, st));
     if (which == 0) lio_residual_kernel<<<grid, LIO_THREADS, sizeof(LioSmem), st>>>(la);
-    else if (which == 1) lio_solve_kernel<<<1, 32, 0, st>>>(sa);
+    else if (which == 1) lio_solve_kernel<<<1, SOLVE_THREADS, 0, st>>>(sa);
     else if (which == 2) vio_patch_kernel<<<grid, VIO_THREADS, sizeof(VioSmem), st>>>(va);
-    else lio_precompute_kernel<<<(ctx->n_pts + 255) / 256, 256, 0, st>>>(ctx->pts.p, ctx->n_pts, ctx->pre.p, ctx->ext_dev.p, (float)ctx->lio_cfg.dept_err,
+    else lio_precompute_kernel<<<(ctx->n_pts + 255) / 256, 256, 0, st>>>(ctx->pts.p, ctx->n_pts, ctx->pre.p, ctx->pre_stride, ctx->ext_dev.p, (float)ctx->lio_cfg.dept_err,
                                                                        (float)ctx->lio_cfg.beam_err);
     CK(cudaEventRecord(e1, st));
     CK(cudaEventSynchronize(e1));
@@ -774,6 +821,19 @@ int esikf_profile_kernel(esikf_ctx *ctx, int32_t which, int32_t arg, int32_t rep
   cudaEventDestroy(e1);
   CK(cudaGetLastError());
   *avg_ms = (float)(total / reps);
+  return ESIKF_OK;
+}
+
+int esikf_set_phase_stamps(esikf_ctx *ctx, int32_t enable) {
+  if (!ctx) return ESIKF_ERR_ARG;
+  ctx->want_stamps = enable != 0;
+  return ESIKF_OK;
+}
+int esikf_get_phase_stamps(esikf_ctx *ctx, uint64_t *out /* 576 */) {
+  if (!ctx || !out) return ESIKF_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(out, ctx->stamps.p, 576 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return ESIKF_OK;
 }
 

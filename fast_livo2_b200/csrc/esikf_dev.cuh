@@ -63,19 +63,51 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+// Fixed-order sum over the per-CTA partial blocks (entry-major [entry][block], nb <= 320 blocks) by the calling CTA:
+// lane l adds blocks l, l+32, ... in order, then a fixed xor-shuffle tree. All loads of two entries are issued before the
+// first add so the sum costs one L2 round trip per pass instead of one per block.
+__device__ __forceinline__ void sum_partials(const double *partials, int partial_stride, int nb, double *info, int nwarps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int e0 = warp; e0 < 66; e0 += 2 * nwarps) {
+    const int e1 = e0 + nwarps;
+    const double *__restrict__ p0 = partials + (size_t)e0 * partial_stride;
+    const double *__restrict__ p1 = partials + (size_t)e1 * partial_stride;
+    double v0[10], v1[10];
+#pragma unroll
+    for (int c = 0; c < 10; c++) {
+      const int b = lane + 32 * c;
+      v0[c] = (b < nb) ? __ldcg(p0 + b) : 0.0;
+      v1[c] = (e1 < 66 && b < nb) ? __ldcg(p1 + b) : 0.0;
+    }
+    double s0 = v0[0], s1 = v1[0];
+#pragma unroll
+    for (int c = 1; c < 10; c++) s0 += v0[c], s1 += v1[c];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    }
+    if (lane == 0) {
+      info[e0] = s0;
+      if (e1 < 66) info[e1] = s1;
+    }
+  }
+}
+
 // Shared scratch of the fixed-order reduction used by both residual kernels.
 template <int WARPS> struct ReduceSmem {
   double warpD[WARPS][66];
-  double seg[3][INFO_N];
   int is_last;
 };
 
 // Combine every warp's 8x8 block (D0, D1 fragments) and scalar count into info[] :
-// warp -> block (fixed warp order) -> grid (last block to finish sums the per-block partials in block order).
+// warp -> block (fixed warp order) -> grid. Per-block partials are stored entry-major ([entry][block]) so the last block
+// to finish can sum each entry with coalesced loads: lane l adds blocks l, l+32, ... in order, then a fixed xor-shuffle
+// tree. The order never depends on which block is last => bit-reproducible.
 // abs_in_77: LIO keeps sum|d| in D[7][7]; it is moved to info[INFO_ABS] and D[7][7] zeroed.
 template <int WARPS>
 __device__ __forceinline__ void reduce_info(ReduceSmem<WARPS> &rs, double D0, double D1, double cnt, bool abs_in_77, double *partials,
-                                            double *info, Ctrl *ctrl) {
+                                            int partial_stride, double *info, Ctrl *ctrl) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   {
     const int g = lane >> 2, t = lane & 3;
@@ -88,18 +120,11 @@ __device__ __forceinline__ void reduce_info(ReduceSmem<WARPS> &rs, double D0, do
     double s = rs.warpD[0][tid];
 #pragma unroll
     for (int w = 1; w < WARPS; w++) s += rs.warpD[w][tid];
-    double *out = partials + (size_t)blockIdx.x * INFO_N;
-    if (tid < 64) {
-      if (abs_in_77 && tid == 63) {
-        out[63] = 0.0;
-        out[INFO_ABS] = s;
-      } else {
-        out[tid] = s;
-        if (tid == 63) out[INFO_ABS] = 0.0;
-      }
-    } else {
-      out[INFO_COUNT] = s;
-    }
+    int e = tid;
+    if (tid == 64) e = INFO_COUNT;
+    if (abs_in_77 && tid == 63) e = INFO_ABS;
+    partials[(size_t)e * partial_stride + blockIdx.x] = s;
+    if (tid == 63) partials[(size_t)(abs_in_77 ? 63 : INFO_ABS) * partial_stride + blockIdx.x] = 0.0;
   }
   __threadfence();
   __syncthreads();
@@ -110,17 +135,8 @@ __device__ __forceinline__ void reduce_info(ReduceSmem<WARPS> &rs, double D0, do
   __syncthreads();
   if (!rs.is_last) return;
   __threadfence();
-  const int nb = gridDim.x;
-  if (tid < 3 * INFO_N) {
-    const int e = tid % INFO_N, seg = tid / INFO_N;
-    const int b0 = (nb * seg) / 3, b1 = (nb * (seg + 1)) / 3;
-    double s = 0.0;
-    if (e < 66)
-      for (int b = b0; b < b1; b++) s += __ldcg(partials + (size_t)b * INFO_N + e);
-    rs.seg[seg][e] = s;
-  }
-  __syncthreads();
-  if (tid < INFO_N) info[tid] = (rs.seg[0][tid] + rs.seg[1][tid]) + rs.seg[2][tid];
+  sum_partials(partials, partial_stride, gridDim.x, info, WARPS);
+  if (tid >= 66 && tid < INFO_N) info[tid] = 0.0;
   if (tid == 0) ctrl->block_counter = 0;
 }
 #endif

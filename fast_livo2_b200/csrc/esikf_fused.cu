@@ -1,0 +1,168 @@
+// Persistent update kernels of the B200 ESIKF update (sm_100a): the WHOLE iteration loop of one LIO / VIO update in a
+// single cooperative launch, so a tick costs one launch instead of 2 x iterations, the state never leaves the chip between
+// iterations and no kernel boundary separates the residual build from the gain solve.
+//
+//   lio_update_kernel : VoxelMapManager::StateEstimation's loop          (reference src/voxel_map.cpp:372-500)
+//   vio_update_kernel : VIOManager::computeJacobianAndUpdateEKF's loops   (src/vio.cpp:784-802, 1520-1688)
+//
+// Per iteration: every CTA (2 per SM, co-resident) builds the residual / Jacobian rows of its slice of the points / patches
+// and contracts them on the fp64 tensor-core path; per-CTA 8x8 partial blocks go to global memory; grid barrier; CTA 0 sums
+// them in a fixed order, runs the m x m gain solve and the boxplus and publishes the new state; grid barrier; everybody
+// reloads the 30 pose / covariance doubles it needs and continues. Results are bit-identical to the per-iteration kernels.
+#include "esikf_dev.cuh"
+
+namespace esikf {
+
+// Optional phase timestamps (ns, %globaltimer) written by CTA 0 / thread 0 — measurement only.
+__device__ __forceinline__ void stamp(unsigned long long *stamps, int &k) {
+  if (stamps && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    stamps[k] = t;
+  }
+  k++;
+}
+
+// Sense-free counting barrier over all CTAs of a cooperative launch. `counter` is zeroed by the host before the launch;
+// the k-th barrier (k = 0, 1, ...) completes when it reaches (k + 1) * gridDim.x.
+__device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int &epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int target = (epoch + 1) * gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+    __threadfence();
+  }
+  epoch++;
+  __syncthreads();
+}
+
+// Fixed-order sum of the per-CTA partial blocks (entry-major [entry][block]) into info[] by the calling CTA.
+__device__ __forceinline__ void reduce_partials_block(const double *partials, int partial_stride, int nb, double *info) {
+  const int tid = threadIdx.x;
+  sum_partials(partials, partial_stride, nb, info, blockDim.x >> 5);
+  if (tid >= 66 && tid < INFO_N) info[tid] = 0.0;
+  __threadfence();
+  __syncthreads();
+}
+
+// Per-CTA partial block -> global (entry-major), same layout / order as reduce_info.
+template <int WARPS>
+__device__ __forceinline__ void store_partials(ReduceSmem<WARPS> &rs, double D0, double D1, double cnt, bool abs_in_77, double *partials,
+                                               int partial_stride) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  {
+    const int g = lane >> 2, t = lane & 3;
+    rs.warpD[warp][g * 8 + 2 * t] = D0;
+    rs.warpD[warp][g * 8 + 2 * t + 1] = D1;
+    if (lane == 0) rs.warpD[warp][64] = cnt;
+  }
+  __syncthreads();
+  if (tid < 65) {
+    double s = rs.warpD[0][tid];
+#pragma unroll
+    for (int w = 1; w < WARPS; w++) s += rs.warpD[w][tid];
+    int e = tid;
+    if (tid == 64) e = INFO_COUNT;
+    if (abs_in_77 && tid == 63) e = INFO_ABS;
+    partials[(size_t)e * partial_stride + blockIdx.x] = s;
+    if (tid == 63) partials[(size_t)(abs_in_77 ? 63 : INFO_ABS) * partial_stride + blockIdx.x] = 0.0;
+  }
+}
+
+struct FusedSolveSmem {
+  SolveSmem sm;
+  SolveIO io;
+};
+
+__global__ void __launch_bounds__(LIO_THREADS, 2) lio_update_kernel(const LioKernelArgs a, const SolveArgs sa, unsigned int *barrier, unsigned long long *stamps) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  LioSmem &sm = *reinterpret_cast<LioSmem *>(smem_raw);
+  // the solve scratch aliases the plane-record staging area (only used between the two barriers, by CTA 0)
+  FusedSolveSmem &fs = *reinterpret_cast<FusedSolveSmem *>(&sm.rec[0][0][0]);
+  static_assert(sizeof(FusedSolveSmem) <= sizeof(sm.rec), "solve scratch must fit in the record staging area");
+  unsigned int epoch = 0;
+  int lo, hi;
+  lio_block_range(a.count, lo, hi);
+  int sk = 0;
+  for (int it = 0; it < sa.max_iterations; it++) {
+    stamp(stamps, sk);  // 0: iteration start
+    lio_load_consts(sm, a);
+    stamp(stamps, sk);  // 1: constants loaded
+    double D0 = 0.0, D1 = 0.0;
+    int cnt = 0;
+    lio_process_range(a, sm, lo, hi, D0, D1, cnt);
+    __syncthreads();
+    stamp(stamps, sk);  // 2: CTA 0 finished its slice
+    store_partials<LIO_WARPS>(sm.red, D0, D1, (double)cnt, true, a.partials, a.partial_stride);
+    grid_barrier(barrier, epoch);
+    stamp(stamps, sk);  // 3: all CTAs arrived
+    if (blockIdx.x == 0) {
+      reduce_partials_block(a.partials, a.partial_stride, gridDim.x, a.info);
+      stamp(stamps, sk);  // 4: partials summed
+      lio_solve_block(sa, fs.sm, fs.io);
+    } else {
+      sk++;
+    }
+    stamp(stamps, sk);  // 5: solved
+    grid_barrier(barrier, epoch);
+    stamp(stamps, sk);  // 6: state published
+    sk++;               // 7: spare
+    if (__ldcg(&a.ctrl->stop)) break;  // EKF_stop_flg (voxel_map.cpp:499)
+  }
+}
+
+__global__ void __launch_bounds__(VIO_THREADS, 2) vio_update_kernel(const VioKernelArgs a, SolveArgs sa, unsigned int *barrier, unsigned long long *stamps) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  VioSmem &sm = *reinterpret_cast<VioSmem *>(smem_raw);
+  FusedSolveSmem &fs = *reinterpret_cast<FusedSolveSmem *>(&sm.rows[0][0][0]);
+  static_assert(sizeof(FusedSolveSmem) <= sizeof(sm.rows), "solve scratch must fit in the row staging area");
+  unsigned int epoch = 0;
+  int lo, hi;
+  vio_block_range(a.count, lo, hi);
+  for (int level = a.levels - 1; level >= 0; level--) {      // vio.cpp:790
+    for (int it = 0; it < sa.max_iterations; it++) {          // :1536
+      int sk = 8 * ((a.levels - 1 - level) * sa.max_iterations + it);
+      stamp(stamps, sk);
+      vio_load_consts(sm, a);
+      stamp(stamps, sk);
+      double D0 = 0.0, D1 = 0.0, n_meas = 0.0;
+      vio_process_range(a, sm, level, lo, hi, D0, D1, n_meas);
+      __syncthreads();
+      stamp(stamps, sk);
+      store_partials<VIO_WARPS>(sm.red, D0, D1, n_meas, false, a.partials, a.partial_stride);
+      grid_barrier(barrier, epoch);
+      stamp(stamps, sk);
+      bool level_done;
+      const bool last_of_level = false;
+      (void)last_of_level;
+      if (blockIdx.x == 0) {
+        reduce_partials_block(a.partials, a.partial_stride, gridDim.x, a.info);
+        stamp(stamps, sk);
+        sa.level = level, sa.slot_iter = it, sa.last_slot = 0;
+        vio_solve_block(sa, fs.sm, fs.io);
+      } else {
+        sk++;
+      }
+      stamp(stamps, sk);
+      grid_barrier(barrier, epoch);
+      stamp(stamps, sk);
+      level_done = __ldcg(&a.ctrl->level_done) != 0;
+      if (level_done) break;  // EKF_end (:1685)
+    }
+  }
+  // state->cov -= G * state->cov (vio.cpp:800): a last-slot pass of the solve routine with the level already finished
+  if (blockIdx.x == 0) {
+    __syncthreads();
+    sa.level = 0, sa.slot_iter = 1, sa.last_slot = 1;
+    if (threadIdx.x == 0) a.ctrl->level_done = 1;
+    __syncthreads();
+    vio_solve_block(sa, fs.sm, fs.io);
+  }
+}
+
+}  // namespace esikf

@@ -18,7 +18,9 @@ namespace esikf {
 
 struct LioKernelArgs {
   const float *pts;          // [n_total][3] body-frame scan
-  const double *pre;         // [n_total][9]: cross vector c(3) | body cov xx xy xz yy yz zz
+  const double *pre;         // SoA [9][pre_stride]: cross vector c(3) | body cov xx xy xz yy yz zz
+  int pre_stride;
+  int partial_stride;
   int begin, count;          // this rank's shard
   const double *state;       // current iterate (device, packed)
   const double *prop;        // state_propagat
@@ -27,6 +29,8 @@ struct LioKernelArgs {
   const esikf_plane *planes;
   double extR[9], extT[3];
   double voxel_size;         // double voxel size used for the key (voxel_map.cpp:646,668)
+  double inv_voxel_size;     // 1 / voxel_size, used when exact
+  int inv_voxel_exact;
   float voxel_size_f;        // float voxel size that positioned the roots (voxel_map.cpp:534,578-581)
   double sigma_num;
   int32_t *match_plane;      // [n_total]
@@ -69,8 +73,8 @@ __device__ __forceinline__ double quad3_sym(const double v[6], double n0, double
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Per-frame precompute: calcBodyCov (voxel_map.cpp:15-34) and the cross-matrix vector extR*p+extT (:356-359).
-__global__ void lio_precompute_kernel(const float *__restrict__ pts, int n, double *__restrict__ pre, const double *__restrict__ ext,
-                                      float dept_err, float beam_err) {
+__global__ void lio_precompute_kernel(const float *__restrict__ pts, int n, double *__restrict__ pre, int pre_stride,
+                                      const double *__restrict__ ext, float dept_err, float beam_err) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double px = pts[3 * i], py = pts[3 * i + 1], pz = pts[3 * i + 2];
@@ -93,18 +97,19 @@ __global__ void lio_precompute_kernel(const float *__restrict__ pts, int n, doub
   double a10 = r * (dz * b1x - dx * b1z), a11 = r * (dz * b2x - dx * b2z);
   double a20 = r * (-dy * b1x + dx * b1y), a21 = r * (-dy * b2x + dx * b2y);
   double rv = (double)range_var;
-  double *o = pre + 9 * (size_t)i;
+  double *o = pre + i;
+  const size_t ns = (size_t)pre_stride;
   // cross vector
-  o[0] = ext[0] * px + ext[1] * py + ext[2] * pz + ext[9];
-  o[1] = ext[3] * px + ext[4] * py + ext[5] * pz + ext[10];
-  o[2] = ext[6] * px + ext[7] * py + ext[8] * pz + ext[11];
+  o[0 * ns] = ext[0] * px + ext[1] * py + ext[2] * pz + ext[9];
+  o[1 * ns] = ext[3] * px + ext[4] * py + ext[5] * pz + ext[10];
+  o[2 * ns] = ext[6] * px + ext[7] * py + ext[8] * pz + ext[11];
   // cov = d rv d^T + A dv A^T  (symmetric; upper triangle stored)
-  o[3] = dx * rv * dx + dv * (a00 * a00 + a01 * a01);
-  o[4] = dx * rv * dy + dv * (a00 * a10 + a01 * a11);
-  o[5] = dx * rv * dz + dv * (a00 * a20 + a01 * a21);
-  o[6] = dy * rv * dy + dv * (a10 * a10 + a11 * a11);
-  o[7] = dy * rv * dz + dv * (a10 * a20 + a11 * a21);
-  o[8] = dz * rv * dz + dv * (a20 * a20 + a21 * a21);
+  o[3 * ns] = dx * rv * dx + dv * (a00 * a00 + a01 * a01);
+  o[4 * ns] = dx * rv * dy + dv * (a00 * a10 + a01 * a11);
+  o[5 * ns] = dx * rv * dz + dv * (a00 * a20 + a01 * a21);
+  o[6 * ns] = dy * rv * dy + dv * (a10 * a10 + a11 * a11);
+  o[7 * ns] = dy * rv * dz + dv * (a10 * a20 + a11 * a21);
+  o[8 * ns] = dz * rv * dz + dv * (a20 * a20 + a21 * a21);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -113,33 +118,45 @@ struct Cand {
   int idx;
   float dis;  // signed n.p + d narrowed to float (PointToPlane::dis_to_plane_, voxel_map.cpp:753)
 };
+struct EvalOut {
+  bool pass;
+  double prob;
+  float dis;
+};
 
-// build_single_residual's plane branch (src/voxel_map.cpp:721-768) for one candidate plane.
-__device__ __forceinline__ void eval_plane(const esikf_plane *__restrict__ pl, int idx, const double pw[3], const double var[6],
-                                           double sigma_num, Cand &best) {
-  const double *__restrict__ q = reinterpret_cast<const double *>(pl);
-  double c0 = q[0], c1 = q[1], c2 = q[2];
-  double n0 = q[3], n1 = q[4], n2 = q[5];
-  float2 dr = *reinterpret_cast<const float2 *>(q + 27);  // d, radius
+// build_single_residual's plane branch (src/voxel_map.cpp:721-768) for one candidate plane record `q` (shared or global
+// memory, 32 doubles). The probability (:740) is only needed to arbitrate between several candidates.
+__device__ __forceinline__ EvalOut eval_rec(const double *__restrict__ q, const double pw[3], const double var[6], double sigma_num,
+                                            bool need_prob) {
+  EvalOut o;
+  o.pass = false, o.prob = 0.0, o.dis = 0.f;
+  const double2 *__restrict__ q2 = reinterpret_cast<const double2 *>(q);
+  const double2 a0 = q2[0], a1 = q2[1], a2 = q2[2];  // c0 c1 | c2 n0 | n1 n2
+  const double c0 = a0.x, c1 = a0.y, c2 = a1.x, n0 = a1.y, n1 = a2.x, n2 = a2.y;
+  const float2 dr = *reinterpret_cast<const float2 *>(q + 27);  // d, radius
   // float-rounded quantities that gate the association: evaluated without FMA contraction, left to right, like the oracle
-  double sd = __dadd_rn(dot3_rn(n0, n1, n2, pw[0], pw[1], pw[2]), (double)dr.x);
-  float dis_to_plane = (float)fabs(sd);
-  double e0 = c0 - pw[0], e1 = c1 - pw[1], e2 = c2 - pw[2];
-  float dis_to_center = (float)dot3_rn(e0, e1, e2, e0, e1, e2);
-  float range_dis = sqrtf(__fsub_rn(dis_to_center, __fmul_rn(dis_to_plane, dis_to_plane)));
+  const double sd = __dadd_rn(dot3_rn(n0, n1, n2, pw[0], pw[1], pw[2]), (double)dr.x);
+  const float dis_to_plane = (float)fabs(sd);
+  const double e0 = c0 - pw[0], e1 = c1 - pw[1], e2 = c2 - pw[2];
+  const float dis_to_center = (float)dot3_rn(e0, e1, e2, e0, e1, e2);
+  const float range_dis = sqrtf(__fsub_rn(dis_to_center, __fmul_rn(dis_to_plane, dis_to_plane)));
   if ((double)range_dis <= 3.0 * (double)dr.y) {  // NaN fails, as in the reference
-    double J[6] = {pw[0] - c0, pw[1] - c1, pw[2] - c2, -n0, -n1, -n2};
-    double sigma_l = quad6(q + 6, J);
+    double pv[22];
+#pragma unroll
+    for (int k = 0; k < 11; k++) {
+      const double2 v = q2[3 + k];  // doubles 6..27: plane_var[0..20] (+ the d|radius slot)
+      pv[2 * k] = v.x, pv[2 * k + 1] = v.y;
+    }
+    const double J[6] = {pw[0] - c0, pw[1] - c1, pw[2] - c2, -n0, -n1, -n2};
+    double sigma_l = quad6(pv, J);
     sigma_l += quad3_sym(var, n0, n1, n2);
     if ((double)dis_to_plane < sigma_num * sqrt(sigma_l)) {
-      double this_prob = 1.0 / sqrt(sigma_l) * exp(-0.5 * (double)dis_to_plane * (double)dis_to_plane / sigma_l);
-      if (this_prob > best.prob) {
-        best.prob = this_prob;
-        best.idx = idx;
-        best.dis = (float)sd;
-      }
+      o.pass = true;
+      o.dis = (float)sd;
+      o.prob = need_prob ? 1.0 / sqrt(sigma_l) * exp(-0.5 * (double)dis_to_plane * (double)dis_to_plane / sigma_l) : 1.0;
     }
   }
+  return o;
 }
 
 __device__ __forceinline__ bool probe(const HashSlot *__restrict__ slots, uint32_t mask, long long kx, long long ky, long long kz,
@@ -159,170 +176,247 @@ __device__ __forceinline__ bool probe(const HashSlot *__restrict__ slots, uint32
   }
 }
 
+// Candidates [first+1, first+count) of ONE point evaluated lane-parallel by the whole warp, arg-max with lowest-index tie
+// break (the recursion of build_single_residual keeps the first of equal probabilities, voxel_map.cpp:741). `src` is the lane
+// that owns the point; its pw / var are broadcast. Returns the winner to every lane (idx < 0: none passed).
+__device__ __forceinline__ Cand warp_eval_extra(const esikf_plane *__restrict__ planes, int src, const double pw[3], const double var[6],
+                                                uint32_t first, uint32_t count, double sigma_num, int lane) {
+  double bpw[3], bvar[6];
+#pragma unroll
+  for (int k = 0; k < 3; k++) bpw[k] = __shfl_sync(0xffffffffu, pw[k], src);
+#pragma unroll
+  for (int k = 0; k < 6; k++) bvar[k] = __shfl_sync(0xffffffffu, var[k], src);
+  const uint32_t bfirst = __shfl_sync(0xffffffffu, first, src), bcount = __shfl_sync(0xffffffffu, count, src);
+  Cand my;
+  my.prob = -1.0, my.idx = 0x7fffffff, my.dis = 0.f;
+  for (uint32_t c = 1 + lane; c < bcount; c += 32) {
+    const EvalOut e = eval_rec(reinterpret_cast<const double *>(planes + bfirst + c), bpw, bvar, sigma_num, true);
+    if (e.pass && e.prob > my.prob) my.prob = e.prob, my.idx = (int)(bfirst + c), my.dis = e.dis;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double op = __shfl_xor_sync(0xffffffffu, my.prob, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, my.idx, off);
+    const float od = __shfl_xor_sync(0xffffffffu, my.dis, off);
+    if (op > my.prob || (op == my.prob && oi < my.idx)) my.prob = op, my.idx = oi, my.dis = od;
+  }
+  if (my.idx == 0x7fffffff) my.idx = -1;
+  return my;
+}
+
+#define REC_STRIDE 34  // doubles per staged plane record slot (272 B: conflict-free 128-bit reads at lane stride)
+
 // shared-memory layout of the residual kernel
 struct __align__(128) LioSmem {
-  double rows[LIO_THREADS][8];        // a_i = [A(3) n(3) z 1]   (first: double4 stores need 32-byte alignment)
-  double R[9], t[3], Ptt[9], Ppp[9];  // current state
-  double Rp[9], tp[3], Mp[9];         // prior pose, Mp = Rp * extR
-  double w[LIO_THREADS];              // R_inv
-  double absd[LIO_THREADS];           // |dis_to_plane|
+  double rec[LIO_WARPS][32][REC_STRIDE];  // first candidate plane of every lane, staged by coalesced warp copies
+  double rows[LIO_THREADS][8];            // a_i = [A(3) n(3) z 1]
+  double R[9], t[3], Ptt[9], Ppp[9];      // current state
+  double Rp[9], tp[3], Mp[9];             // prior pose, Mp = Rp * extR
+  double w[LIO_THREADS];                  // R_inv
+  double absd[LIO_THREADS];               // |dis_to_plane|
   ReduceSmem<LIO_WARPS> red;
 };
 
-__global__ void __launch_bounds__(LIO_THREADS, 2) lio_residual_kernel(const LioKernelArgs a) {
-  if (a.ctrl->stop) return;  // EKF_stop_flg: remaining iterations of the unrolled loop do nothing
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  LioSmem &sm = *reinterpret_cast<LioSmem *>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
+// Load the per-iteration constants (current pose / covariance blocks, prior pose) into shared memory.
+__device__ __forceinline__ void lio_load_consts(LioSmem &sm, const LioKernelArgs &a) {
+  const int tid = threadIdx.x;
   if (tid < 9) {
-    sm.R[tid] = a.state[S_R + tid];
+    sm.R[tid] = __ldcg(a.state + S_R + tid);
     sm.Rp[tid] = a.prop[S_R + tid];
     int r = tid / 3, c = tid % 3;
-    sm.Ptt[tid] = a.state[S_COV + r * 19 + c];
-    sm.Ppp[tid] = a.state[S_COV + (3 + r) * 19 + (3 + c)];
+    sm.Ptt[tid] = __ldcg(a.state + S_COV + r * 19 + c);
+    sm.Ppp[tid] = __ldcg(a.state + S_COV + (3 + r) * 19 + (3 + c));
     // Mp = Rp * extR  (state_propagat.rot_end * extR_, voxel_map.cpp:445)
     double s = 0;
     for (int k = 0; k < 3; k++) s += a.prop[S_R + r * 3 + k] * a.extR[k * 3 + c];
     sm.Mp[tid] = s;
   } else if (tid < 12) {
-    sm.t[tid - 9] = a.state[S_P + tid - 9];
+    sm.t[tid - 9] = __ldcg(a.state + S_P + tid - 9);
     sm.tp[tid - 9] = a.prop[S_P + tid - 9];
   }
   __syncthreads();
+}
 
-  double D0 = 0.0, D1 = 0.0;  // this lane's two entries of the warp's 8x8 block
-  int cnt = 0;
-
-  const int tiles = (a.count + LIO_THREADS - 1) / LIO_THREADS;
-  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int li = tile * LIO_THREADS + tid;
-    const bool valid = li < a.count;
+// Residual / Jacobian build over the points [lo, hi) of this rank's shard (indices local to the shard), accumulated into
+// the calling warp's 8x8 tensor-core block (D0, D1) and matched-point count.
+__device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSmem &sm, int lo, int hi, double &D0, double &D1, int &cnt) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double *const myrec = &sm.rec[warp][lane][0];
+  for (int base = lo; base < hi; base += LIO_THREADS) {
+    const int li = base + tid;
+    const bool valid = li < hi;
     const int i = a.begin + li;
-    bool matched = false;
     int midx = -1;
-    double row[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    double wgt = 0.0, absd = 0.0;
+    float mdis = 0.f;
+    double pi0 = 0, pi1 = 0, pi2 = 0;
+    double pw[3] = {0, 0, 0}, var[6] = {0, 0, 0, 0, 0, 0};
+    float loc[3] = {0, 0, 0};
+    long long key[3] = {0, 0, 0};
+    uint32_t first = 0, count = 0;
+    bool found = false;
+
+    // ---- phase 1: transform, voxel key, home-voxel probe
     if (valid) {
       const double px = a.pts[3 * (size_t)i], py = a.pts[3 * (size_t)i + 1], pz = a.pts[3 * (size_t)i + 2];
-      const double *__restrict__ pre = a.pre + 9 * (size_t)i;
       // p_imu = extR p + extT ; p_w = R p_imu + t, narrowed to float (TransformLidar, voxel_map.cpp:522-526). No FMA contraction
       // on this chain: the float rounding of p_w decides the voxel key.
-      const double pi0 = __dadd_rn(dot3_rn(a.extR[0], a.extR[1], a.extR[2], px, py, pz), a.extT[0]);
-      const double pi1 = __dadd_rn(dot3_rn(a.extR[3], a.extR[4], a.extR[5], px, py, pz), a.extT[1]);
-      const double pi2 = __dadd_rn(dot3_rn(a.extR[6], a.extR[7], a.extR[8], px, py, pz), a.extT[2]);
-      double pw[3];
+      pi0 = __dadd_rn(dot3_rn(a.extR[0], a.extR[1], a.extR[2], px, py, pz), a.extT[0]);
+      pi1 = __dadd_rn(dot3_rn(a.extR[3], a.extR[4], a.extR[5], px, py, pz), a.extT[1]);
+      pi2 = __dadd_rn(dot3_rn(a.extR[6], a.extR[7], a.extR[8], px, py, pz), a.extT[2]);
       pw[0] = (double)(float)__dadd_rn(dot3_rn(sm.R[0], sm.R[1], sm.R[2], pi0, pi1, pi2), sm.t[0]);
       pw[1] = (double)(float)__dadd_rn(dot3_rn(sm.R[3], sm.R[4], sm.R[5], pi0, pi1, pi2), sm.t[1]);
       pw[2] = (double)(float)__dadd_rn(dot3_rn(sm.R[6], sm.R[7], sm.R[8], pi0, pi1, pi2), sm.t[2]);
-
-      // voxel key (voxel_map.cpp:665-671): float quotient, "-1 if negative", truncate
-      float loc[3];
-      long long key[3];
+      // voxel key (voxel_map.cpp:665-671): float quotient, "-1 if negative", truncate. When 1/voxel_size is exact (a power
+      // of two: 0.5, 2.0, ...) the multiply gives the bit-identical quotient without the slow fp64 division.
       bool finite = true;
 #pragma unroll
       for (int j = 0; j < 3; j++) {
-        loc[j] = (float)__ddiv_rn(pw[j], a.voxel_size);
+        loc[j] = a.inv_voxel_exact ? (float)__dmul_rn(pw[j], a.inv_voxel_size) : (float)__ddiv_rn(pw[j], a.voxel_size);
         if (loc[j] < 0) loc[j] = (float)__dadd_rn((double)loc[j], -1.0);
         finite = finite && (fabsf(loc[j]) < 3.0e6f);
         key[j] = (long long)loc[j];
       }
+      found = finite && probe(a.slots, a.hash_mask, key[0], key[1], key[2], first, count);
+    }
 
-      uint32_t first = 0, count = 0;
-      if (finite && probe(a.slots, a.hash_mask, key[0], key[1], key[2], first, count)) {
-        // pv.var = R body_cov R^T + (-C) P_tt (-C)^T + P_pp   (voxel_map.cpp:385-388), symmetric 6
-        double var[6];
-        {
-          const double b0 = pre[3], b1 = pre[4], b2 = pre[5], b3 = pre[6], b4 = pre[7], b5 = pre[8];
-          double T[9];
+    // ---- phase 2: stage every lane's first candidate record (256 B) with coalesced half-warp copies
+    {
+      const int cand0 = (found && count > 0) ? (int)first : -1;
+      const int half = lane >> 4, sub = lane & 15;
 #pragma unroll
-          for (int r = 0; r < 3; r++) {
-            const double r0 = sm.R[3 * r], r1 = sm.R[3 * r + 1], r2 = sm.R[3 * r + 2];
-            T[3 * r + 0] = r0 * b0 + r1 * b1 + r2 * b2;
-            T[3 * r + 1] = r0 * b1 + r1 * b3 + r2 * b4;
-            T[3 * r + 2] = r0 * b2 + r1 * b4 + r2 * b5;
-          }
-          const double cx = pre[0], cy = pre[1], cz = pre[2];
-          // C = [c]x ; U = C * Ptt
-          double U[9];
-#pragma unroll
-          for (int c = 0; c < 3; c++) {
-            const double p0 = sm.Ptt[c], p1 = sm.Ptt[3 + c], p2 = sm.Ptt[6 + c];
-            U[0 + c] = -cz * p1 + cy * p2;
-            U[3 + c] = cz * p0 - cx * p2;
-            U[6 + c] = -cy * p0 + cx * p1;
-          }
-          // (C Ptt) C^T : column j of C^T is row j of C
-          // row of C: C0 = (0,-cz,cy), C1 = (cz,0,-cx), C2 = (-cy,cx,0)
-          const double V00 = -U[1] * cz + U[2] * cy, V01 = U[0] * cz - U[2] * cx, V02 = -U[0] * cy + U[1] * cx;
-          const double V11 = U[3] * cz - U[5] * cx, V12 = -U[3] * cy + U[4] * cx;
-          const double V22 = -U[6] * cy + U[7] * cx;
-          var[0] = (T[0] * sm.R[0] + T[1] * sm.R[1] + T[2] * sm.R[2]) + V00 + sm.Ppp[0];
-          var[1] = (T[0] * sm.R[3] + T[1] * sm.R[4] + T[2] * sm.R[5]) + V01 + sm.Ppp[1];
-          var[2] = (T[0] * sm.R[6] + T[1] * sm.R[7] + T[2] * sm.R[8]) + V02 + sm.Ppp[2];
-          var[3] = (T[3] * sm.R[3] + T[4] * sm.R[4] + T[5] * sm.R[5]) + V11 + sm.Ppp[4];
-          var[4] = (T[3] * sm.R[6] + T[4] * sm.R[7] + T[5] * sm.R[8]) + V12 + sm.Ppp[5];
-          var[5] = (T[6] * sm.R[6] + T[7] * sm.R[7] + T[8] * sm.R[8]) + V22 + sm.Ppp[8];
-        }
-
-        Cand best;
-        best.prob = 0.0, best.idx = -1, best.dis = 0.f;
-        for (uint32_t c = 0; c < count; c++) eval_plane(a.planes + first + c, (int)(first + c), pw, var, a.sigma_num, best);
-        if (best.idx < 0) {
-          // one neighbour voxel (voxel_map.cpp:680-691). loc is in voxel units, centre/quarter length in metres: reproduced literally.
-          const double vsf = (double)a.voxel_size_f;
-          const double ql = (double)(a.voxel_size_f / 4.0f);
-          long long nk[3] = {key[0], key[1], key[2]};
-#pragma unroll
-          for (int j = 0; j < 3; j++) {
-            const double center = (0.5 + (double)key[j]) * vsf;
-            if ((double)loc[j] > center + ql) nk[j] = key[j] + 1;
-            else if ((double)loc[j] < center - ql) nk[j] = key[j] - 1;
-          }
-          uint32_t f2 = 0, c2 = 0;
-          if (probe(a.slots, a.hash_mask, nk[0], nk[1], nk[2], f2, c2))
-            for (uint32_t c = 0; c < c2; c++) eval_plane(a.planes + f2 + c, (int)(f2 + c), pw, var, a.sigma_num, best);
-        }
-
-        if (best.idx >= 0) {
-          matched = true;
-          midx = best.idx;
-          // Jacobian / measurement-noise loop (voxel_map.cpp:414-458) for this point
-          const double *__restrict__ q = reinterpret_cast<const double *>(a.planes + best.idx);
-          const double c0 = q[0], c1 = q[1], c2 = q[2];
-          const double n0 = q[3], n1 = q[4], n2 = q[5];
-          // point_world with the PRIOR pose (:425)
-          const double w0 = sm.Rp[0] * pi0 + sm.Rp[1] * pi1 + sm.Rp[2] * pi2 + sm.tp[0];
-          const double w1 = sm.Rp[3] * pi0 + sm.Rp[4] * pi1 + sm.Rp[5] * pi2 + sm.tp[1];
-          const double w2 = sm.Rp[6] * pi0 + sm.Rp[7] * pi1 + sm.Rp[8] * pi2 + sm.tp[2];
-          double J[6] = {w0 - c0, w1 - c1, w2 - c2, -n0, -n1, -n2};
-          const double sigma_l = quad6(q + 6, J);
-          // n^T (Mp body_cov Mp^T) n = m^T body_cov m, m = Mp^T n   (:445-449)
-          const double m0 = sm.Mp[0] * n0 + sm.Mp[3] * n1 + sm.Mp[6] * n2;
-          const double m1 = sm.Mp[1] * n0 + sm.Mp[4] * n1 + sm.Mp[7] * n2;
-          const double m2 = sm.Mp[2] * n0 + sm.Mp[5] * n1 + sm.Mp[8] * n2;
-          const double nvn = quad3_sym(pre + 3, m0, m1, m2);
-          wgt = 1.0 / (0.001 + sigma_l + nvn);
-          // A = [p_imu]x R^T n with the CURRENT rotation (:453)
-          const double g0 = sm.R[0] * n0 + sm.R[3] * n1 + sm.R[6] * n2;
-          const double g1 = sm.R[1] * n0 + sm.R[4] * n1 + sm.R[7] * n2;
-          const double g2 = sm.R[2] * n0 + sm.R[5] * n1 + sm.R[8] * n2;
-          row[0] = -pi2 * g1 + pi1 * g2;
-          row[1] = pi2 * g0 - pi0 * g2;
-          row[2] = -pi1 * g0 + pi0 * g1;
-          row[3] = n0, row[4] = n1, row[5] = n2;
-          row[6] = -(double)best.dis;  // meas_vec (:457)
-          row[7] = 1.0;
-          absd = fabs((double)best.dis);
-          a.normal_plane[i] = best.idx;  // pv.normal = plane.normal_ (:744), sticky across iterations
+      for (int j = 0; j < 32; j += 2) {
+        const int src = j + half;
+        const int pidx = __shfl_sync(0xffffffffu, cand0, src);
+        if (pidx >= 0) {
+          const double2 v = __ldg(reinterpret_cast<const double2 *>(a.planes + pidx) + sub);
+          *reinterpret_cast<double2 *>(&sm.rec[warp][src][2 * sub]) = v;
         }
       }
-      a.match_plane[i] = midx;  // ptpl_list_ membership of this iteration
-      a.dis_to_plane[i] = (float)(-row[6]);  // PointToPlane::dis_to_plane_ of this iteration (0 when unmatched)
+      __syncwarp();
+    }
+
+    // ---- phase 3: association
+    Cand best;
+    best.prob = 0.0, best.idx = -1, best.dis = 0.f;
+    if (found) {
+      // pv.var = R body_cov R^T + (-C) P_tt (-C)^T + P_pp   (voxel_map.cpp:385-388), symmetric 6
+      const size_t ns = (size_t)a.pre_stride;
+      const double *__restrict__ pre = a.pre + i;
+      const double cx = pre[0], cy = pre[ns], cz = pre[2 * ns];
+      const double b0 = pre[3 * ns], b1 = pre[4 * ns], b2 = pre[5 * ns], b3 = pre[6 * ns], b4 = pre[7 * ns], b5 = pre[8 * ns];
+      double T[9];
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const double r0 = sm.R[3 * r], r1 = sm.R[3 * r + 1], r2 = sm.R[3 * r + 2];
+        T[3 * r + 0] = r0 * b0 + r1 * b1 + r2 * b2;
+        T[3 * r + 1] = r0 * b1 + r1 * b3 + r2 * b4;
+        T[3 * r + 2] = r0 * b2 + r1 * b4 + r2 * b5;
+      }
+      double U[9];  // U = [c]x * Ptt
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const double p0 = sm.Ptt[c], p1 = sm.Ptt[3 + c], p2 = sm.Ptt[6 + c];
+        U[0 + c] = -cz * p1 + cy * p2;
+        U[3 + c] = cz * p0 - cx * p2;
+        U[6 + c] = -cy * p0 + cx * p1;
+      }
+      const double V00 = -U[1] * cz + U[2] * cy, V01 = U[0] * cz - U[2] * cx, V02 = -U[0] * cy + U[1] * cx;
+      const double V11 = U[3] * cz - U[5] * cx, V12 = -U[3] * cy + U[4] * cx;
+      const double V22 = -U[6] * cy + U[7] * cx;
+      var[0] = (T[0] * sm.R[0] + T[1] * sm.R[1] + T[2] * sm.R[2]) + V00 + sm.Ppp[0];
+      var[1] = (T[0] * sm.R[3] + T[1] * sm.R[4] + T[2] * sm.R[5]) + V01 + sm.Ppp[1];
+      var[2] = (T[0] * sm.R[6] + T[1] * sm.R[7] + T[2] * sm.R[8]) + V02 + sm.Ppp[2];
+      var[3] = (T[3] * sm.R[3] + T[4] * sm.R[4] + T[5] * sm.R[5]) + V11 + sm.Ppp[4];
+      var[4] = (T[3] * sm.R[6] + T[4] * sm.R[7] + T[5] * sm.R[8]) + V12 + sm.Ppp[5];
+      var[5] = (T[6] * sm.R[6] + T[7] * sm.R[7] + T[8] * sm.R[8]) + V22 + sm.Ppp[8];
+      if (count > 0) {
+        const EvalOut e = eval_rec(myrec, pw, var, a.sigma_num, count > 1);
+        if (e.pass) best.prob = e.prob, best.idx = (int)first, best.dis = e.dis;
+      }
+    }
+    // further candidates of sub-divided root voxels (rare): one point at a time, lane-parallel over its candidate list
+    for (unsigned more = __ballot_sync(0xffffffffu, found && count > 1); more; more &= more - 1) {
+      const int src = __ffs(more) - 1;
+      const Cand c = warp_eval_extra(a.planes, src, pw, var, first, count, a.sigma_num, lane);
+      if (lane == src && c.idx >= 0 && c.prob > best.prob) best = c;
+    }
+    // one neighbour voxel when the home voxel gave nothing (voxel_map.cpp:680-691). loc is in voxel units, centre / quarter
+    // length in metres: reproduced literally.
+    uint32_t f2 = 0, c2 = 0;
+    bool found2 = false;
+    if (found && best.idx < 0) {
+      const double vsf = (double)a.voxel_size_f;
+      const double ql = (double)(a.voxel_size_f / 4.0f);
+      long long nk[3] = {key[0], key[1], key[2]};
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const double center = (0.5 + (double)key[j]) * vsf;
+        if ((double)loc[j] > center + ql) nk[j] = key[j] + 1;
+        else if ((double)loc[j] < center - ql) nk[j] = key[j] - 1;
+      }
+      found2 = probe(a.slots, a.hash_mask, nk[0], nk[1], nk[2], f2, c2) && c2 > 0;
+      if (found2) {
+        const EvalOut e = eval_rec(reinterpret_cast<const double *>(a.planes + f2), pw, var, a.sigma_num, c2 > 1);
+        if (e.pass) best.prob = e.prob, best.idx = (int)f2, best.dis = e.dis;
+      }
+    }
+    for (unsigned more = __ballot_sync(0xffffffffu, found2 && c2 > 1); more; more &= more - 1) {
+      const int src = __ffs(more) - 1;
+      const Cand c = warp_eval_extra(a.planes, src, pw, var, f2, c2, a.sigma_num, lane);
+      if (lane == src && c.idx >= 0 && c.prob > best.prob) best = c;
+    }
+
+    // ---- phase 4: Jacobian / measurement-noise loop (voxel_map.cpp:414-458) for matched points
+    double row[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double wgt = 0.0, absd = 0.0;
+    const bool matched = best.idx >= 0;
+    if (matched) {
+      midx = best.idx, mdis = best.dis;
+      const double *__restrict__ q = (best.idx == (int)first && count > 0 && found) ? myrec : reinterpret_cast<const double *>(a.planes + best.idx);
+      const double2 *__restrict__ q2 = reinterpret_cast<const double2 *>(q);
+      const double2 a0 = q2[0], a1 = q2[1], a2 = q2[2];
+      const double c0 = a0.x, c1 = a0.y, c2_ = a1.x, n0 = a1.y, n1 = a2.x, n2 = a2.y;
+      double pv[22];
+#pragma unroll
+      for (int k = 0; k < 11; k++) {
+        const double2 v = q2[3 + k];
+        pv[2 * k] = v.x, pv[2 * k + 1] = v.y;
+      }
+      // point_world with the PRIOR pose (:425)
+      const double w0 = sm.Rp[0] * pi0 + sm.Rp[1] * pi1 + sm.Rp[2] * pi2 + sm.tp[0];
+      const double w1 = sm.Rp[3] * pi0 + sm.Rp[4] * pi1 + sm.Rp[5] * pi2 + sm.tp[1];
+      const double w2 = sm.Rp[6] * pi0 + sm.Rp[7] * pi1 + sm.Rp[8] * pi2 + sm.tp[2];
+      const double J[6] = {w0 - c0, w1 - c1, w2 - c2_, -n0, -n1, -n2};
+      const double sigma_l = quad6(pv, J);
+      // n^T (Mp body_cov Mp^T) n = m^T body_cov m, m = Mp^T n   (:445-449)
+      const double m0 = sm.Mp[0] * n0 + sm.Mp[3] * n1 + sm.Mp[6] * n2;
+      const double m1 = sm.Mp[1] * n0 + sm.Mp[4] * n1 + sm.Mp[7] * n2;
+      const double m2 = sm.Mp[2] * n0 + sm.Mp[5] * n1 + sm.Mp[8] * n2;
+      const size_t ns = (size_t)a.pre_stride;
+      const double *__restrict__ pre = a.pre + i;
+      const double bc[6] = {pre[3 * ns], pre[4 * ns], pre[5 * ns], pre[6 * ns], pre[7 * ns], pre[8 * ns]};
+      const double nvn = quad3_sym(bc, m0, m1, m2);
+      wgt = 1.0 / (0.001 + sigma_l + nvn);
+      // A = [p_imu]x R^T n with the CURRENT rotation (:453)
+      const double g0 = sm.R[0] * n0 + sm.R[3] * n1 + sm.R[6] * n2;
+      const double g1 = sm.R[1] * n0 + sm.R[4] * n1 + sm.R[7] * n2;
+      const double g2 = sm.R[2] * n0 + sm.R[5] * n1 + sm.R[8] * n2;
+      row[0] = -pi2 * g1 + pi1 * g2;
+      row[1] = pi2 * g0 - pi0 * g2;
+      row[2] = -pi1 * g0 + pi0 * g1;
+      row[3] = n0, row[4] = n1, row[5] = n2;
+      row[6] = -(double)best.dis;  // meas_vec (:457)
+      row[7] = 1.0;
+      absd = fabs((double)best.dis);
+    }
+    if (valid) {
+      a.match_plane[i] = midx;    // ptpl_list_ membership of this iteration
+      a.dis_to_plane[i] = mdis;   // PointToPlane::dis_to_plane_ of this iteration (0 when unmatched)
+      if (matched) a.normal_plane[i] = midx;  // pv.normal = plane.normal_ (:744), sticky across iterations
     }
     cnt += __popc(__ballot_sync(0xffffffffu, matched));
 
-    // stage the 32 rows of this warp and contract them on the fp64 tensor path
+    // ---- phase 5: stage the 32 rows of this warp and contract them on the fp64 tensor path
     double4 *dst = reinterpret_cast<double4 *>(&sm.rows[tid][0]);
     dst[0] = make_double4(row[0], row[1], row[2], row[3]);
     dst[1] = make_double4(row[4], row[5], row[6], row[7]);
@@ -343,7 +437,27 @@ __global__ void __launch_bounds__(LIO_THREADS, 2) lio_residual_kernel(const LioK
     __syncwarp();
   }
 
-  reduce_info<LIO_WARPS>(sm.red, D0, D1, (double)cnt, true, a.partials, a.info, a.ctrl);
+}
+
+// Contiguous, equal slices of the shard per block: every SM gets the same number of points.
+__device__ __forceinline__ void lio_block_range(int count, int &lo, int &hi) {
+  const int per = (count + gridDim.x - 1) / gridDim.x;
+  lo = blockIdx.x * per;
+  hi = lo + per < count ? lo + per : count;
+  if (lo > count) lo = count;
+}
+
+__global__ void __launch_bounds__(LIO_THREADS, 2) lio_residual_kernel(const LioKernelArgs a) {
+  if (a.ctrl->stop) return;  // EKF_stop_flg: remaining iterations of the unrolled loop do nothing
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  LioSmem &sm = *reinterpret_cast<LioSmem *>(smem_raw);
+  lio_load_consts(sm, a);
+  double D0 = 0.0, D1 = 0.0;  // this lane's two entries of the warp's 8x8 block
+  int cnt = 0;
+  int lo, hi;
+  lio_block_range(a.count, lo, hi);
+  lio_process_range(a, sm, lo, hi, D0, D1, cnt);
+  reduce_info<LIO_WARPS>(sm.red, D0, D1, (double)cnt, true, a.partials, a.partial_stride, a.info, a.ctrl);
 }
 
 }  // namespace esikf

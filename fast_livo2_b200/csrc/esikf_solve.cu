@@ -1,5 +1,6 @@
-// Solve kernels of the B200 ESIKF update: the Kalman gain, the boxplus state update, loop control and the final
-// covariance update, executed by ONE warp so the whole iteration loop runs on the device with no host round trip.
+// Solve routines of the B200 ESIKF update: the Kalman gain, the boxplus state update, loop control and the final
+// covariance update. One block: all threads stage P / info / poses in a single global round trip, one warp runs the
+// m x m gain solve, all threads write back. The whole iteration loop runs on the device with no host round trip.
 //
 //   lio_solve_kernel : src/voxel_map.cpp:462-499  (K_1, G, solution, state_ += solution, convergence / rematch / (I-G)P)
 //   vio_solve_kernel : src/vio.cpp:1636-1685 + :800 (error-gated accept / rollback, K_1, G, solution, final cov -= G cov)
@@ -203,169 +204,230 @@ __device__ inline void gain_rows(SolveSmem &sm, double pscale, int solve_mode, i
 
 __device__ inline double warp_norm3(const double *v) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
 
-// ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32, 1) lio_solve_kernel(const SolveArgs a) {
-  Ctrl &ctrl = *a.ctrl;
-  if (ctrl.stop) return;
-  __shared__ SolveSmem sm;
-  const int lane = threadIdx.x;
-  double *st = a.state;
-  for (int idx = lane; idx < 361; idx += 32) sm.P[idx] = st[S_COV + idx];
-  for (int idx = lane; idx < 36; idx += 32) sm.A[idx] = a.info[(idx / 6) * 8 + (idx % 6)];  // H^T R^-1 H
-  if (lane < 6) sm.HTz[lane] = a.info[lane * 8 + 6];                                        // H^T R^-1 z
-  boxminus_warp(a.prop, st, sm.vec, lane);
-  __syncwarp();
+#define SOLVE_THREADS 512
 
-  double x[6];
-  gain_rows<6>(sm, 1.0, a.solve_mode, lane, x);
-  // G[lane, 0:6] = K_1[lane, 0:6] * HTH   (voxel_map.cpp:469)
-  double g[6];
-#pragma unroll
-  for (int j = 0; j < 6; j++) {
-    double s = 0.0;
-#pragma unroll
-    for (int k = 0; k < 6; k++) s += x[k] * sm.A[k * 6 + j];
-    g[j] = s;
+// Staging shared by both solve routines: one global round trip brings P, info, the pose parts of state / prior / old_state.
+struct SolveIO {
+  double info[INFO_N];
+  double st[32];   // first 25 doubles of the packed state (R p expo v bg ba g)
+  double pr[32];   // same of state_propagat
+  double old[32];  // VIO old_state
+  double g[19][8]; // gain block G[:, :m]
+  int flags[8];
+};
+
+// Block-size agnostic (any multiple of 32 threads >= 32). __ldcg: the data was written by other SMs in this same grid
+// when called from the persistent kernels.
+__device__ __forceinline__ void solve_load(SolveSmem &sm, SolveIO &io, const SolveArgs &a, bool want_old) {
+  for (int t = threadIdx.x; t < 361; t += blockDim.x) sm.P[t] = __ldcg(a.state + S_COV + t);
+  for (int t = threadIdx.x; t < INFO_N; t += blockDim.x) io.info[t] = __ldcg(a.info + t);
+  for (int t = threadIdx.x; t < 25; t += blockDim.x) {
+    io.st[t] = __ldcg(a.state + t);
+    io.pr[t] = a.prop[t];
+    if (want_old) io.old[t] = __ldcg(a.old_state + t);
   }
-  // solution = K_1[:, :6] HTz + vec - G[:, :6] vec[:6]   (:471-472)
-  if (lane < 19) {
-    double s1 = 0.0, s2 = 0.0;
-#pragma unroll
-    for (int k = 0; k < 6; k++) s1 += x[k] * sm.HTz[k], s2 += g[k] * sm.vec[k];
-    sm.sol[lane] = s1 + sm.vec[lane] - s2;
-  }
-  __syncwarp();
-  boxplus_warp(st, sm.sol, lane);  // state_ += solution (:474)
-  const bool converged = (warp_norm3(sm.sol) * 57.3 < 0.01) && (warp_norm3(sm.sol + 3) * 100 < 0.015);  // :477
+}
+
+// One LIO gain solve + state update (src/voxel_map.cpp:462-499) by the calling block. Returns EKF_stop_flg.
+__device__ __forceinline__ bool lio_solve_block(const SolveArgs &a, SolveSmem &sm, SolveIO &io) {
+  Ctrl &ctrl = *a.ctrl;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int iterCount = ctrl.iter;
-  int rematch = ctrl.rematch_num;
-  if (converged || ((rematch == 0) && (iterCount == (a.max_iterations - 2)))) rematch++;  // :482
-  const bool stop = (rematch >= 2) || (iterCount == a.max_iterations - 1);                // :485
-  if (stop && lane < 19) {
-    // cov = (I - G) cov   (:489-490); G only has its first 6 columns
-    for (int c = 0; c < 19; c++) {
-      double s = sm.P[lane * 19 + c];
+  const int rematch0 = ctrl.rematch_num;
+  solve_load(sm, io, a, false);
+  __syncthreads();
+  if (tid < 32) {
+    for (int idx = lane; idx < 36; idx += 32) sm.A[idx] = io.info[(idx / 6) * 8 + (idx % 6)];  // H^T R^-1 H
+    if (lane < 6) sm.HTz[lane] = io.info[lane * 8 + 6];                                          // H^T R^-1 z
+    boxminus_warp(io.pr, io.st, sm.vec, lane);
+    __syncwarp();
+    double x[6];
+    gain_rows<6>(sm, 1.0, a.solve_mode, lane, x);
+    // G[lane, 0:6] = K_1[lane, 0:6] * HTH   (voxel_map.cpp:469)
+    double g[6];
 #pragma unroll
-      for (int j = 0; j < 6; j++) s -= g[j] * sm.P[j * 19 + c];
-      st[S_COV + lane * 19 + c] = s;
+    for (int j = 0; j < 6; j++) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) s += x[k] * sm.A[k * 6 + j];
+      g[j] = s;
+    }
+    // solution = K_1[:, :6] HTz + vec - G[:, :6] vec[:6]   (:471-472)
+    if (lane < 19) {
+      double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) s1 += x[k] * sm.HTz[k], s2 += g[k] * sm.vec[k];
+      sm.sol[lane] = s1 + sm.vec[lane] - s2;
+#pragma unroll
+      for (int j = 0; j < 6; j++) io.g[lane][j] = g[j];
+    }
+    __syncwarp();
+    boxplus_warp(io.st, sm.sol, lane);  // state_ += solution (:474)
+    if (lane == 0) {
+      const bool converged = (warp_norm3(sm.sol) * 57.3 < 0.01) && (warp_norm3(sm.sol + 3) * 100 < 0.015);  // :477
+      int rematch = rematch0;
+      if (converged || ((rematch == 0) && (iterCount == (a.max_iterations - 2)))) rematch++;  // :482
+      const bool stop = (rematch >= 2) || (iterCount == a.max_iterations - 1);                // :485
+      io.flags[0] = converged, io.flags[1] = rematch, io.flags[2] = stop;
+    }
+  }
+  __syncthreads();
+  const bool stop = io.flags[2] != 0;
+  for (int t = tid; t < 25; t += blockDim.x) a.state[t] = io.st[t];
+  if (stop) {
+    // cov = (I - G) cov   (:489-490); G only has its first 6 columns
+    for (int t = tid; t < 361; t += blockDim.x) {
+      const int r = t / 19, c = t - 19 * r;
+      double s = sm.P[t];
+#pragma unroll
+      for (int j = 0; j < 6; j++) s -= io.g[r][j] * sm.P[j * 19 + c];
+      a.state[S_COV + t] = s;
     }
   }
   if (a.lio_stats && iterCount < 8) {
     esikf_lio_stats &S = *a.lio_stats;
-    for (int idx = lane; idx < 36; idx += 32) S.HTH[iterCount][idx] = sm.A[idx];
-    if (lane < 6) S.HTz[iterCount][lane] = sm.HTz[lane];
-    if (lane < 19) S.solution[iterCount][lane] = sm.sol[lane];
-    if (lane == 0) {
+    for (int t = tid; t < 36; t += blockDim.x) S.HTH[iterCount][t] = sm.A[t];
+    for (int t = tid; t < 6; t += blockDim.x) S.HTz[iterCount][t] = sm.HTz[t];
+    for (int t = tid; t < 19; t += blockDim.x) S.solution[iterCount][t] = sm.sol[t];
+    if (tid == 0) {
       S.iters = iterCount + 1;
-      S.effct_feat_num[iterCount] = (int)a.info[INFO_COUNT];
-      S.total_residual[iterCount] = a.info[INFO_ABS];
-      S.converged[iterCount] = converged;
+      S.effct_feat_num[iterCount] = (int)io.info[INFO_COUNT];
+      S.total_residual[iterCount] = io.info[INFO_ABS];
+      S.converged[iterCount] = io.flags[0];
     }
   }
-  __syncwarp();
-  if (lane == 0) {
+  __syncthreads();
+  if (tid == 0) {
     ctrl.iter = iterCount + 1;
-    ctrl.rematch_num = rematch;
+    ctrl.rematch_num = io.flags[1];
     ctrl.stop = stop ? 1 : 0;
   }
+  return stop;
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32, 1) vio_solve_kernel(const SolveArgs a) {
-  Ctrl &ctrl = *a.ctrl;
+__global__ void __launch_bounds__(SOLVE_THREADS, 1) lio_solve_kernel(const SolveArgs a) {
+  if (a.ctrl->stop) return;
   __shared__ SolveSmem sm;
-  const int lane = threadIdx.x;
-  double *st = a.state;
-  bool level_done = ctrl.level_done != 0;
-  float last_error = ctrl.last_error;
-  if (a.slot_iter == 0) {
-    // entering a level: old_state = *state, last_error = FLT_MAX, EKF_end = false  (vio.cpp:1523-1528)
-    level_done = false;
-    last_error = FLT_MAX;
-    if (lane < 25) a.old_state[lane] = st[lane];
-  }
-  if (!level_done) {
-    for (int idx = lane; idx < 361; idx += 32) sm.P[idx] = st[S_COV + idx];
-    __syncwarp();
-    const int level = a.level, iteration = a.slot_iter;
-    // error = sum(res^2) / n_meas as float (vio.cpp:1636)
-    const double sum_sq = a.info[7 * 8 + 7];
-    const int n_meas = (int)a.info[INFO_COUNT];
-    const float error = __fdiv_rn((float)sum_sq, (float)n_meas);
-    bool accepted = false;
-    bool ekf_end = false;
-    if (error <= last_error) {  // :1648
-      accepted = true;
-      if (lane < 25) a.old_state[lane] = st[lane];  // old_state = *state
-      last_error = error;
-      for (int idx = lane; idx < 49; idx += 32) sm.A[idx] = a.info[(idx / 7) * 8 + (idx % 7)];  // H^T H 7x7
-      if (lane < 7) sm.HTz[lane] = a.info[lane * 8 + 7];
-      boxminus_warp(a.prop, st, sm.vec, lane);
-      __syncwarp();
-      double x[7];
-      gain_rows<7>(sm, 1.0 / a.img_point_cov, a.solve_mode, lane, x);
-      double g[7];
+  __shared__ SolveIO io;
+  lio_solve_block(a, sm, io);
+}
+
+// One VIO accept/rollback + gain solve (src/vio.cpp:1636-1685) by the calling block; on the last slot also the final
+// covariance update (:800). Returns EKF_end of the level.
+__device__ __forceinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &sm, SolveIO &io) {
+  Ctrl &ctrl = *a.ctrl;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const bool level_done_in = (a.slot_iter == 0) ? false : (ctrl.level_done != 0);   // entering a level: EKF_end = false (vio.cpp:1527)
+  const float last_error_in = (a.slot_iter == 0) ? FLT_MAX : ctrl.last_error;       // :1528
+  const int has_G_in = ctrl.has_G;
+  if (level_done_in && !a.last_slot) return true;
+  solve_load(sm, io, a, a.slot_iter != 0);
+  __syncthreads();
+  if (a.slot_iter == 0)
+    for (int t = tid; t < 25; t += blockDim.x) io.old[t] = io.st[t];  // old_state = *state at level entry (:1523)
+  __syncthreads();
+  const int level = a.level, iteration = a.slot_iter;
+  if (tid < 32) {
+    bool accepted = false, ekf_end = level_done_in;
+    float error = 0.f, last_error = last_error_in;
+    if (!level_done_in) {
+      // error = sum(res^2) / n_meas as float (vio.cpp:1636)
+      const double sum_sq = io.info[7 * 8 + 7];
+      const int n_meas = (int)io.info[INFO_COUNT];
+      error = __fdiv_rn((float)sum_sq, (float)n_meas);
+      if (error <= last_error) {  // :1648
+        accepted = true;
+        if (lane < 25) io.old[lane] = io.st[lane];  // old_state = *state
+        last_error = error;
+        for (int idx = lane; idx < 49; idx += 32) sm.A[idx] = io.info[(idx / 7) * 8 + (idx % 7)];  // H^T H 7x7
+        if (lane < 7) sm.HTz[lane] = io.info[lane * 8 + 7];
+        boxminus_warp(io.pr, io.st, sm.vec, lane);
+        __syncwarp();
+        double x[7];
+        gain_rows<7>(sm, 1.0 / a.img_point_cov, a.solve_mode, lane, x);
+        double g[7];
 #pragma unroll
-      for (int j = 0; j < 7; j++) {
-        double s = 0.0;
+        for (int j = 0; j < 7; j++) {
+          double s = 0.0;
 #pragma unroll
-        for (int k = 0; k < 7; k++) s += x[k] * sm.A[k * 7 + j];
-        g[j] = s;
+          for (int k = 0; k < 7; k++) s += x[k] * sm.A[k * 7 + j];
+          g[j] = s;
+        }
+        if (lane < 19) {
+          double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+          for (int k = 0; k < 7; k++) s1 += x[k] * sm.HTz[k], s2 += g[k] * sm.vec[k];
+          sm.sol[lane] = -s1 + sm.vec[lane] - s2;  // :1667
+#pragma unroll
+          for (int j = 0; j < 7; j++) io.g[lane][j] = g[j];  // G.block<19,7>  (:1665)
+        }
+        __syncwarp();
+        boxplus_warp(io.st, sm.sol, lane);
+        // :1675 (float constants 57.3f / 100.0f / 0.001f promote to double against the double norm)
+        ekf_end = (warp_norm3(sm.sol) * (double)57.3f < (double)0.001f) && (warp_norm3(sm.sol + 3) * (double)100.0f < (double)0.001f);
+      } else {
+        if (lane < 25) io.st[lane] = io.old[lane];  // *state = old_state  (:1679)
+        ekf_end = true;
       }
-      if (lane < 19) {
-        double s1 = 0.0, s2 = 0.0;
-#pragma unroll
-        for (int k = 0; k < 7; k++) s1 += x[k] * sm.HTz[k], s2 += g[k] * sm.vec[k];
-        sm.sol[lane] = -s1 + sm.vec[lane] - s2;  // :1667
-#pragma unroll
-        for (int j = 0; j < 7; j++) a.G[lane * 7 + j] = g[j];  // G.block<19,7>  (:1665)
-      }
-      __syncwarp();
-      boxplus_warp(st, sm.sol, lane);
-      // :1675 (float constants 57.3f / 100.0f / 0.001f promote to double against the double norm)
-      ekf_end = (warp_norm3(sm.sol) * (double)57.3f < (double)0.001f) && (warp_norm3(sm.sol + 3) * (double)100.0f < (double)0.001f);
-      if (a.vio_stats && level < 8 && iteration < 8) {
-        esikf_vio_stats &S = *a.vio_stats;
-        for (int idx = lane; idx < 49; idx += 32) S.HTH[level][iteration][idx] = sm.A[idx];
-        if (lane < 7) S.HTz[level][iteration][lane] = sm.HTz[lane];
-        if (lane < 19) S.solution[level][iteration][lane] = sm.sol[lane];
-      }
-    } else {
-      if (lane < 25) st[lane] = a.old_state[lane];  // *state = old_state  (:1679)
-      ekf_end = true;
     }
-    if (a.vio_stats && lane == 0 && level < 8) {
+    if (lane == 0) {
+      io.flags[0] = accepted, io.flags[1] = ekf_end, io.flags[2] = !level_done_in;
+      reinterpret_cast<float *>(io.flags)[3] = last_error;
+      reinterpret_cast<float *>(io.flags)[4] = error;
+    }
+  }
+  __syncthreads();
+  const bool accepted = io.flags[0] != 0, ran = io.flags[2] != 0;
+  if (ran) {
+    for (int t = tid; t < 25; t += blockDim.x) {
+      a.state[t] = io.st[t];
+      a.old_state[t] = io.old[t];
+    }
+    if (accepted)
+      for (int t = tid; t < 133; t += blockDim.x) a.G[t] = io.g[t / 7][t % 7];
+    if (a.vio_stats && level < 8) {
       esikf_vio_stats &S = *a.vio_stats;
-      if (iteration < 8) S.error_trace[level][iteration] = error;
-      S.iters_per_level[level] = iteration + 1;
-      if (accepted) S.accepted_per_level[level] += 1;
-      S.total_iters += 1;
-    }
-    if (accepted) ctrl.has_G = 1;
-    level_done = ekf_end;
-    if (lane == 0) ctrl.iter += 1;
-  }
-  __syncwarp();
-  if (a.last_slot) {
-    // state->cov -= G * state->cov   (vio.cpp:800) with the last accepted G
-    __threadfence_block();
-    for (int idx = lane; idx < 361; idx += 32) sm.P[idx] = st[S_COV + idx];
-    __syncwarp();
-    if (ctrl.has_G && lane < 19) {
-      double g[7];
-      for (int j = 0; j < 7; j++) g[j] = a.G[lane * 7 + j];
-      for (int c = 0; c < 19; c++) {
-        double s = 0.0;
-        for (int j = 0; j < 7; j++) s += g[j] * sm.P[j * 19 + c];
-        st[S_COV + lane * 19 + c] = sm.P[lane * 19 + c] - s;
+      if (accepted && iteration < 8) {
+        for (int t = tid; t < 49; t += blockDim.x) S.HTH[level][iteration][t] = sm.A[t];
+        for (int t = tid; t < 7; t += blockDim.x) S.HTz[level][iteration][t] = sm.HTz[t];
+        for (int t = tid; t < 19; t += blockDim.x) S.solution[level][iteration][t] = sm.sol[t];
+      }
+      if (tid == 0) {
+        if (iteration < 8) S.error_trace[level][iteration] = reinterpret_cast<float *>(io.flags)[4];
+        S.iters_per_level[level] = iteration + 1;
+        if (accepted) S.accepted_per_level[level] += 1;
+        S.total_iters += 1;
       }
     }
-    if (lane == 0) ctrl.stop = 1;
   }
-  if (lane == 0) {
-    ctrl.level_done = level_done ? 1 : 0;
-    ctrl.last_error = last_error;
+  if (a.last_slot) {
+    // state->cov -= G * state->cov   (vio.cpp:800) with the last accepted G (this slot's if accepted, else the stored one)
+    const bool haveG = accepted || has_G_in;
+    if (haveG)
+      for (int t = tid; t < 361; t += blockDim.x) {
+        const int r = t / 19, c = t - 19 * r;
+        double s = 0.0;
+        for (int j = 0; j < 7; j++) s += (accepted ? io.g[r][j] : __ldcg(a.G + r * 7 + j)) * sm.P[j * 19 + c];
+        a.state[S_COV + t] = sm.P[t] - s;
+      }
   }
+  __syncthreads();
+  if (tid == 0) {
+    if (ran) {
+      ctrl.iter += 1;
+      ctrl.last_error = reinterpret_cast<float *>(io.flags)[3];
+      if (accepted) ctrl.has_G = 1;
+    }
+    ctrl.level_done = io.flags[1];
+    if (a.last_slot) ctrl.stop = 1;
+  }
+  return io.flags[1] != 0;
+}
+
+__global__ void __launch_bounds__(SOLVE_THREADS, 1) vio_solve_kernel(const SolveArgs a) {
+  __shared__ SolveSmem sm;
+  __shared__ SolveIO io;
+  vio_solve_block(a, sm, io);
 }
 
 }  // namespace esikf

@@ -95,6 +95,7 @@ struct VioKernelArgs {
   double Rci[9], Pci[3], Jdp_dR[9];
   float *errors;               // [n_total]
   double *partials;
+  int partial_stride;
   double *info;
   Ctrl *ctrl;
 };
@@ -110,43 +111,47 @@ __device__ __forceinline__ float bil(float wtl, float wtr, float wbl, float wbr,
 
 struct __align__(128) VioSmem {
   double rows[VIO_WARPS][64][8];  // first: double4 stores need 32-byte alignment
+  float taps[VIO_WARPS][128];     // 11 x 11 strided image taps of the patch footprint (level-0 image, stride 2^pyramid_level)
+  float grid[VIO_WARPS][104];     // 10 x 10 bilinear values: patch pixels plus a one-pixel ring for the central differences
   double Rcw[9], Pcw[3];
   double inv_expo;
   ReduceSmem<VIO_WARPS> red;
 };
 
-__global__ void __launch_bounds__(VIO_THREADS, 2) vio_patch_kernel(const VioKernelArgs a) {
-  if (a.slot_iter > 0 && a.ctrl->level_done) return;  // EKF_end of this level: remaining slots do nothing
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  VioSmem &sm = *reinterpret_cast<VioSmem *>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// Per-iteration constants of updateState (vio.cpp:1540-1544): Rcw, Pcw, inv_expo_time.
+__device__ __forceinline__ void vio_load_consts(VioSmem &sm, const VioKernelArgs &a) {
+  const int tid = threadIdx.x;
   if (tid < 9) {
     // Rcw = Rci * Rwi^T  (vio.cpp:1542)
     int r = tid / 3, c = tid % 3;
     double s = 0;
-    for (int k = 0; k < 3; k++) s += a.Rci[r * 3 + k] * a.state[S_R + c * 3 + k];
+    for (int k = 0; k < 3; k++) s += a.Rci[r * 3 + k] * __ldcg(a.state + S_R + c * 3 + k);
     sm.Rcw[tid] = s;
   }
-  if (tid == 0) sm.inv_expo = a.state[S_EXPO];
+  if (tid == 0) sm.inv_expo = __ldcg(a.state + S_EXPO);
   __syncthreads();
   if (tid < 3) {
     // Pcw = -Rci Rwi^T Pwi + Pci  (:1543)
     double s = 0;
-    for (int k = 0; k < 3; k++) s += sm.Rcw[tid * 3 + k] * a.state[S_P + k];
+    for (int k = 0; k < 3; k++) s += sm.Rcw[tid * 3 + k] * __ldcg(a.state + S_P + k);
     sm.Pcw[tid] = -s + a.Pci[tid];
   }
   __syncthreads();
+}
 
+// Photometric residual / Jacobian build of the patches [lo, hi) of this rank's shard at pyramid level `level`.
+__device__ __forceinline__ void vio_process_range(const VioKernelArgs &a, VioSmem &sm, int level, int lo, int hi, double &D0, double &D1,
+                                                  double &n_meas) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long npix = (long)a.cam.width * a.cam.height;
   const int width = a.cam.width;
   const double inv_expo = sm.inv_expo;
-  double D0 = 0.0, D1 = 0.0;
-  double n_meas = 0.0;
-
-  for (int lp = blockIdx.x * VIO_WARPS + warp; lp < a.count; lp += gridDim.x * VIO_WARPS) {
+  float *const sT = sm.taps[warp];
+  float *const sG = sm.grid[warp];
+  for (int lp = lo + warp; lp < hi; lp += VIO_WARPS) {
     const int i = a.begin + lp;
     const int search_level = a.search_levels[i];
-    const int pyramid_level = a.level + search_level;
+    const int pyramid_level = level + search_level;
     const int scale = 1 << pyramid_level;
     const float inv_scale = 1.0f / (float)scale;
     const double X = a.pos[3 * (size_t)i], Y = a.pos[3 * (size_t)i + 1], Z = a.pos[3 * (size_t)i + 2];
@@ -155,24 +160,6 @@ __global__ void __launch_bounds__(VIO_THREADS, 2) vio_patch_kernel(const VioKern
     const double pf2 = sm.Rcw[6] * X + sm.Rcw[7] * Y + sm.Rcw[8] * Z + sm.Pcw[2];
     double pcu, pcv;
     world2cam(a.cam, pf0, pf1, pf2, pcu, pcv);
-    // computeProjectionJacobian (:189-201)
-    const double z_inv = 1. / pf2, z_inv_2 = z_inv * z_inv;
-    const double J00 = a.cam.fx * z_inv, J02 = -a.cam.fx * pf0 * z_inv_2, J11 = a.cam.fy * z_inv, J12 = -a.cam.fy * pf1 * z_inv_2;
-    // Per-patch 2x3 maps so that per pixel  JdR = [du dv] WR,  Jdt = [du dv] WT  (vio.cpp:1611-1617):
-    //   Jimg = [du dv] * inv_expo * inv_scale ; Jdphi = Jimg Jdpi [pf]x ; Jdp = -Jimg Jdpi
-    //   JdR = Jdphi Rci + Jdp Jdp_dR ; Jdt = Jdp Rcw
-    const double sc = inv_expo * (double)inv_scale;
-    // Jdpi [pf]x  (2x3);  [pf]x = [0 -z y; z 0 -x; -y x 0]
-    const double Q00 = J02 * (-pf1), Q01 = J00 * (-pf2) + J02 * pf0, Q02 = J00 * pf1;
-    const double Q10 = J11 * pf2 + J12 * (-pf1), Q11 = J12 * pf0, Q12 = J11 * (-pf0);
-    double WR[2][3], WT[2][3];
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      WR[0][c] = sc * ((Q00 * a.Rci[c] + Q01 * a.Rci[3 + c] + Q02 * a.Rci[6 + c]) - (J00 * a.Jdp_dR[c] + J02 * a.Jdp_dR[6 + c]));
-      WR[1][c] = sc * ((Q10 * a.Rci[c] + Q11 * a.Rci[3 + c] + Q12 * a.Rci[6 + c]) - (J11 * a.Jdp_dR[3 + c] + J12 * a.Jdp_dR[6 + c]));
-      WT[0][c] = -sc * (J00 * sm.Rcw[c] + J02 * sm.Rcw[6 + c]);
-      WT[1][c] = -sc * (J11 * sm.Rcw[3 + c] + J12 * sm.Rcw[6 + c]);
-    }
     // bilinear weights (:1580-1589) — float, via double (1.0 - subpix)
     const float u_ref = (float)pcu, v_ref = (float)pcv;
     const int u_ref_i = (int)(floorf((float)(pcu / scale)) * scale);
@@ -183,26 +170,61 @@ __global__ void __launch_bounds__(VIO_THREADS, 2) vio_patch_kernel(const VioKern
     const float w_tr = (float)(subpix_u * (1.0 - subpix_v));
     const float w_bl = (float)((1.0 - subpix_u) * subpix_v);
     const float w_br = subpix_u * subpix_v;
-    const double inv_ref_expo = a.inv_expo_list[i];
-    const float *__restrict__ P = a.warp_patch + (size_t)i * 64 * a.levels + 64 * a.level;
 
+    // stage the 11 x 11 tap footprint: tile (r, c) <-> image linear index base0 + r*scale*width + c*scale, where tile
+    // (1,1) is the top-left tap of patch pixel (0,0) (:1597)
+    {
+      const long base0 = (long)(v_ref_i - 5 * scale) * width + (u_ref_i - 5 * scale);
+      const long sw = (long)scale * width;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int t = lane + 32 * k;
+        if (t < 121) {
+          const int r = t / 11, c = t - 11 * r;
+          sT[t] = tap(a.img, base0 + r * sw + (long)c * scale, npix);
+        }
+      }
+    }
+    // computeProjectionJacobian (:189-201) and the per-patch 2x3 maps so that per pixel JdR = [du dv] WR, Jdt = [du dv] WT (:1611-1617):
+    //   Jimg = [du dv] * inv_expo * inv_scale ; Jdphi = Jimg Jdpi [pf]x ; Jdp = -Jimg Jdpi ; JdR = Jdphi Rci + Jdp Jdp_dR ; Jdt = Jdp Rcw
+    const double z_inv = 1. / pf2, z_inv_2 = z_inv * z_inv;
+    const double J00 = a.cam.fx * z_inv, J02 = -a.cam.fx * pf0 * z_inv_2, J11 = a.cam.fy * z_inv, J12 = -a.cam.fy * pf1 * z_inv_2;
+    const double sc = inv_expo * (double)inv_scale;
+    const double Q00 = J02 * (-pf1), Q01 = J00 * (-pf2) + J02 * pf0, Q02 = J00 * pf1;  // Jdpi [pf]x
+    const double Q10 = J11 * pf2 + J12 * (-pf1), Q11 = J12 * pf0, Q12 = J11 * (-pf0);
+    double WR[2][3], WT[2][3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      WR[0][c] = sc * ((Q00 * a.Rci[c] + Q01 * a.Rci[3 + c] + Q02 * a.Rci[6 + c]) - (J00 * a.Jdp_dR[c] + J02 * a.Jdp_dR[6 + c]));
+      WR[1][c] = sc * ((Q10 * a.Rci[c] + Q11 * a.Rci[3 + c] + Q12 * a.Rci[6 + c]) - (J11 * a.Jdp_dR[3 + c] + J12 * a.Jdp_dR[6 + c]));
+      WT[0][c] = -sc * (J00 * sm.Rcw[c] + J02 * sm.Rcw[6 + c]);
+      WT[1][c] = -sc * (J11 * sm.Rcw[3 + c] + J12 * sm.Rcw[6 + c]);
+    }
+    const double inv_ref_expo = a.inv_expo_list[i];
+    const float2 Pv = *reinterpret_cast<const float2 *>(a.warp_patch + (size_t)i * 64 * a.levels + 64 * level + 2 * lane);
+    __syncwarp();
+    // bilinear value grid: G(a,b) = cur_value of patch pixel (a-1, b-1), a,b in 0..9 (same float op order as :1619-1620)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int g = lane + 32 * k;
+      if (g < 100) {
+        const int ga = g / 10, gb = g - 10 * ga;
+        const float *t0 = sT + ga * 11 + gb;
+        sG[g] = bil(w_tl, w_tr, w_bl, w_br, t0[0], t0[1], t0[11], t0[12]);
+      }
+    }
+    __syncwarp();
     double sq = 0.0;
 #pragma unroll
     for (int k = 0; k < 2; k++) {
       const int pix = 2 * lane + k;  // = x*8 + y
       const int x = pix >> 3, y = pix & 7;
-      const long b = (long)(v_ref_i + x * scale - 4 * scale) * width + u_ref_i - 4 * scale + (long)y * scale;
-      const long sw = (long)scale * width;
-      const float i_m10 = tap(a.img, b - sw, npix), i_m11 = tap(a.img, b - sw + scale, npix);
-      const float i_0m = tap(a.img, b - scale, npix), i_00 = tap(a.img, b, npix), i_01 = tap(a.img, b + scale, npix),
-                  i_02 = tap(a.img, b + 2 * scale, npix);
-      const float i_1m = tap(a.img, b + sw - scale, npix), i_10 = tap(a.img, b + sw, npix), i_11 = tap(a.img, b + sw + scale, npix),
-                  i_12 = tap(a.img, b + sw + 2 * scale, npix);
-      const float i_20 = tap(a.img, b + 2 * sw, npix), i_21 = tap(a.img, b + 2 * sw + scale, npix);
-      const float du = __fmul_rn(0.5f, __fsub_rn(bil(w_tl, w_tr, w_bl, w_br, i_01, i_02, i_11, i_12), bil(w_tl, w_tr, w_bl, w_br, i_0m, i_00, i_1m, i_10)));
-      const float dv = __fmul_rn(0.5f, __fsub_rn(bil(w_tl, w_tr, w_bl, w_br, i_10, i_11, i_20, i_21), bil(w_tl, w_tr, w_bl, w_br, i_m10, i_m11, i_00, i_01)));
-      const double cur_value = (double)bil(w_tl, w_tr, w_bl, w_br, i_00, i_01, i_10, i_11);
-      const double res = inv_expo * cur_value - inv_ref_expo * (double)P[pix];
+      const float *gc = sG + (x + 1) * 10 + (y + 1);
+      // du = 0.5f * (cur(x, y+1) - cur(x, y-1)), dv = 0.5f * (cur(x+1, y) - cur(x-1, y))   (:1600-1609)
+      const float du = __fmul_rn(0.5f, __fsub_rn(gc[1], gc[-1]));
+      const float dv = __fmul_rn(0.5f, __fsub_rn(gc[10], gc[-10]));
+      const double cur_value = (double)gc[0];
+      const double res = inv_expo * cur_value - inv_ref_expo * (double)(k == 0 ? Pv.x : Pv.y);
       const double ddu = (double)du, ddv = (double)dv;
       double4 *dst = reinterpret_cast<double4 *>(&sm.rows[warp][pix][0]);
       dst[0] = make_double4(ddu * WR[0][0] + ddv * WR[1][0], ddu * WR[0][1] + ddv * WR[1][1], ddu * WR[0][2] + ddv * WR[1][2],
@@ -226,8 +248,27 @@ __global__ void __launch_bounds__(VIO_THREADS, 2) vio_patch_kernel(const VioKern
     }
     __syncwarp();
   }
-  reduce_info<VIO_WARPS>(sm.red, D0, D1, n_meas, false, a.partials, a.info, a.ctrl);
 }
+
+__device__ __forceinline__ void vio_block_range(int count, int &lo, int &hi) {
+  const int per = (count + gridDim.x - 1) / gridDim.x;
+  lo = blockIdx.x * per;
+  hi = lo + per < count ? lo + per : count;
+  if (lo > count) lo = count;
+}
+
+__global__ void __launch_bounds__(VIO_THREADS, 2) vio_patch_kernel(const VioKernelArgs a) {
+  if (a.slot_iter > 0 && a.ctrl->level_done) return;  // EKF_end of this level: remaining slots do nothing
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  VioSmem &sm = *reinterpret_cast<VioSmem *>(smem_raw);
+  vio_load_consts(sm, a);
+  double D0 = 0.0, D1 = 0.0, n_meas = 0.0;
+  int lo, hi;
+  vio_block_range(a.count, lo, hi);
+  vio_process_range(a, sm, a.level, lo, hi, D0, D1, n_meas);
+  reduce_info<VIO_WARPS>(sm.red, D0, D1, n_meas, false, a.partials, a.partial_stride, a.info, a.ctrl);
+}
+
 
 // ---------------------------------------------------------------------------------------------------------------------
 // getImagePatch (vio.cpp:203-225), one thread per output pixel.

@@ -124,6 +124,9 @@ int64_t esikf_launch_count(const esikf_ctx *ctx);
 /* solve_mode: 0 = Woodbury 6x6/7x7 form of (H^T H + P^-1)^-1 (default), 1 = literal two 19x19
  * partial-pivot inversions as at src/voxel_map.cpp:468 / src/vio.cpp:1661. */
 int esikf_set_solve_mode(esikf_ctx *ctx, int mode);
+/* loop_mode: 1 (default) = one persistent cooperative kernel runs the whole iteration loop of an update (single GPU);
+ * 0 = one residual + one solve launch per iteration (also used when a communicator is attached or timing is on). */
+int esikf_set_loop_mode(esikf_ctx *ctx, int mode);
 int esikf_set_extrinsics(esikf_ctx *ctx, const esikf_extrinsics *ext);
 
 /* ---------------------------------------------------------------- voxel map mirror
@@ -211,6 +214,12 @@ int esikf_profile_kernel(esikf_ctx *ctx, int32_t which, int32_t arg, int32_t rep
 int esikf_set_kernel_timing(esikf_ctx *ctx, int32_t enable);
 int esikf_get_kernel_timing(esikf_ctx *ctx, float *lio_residual_ms /* 8 */, float *lio_solve_ms /* 8 */,
                             float *vio_patch_ms /* 64 */, float *vio_solve_ms /* 64 */);
+
+/* Phase timestamps of the persistent update kernels (ns, %globaltimer, written by CTA 0): 8 per iteration slot
+ * [start, consts loaded, slice done, all CTAs arrived, partials summed, solved, state published, spare];
+ * slots 0..7 = LIO iterations, 8..71 = VIO (levels-1-level)*max_iterations + iteration. 0 = slot not executed. */
+int esikf_set_phase_stamps(esikf_ctx *ctx, int32_t enable);
+int esikf_get_phase_stamps(esikf_ctx *ctx, uint64_t *out /* 576 */);
 
 #ifdef __cplusplus
 }

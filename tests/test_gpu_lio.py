@@ -161,3 +161,16 @@ def test_full_size_properties(gpu_ctx):
         assert np.linalg.eigvalsh(0.5 * (H + H.T)).min() > 0
     assert a["M"][0] > 0.85 * 100_000
     _compare(a, _oracle(fr))
+
+
+def test_persistent_and_per_iteration_loops_are_bit_identical(gpu_ctx, small_frame):
+    """loop_mode 1 (one cooperative kernel for the whole update) vs loop_mode 0 (residual + solve launch per iteration)."""
+    fr = get_frame(seed=4, n_pts=20000, n_map=150_000, scene_scale=0.5)
+    gpu_ctx.set_loop_mode(1)
+    a = _gpu(gpu_ctx, fr)
+    gpu_ctx.set_loop_mode(0)
+    b = _gpu(gpu_ctx, fr)
+    gpu_ctx.set_loop_mode(1)
+    assert a["iters"] == b["iters"]
+    assert np.array_equal(a["state"], b["state"]) and np.array_equal(a["HTH"], b["HTH"]) and np.array_equal(a["match_plane"], b["match_plane"])
+    _compare(b, _oracle(fr))

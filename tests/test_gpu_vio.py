@@ -167,3 +167,20 @@ def test_vio_full_size_properties(gpu_ctx):
     assert rel(H, H.T) < 1e-12 and np.linalg.eigvalsh(0.5 * (H + H.T)).min() > -1e-9 * np.abs(H).max()
     vio = O.OracleVIO(fr["cam_cfg"], fr["ext"], fr["vio_cfg"], threads=1)
     _compare_vio(a, vio.update(*args), 4)
+
+
+def test_persistent_and_per_iteration_loops_are_bit_identical(gpu_ctx, small_vio_frame):
+    fr = small_vio_frame
+    _setup(gpu_ctx, fr)
+    prior = _vio_prior(fr)
+    w = _gpu_warp(gpu_ctx, fr, prior)
+    args = (fr["img"], fr["vis_pos"], w["warp_patch"], w["search_levels"], fr["inv_ref_expo"], prior, prior)
+    gpu_ctx.set_loop_mode(1)
+    a = gpu_ctx.vio_update(*args)
+    gpu_ctx.set_loop_mode(0)
+    b = gpu_ctx.vio_update(*args)
+    gpu_ctx.set_loop_mode(1)
+    assert a["total_iters"] == b["total_iters"]
+    assert np.array_equal(a["state"], b["state"]) and np.array_equal(a["HTH"], b["HTH"]) and np.array_equal(a["errors"], b["errors"])
+    vio = O.OracleVIO(fr["cam_cfg"], fr["ext"], fr["vio_cfg"])
+    _compare_vio(b, vio.update(*args), fr["vio_cfg"].levels)
