@@ -207,7 +207,7 @@ int esikf_create(esikf_ctx **out, int device) {
             ctx->lio_stats.reserve(1) == cudaSuccess && ctx->vio_stats.reserve(1) == cudaSuccess && ctx->ext_dev.reserve(12) == cudaSuccess &&
             ctx->scratch_state.reserve(S_N) == cudaSuccess;
   ctx->partial_blocks = ctx->sm_count * 2;  // residual kernels are persistent: 2 resident CTAs per SM
-  ok = ok && ctx->partials.reserve((size_t)ctx->partial_blocks * INFO_N) == cudaSuccess && ctx->barrier.reserve(4) == cudaSuccess && ctx->stamps.reserve(8 * 72) == cudaSuccess;
+  ok = ok && ctx->partials.reserve((size_t)ctx->partial_blocks * INFO_N) == cudaSuccess && ctx->barrier.reserve(4) == cudaSuccess && ctx->stamps.reserve(8 * 72 + 64) == cudaSuccess;
   cudaDeviceGetAttribute(&ctx->coop_ok, cudaDevAttrCooperativeLaunch, device);
   if (!ok) {
     esikf_destroy(ctx);
@@ -407,6 +407,7 @@ int esikf_lio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
     unsigned int *bar = ctx->barrier.p;
     unsigned long long *stamps = ctx->want_stamps ? ctx->stamps.p : nullptr;
     if (stamps) CK(cudaMemsetAsync(stamps, 0, 64 * sizeof(unsigned long long), st));
+    ka.dbg = sa.dbg = ctx->want_stamps ? ctx->stamps.p + 576 : nullptr;
     void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&stamps};
     CK(cudaLaunchCooperativeKernel((const void *)lio_update_kernel, dim3(grid), dim3(LIO_THREADS), kargs, sizeof(LioSmem), st));
     ctx->launches += 1;
@@ -829,10 +830,10 @@ int esikf_set_phase_stamps(esikf_ctx *ctx, int32_t enable) {
   ctx->want_stamps = enable != 0;
   return ESIKF_OK;
 }
-int esikf_get_phase_stamps(esikf_ctx *ctx, uint64_t *out /* 576 */) {
+int esikf_get_phase_stamps(esikf_ctx *ctx, uint64_t *out /* 640 */) {
   if (!ctx || !out) return ESIKF_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  CK(cudaMemcpyAsync(out, ctx->stamps.p, 576 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out, ctx->stamps.p, 640 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return ESIKF_OK;
 }

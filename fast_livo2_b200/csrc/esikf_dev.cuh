@@ -57,6 +57,15 @@ struct Ctrl {
 
 
 #ifdef __CUDACC__
+// Measurement-only fine-grained timestamps (ns) by CTA 0 / thread 0 into a 64-entry debug array (nullable).
+__device__ __forceinline__ void dbg_stamp(unsigned long long *dbg, int k) {
+  if (dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    dbg[k] = t;
+  }
+}
+
 // fp64 tensor-core contraction step: D(8x8) += A(8x4) * B(4x8), mma.sync.m8n8k4.f64 (SASS DMMA).
 // Lane l holds A[l/4][l%4], B[l%4][l/4] and D[l/4][2*(l%4) + {0,1}].
 __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {

@@ -102,7 +102,9 @@ __global__ void __launch_bounds__(LIO_THREADS, 2) lio_update_kernel(const LioKer
     grid_barrier(barrier, epoch);
     stamp(stamps, sk);  // 3: all CTAs arrived
     if (blockIdx.x == 0) {
+      dbg_stamp(a.dbg, 12);
       reduce_partials_block(a.partials, a.partial_stride, gridDim.x, a.info);
+      dbg_stamp(a.dbg, 13);
       stamp(stamps, sk);  // 4: partials summed
       lio_solve_block(sa, fs.sm, fs.io);
     } else {

@@ -39,6 +39,7 @@ struct LioKernelArgs {
   double *partials;          // [grid][INFO_N]
   double *info;              // [INFO_N]
   Ctrl *ctrl;
+  unsigned long long *dbg;   // measurement only
 };
 
 __device__ __forceinline__ double dot3_rn(double a0, double a1, double a2, double b0, double b1, double b2) {
@@ -255,6 +256,8 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
     uint32_t first = 0, count = 0;
     bool found = false;
 
+    const bool first_tile = (base == lo);
+    if (first_tile) dbg_stamp(a.dbg, 0);
     // ---- phase 1: transform, voxel key, home-voxel probe
     if (valid) {
       const double px = a.pts[3 * (size_t)i], py = a.pts[3 * (size_t)i + 1], pz = a.pts[3 * (size_t)i + 2];
@@ -279,6 +282,7 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
       found = finite && probe(a.slots, a.hash_mask, key[0], key[1], key[2], first, count);
     }
 
+    if (first_tile) dbg_stamp(a.dbg, 1);
     // ---- phase 2: stage every lane's first candidate record (256 B) with coalesced half-warp copies
     {
       const int cand0 = (found && count > 0) ? (int)first : -1;
@@ -295,6 +299,7 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
       __syncwarp();
     }
 
+    if (first_tile) dbg_stamp(a.dbg, 2);
     // ---- phase 3: association
     Cand best;
     best.prob = 0.0, best.idx = -1, best.dis = 0.f;
@@ -334,12 +339,14 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
         if (e.pass) best.prob = e.prob, best.idx = (int)first, best.dis = e.dis;
       }
     }
+    if (first_tile) dbg_stamp(a.dbg, 3);
     // further candidates of sub-divided root voxels (rare): one point at a time, lane-parallel over its candidate list
     for (unsigned more = __ballot_sync(0xffffffffu, found && count > 1); more; more &= more - 1) {
       const int src = __ffs(more) - 1;
       const Cand c = warp_eval_extra(a.planes, src, pw, var, first, count, a.sigma_num, lane);
       if (lane == src && c.idx >= 0 && c.prob > best.prob) best = c;
     }
+    if (first_tile) dbg_stamp(a.dbg, 4);
     // one neighbour voxel when the home voxel gave nothing (voxel_map.cpp:680-691). loc is in voxel units, centre / quarter
     // length in metres: reproduced literally.
     uint32_t f2 = 0, c2 = 0;
@@ -366,6 +373,7 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
       if (lane == src && c.idx >= 0 && c.prob > best.prob) best = c;
     }
 
+    if (first_tile) dbg_stamp(a.dbg, 5);
     // ---- phase 4: Jacobian / measurement-noise loop (voxel_map.cpp:414-458) for matched points
     double row[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double wgt = 0.0, absd = 0.0;
@@ -416,6 +424,7 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
     }
     cnt += __popc(__ballot_sync(0xffffffffu, matched));
 
+    if (first_tile) dbg_stamp(a.dbg, 6);
     // ---- phase 5: stage the 32 rows of this warp and contract them on the fp64 tensor path
     double4 *dst = reinterpret_cast<double4 *>(&sm.rows[tid][0]);
     dst[0] = make_double4(row[0], row[1], row[2], row[3]);

@@ -30,6 +30,7 @@ struct SolveArgs {
   double *G;            // 19 x 7 last accepted gain block
   double img_point_cov;
   int level, slot_iter, last_slot;
+  unsigned long long *dbg;  // measurement only
 };
 
 struct SolveSmem {
@@ -234,15 +235,19 @@ __device__ __forceinline__ bool lio_solve_block(const SolveArgs &a, SolveSmem &s
   const int tid = threadIdx.x, lane = tid & 31;
   const int iterCount = ctrl.iter;
   const int rematch0 = ctrl.rematch_num;
+  dbg_stamp(a.dbg, 16);
   solve_load(sm, io, a, false);
   __syncthreads();
+  dbg_stamp(a.dbg, 17);
   if (tid < 32) {
     for (int idx = lane; idx < 36; idx += 32) sm.A[idx] = io.info[(idx / 6) * 8 + (idx % 6)];  // H^T R^-1 H
     if (lane < 6) sm.HTz[lane] = io.info[lane * 8 + 6];                                          // H^T R^-1 z
     boxminus_warp(io.pr, io.st, sm.vec, lane);
     __syncwarp();
+    dbg_stamp(a.dbg, 18);
     double x[6];
     gain_rows<6>(sm, 1.0, a.solve_mode, lane, x);
+    dbg_stamp(a.dbg, 19);
     // G[lane, 0:6] = K_1[lane, 0:6] * HTH   (voxel_map.cpp:469)
     double g[6];
 #pragma unroll
@@ -262,7 +267,9 @@ __device__ __forceinline__ bool lio_solve_block(const SolveArgs &a, SolveSmem &s
       for (int j = 0; j < 6; j++) io.g[lane][j] = g[j];
     }
     __syncwarp();
+    dbg_stamp(a.dbg, 20);
     boxplus_warp(io.st, sm.sol, lane);  // state_ += solution (:474)
+    dbg_stamp(a.dbg, 21);
     if (lane == 0) {
       const bool converged = (warp_norm3(sm.sol) * 57.3 < 0.01) && (warp_norm3(sm.sol + 3) * 100 < 0.015);  // :477
       int rematch = rematch0;
@@ -297,6 +304,7 @@ __device__ __forceinline__ bool lio_solve_block(const SolveArgs &a, SolveSmem &s
     }
   }
   __syncthreads();
+  dbg_stamp(a.dbg, 22);
   if (tid == 0) {
     ctrl.iter = iterCount + 1;
     ctrl.rematch_num = io.flags[1];

@@ -21,6 +21,10 @@ for _ in range(steps):
 print("iters", r["iters"], v["total_iters"], "M", r["M"])
 if os.environ.get("STAMPS"):
     ctx.set_phase_stamps(True)
+    r = ctx.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"])
+    ctx.get_phase_stamps(); d = ctx.debug_stamps.astype(np.int64)
+    print('LIO tile phases (us): probe,stage,assoc,extra,neigh,jac,dmma =', np.round(np.diff(d[0:8])/1000,2))
+    print('reduce (us)', (d[13]-d[12])/1000, ' solve phases load,boxminus,gain,sol,boxplus,write =', np.round(np.diff(d[16:23])/1000,2))
     for rep in range(2):
         r = ctx.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"])
         v = ctx.vio_update(fr["img"], fr["vis_pos"], w["warp_patch"], w["search_levels"], fr["inv_ref_expo"], r["state"], r["state"])
