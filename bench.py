@@ -58,7 +58,7 @@ def make_workload(args):
     from fast_livo2_b200 import synthetic as S
 
     t0 = time.time()
-    fr = S.make_frame(seed=args.seed, n_pts=args.n_pts, n_map=args.n_map, n_patches=args.n_patches)
+    fr = S.cached_frame(seed=args.seed, n_pts=args.n_pts, n_map=args.n_map, n_patches=args.n_patches)
     fr["gen_seconds"] = time.time() - t0
     return fr
 

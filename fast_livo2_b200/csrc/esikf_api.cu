@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -89,6 +90,7 @@ struct esikf_ctx {
   int solve_mode = 0;
   int loop_mode = 1;      // 1: persistent cooperative kernel per update (single GPU), 0: one residual + one solve launch per iteration
   int coop_ok = 0;
+  int coop_lio = 0, coop_vio = 0;  // co-resident CTAs per SM of the persistent kernels
   DevBuf<unsigned int> barrier;
   DevBuf<unsigned long long> stamps;  // 8 per slot: 8 LIO slots then 64 VIO slots
   bool want_stamps = false;
@@ -206,7 +208,7 @@ int esikf_create(esikf_ctx **out, int device) {
             ctx->old_state.reserve(32) == cudaSuccess && ctx->G.reserve(19 * 7) == cudaSuccess && ctx->ctrl.reserve(1) == cudaSuccess &&
             ctx->lio_stats.reserve(1) == cudaSuccess && ctx->vio_stats.reserve(1) == cudaSuccess && ctx->ext_dev.reserve(12) == cudaSuccess &&
             ctx->scratch_state.reserve(S_N) == cudaSuccess;
-  ctx->partial_blocks = ctx->sm_count * 2;  // residual kernels are persistent: 2 resident CTAs per SM
+  ctx->partial_blocks = ctx->sm_count < 160 ? ctx->sm_count : 160;  // persistent residual kernels: one CTA per SM
   ok = ok && ctx->partials.reserve((size_t)ctx->partial_blocks * INFO_N) == cudaSuccess && ctx->barrier.reserve(4) == cudaSuccess && ctx->stamps.reserve(8 * 72 + 64) == cudaSuccess;
   cudaDeviceGetAttribute(&ctx->coop_ok, cudaDevAttrCooperativeLaunch, device);
   if (!ok) {
@@ -216,8 +218,27 @@ int esikf_create(esikf_ctx **out, int device) {
   cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), ctx->stream);
   cudaFuncSetAttribute(lio_residual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
   cudaFuncSetAttribute(vio_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VioSmem));
-  cudaFuncSetAttribute(lio_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
-  cudaFuncSetAttribute(vio_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VioSmem));
+  cudaError_t ea = cudaFuncSetAttribute(lio_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
+  cudaError_t eb = cudaFuncSetAttribute(vio_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VioSmem));
+  // the persistent kernels need every CTA co-resident: check what the device can hold
+  int occ_l = 0, occ_v = 0, occ_r = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, lio_update_kernel, LIO_THREADS, sizeof(LioSmem));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_v, vio_update_kernel, VIO_THREADS, sizeof(VioSmem));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, lio_residual_kernel, LIO_THREADS, sizeof(LioSmem));
+  ctx->coop_lio = occ_l, ctx->coop_vio = occ_v;
+  if (getenv("ESIKF_DEBUG"))
+    fprintf(stderr, "[esikf] SMs=%d smem LIO=%zu VIO=%zu attr=%d/%d occupancy: lio_update=%d vio_update=%d lio_residual=%d coop=%d\n", ctx->sm_count, sizeof(LioSmem),
+            sizeof(VioSmem), (int)ea, (int)eb, occ_l, occ_v, occ_r, ctx->coop_ok);
+  if (getenv("ESIKF_DEBUG")) {
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, lio_residual_kernel);
+    fprintf(stderr, "[esikf] lio_residual: regs=%d maxThreads=%d static=%zu maxDyn=%d local=%zu\n", fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.localSizeBytes);
+    cudaFuncGetAttributes(&fa, lio_update_kernel);
+    fprintf(stderr, "[esikf] lio_update: regs=%d maxThreads=%d static=%zu maxDyn=%d local=%zu\n", fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.localSizeBytes);
+    cudaFuncGetAttributes(&fa, vio_update_kernel);
+    fprintf(stderr, "[esikf] vio_update: regs=%d maxThreads=%d static=%zu maxDyn=%d local=%zu\n", fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.localSizeBytes);
+  }
+  cudaGetLastError();
   *out = ctx;
   return ESIKF_OK;
 }
@@ -402,7 +423,7 @@ int esikf_lio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   sa.state = ctx->state.p, sa.prop = ctx->prop.p, sa.info = ctx->info.p, sa.ctrl = ctx->ctrl.p;
   sa.max_iterations = cfg->max_iterations, sa.solve_mode = ctx->solve_mode, sa.lio_stats = ctx->lio_stats.p;
   const int grid = lio_grid(ctx, ka.count);
-  if (ctx->loop_mode == 1 && ctx->nranks == 1 && ctx->coop_ok && !ctx->timing) {
+  if (ctx->loop_mode == 1 && ctx->nranks == 1 && ctx->coop_ok && ctx->coop_lio > 0 && !ctx->timing) {
     CK(cudaMemsetAsync(ctx->barrier.p, 0, sizeof(unsigned int), st));
     unsigned int *bar = ctx->barrier.p;
     unsigned long long *stamps = ctx->want_stamps ? ctx->stamps.p : nullptr;
@@ -565,7 +586,7 @@ static void vio_fill_args(esikf_ctx *ctx, VioKernelArgs &ka, double *state_ptr) 
   ka.partial_stride = ctx->partial_blocks;
 }
 static int vio_grid(const esikf_ctx *ctx, int count) {
-  int g = (count + VIO_WARPS - 1) / VIO_WARPS;
+  int g = (count + VIO_WARPS - 1) / VIO_WARPS;  // one patch per warp while the patches last
   if (g > ctx->partial_blocks) g = ctx->partial_blocks;
   return g < 1 ? 1 : g;
 }
@@ -589,7 +610,7 @@ int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   sa.max_iterations = ctx->vio_cfg.max_iterations, sa.solve_mode = ctx->solve_mode, sa.vio_stats = ctx->vio_stats.p;
   sa.old_state = ctx->old_state.p, sa.G = ctx->G.p, sa.img_point_cov = ctx->vio_cfg.img_point_cov;
   const int grid = vio_grid(ctx, ka.count);
-  if (ctx->loop_mode == 1 && ctx->nranks == 1 && ctx->coop_ok && !ctx->timing) {
+  if (ctx->loop_mode == 1 && ctx->nranks == 1 && ctx->coop_ok && ctx->coop_vio > 0 && !ctx->timing) {
     CK(cudaMemsetAsync(ctx->barrier.p, 0, sizeof(unsigned int), st));
     unsigned int *bar = ctx->barrier.p;
     unsigned long long *stamps = ctx->want_stamps ? ctx->stamps.p + 64 : nullptr;

@@ -72,34 +72,33 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// Fixed-order sum over the per-CTA partial blocks (entry-major [entry][block], nb <= 320 blocks) by the calling CTA:
-// lane l adds blocks l, l+32, ... in order, then a fixed xor-shuffle tree. All loads of two entries are issued before the
-// first add so the sum costs one L2 round trip per pass instead of one per block.
+// Fixed-order sum over the per-CTA partial blocks (entry-major [entry][block]) by the calling CTA (>= 14 warps, nb <= 160
+// blocks): warp w owns entries w, w+nwarps, ...; lane l adds blocks l, l+32, ... in order, then a fixed xor-shuffle tree.
+// Every load is issued before the first add, so the whole sum costs ONE L2 round trip.
+#define SUM_MAXE 5
+#define SUM_MAXC 5
 __device__ __forceinline__ void sum_partials(const double *partials, int partial_stride, int nb, double *info, int nwarps) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int e0 = warp; e0 < 66; e0 += 2 * nwarps) {
-    const int e1 = e0 + nwarps;
-    const double *__restrict__ p0 = partials + (size_t)e0 * partial_stride;
-    const double *__restrict__ p1 = partials + (size_t)e1 * partial_stride;
-    double v0[10], v1[10];
+  double v[SUM_MAXE][SUM_MAXC];
 #pragma unroll
-    for (int c = 0; c < 10; c++) {
+  for (int k = 0; k < SUM_MAXE; k++) {
+    const int e = warp + k * nwarps;
+    const double *__restrict__ p = partials + (size_t)e * partial_stride;
+#pragma unroll
+    for (int c = 0; c < SUM_MAXC; c++) {
       const int b = lane + 32 * c;
-      v0[c] = (b < nb) ? __ldcg(p0 + b) : 0.0;
-      v1[c] = (e1 < 66 && b < nb) ? __ldcg(p1 + b) : 0.0;
+      v[k][c] = (e < 66 && b < nb) ? __ldcg(p + b) : 0.0;
     }
-    double s0 = v0[0], s1 = v1[0];
+  }
 #pragma unroll
-    for (int c = 1; c < 10; c++) s0 += v0[c], s1 += v1[c];
+  for (int k = 0; k < SUM_MAXE; k++) {
+    const int e = warp + k * nwarps;
+    double s = v[k][0];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      s0 += __shfl_xor_sync(0xffffffffu, s0, off);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, off);
-    }
-    if (lane == 0) {
-      info[e0] = s0;
-      if (e1 < 66) info[e1] = s1;
-    }
+    for (int c = 1; c < SUM_MAXC; c++) s += v[k][c];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0 && e < 66) info[e] = s;
   }
 }
 

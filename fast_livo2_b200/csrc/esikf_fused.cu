@@ -5,7 +5,7 @@
 //   lio_update_kernel : VoxelMapManager::StateEstimation's loop          (reference src/voxel_map.cpp:372-500)
 //   vio_update_kernel : VIOManager::computeJacobianAndUpdateEKF's loops   (src/vio.cpp:784-802, 1520-1688)
 //
-// Per iteration: every CTA (2 per SM, co-resident) builds the residual / Jacobian rows of its slice of the points / patches
+// Per iteration: every CTA (one per SM, co-resident) builds the residual / Jacobian rows of its slice of the points / patches
 // and contracts them on the fp64 tensor-core path; per-CTA 8x8 partial blocks go to global memory; grid barrier; CTA 0 sums
 // them in a fixed order, runs the m x m gain solve and the boxplus and publishes the new state; grid barrier; everybody
 // reloads the 30 pose / covariance doubles it needs and continues. Results are bit-identical to the per-iteration kernels.
@@ -79,7 +79,7 @@ struct FusedSolveSmem {
   SolveIO io;
 };
 
-__global__ void __launch_bounds__(LIO_THREADS, 2) lio_update_kernel(const LioKernelArgs a, const SolveArgs sa, unsigned int *barrier, unsigned long long *stamps) {
+__global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_kernel(const LioKernelArgs a, const SolveArgs sa, unsigned int *barrier, unsigned long long *stamps) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   LioSmem &sm = *reinterpret_cast<LioSmem *>(smem_raw);
   // the solve scratch aliases the plane-record staging area (only used between the two barriers, by CTA 0)
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(LIO_THREADS, 2) lio_update_kernel(const LioKer
   }
 }
 
-__global__ void __launch_bounds__(VIO_THREADS, 2) vio_update_kernel(const VioKernelArgs a, SolveArgs sa, unsigned int *barrier, unsigned long long *stamps) {
+__global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKernelArgs a, SolveArgs sa, unsigned int *barrier, unsigned long long *stamps) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   VioSmem &sm = *reinterpret_cast<VioSmem *>(smem_raw);
   FusedSolveSmem &fs = *reinterpret_cast<FusedSolveSmem *>(&sm.rows[0][0][0]);

@@ -13,7 +13,7 @@
 
 namespace esikf {
 
-#define LIO_THREADS 256
+#define LIO_THREADS 704  // 22 warps, one CTA per SM: 148 x 704 = 104k points in a single round
 #define LIO_WARPS (LIO_THREADS / 32)
 
 struct LioKernelArgs {
@@ -209,12 +209,11 @@ __device__ __forceinline__ Cand warp_eval_extra(const esikf_plane *__restrict__ 
 
 // shared-memory layout of the residual kernel
 struct __align__(128) LioSmem {
-  double rec[LIO_WARPS][32][REC_STRIDE];  // first candidate plane of every lane, staged by coalesced warp copies
-  double rows[LIO_THREADS][8];            // a_i = [A(3) n(3) z 1]
+  // First candidate plane of every lane, staged by coalesced warp copies. After the lane has consumed its record the
+  // slot is reused for its row a_i = [A(3) n(3) z 1] (doubles 0..7), R_inv (8) and |dis_to_plane| (9).
+  double rec[LIO_WARPS][32][REC_STRIDE];
   double R[9], t[3], Ptt[9], Ppp[9];      // current state
   double Rp[9], tp[3], Mp[9];             // prior pose, Mp = Rp * extR
-  double w[LIO_THREADS];                  // R_inv
-  double absd[LIO_THREADS];               // |dis_to_plane|
   ReduceSmem<LIO_WARPS> red;
 };
 
@@ -426,20 +425,23 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
 
     if (first_tile) dbg_stamp(a.dbg, 6);
     // ---- phase 5: stage the 32 rows of this warp and contract them on the fp64 tensor path
-    double4 *dst = reinterpret_cast<double4 *>(&sm.rows[tid][0]);
-    dst[0] = make_double4(row[0], row[1], row[2], row[3]);
-    dst[1] = make_double4(row[4], row[5], row[6], row[7]);
-    sm.w[tid] = wgt;
-    sm.absd[tid] = absd;
+    __syncwarp();
+    {
+      double2 *dst = reinterpret_cast<double2 *>(myrec);
+      dst[0] = make_double2(row[0], row[1]);
+      dst[1] = make_double2(row[2], row[3]);
+      dst[2] = make_double2(row[4], row[5]);
+      dst[3] = make_double2(row[6], row[7]);
+      dst[4] = make_double2(wgt, absd);
+    }
     __syncwarp();
     {
       const int g = lane >> 2, t = lane & 3;
-      const int base = warp * 32;
 #pragma unroll
       for (int s = 0; s < 8; s++) {
-        const int r = base + 4 * s + t;
-        const double v = sm.rows[r][g];
-        const double b = (g == 7) ? sm.absd[r] : sm.w[r] * v;
+        const double *r = &sm.rec[warp][4 * s + t][0];
+        const double v = r[g];
+        const double b = (g == 7) ? r[9] : r[8] * v;
         dmma_m8n8k4(D0, D1, v, b);
       }
     }
@@ -456,7 +458,7 @@ __device__ __forceinline__ void lio_block_range(int count, int &lo, int &hi) {
   if (lo > count) lo = count;
 }
 
-__global__ void __launch_bounds__(LIO_THREADS, 2) lio_residual_kernel(const LioKernelArgs a) {
+__global__ void __launch_bounds__(LIO_THREADS, 1) lio_residual_kernel(const LioKernelArgs a) {
   if (a.ctrl->stop) return;  // EKF_stop_flg: remaining iterations of the unrolled loop do nothing
   extern __shared__ __align__(128) unsigned char smem_raw[];
   LioSmem &sm = *reinterpret_cast<LioSmem *>(smem_raw);

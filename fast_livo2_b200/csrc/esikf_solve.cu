@@ -166,6 +166,7 @@ __device__ inline void gain_rows(SolveSmem &sm, double pscale, int solve_mode, i
   __syncwarp();
   // every lane eliminates its own copy of [Mt | b], b = P[lane, 0:m] * pscale  (solves Mt x^T = b^T)
   double Mt[m][m + 1];
+  double pinv[m];
   const int row = lane < 19 ? lane : 0;
 #pragma unroll
   for (int i = 0; i < m; i++) {
@@ -186,7 +187,8 @@ __device__ inline void gain_rows(SolveSmem &sm, double pscale, int solve_mode, i
         Mt[r][c] = sw ? u : v;
       }
     }
-    double inv = 1.0 / Mt[k][k];
+    const double inv = 1.0 / Mt[k][k];
+    pinv[k] = inv;
 #pragma unroll
     for (int r = k + 1; r < m; r++) {
       double f = Mt[r][k] * inv;
@@ -199,7 +201,7 @@ __device__ inline void gain_rows(SolveSmem &sm, double pscale, int solve_mode, i
     double s = Mt[i][m];
 #pragma unroll
     for (int j = i + 1; j < m; j++) s -= Mt[i][j] * x[j];
-    x[i] = s / Mt[i][i];
+    x[i] = s * pinv[i];
   }
 }
 
@@ -217,20 +219,28 @@ struct SolveIO {
   int flags[8];
 };
 
-// Block-size agnostic (any multiple of 32 threads >= 32). __ldcg: the data was written by other SMs in this same grid
-// when called from the persistent kernels.
+// Needs >= 192 threads. Every global load is issued before the first shared-memory store, so the staging costs one
+// L2 round trip. __ldcg: the data was written by other SMs of this same grid when called from the persistent kernels.
 __device__ __forceinline__ void solve_load(SolveSmem &sm, SolveIO &io, const SolveArgs &a, bool want_old) {
-  for (int t = threadIdx.x; t < 361; t += blockDim.x) sm.P[t] = __ldcg(a.state + S_COV + t);
-  for (int t = threadIdx.x; t < INFO_N; t += blockDim.x) io.info[t] = __ldcg(a.info + t);
-  for (int t = threadIdx.x; t < 25; t += blockDim.x) {
-    io.st[t] = __ldcg(a.state + t);
-    io.pr[t] = a.prop[t];
-    if (want_old) io.old[t] = __ldcg(a.old_state + t);
+  const int t = threadIdx.x, nt = blockDim.x;
+  const double p0 = (t < 361) ? __ldcg(a.state + S_COV + t) : 0.0;
+  const double p1 = (t + nt < 361) ? __ldcg(a.state + S_COV + t + nt) : 0.0;
+  const double i0 = (t < INFO_N) ? __ldcg(a.info + t) : 0.0;
+  const double s0 = (t < 25) ? __ldcg(a.state + t) : 0.0;
+  const double r0 = (t < 25) ? a.prop[t] : 0.0;
+  const double o0 = (want_old && t < 25) ? __ldcg(a.old_state + t) : 0.0;
+  if (t < 361) sm.P[t] = p0;
+  if (t + nt < 361) sm.P[t + nt] = p1;
+  if (t < INFO_N) io.info[t] = i0;
+  if (t < 25) {
+    io.st[t] = s0;
+    io.pr[t] = r0;
+    if (want_old) io.old[t] = o0;
   }
 }
 
 // One LIO gain solve + state update (src/voxel_map.cpp:462-499) by the calling block. Returns EKF_stop_flg.
-__device__ __forceinline__ bool lio_solve_block(const SolveArgs &a, SolveSmem &sm, SolveIO &io) {
+__device__ __noinline__ bool lio_solve_block(const SolveArgs &a, SolveSmem &sm, SolveIO &io) {
   Ctrl &ctrl = *a.ctrl;
   const int tid = threadIdx.x, lane = tid & 31;
   const int iterCount = ctrl.iter;
@@ -239,17 +249,20 @@ __device__ __forceinline__ bool lio_solve_block(const SolveArgs &a, SolveSmem &s
   solve_load(sm, io, a, false);
   __syncthreads();
   dbg_stamp(a.dbg, 17);
+  double x[6], g[6];
   if (tid < 32) {
     for (int idx = lane; idx < 36; idx += 32) sm.A[idx] = io.info[(idx / 6) * 8 + (idx % 6)];  // H^T R^-1 H
     if (lane < 6) sm.HTz[lane] = io.info[lane * 8 + 6];                                          // H^T R^-1 z
-    boxminus_warp(io.pr, io.st, sm.vec, lane);
     __syncwarp();
     dbg_stamp(a.dbg, 18);
-    double x[6];
     gain_rows<6>(sm, 1.0, a.solve_mode, lane, x);
     dbg_stamp(a.dbg, 19);
+  } else if (tid < 64) {
+    boxminus_warp(io.pr, io.st, sm.vec, lane);  // vec = state_propagat (-) state_, concurrently on warp 1 (:470)
+  }
+  __syncthreads();
+  if (tid < 32) {
     // G[lane, 0:6] = K_1[lane, 0:6] * HTH   (voxel_map.cpp:469)
-    double g[6];
 #pragma unroll
     for (int j = 0; j < 6; j++) {
       double s = 0.0;
@@ -322,7 +335,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lio_solve_kernel(const Solve
 
 // One VIO accept/rollback + gain solve (src/vio.cpp:1636-1685) by the calling block; on the last slot also the final
 // covariance update (:800). Returns EKF_end of the level.
-__device__ __forceinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &sm, SolveIO &io) {
+__device__ __noinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &sm, SolveIO &io) {
   Ctrl &ctrl = *a.ctrl;
   const int tid = threadIdx.x, lane = tid & 31;
   const bool level_done_in = (a.slot_iter == 0) ? false : (ctrl.level_done != 0);   // entering a level: EKF_end = false (vio.cpp:1527)
@@ -335,6 +348,9 @@ __device__ __forceinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &s
     for (int t = tid; t < 25; t += blockDim.x) io.old[t] = io.st[t];  // old_state = *state at level entry (:1523)
   __syncthreads();
   const int level = a.level, iteration = a.slot_iter;
+  // vec = state_propagat (-) state on warp 1 while warp 0 decides accept / rollback and runs the gain solve (:1664)
+  if (tid >= 32 && tid < 64 && !level_done_in) boxminus_warp(io.pr, io.st, sm.vec, lane);
+  __syncthreads();
   if (tid < 32) {
     bool accepted = false, ekf_end = level_done_in;
     float error = 0.f, last_error = last_error_in;
@@ -349,7 +365,6 @@ __device__ __forceinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &s
         last_error = error;
         for (int idx = lane; idx < 49; idx += 32) sm.A[idx] = io.info[(idx / 7) * 8 + (idx % 7)];  // H^T H 7x7
         if (lane < 7) sm.HTz[lane] = io.info[lane * 8 + 7];
-        boxminus_warp(io.pr, io.st, sm.vec, lane);
         __syncwarp();
         double x[7];
         gain_rows<7>(sm, 1.0 / a.img_point_cov, a.solve_mode, lane, x);

@@ -15,7 +15,7 @@
 
 namespace esikf {
 
-#define VIO_THREADS 256
+#define VIO_THREADS 512  // 16 warps, one CTA per SM
 #define VIO_WARPS (VIO_THREADS / 32)
 
 struct CamDev {
@@ -257,7 +257,7 @@ __device__ __forceinline__ void vio_block_range(int count, int &lo, int &hi) {
   if (lo > count) lo = count;
 }
 
-__global__ void __launch_bounds__(VIO_THREADS, 2) vio_patch_kernel(const VioKernelArgs a) {
+__global__ void __launch_bounds__(VIO_THREADS, 1) vio_patch_kernel(const VioKernelArgs a) {
   if (a.slot_iter > 0 && a.ctrl->level_done) return;  // EKF_end of this level: remaining slots do nothing
   extern __shared__ __align__(128) unsigned char smem_raw[];
   VioSmem &sm = *reinterpret_cast<VioSmem *>(smem_raw);

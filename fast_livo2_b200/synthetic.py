@@ -596,3 +596,31 @@ def make_frame(seed=0, n_pts=5000, n_map=200_000, n_patches=0, lio: LioCfg | Non
                      px_ref=np.ascontiguousarray(px_ref[sel]), T_ref=(Rcw_r, Pcw_r), T_cur_true=(Rcw, Pcw),
                      inv_ref_expo=np.ones(len(sel)))
     return frame
+
+
+# ----------------------------------------------------------------------------- on-disk cache (frames take tens of seconds to build)
+def cached_frame(cache_dir=None, **kw):
+    """make_frame(**kw) with a pickle cache keyed by the arguments (defaults to <repo>/.frame_cache)."""
+    import hashlib
+    import os
+    import pickle
+
+    cache_dir = cache_dir or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), ".frame_cache")
+    key = hashlib.sha1(repr(sorted((k, repr(v)) for k, v in kw.items())).encode()).hexdigest()[:16]
+    path = os.path.join(cache_dir, f"frame_{key}.pkl")
+    if os.path.exists(path):
+        try:
+            with open(path, "rb") as f:
+                return pickle.load(f)
+        except Exception:
+            pass
+    fr = make_frame(**kw)
+    try:
+        os.makedirs(cache_dir, exist_ok=True)
+        tmp = path + f".{os.getpid()}.tmp"
+        with open(tmp, "wb") as f:
+            pickle.dump(fr, f, protocol=4)
+        os.replace(tmp, path)
+    except Exception:
+        pass
+    return fr

@@ -23,7 +23,7 @@ def get_frame(**kw):
 
     key = tuple(sorted((k, repr(v)) for k, v in kw.items()))
     if key not in _frames:
-        _frames[key] = S.make_frame(**kw)
+        _frames[key] = S.cached_frame(**kw)
     return _frames[key]
 
 

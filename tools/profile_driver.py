@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 from fast_livo2_b200 import api, synthetic as S
 
 n_pts = int(os.environ.get("N_PTS", 100000)); n_patch = int(os.environ.get("N_PATCH", 2000)); steps = int(os.environ.get("STEPS", 3))
-fr = S.make_frame(seed=0, n_pts=n_pts, n_map=int(os.environ.get("N_MAP", 1000000)), n_patches=n_patch)
+fr = S.cached_frame(seed=0, n_pts=n_pts, n_map=int(os.environ.get("N_MAP", 1000000)), n_patches=n_patch)
 ctx = api.Context(0)
 ctx.set_extrinsics(fr["ext"]); ctx.map_upload(fr["map"], fr["lio_cfg"].voxel_size); ctx.vio_set_camera(fr["cam_cfg"], fr["vio_cfg"])
 r = ctx.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"])
