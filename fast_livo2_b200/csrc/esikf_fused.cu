@@ -89,13 +89,14 @@ __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_kernel(const LioKer
   int lo, hi;
   lio_block_range(a.count, lo, hi);
   int sk = 0;
+  int staged_idx = -1;  // plane record resident in this lane's shared-memory slot
   for (int it = 0; it < sa.max_iterations; it++) {
     stamp(stamps, sk);  // 0: iteration start
     lio_load_consts(sm, a);
     stamp(stamps, sk);  // 1: constants loaded
     double D0 = 0.0, D1 = 0.0;
     int cnt = 0;
-    lio_process_range(a, sm, lo, hi, D0, D1, cnt);
+    lio_process_range(a, sm, lo, hi, D0, D1, cnt, staged_idx);
     __syncthreads();
     stamp(stamps, sk);  // 2: CTA 0 finished its slice
     store_partials<LIO_WARPS>(sm.red, D0, D1, (double)cnt, true, a.partials, a.partial_stride);
@@ -106,12 +107,14 @@ __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_kernel(const LioKer
       reduce_partials_block(a.partials, a.partial_stride, gridDim.x, a.info);
       dbg_stamp(a.dbg, 13);
       stamp(stamps, sk);  // 4: partials summed
-      lio_solve_block(sa, fs.sm, fs.io);
+      lio_solve_block(sa, fs.sm, fs.io, true);
+      staged_idx = -1;  // the solve scratch aliases CTA 0's record slots
     } else {
       sk++;
     }
     stamp(stamps, sk);  // 5: solved
     grid_barrier(barrier, epoch);
+    if (blockIdx.x == 0) lio_write_stats(sa, fs.sm, fs.io);
     stamp(stamps, sk);  // 6: state published
     sk++;               // 7: spare
     if (__ldcg(&a.ctrl->stop)) break;  // EKF_stop_flg (voxel_map.cpp:499)
@@ -146,12 +149,16 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKer
         reduce_partials_block(a.partials, a.partial_stride, gridDim.x, a.info);
         stamp(stamps, sk);
         sa.level = level, sa.slot_iter = it, sa.last_slot = 0;
-        vio_solve_block(sa, fs.sm, fs.io);
+        vio_solve_block(sa, fs.sm, fs.io, true);
       } else {
         sk++;
       }
       stamp(stamps, sk);
       grid_barrier(barrier, epoch);
+      if (blockIdx.x == 0) {
+        vio_write_stats(sa, fs.sm, fs.io);
+        __syncthreads();  // the next iteration's rows reuse the scratch
+      }
       stamp(stamps, sk);
       level_done = __ldcg(&a.ctrl->level_done) != 0;
       if (level_done) break;  // EKF_end (:1685)
@@ -163,7 +170,7 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKer
     sa.level = 0, sa.slot_iter = 1, sa.last_slot = 1;
     if (threadIdx.x == 0) a.ctrl->level_done = 1;
     __syncthreads();
-    vio_solve_block(sa, fs.sm, fs.io);
+    vio_solve_block(sa, fs.sm, fs.io, false);
   }
 }
 

@@ -205,12 +205,14 @@ __device__ __forceinline__ Cand warp_eval_extra(const esikf_plane *__restrict__ 
   return my;
 }
 
-#define REC_STRIDE 34  // doubles per staged plane record slot (272 B: conflict-free 128-bit reads at lane stride)
+#define REC_STRIDE 38  // doubles per lane slot (304 B = 19 x 16 B: conflict-free 128-bit reads at lane stride)
+#define REC_ROW 28     // slot layout: [0,28) staged plane record | [28,36) row a_i | 36 R_inv | 37 |dis_to_plane|
 
 // shared-memory layout of the residual kernel
 struct __align__(128) LioSmem {
-  // First candidate plane of every lane, staged by coalesced warp copies. After the lane has consumed its record the
-  // slot is reused for its row a_i = [A(3) n(3) z 1] (doubles 0..7), R_inv (8) and |dis_to_plane| (9).
+  // Per-lane slot: the first candidate plane of the lane's point, staged by coalesced warp copies and kept resident
+  // across the iterations of the persistent kernel (re-copied only when the point changes voxel), followed by the
+  // lane's row a_i = [A(3) n(3) z 1], R_inv and |dis_to_plane| for the tensor-core contraction.
   double rec[LIO_WARPS][32][REC_STRIDE];
   double R[9], t[3], Ptt[9], Ppp[9];      // current state
   double Rp[9], tp[3], Mp[9];             // prior pose, Mp = Rp * extR
@@ -239,13 +241,15 @@ __device__ __forceinline__ void lio_load_consts(LioSmem &sm, const LioKernelArgs
 
 // Residual / Jacobian build over the points [lo, hi) of this rank's shard (indices local to the shard), accumulated into
 // the calling warp's 8x8 tensor-core block (D0, D1) and matched-point count.
-__device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSmem &sm, int lo, int hi, double &D0, double &D1, int &cnt) {
+__device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSmem &sm, int lo, int hi, double &D0, double &D1, int &cnt,
+                                                  int &staged_idx) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double *const myrec = &sm.rec[warp][lane][0];
   for (int base = lo; base < hi; base += LIO_THREADS) {
     const int li = base + tid;
     const bool valid = li < hi;
     const int i = a.begin + li;
+    if (hi - lo > LIO_THREADS) staged_idx = -1;  // several tiles share the slots: nothing stays resident
     int midx = -1;
     float mdis = 0.f;
     double pi0 = 0, pi1 = 0, pi2 = 0;
@@ -282,19 +286,24 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
     }
 
     if (first_tile) dbg_stamp(a.dbg, 1);
-    // ---- phase 2: stage every lane's first candidate record (256 B) with coalesced half-warp copies
+    // ---- phase 2: stage every lane's first candidate record (224 B) with coalesced half-warp copies. A record already
+    // resident in the lane's slot (same plane as in the previous iteration of the persistent kernel) is not re-read.
     {
       const int cand0 = (found && count > 0) ? (int)first : -1;
+      const int want = (cand0 >= 0 && cand0 != staged_idx) ? cand0 : -1;
       const int half = lane >> 4, sub = lane & 15;
+      if (__any_sync(0xffffffffu, want >= 0)) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        const int src = j + half;
-        const int pidx = __shfl_sync(0xffffffffu, cand0, src);
-        if (pidx >= 0) {
-          const double2 v = __ldg(reinterpret_cast<const double2 *>(a.planes + pidx) + sub);
-          *reinterpret_cast<double2 *>(&sm.rec[warp][src][2 * sub]) = v;
+        for (int j = 0; j < 32; j += 2) {
+          const int src = j + half;
+          const int pidx = __shfl_sync(0xffffffffu, want, src);
+          if (pidx >= 0 && sub < 14) {
+            const double2 v = __ldg(reinterpret_cast<const double2 *>(a.planes + pidx) + sub);
+            *reinterpret_cast<double2 *>(&sm.rec[warp][src][2 * sub]) = v;
+          }
         }
       }
+      if (cand0 >= 0) staged_idx = cand0;
       __syncwarp();
     }
 
@@ -427,7 +436,7 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
     // ---- phase 5: stage the 32 rows of this warp and contract them on the fp64 tensor path
     __syncwarp();
     {
-      double2 *dst = reinterpret_cast<double2 *>(myrec);
+      double2 *dst = reinterpret_cast<double2 *>(myrec + REC_ROW);
       dst[0] = make_double2(row[0], row[1]);
       dst[1] = make_double2(row[2], row[3]);
       dst[2] = make_double2(row[4], row[5]);
@@ -439,7 +448,7 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
       const int g = lane >> 2, t = lane & 3;
 #pragma unroll
       for (int s = 0; s < 8; s++) {
-        const double *r = &sm.rec[warp][4 * s + t][0];
+        const double *r = &sm.rec[warp][4 * s + t][REC_ROW];
         const double v = r[g];
         const double b = (g == 7) ? r[9] : r[8] * v;
         dmma_m8n8k4(D0, D1, v, b);
@@ -467,7 +476,8 @@ __global__ void __launch_bounds__(LIO_THREADS, 1) lio_residual_kernel(const LioK
   int cnt = 0;
   int lo, hi;
   lio_block_range(a.count, lo, hi);
-  lio_process_range(a, sm, lo, hi, D0, D1, cnt);
+  int staged_idx = -1;
+  lio_process_range(a, sm, lo, hi, D0, D1, cnt, staged_idx);
   reduce_info<LIO_WARPS>(sm.red, D0, D1, (double)cnt, true, a.partials, a.partial_stride, a.info, a.ctrl);
 }
 

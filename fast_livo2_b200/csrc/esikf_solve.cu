@@ -51,7 +51,9 @@ __device__ inline void so3_exp(const double v[3], double E[9]) {
   if (nrm > 0.00001) {
     double r[3] = {v[0] / nrm, v[1] / nrm, v[2] / nrm};
     double K[9] = {0.0, -r[2], r[1], r[2], 0.0, -r[0], -r[1], r[0], 0.0};
-    double s = sin(nrm), c = 1.0 - cos(nrm);
+    double s, cc;
+    sincos(nrm, &s, &cc);
+    const double c = 1.0 - cc;
     for (int i = 0; i < 3; i++)
       for (int j = 0; j < 3; j++) {
         double kk = K[i * 3] * K[j] + K[i * 3 + 1] * K[3 + j] + K[i * 3 + 2] * K[6 + j];
@@ -156,53 +158,53 @@ __device__ inline void gain_rows(SolveSmem &sm, double pscale, int solve_mode, i
       for (int j = 0; j < m; j++) x[j] = sm.K[lane * 19 + j];
     return;
   }
-  // Mt = (I + A P_mm)^T, built cooperatively
-  for (int idx = lane; idx < m * m; idx += 32) {
-    int i = idx / m, j = idx % m;
-    double s = (i == j) ? 1.0 : 0.0;
-    for (int k = 0; k < m; k++) s += sm.A[i * m + k] * (sm.P[k * 19 + j] * pscale);
-    sm.M[j * m + i] = s;  // transposed
-  }
-  __syncwarp();
-  // every lane eliminates its own copy of [Mt | b], b = P[lane, 0:m] * pscale  (solves Mt x^T = b^T)
-  double Mt[m][m + 1];
-  double pinv[m];
-  const int row = lane < 19 ? lane : 0;
+  // Warp-cooperative Gauss-Jordan with partial pivoting on the augmented system  M^T [X^T] = [P[:, :m]^T] :
+  // lane c < m owns column c of M^T (= row c of M = I + A P_mm), lane m + r owns the right-hand side of state row r
+  // (P[r, 0:m] * pscale). After the sweep lane m + r holds K_1[r, 0:m]. m + 19 <= 32 columns, m pivots.
+  double col[m];
+  if (lane < m) {
 #pragma unroll
-  for (int i = 0; i < m; i++) {
+    for (int i = 0; i < m; i++) {
+      double s = (i == lane) ? 1.0 : 0.0;
 #pragma unroll
-    for (int j = 0; j < m; j++) Mt[i][j] = sm.M[i * m + j];
-    Mt[i][m] = sm.P[row * 19 + i] * pscale;
+      for (int k = 0; k < m; k++) s += sm.A[lane * m + k] * (sm.P[k * 19 + i] * pscale);
+      col[i] = s;
+    }
+  } else {
+    const int r = (lane - m) < 19 ? (lane - m) : 0;
+#pragma unroll
+    for (int i = 0; i < m; i++) col[i] = sm.P[r * 19 + i] * pscale;
   }
 #pragma unroll
   for (int k = 0; k < m; k++) {
-    // bring the largest |pivot| of column k to row k by compare-swaps (static indices keep Mt in registers)
+    // pivot row: largest |entry| of column k among rows k..m-1, found by the lane that owns column k
+    int p = k;
+    double best = fabs(col[k]);
 #pragma unroll
-    for (int r = k + 1; r < m; r++) {
-      bool sw = fabs(Mt[r][k]) > fabs(Mt[k][k]);
-#pragma unroll
-      for (int c = k; c <= m; c++) {
-        double u = Mt[k][c], v = Mt[r][c];
-        Mt[k][c] = sw ? v : u;
-        Mt[r][c] = sw ? u : v;
-      }
+    for (int i = k + 1; i < m; i++) {
+      const double v = fabs(col[i]);
+      if (v > best) best = v, p = i;
     }
-    const double inv = 1.0 / Mt[k][k];
-    pinv[k] = inv;
+    p = __shfl_sync(0xffffffffu, p, k);
 #pragma unroll
-    for (int r = k + 1; r < m; r++) {
-      double f = Mt[r][k] * inv;
-#pragma unroll
-      for (int c = k + 1; c <= m; c++) Mt[r][c] -= f * Mt[k][c];
+    for (int i = k + 1; i < m; i++) {
+      const bool sw = (p == i);
+      const double u = col[k], v = col[i];
+      col[k] = sw ? v : u;
+      col[i] = sw ? u : v;
     }
+    const double pv = __shfl_sync(0xffffffffu, col[k], k);
+    double f[m];
+#pragma unroll
+    for (int i = 0; i < m; i++) f[i] = __shfl_sync(0xffffffffu, col[i], k);
+    const double vk = col[k] * (1.0 / pv);
+    col[k] = vk;
+#pragma unroll
+    for (int i = 0; i < m; i++)
+      if (i != k) col[i] -= f[i] * vk;
   }
 #pragma unroll
-  for (int i = m - 1; i >= 0; i--) {
-    double s = Mt[i][m];
-#pragma unroll
-    for (int j = i + 1; j < m; j++) s -= Mt[i][j] * x[j];
-    x[i] = s * pinv[i];
-  }
+  for (int i = 0; i < m; i++) x[i] = __shfl_sync(0xffffffffu, col[i], (lane + m) & 31);
 }
 
 __device__ inline double warp_norm3(const double *v) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
@@ -239,8 +241,26 @@ __device__ __forceinline__ void solve_load(SolveSmem &sm, SolveIO &io, const Sol
   }
 }
 
+// Diagnostics of the iteration just solved (what the reference prints at voxel_map.cpp:404-405). Not needed by the other
+// CTAs, so the persistent kernel writes them after publishing the state.
+__device__ __forceinline__ void lio_write_stats(const SolveArgs &a, SolveSmem &sm, SolveIO &io) {
+  const int tid = threadIdx.x, iterCount = io.flags[3];
+  if (a.lio_stats && iterCount < 8) {
+    esikf_lio_stats &S = *a.lio_stats;
+    for (int t = tid; t < 36; t += blockDim.x) S.HTH[iterCount][t] = sm.A[t];
+    for (int t = tid; t < 6; t += blockDim.x) S.HTz[iterCount][t] = sm.HTz[t];
+    for (int t = tid; t < 19; t += blockDim.x) S.solution[iterCount][t] = sm.sol[t];
+    if (tid == 0) {
+      S.iters = iterCount + 1;
+      S.effct_feat_num[iterCount] = (int)io.info[INFO_COUNT];
+      S.total_residual[iterCount] = io.info[INFO_ABS];
+      S.converged[iterCount] = io.flags[0];
+    }
+  }
+}
+
 // One LIO gain solve + state update (src/voxel_map.cpp:462-499) by the calling block. Returns EKF_stop_flg.
-__device__ __noinline__ bool lio_solve_block(const SolveArgs &a, SolveSmem &sm, SolveIO &io) {
+__device__ __noinline__ bool lio_solve_block(const SolveArgs &a, SolveSmem &sm, SolveIO &io, bool defer_stats) {
   Ctrl &ctrl = *a.ctrl;
   const int tid = threadIdx.x, lane = tid & 31;
   const int iterCount = ctrl.iter;
@@ -304,18 +324,7 @@ __device__ __noinline__ bool lio_solve_block(const SolveArgs &a, SolveSmem &sm, 
       a.state[S_COV + t] = s;
     }
   }
-  if (a.lio_stats && iterCount < 8) {
-    esikf_lio_stats &S = *a.lio_stats;
-    for (int t = tid; t < 36; t += blockDim.x) S.HTH[iterCount][t] = sm.A[t];
-    for (int t = tid; t < 6; t += blockDim.x) S.HTz[iterCount][t] = sm.HTz[t];
-    for (int t = tid; t < 19; t += blockDim.x) S.solution[iterCount][t] = sm.sol[t];
-    if (tid == 0) {
-      S.iters = iterCount + 1;
-      S.effct_feat_num[iterCount] = (int)io.info[INFO_COUNT];
-      S.total_residual[iterCount] = io.info[INFO_ABS];
-      S.converged[iterCount] = io.flags[0];
-    }
-  }
+  io.flags[3] = iterCount;
   __syncthreads();
   dbg_stamp(a.dbg, 22);
   if (tid == 0) {
@@ -323,6 +332,7 @@ __device__ __noinline__ bool lio_solve_block(const SolveArgs &a, SolveSmem &sm, 
     ctrl.rematch_num = io.flags[1];
     ctrl.stop = stop ? 1 : 0;
   }
+  if (!defer_stats) lio_write_stats(a, sm, io);
   return stop;
 }
 
@@ -330,12 +340,31 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lio_solve_kernel(const Solve
   if (a.ctrl->stop) return;
   __shared__ SolveSmem sm;
   __shared__ SolveIO io;
-  lio_solve_block(a, sm, io);
+  lio_solve_block(a, sm, io, false);
+}
+
+__device__ __forceinline__ void vio_write_stats(const SolveArgs &a, SolveSmem &sm, SolveIO &io) {
+  const int tid = threadIdx.x, level = a.level, iteration = a.slot_iter;
+  const bool accepted = io.flags[0] != 0, ran = io.flags[2] != 0;
+  if (ran && a.vio_stats && level < 8) {
+    esikf_vio_stats &S = *a.vio_stats;
+    if (accepted && iteration < 8) {
+      for (int t = tid; t < 49; t += blockDim.x) S.HTH[level][iteration][t] = sm.A[t];
+      for (int t = tid; t < 7; t += blockDim.x) S.HTz[level][iteration][t] = sm.HTz[t];
+      for (int t = tid; t < 19; t += blockDim.x) S.solution[level][iteration][t] = sm.sol[t];
+    }
+    if (tid == 0) {
+      if (iteration < 8) S.error_trace[level][iteration] = reinterpret_cast<float *>(io.flags)[4];
+      S.iters_per_level[level] = iteration + 1;
+      if (accepted) S.accepted_per_level[level] += 1;
+      S.total_iters += 1;
+    }
+  }
 }
 
 // One VIO accept/rollback + gain solve (src/vio.cpp:1636-1685) by the calling block; on the last slot also the final
 // covariance update (:800). Returns EKF_end of the level.
-__device__ __noinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &sm, SolveIO &io) {
+__device__ __forceinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &sm, SolveIO &io, bool defer_stats) {
   Ctrl &ctrl = *a.ctrl;
   const int tid = threadIdx.x, lane = tid & 31;
   const bool level_done_in = (a.slot_iter == 0) ? false : (ctrl.level_done != 0);   // entering a level: EKF_end = false (vio.cpp:1527)
@@ -408,20 +437,7 @@ __device__ __noinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &sm, 
     }
     if (accepted)
       for (int t = tid; t < 133; t += blockDim.x) a.G[t] = io.g[t / 7][t % 7];
-    if (a.vio_stats && level < 8) {
-      esikf_vio_stats &S = *a.vio_stats;
-      if (accepted && iteration < 8) {
-        for (int t = tid; t < 49; t += blockDim.x) S.HTH[level][iteration][t] = sm.A[t];
-        for (int t = tid; t < 7; t += blockDim.x) S.HTz[level][iteration][t] = sm.HTz[t];
-        for (int t = tid; t < 19; t += blockDim.x) S.solution[level][iteration][t] = sm.sol[t];
-      }
-      if (tid == 0) {
-        if (iteration < 8) S.error_trace[level][iteration] = reinterpret_cast<float *>(io.flags)[4];
-        S.iters_per_level[level] = iteration + 1;
-        if (accepted) S.accepted_per_level[level] += 1;
-        S.total_iters += 1;
-      }
-    }
+    if (!defer_stats) vio_write_stats(a, sm, io);
   }
   if (a.last_slot) {
     // state->cov -= G * state->cov   (vio.cpp:800) with the last accepted G (this slot's if accepted, else the stored one)
@@ -450,7 +466,7 @@ __device__ __noinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &sm, 
 __global__ void __launch_bounds__(SOLVE_THREADS, 1) vio_solve_kernel(const SolveArgs a) {
   __shared__ SolveSmem sm;
   __shared__ SolveIO io;
-  vio_solve_block(a, sm, io);
+  vio_solve_block(a, sm, io, false);
 }
 
 }  // namespace esikf
