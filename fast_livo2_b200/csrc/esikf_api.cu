@@ -91,7 +91,7 @@ struct esikf_ctx {
   int loop_mode = 1;      // 1: persistent cooperative kernel per update (single GPU), 0: one residual + one solve launch per iteration
   int coop_ok = 0;
   int coop_lio = 0, coop_vio = 0;  // co-resident CTAs per SM of the persistent kernels
-  DevBuf<unsigned int> barrier;
+  struct { unsigned int *p; } barrier;
   DevBuf<unsigned long long> stamps;  // 8 per slot: 8 LIO slots then 64 VIO slots
   bool want_stamps = false;
   esikf_extrinsics ext{};
@@ -118,9 +118,10 @@ struct esikf_ctx {
 
   // shared update state
   DevBuf<double> state, prop, info, partials, old_state, G;
-  DevBuf<Ctrl> ctrl;
-  DevBuf<esikf_lio_stats> lio_stats;
-  DevBuf<esikf_vio_stats> vio_stats;
+  DevBuf<unsigned char> ctl_block;  // [esikf_lio_stats | Ctrl | barrier (64 B) | esikf_vio_stats], zeroed with one memset per update
+  struct { Ctrl *p; } ctrl;
+  struct { esikf_lio_stats *p; } lio_stats;
+  struct { esikf_vio_stats *p; } vio_stats;
   int partial_blocks = 0;
 
   // VIO
@@ -205,25 +206,32 @@ int esikf_create(esikf_ctx **out, int device) {
     return ESIKF_ERR_CUDA;
   }
   bool ok = ctx->state.reserve(S_N) == cudaSuccess && ctx->prop.reserve(S_N) == cudaSuccess && ctx->info.reserve(INFO_N) == cudaSuccess &&
-            ctx->old_state.reserve(32) == cudaSuccess && ctx->G.reserve(19 * 7) == cudaSuccess && ctx->ctrl.reserve(1) == cudaSuccess &&
-            ctx->lio_stats.reserve(1) == cudaSuccess && ctx->vio_stats.reserve(1) == cudaSuccess && ctx->ext_dev.reserve(12) == cudaSuccess &&
+            ctx->old_state.reserve(32) == cudaSuccess && ctx->G.reserve(19 * 7) == cudaSuccess &&
+            ctx->ctl_block.reserve(sizeof(esikf_lio_stats) + sizeof(Ctrl) + 64 + sizeof(esikf_vio_stats)) == cudaSuccess && ctx->ext_dev.reserve(12) == cudaSuccess &&
             ctx->scratch_state.reserve(S_N) == cudaSuccess;
   ctx->partial_blocks = ctx->sm_count < 160 ? ctx->sm_count : 160;  // persistent residual kernels: one CTA per SM
-  ok = ok && ctx->partials.reserve((size_t)ctx->partial_blocks * INFO_N) == cudaSuccess && ctx->barrier.reserve(4) == cudaSuccess && ctx->stamps.reserve(8 * 72 + 64) == cudaSuccess;
+  ok = ok && ctx->partials.reserve((size_t)ctx->partial_blocks * INFO_N) == cudaSuccess && ctx->stamps.reserve(8 * 72 + 64) == cudaSuccess;
+  if (ok) {
+    unsigned char *b = ctx->ctl_block.p;
+    ctx->lio_stats.p = reinterpret_cast<esikf_lio_stats *>(b);
+    ctx->ctrl.p = reinterpret_cast<Ctrl *>(b + sizeof(esikf_lio_stats));
+    ctx->barrier.p = reinterpret_cast<unsigned int *>(b + sizeof(esikf_lio_stats) + sizeof(Ctrl));
+    ctx->vio_stats.p = reinterpret_cast<esikf_vio_stats *>(b + sizeof(esikf_lio_stats) + sizeof(Ctrl) + 64);
+    cudaMemsetAsync(b, 0, ctx->ctl_block.cap, ctx->stream);
+  }
   cudaDeviceGetAttribute(&ctx->coop_ok, cudaDevAttrCooperativeLaunch, device);
   if (!ok) {
     esikf_destroy(ctx);
     return ESIKF_ERR_CUDA;
   }
-  cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), ctx->stream);
   cudaFuncSetAttribute(lio_residual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
   cudaFuncSetAttribute(vio_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VioSmem));
   cudaError_t ea = cudaFuncSetAttribute(lio_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
-  cudaError_t eb = cudaFuncSetAttribute(vio_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VioSmem));
+  cudaError_t eb = cudaFuncSetAttribute(vio_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(VioSmem) + sizeof(FusedSolveSmem)));
   // the persistent kernels need every CTA co-resident: check what the device can hold
   int occ_l = 0, occ_v = 0, occ_r = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, lio_update_kernel, LIO_THREADS, sizeof(LioSmem));
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_v, vio_update_kernel, VIO_THREADS, sizeof(VioSmem));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_v, vio_update_kernel, VIO_THREADS, sizeof(VioSmem) + sizeof(FusedSolveSmem));
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, lio_residual_kernel, LIO_THREADS, sizeof(LioSmem));
   ctx->coop_lio = occ_l, ctx->coop_vio = occ_v;
   if (getenv("ESIKF_DEBUG"))
@@ -250,8 +258,8 @@ void esikf_destroy(esikf_ctx *ctx) {
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   ctx->slots.release(), ctx->planes.release(), ctx->pts.release(), ctx->pre.release(), ctx->match_plane.release();
   ctx->normal_plane.release(), ctx->dis.release(), ctx->ext_dev.release(), ctx->state.release(), ctx->prop.release();
-  ctx->info.release(), ctx->partials.release(), ctx->old_state.release(), ctx->G.release(), ctx->ctrl.release();
-  ctx->barrier.release(), ctx->stamps.release(), ctx->lio_stats.release(), ctx->vio_stats.release(), ctx->img.release(), ctx->vis_pos.release(), ctx->inv_expo.release();
+  ctx->info.release(), ctx->partials.release(), ctx->old_state.release(), ctx->G.release(), ctx->ctl_block.release();
+  ctx->stamps.release(), ctx->img.release(), ctx->vis_pos.release(), ctx->inv_expo.release();
   ctx->warp_patch.release(), ctx->errors.release(), ctx->search_levels.release(), ctx->ref_img_ptrs.release(), ctx->ref_idx.release();
   ctx->px_ref.release(), ctx->pos_w.release(), ctx->normal_w.release(), ctx->T_ref.release(), ctx->T_cur.release();
   ctx->A_cur_ref.release(), ctx->pc_buf.release(), ctx->patch_buf.release(), ctx->flush.release(), ctx->scratch_state.release();
@@ -401,20 +409,14 @@ int esikf_lio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   cudaStream_t st = ctx->stream;
   CK(cudaMemcpyAsync(ctx->state.p, state_in, S_N * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->prop.p, state_prop, S_N * sizeof(double), cudaMemcpyHostToDevice, st));
-  CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), st));
-  CK(cudaMemsetAsync(ctx->lio_stats.p, 0, sizeof(esikf_lio_stats), st));
+  CK(cudaMemsetAsync(ctx->lio_stats.p, 0, sizeof(esikf_lio_stats) + sizeof(Ctrl) + 64, st));  // stats + loop control + grid barrier
   const int n = ctx->n_pts;
   if (ctx->scan_fresh) {
     if (n > 0) {
       lio_precompute_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->pts.p, n, ctx->pre.p, ctx->pre_stride, ctx->ext_dev.p, (float)cfg->dept_err, (float)cfg->beam_err);
       ctx->launches++;
-      CK(cudaMemsetAsync(ctx->normal_plane.p, 0xff, (size_t)n * sizeof(int32_t), st));  // pv.normal = 0 <=> no plane yet
-      CK(cudaMemsetAsync(ctx->match_plane.p, 0xff, (size_t)n * sizeof(int32_t), st));
-      CK(cudaMemsetAsync(ctx->dis.p, 0, (size_t)n * sizeof(float), st));
     }
     ctx->scan_fresh = false;
-  } else if (n > 0) {
-    CK(cudaMemsetAsync(ctx->normal_plane.p, 0xff, (size_t)n * sizeof(int32_t), st));
   }
   LioKernelArgs ka;
   lio_fill_args(ctx, ka, ctx->state.p);
@@ -424,7 +426,6 @@ int esikf_lio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   sa.max_iterations = cfg->max_iterations, sa.solve_mode = ctx->solve_mode, sa.lio_stats = ctx->lio_stats.p;
   const int grid = lio_grid(ctx, ka.count);
   if (ctx->loop_mode == 1 && ctx->nranks == 1 && ctx->coop_ok && ctx->coop_lio > 0 && !ctx->timing) {
-    CK(cudaMemsetAsync(ctx->barrier.p, 0, sizeof(unsigned int), st));
     unsigned int *bar = ctx->barrier.p;
     unsigned long long *stamps = ctx->want_stamps ? ctx->stamps.p : nullptr;
     if (stamps) CK(cudaMemsetAsync(stamps, 0, 64 * sizeof(unsigned long long), st));
@@ -440,6 +441,7 @@ int esikf_lio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   for (int it = 0; it < cfg->max_iterations; it++) {
     cudaEvent_t *e = ctx->timing ? timing_events(ctx, EV_LIO_BASE, it) : nullptr;
     if (e) cudaEventRecord(e[0], st);
+    ka.init_normal = (it == 0);
     lio_residual_kernel<<<grid, LIO_THREADS, sizeof(LioSmem), st>>>(ka);
     if (e) cudaEventRecord(e[1], st);
     int rc = allreduce_info(ctx);
@@ -599,8 +601,7 @@ int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   cudaStream_t st = ctx->stream;
   CK(cudaMemcpyAsync(ctx->state.p, state_in, S_N * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->prop.p, state_prop, S_N * sizeof(double), cudaMemcpyHostToDevice, st));
-  CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), st));
-  CK(cudaMemsetAsync(ctx->vio_stats.p, 0, sizeof(esikf_vio_stats), st));
+  CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl) + 64 + sizeof(esikf_vio_stats), st));  // loop control + grid barrier + stats
   if (ctx->n_patches == 0) return ESIKF_OK;  // total_points == 0: early return (vio.cpp:786)
   VioKernelArgs ka;
   vio_fill_args(ctx, ka, ctx->state.p);
@@ -611,12 +612,11 @@ int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   sa.old_state = ctx->old_state.p, sa.G = ctx->G.p, sa.img_point_cov = ctx->vio_cfg.img_point_cov;
   const int grid = vio_grid(ctx, ka.count);
   if (ctx->loop_mode == 1 && ctx->nranks == 1 && ctx->coop_ok && ctx->coop_vio > 0 && !ctx->timing) {
-    CK(cudaMemsetAsync(ctx->barrier.p, 0, sizeof(unsigned int), st));
     unsigned int *bar = ctx->barrier.p;
     unsigned long long *stamps = ctx->want_stamps ? ctx->stamps.p + 64 : nullptr;
     if (stamps) CK(cudaMemsetAsync(stamps, 0, 512 * sizeof(unsigned long long), st));
     void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&stamps};
-    CK(cudaLaunchCooperativeKernel((const void *)vio_update_kernel, dim3(grid), dim3(VIO_THREADS), kargs, sizeof(VioSmem), st));
+    CK(cudaLaunchCooperativeKernel((const void *)vio_update_kernel, dim3(grid), dim3(VIO_THREADS), kargs, sizeof(VioSmem) + sizeof(FusedSolveSmem), st));
     ctx->launches += 1;
     ctx->vio_timed = false;
     return ESIKF_OK;

@@ -82,21 +82,28 @@ struct FusedSolveSmem {
 __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_kernel(const LioKernelArgs a, const SolveArgs sa, unsigned int *barrier, unsigned long long *stamps) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   LioSmem &sm = *reinterpret_cast<LioSmem *>(smem_raw);
-  // the solve scratch aliases the plane-record staging area (only used between the two barriers, by CTA 0)
-  FusedSolveSmem &fs = *reinterpret_cast<FusedSolveSmem *>(&sm.rec[0][0][0]);
-  static_assert(sizeof(FusedSolveSmem) <= sizeof(sm.rec), "solve scratch must fit in the record staging area");
+  // CTA 0's solve scratch lives in the reduction scratch (free between the two barriers); only the literal-mode
+  // workspace (solve_mode 1, parity checks) borrows the record slots and forces a re-stage.
+  FusedSolveSmem &fs = *reinterpret_cast<FusedSolveSmem *>(&sm.red);
+  static_assert(sizeof(FusedSolveSmem) <= sizeof(sm.red), "solve scratch must fit in the reduction scratch");
+  static_assert(sizeof(SolveLiteralScratch) <= sizeof(sm.rec), "literal scratch must fit in the record slots");
+  if (threadIdx.x == 0) {
+    SolveLiteralScratch *lit = reinterpret_cast<SolveLiteralScratch *>(&sm.rec[0][0][0]);
+    fs.sm.W = lit->W, fs.sm.K = lit->K;
+  }
   unsigned int epoch = 0;
   int lo, hi;
   lio_block_range(a.count, lo, hi);
   int sk = 0;
-  int staged_idx = -1;  // plane record resident in this lane's shared-memory slot
+  LaneCache lc;  // what stays with this lane's point across iterations (registers + its shared-memory slot)
+  lc.staged_idx = -1, lc.have_pt = false, lc.px = lc.py = lc.pz = 0.f;
   for (int it = 0; it < sa.max_iterations; it++) {
     stamp(stamps, sk);  // 0: iteration start
     lio_load_consts(sm, a);
     stamp(stamps, sk);  // 1: constants loaded
     double D0 = 0.0, D1 = 0.0;
     int cnt = 0;
-    lio_process_range(a, sm, lo, hi, D0, D1, cnt, staged_idx);
+    lio_process_range(a, sm, lo, hi, D0, D1, cnt, lc, it == 0);
     __syncthreads();
     stamp(stamps, sk);  // 2: CTA 0 finished its slice
     store_partials<LIO_WARPS>(sm.red, D0, D1, (double)cnt, true, a.partials, a.partial_stride);
@@ -107,8 +114,13 @@ __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_kernel(const LioKer
       reduce_partials_block(a.partials, a.partial_stride, gridDim.x, a.info);
       dbg_stamp(a.dbg, 13);
       stamp(stamps, sk);  // 4: partials summed
+      if (threadIdx.x == 0) {
+        SolveLiteralScratch *lit = reinterpret_cast<SolveLiteralScratch *>(&sm.rec[0][0][0]);
+        fs.sm.W = lit->W, fs.sm.K = lit->K;
+      }
+      __syncthreads();
       lio_solve_block(sa, fs.sm, fs.io, true);
-      staged_idx = -1;  // the solve scratch aliases CTA 0's record slots
+      if (sa.solve_mode == 1) lc.staged_idx = -1;  // the literal workspace borrowed CTA 0's record slots
     } else {
       sk++;
     }
@@ -124,8 +136,14 @@ __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_kernel(const LioKer
 __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKernelArgs a, SolveArgs sa, unsigned int *barrier, unsigned long long *stamps) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   VioSmem &sm = *reinterpret_cast<VioSmem *>(smem_raw);
-  FusedSolveSmem &fs = *reinterpret_cast<FusedSolveSmem *>(&sm.rows[0][0][0]);
-  static_assert(sizeof(FusedSolveSmem) <= sizeof(sm.rows), "solve scratch must fit in the row staging area");
+  // the solve scratch has its own shared memory behind VioSmem (so the diagnostics can be written while the next
+  // iteration already stages rows); only the literal-mode workspace borrows the row area
+  FusedSolveSmem &fs = *reinterpret_cast<FusedSolveSmem *>(smem_raw + sizeof(VioSmem));
+  struct VioFused {
+    SolveLiteralScratch lit;
+  };
+  VioFused &vf = *reinterpret_cast<VioFused *>(&sm.rows[0][0][0]);
+  static_assert(sizeof(VioFused) <= sizeof(sm.rows), "literal scratch must fit in the row staging area");
   unsigned int epoch = 0;
   int lo, hi;
   vio_block_range(a.count, lo, hi);
@@ -149,16 +167,15 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKer
         reduce_partials_block(a.partials, a.partial_stride, gridDim.x, a.info);
         stamp(stamps, sk);
         sa.level = level, sa.slot_iter = it, sa.last_slot = 0;
+        if (threadIdx.x == 0) fs.sm.W = vf.lit.W, fs.sm.K = vf.lit.K;
+        __syncthreads();
         vio_solve_block(sa, fs.sm, fs.io, true);
       } else {
         sk++;
       }
       stamp(stamps, sk);
       grid_barrier(barrier, epoch);
-      if (blockIdx.x == 0) {
-        vio_write_stats(sa, fs.sm, fs.io);
-        __syncthreads();  // the next iteration's rows reuse the scratch
-      }
+      if (blockIdx.x == 0) vio_write_stats(sa, fs.sm, fs.io);
       stamp(stamps, sk);
       level_done = __ldcg(&a.ctrl->level_done) != 0;
       if (level_done) break;  // EKF_end (:1685)
@@ -168,7 +185,10 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKer
   if (blockIdx.x == 0) {
     __syncthreads();
     sa.level = 0, sa.slot_iter = 1, sa.last_slot = 1;
-    if (threadIdx.x == 0) a.ctrl->level_done = 1;
+    if (threadIdx.x == 0) {
+      a.ctrl->level_done = 1;
+      fs.sm.W = vf.lit.W, fs.sm.K = vf.lit.K;
+    }
     __syncthreads();
     vio_solve_block(sa, fs.sm, fs.io, false);
   }

@@ -40,6 +40,7 @@ struct LioKernelArgs {
   double *info;              // [INFO_N]
   Ctrl *ctrl;
   unsigned long long *dbg;   // measurement only
+  int init_normal;           // first iteration of an update: unmatched points get normal_plane = -1 (pv.normal = 0)
 };
 
 __device__ __forceinline__ double dot3_rn(double a0, double a1, double a2, double b0, double b1, double b2) {
@@ -51,8 +52,10 @@ __device__ __forceinline__ constexpr int tri6(int i, int j) {
   return (i <= j) ? (i * 6 - (i * (i - 1)) / 2 + (j - i)) : (j * 6 - (j * (j - 1)) / 2 + (i - j));
 }
 
-// sigma = J^T PV J evaluated as (J PV) J, the order of src/voxel_map.cpp:735
-__device__ __forceinline__ double quad6(const double *__restrict__ pv, const double J[6]) {
+// sigma = J^T PV J evaluated as (J PV) J, the order of src/voxel_map.cpp:735. pv points at the packed upper triangle inside
+// the plane record (shared or global memory); the per-column fences keep the 21 loads from being hoisted into one
+// 44-register burst (the kernel runs at 80 registers / thread).
+__device__ __forceinline__ double quad6(const double *pv, const double J[6]) {
   double s = 0.0;
 #pragma unroll
   for (int j = 0; j < 6; j++) {
@@ -60,6 +63,7 @@ __device__ __forceinline__ double quad6(const double *__restrict__ pv, const dou
 #pragma unroll
     for (int i = 1; i < 6; i++) t += J[i] * pv[tri6(i, j)];
     s = (j == 0) ? t * J[0] : s + t * J[j];
+    asm volatile("" ::: "memory");
   }
   return s;
 }
@@ -142,14 +146,8 @@ __device__ __forceinline__ EvalOut eval_rec(const double *__restrict__ q, const 
   const float dis_to_center = (float)dot3_rn(e0, e1, e2, e0, e1, e2);
   const float range_dis = sqrtf(__fsub_rn(dis_to_center, __fmul_rn(dis_to_plane, dis_to_plane)));
   if ((double)range_dis <= 3.0 * (double)dr.y) {  // NaN fails, as in the reference
-    double pv[22];
-#pragma unroll
-    for (int k = 0; k < 11; k++) {
-      const double2 v = q2[3 + k];  // doubles 6..27: plane_var[0..20] (+ the d|radius slot)
-      pv[2 * k] = v.x, pv[2 * k + 1] = v.y;
-    }
     const double J[6] = {pw[0] - c0, pw[1] - c1, pw[2] - c2, -n0, -n1, -n2};
-    double sigma_l = quad6(pv, J);
+    double sigma_l = quad6(q + 6, J);
     sigma_l += quad3_sym(var, n0, n1, n2);
     if ((double)dis_to_plane < sigma_num * sqrt(sigma_l)) {
       o.pass = true;
@@ -206,7 +204,14 @@ __device__ __forceinline__ Cand warp_eval_extra(const esikf_plane *__restrict__ 
 }
 
 #define REC_STRIDE 38  // doubles per lane slot (304 B = 19 x 16 B: conflict-free 128-bit reads at lane stride)
-#define REC_ROW 28     // slot layout: [0,28) staged plane record | [28,36) row a_i | 36 R_inv | 37 |dis_to_plane|
+#define REC_ROW 28     // slot layout: [0,28) staged plane record | [28,35) row a_i(7) | 35 R_inv | 36 {f32 |dis|, u32 count} | 37 packed voxel key
+
+// Per-lane state that survives from one iteration to the next inside the persistent kernel (a lane keeps its point).
+struct LaneCache {
+  int staged_idx;   // plane whose record is resident in the lane's slot (-1: none); its voxel key / candidate count sit in the slot tail
+  bool have_pt;
+  float px, py, pz; // the body-frame point
+};
 
 // shared-memory layout of the residual kernel
 struct __align__(128) LioSmem {
@@ -242,20 +247,18 @@ __device__ __forceinline__ void lio_load_consts(LioSmem &sm, const LioKernelArgs
 // Residual / Jacobian build over the points [lo, hi) of this rank's shard (indices local to the shard), accumulated into
 // the calling warp's 8x8 tensor-core block (D0, D1) and matched-point count.
 __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSmem &sm, int lo, int hi, double &D0, double &D1, int &cnt,
-                                                  int &staged_idx) {
+                                                  LaneCache &lc, bool init_normal) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double *const myrec = &sm.rec[warp][lane][0];
   for (int base = lo; base < hi; base += LIO_THREADS) {
     const int li = base + tid;
     const bool valid = li < hi;
     const int i = a.begin + li;
-    if (hi - lo > LIO_THREADS) staged_idx = -1;  // several tiles share the slots: nothing stays resident
+    if (hi - lo > LIO_THREADS) lc.staged_idx = -1, lc.have_pt = false;  // several tiles share the lanes: nothing stays resident
     int midx = -1;
     float mdis = 0.f;
-    double pi0 = 0, pi1 = 0, pi2 = 0;
     double pw[3] = {0, 0, 0}, var[6] = {0, 0, 0, 0, 0, 0};
     float loc[3] = {0, 0, 0};
-    long long key[3] = {0, 0, 0};
     uint32_t first = 0, count = 0;
     bool found = false;
 
@@ -263,12 +266,16 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
     if (first_tile) dbg_stamp(a.dbg, 0);
     // ---- phase 1: transform, voxel key, home-voxel probe
     if (valid) {
-      const double px = a.pts[3 * (size_t)i], py = a.pts[3 * (size_t)i + 1], pz = a.pts[3 * (size_t)i + 2];
+      if (!lc.have_pt) {
+        lc.px = a.pts[3 * (size_t)i], lc.py = a.pts[3 * (size_t)i + 1], lc.pz = a.pts[3 * (size_t)i + 2];
+        lc.have_pt = (hi - lo <= LIO_THREADS);
+      }
+      const double px = lc.px, py = lc.py, pz = lc.pz;
       // p_imu = extR p + extT ; p_w = R p_imu + t, narrowed to float (TransformLidar, voxel_map.cpp:522-526). No FMA contraction
       // on this chain: the float rounding of p_w decides the voxel key.
-      pi0 = __dadd_rn(dot3_rn(a.extR[0], a.extR[1], a.extR[2], px, py, pz), a.extT[0]);
-      pi1 = __dadd_rn(dot3_rn(a.extR[3], a.extR[4], a.extR[5], px, py, pz), a.extT[1]);
-      pi2 = __dadd_rn(dot3_rn(a.extR[6], a.extR[7], a.extR[8], px, py, pz), a.extT[2]);
+      const double pi0 = __dadd_rn(dot3_rn(a.extR[0], a.extR[1], a.extR[2], px, py, pz), a.extT[0]);
+      const double pi1 = __dadd_rn(dot3_rn(a.extR[3], a.extR[4], a.extR[5], px, py, pz), a.extT[1]);
+      const double pi2 = __dadd_rn(dot3_rn(a.extR[6], a.extR[7], a.extR[8], px, py, pz), a.extT[2]);
       pw[0] = (double)(float)__dadd_rn(dot3_rn(sm.R[0], sm.R[1], sm.R[2], pi0, pi1, pi2), sm.t[0]);
       pw[1] = (double)(float)__dadd_rn(dot3_rn(sm.R[3], sm.R[4], sm.R[5], pi0, pi1, pi2), sm.t[1]);
       pw[2] = (double)(float)__dadd_rn(dot3_rn(sm.R[6], sm.R[7], sm.R[8], pi0, pi1, pi2), sm.t[2]);
@@ -280,9 +287,17 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
         loc[j] = a.inv_voxel_exact ? (float)__dmul_rn(pw[j], a.inv_voxel_size) : (float)__ddiv_rn(pw[j], a.voxel_size);
         if (loc[j] < 0) loc[j] = (float)__dadd_rn((double)loc[j], -1.0);
         finite = finite && (fabsf(loc[j]) < 3.0e6f);
-        key[j] = (long long)loc[j];
       }
-      found = finite && probe(a.slots, a.hash_mask, key[0], key[1], key[2], first, count);
+      const long long key[3] = {(long long)loc[0], (long long)loc[1], (long long)loc[2]};
+      // the voxel of the previous iteration (key + candidate range cached in the slot tail) needs no second hash probe
+      if (finite && lc.staged_idx >= 0 && key_in_range(key[0], key[1], key[2]) &&
+          pack_key(key[0], key[1], key[2]) == *reinterpret_cast<const unsigned long long *>(myrec + 37)) {
+        found = true;
+        first = (uint32_t)lc.staged_idx;
+        count = reinterpret_cast<const uint32_t *>(myrec + 36)[1];
+      } else {
+        found = finite && probe(a.slots, a.hash_mask, key[0], key[1], key[2], first, count);
+      }
     }
 
     if (first_tile) dbg_stamp(a.dbg, 1);
@@ -290,7 +305,7 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
     // resident in the lane's slot (same plane as in the previous iteration of the persistent kernel) is not re-read.
     {
       const int cand0 = (found && count > 0) ? (int)first : -1;
-      const int want = (cand0 >= 0 && cand0 != staged_idx) ? cand0 : -1;
+      const int want = (cand0 >= 0 && cand0 != lc.staged_idx) ? cand0 : -1;
       const int half = lane >> 4, sub = lane & 15;
       if (__any_sync(0xffffffffu, want >= 0)) {
 #pragma unroll
@@ -303,7 +318,7 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
           }
         }
       }
-      if (cand0 >= 0) staged_idx = cand0;
+      lc.staged_idx = cand0;
       __syncwarp();
     }
 
@@ -362,6 +377,7 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
     if (found && best.idx < 0) {
       const double vsf = (double)a.voxel_size_f;
       const double ql = (double)(a.voxel_size_f / 4.0f);
+      const long long key[3] = {(long long)loc[0], (long long)loc[1], (long long)loc[2]};
       long long nk[3] = {key[0], key[1], key[2]};
 #pragma unroll
       for (int j = 0; j < 3; j++) {
@@ -392,18 +408,16 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
       const double2 *__restrict__ q2 = reinterpret_cast<const double2 *>(q);
       const double2 a0 = q2[0], a1 = q2[1], a2 = q2[2];
       const double c0 = a0.x, c1 = a0.y, c2_ = a1.x, n0 = a1.y, n1 = a2.x, n2 = a2.y;
-      double pv[22];
-#pragma unroll
-      for (int k = 0; k < 11; k++) {
-        const double2 v = q2[3 + k];
-        pv[2 * k] = v.x, pv[2 * k + 1] = v.y;
-      }
-      // point_world with the PRIOR pose (:425)
+      // p_imu recomputed (cheaper than keeping it live across the association) ; point_world with the PRIOR pose (:425)
+      const double px = lc.px, py = lc.py, pz = lc.pz;
+      const double pi0 = __dadd_rn(dot3_rn(a.extR[0], a.extR[1], a.extR[2], px, py, pz), a.extT[0]);
+      const double pi1 = __dadd_rn(dot3_rn(a.extR[3], a.extR[4], a.extR[5], px, py, pz), a.extT[1]);
+      const double pi2 = __dadd_rn(dot3_rn(a.extR[6], a.extR[7], a.extR[8], px, py, pz), a.extT[2]);
       const double w0 = sm.Rp[0] * pi0 + sm.Rp[1] * pi1 + sm.Rp[2] * pi2 + sm.tp[0];
       const double w1 = sm.Rp[3] * pi0 + sm.Rp[4] * pi1 + sm.Rp[5] * pi2 + sm.tp[1];
       const double w2 = sm.Rp[6] * pi0 + sm.Rp[7] * pi1 + sm.Rp[8] * pi2 + sm.tp[2];
       const double J[6] = {w0 - c0, w1 - c1, w2 - c2_, -n0, -n1, -n2};
-      const double sigma_l = quad6(pv, J);
+      const double sigma_l = quad6(q + 6, J);
       // n^T (Mp body_cov Mp^T) n = m^T body_cov m, m = Mp^T n   (:445-449)
       const double m0 = sm.Mp[0] * n0 + sm.Mp[3] * n1 + sm.Mp[6] * n2;
       const double m1 = sm.Mp[1] * n0 + sm.Mp[4] * n1 + sm.Mp[7] * n2;
@@ -429,6 +443,7 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
       a.match_plane[i] = midx;    // ptpl_list_ membership of this iteration
       a.dis_to_plane[i] = mdis;   // PointToPlane::dis_to_plane_ of this iteration (0 when unmatched)
       if (matched) a.normal_plane[i] = midx;  // pv.normal = plane.normal_ (:744), sticky across iterations
+      else if (init_normal) a.normal_plane[i] = -1;
     }
     cnt += __popc(__ballot_sync(0xffffffffu, matched));
 
@@ -440,8 +455,21 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
       dst[0] = make_double2(row[0], row[1]);
       dst[1] = make_double2(row[2], row[3]);
       dst[2] = make_double2(row[4], row[5]);
-      dst[3] = make_double2(row[6], row[7]);
-      dst[4] = make_double2(wgt, absd);
+      union {
+        double d;
+        struct { float f; uint32_t u; } s;
+      } pk;
+      pk.s.f = (float)absd, pk.s.u = count;
+      union {
+        double d;
+        unsigned long long u;
+      } kk;
+      {
+        const long long k0 = (long long)loc[0], k1 = (long long)loc[1], k2 = (long long)loc[2];
+        kk.u = (found && key_in_range(k0, k1, k2)) ? pack_key(k0, k1, k2) : ESIKF_KEY_EMPTY;
+      }
+      dst[3] = make_double2(row[6], wgt);
+      dst[4] = make_double2(pk.d, kk.d);
     }
     __syncwarp();
     {
@@ -449,8 +477,9 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
 #pragma unroll
       for (int s = 0; s < 8; s++) {
         const double *r = &sm.rec[warp][4 * s + t][REC_ROW];
-        const double v = r[g];
-        const double b = (g == 7) ? r[9] : r[8] * v;
+        const double wv = r[7];
+        const double v = (g == 7) ? ((wv != 0.0) ? 1.0 : 0.0) : r[g];  // a_7 = 1 for matched rows (R_inv > 0), else 0
+        const double b = (g == 7) ? (double)reinterpret_cast<const float *>(r + 8)[0] : wv * v;
         dmma_m8n8k4(D0, D1, v, b);
       }
     }
@@ -476,8 +505,9 @@ __global__ void __launch_bounds__(LIO_THREADS, 1) lio_residual_kernel(const LioK
   int cnt = 0;
   int lo, hi;
   lio_block_range(a.count, lo, hi);
-  int staged_idx = -1;
-  lio_process_range(a, sm, lo, hi, D0, D1, cnt, staged_idx);
+  LaneCache lc;
+  lc.staged_idx = -1, lc.have_pt = false, lc.px = lc.py = lc.pz = 0.f;
+  lio_process_range(a, sm, lo, hi, D0, D1, cnt, lc, a.init_normal != 0);
   reduce_info<LIO_WARPS>(sm.red, D0, D1, (double)cnt, true, a.partials, a.partial_stride, a.info, a.ctrl);
 }
 

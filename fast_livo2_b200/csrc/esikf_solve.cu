@@ -36,11 +36,14 @@ struct SolveArgs {
 struct SolveSmem {
   double P[19 * 19];
   double A[49];     // m x m information block
-  double M[49];     // I + A P_mm, transposed for the per-lane solve
   double HTz[8];
   double vec[19];
   double sol[19];
-  double W[19 * 38];  // literal mode workspace
+  double *W;        // literal mode (solve_mode 1) workspace, 19 x 38 doubles
+  double *K;        // literal mode, 19 x 19 doubles
+};
+struct SolveLiteralScratch {
+  double W[19 * 38];
   double K[19 * 19];
 };
 
@@ -340,6 +343,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lio_solve_kernel(const Solve
   if (a.ctrl->stop) return;
   __shared__ SolveSmem sm;
   __shared__ SolveIO io;
+  __shared__ SolveLiteralScratch lit;
+  if (threadIdx.x == 0) sm.W = lit.W, sm.K = lit.K;
+  __syncthreads();
   lio_solve_block(a, sm, io, false);
 }
 
@@ -466,6 +472,9 @@ __device__ __forceinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &s
 __global__ void __launch_bounds__(SOLVE_THREADS, 1) vio_solve_kernel(const SolveArgs a) {
   __shared__ SolveSmem sm;
   __shared__ SolveIO io;
+  __shared__ SolveLiteralScratch lit;
+  if (threadIdx.x == 0) sm.W = lit.W, sm.K = lit.K;
+  __syncthreads();
   vio_solve_block(a, sm, io, false);
 }
 
