@@ -192,6 +192,7 @@ def b200_arm(args, rank, world, local_rank):
 
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         import torch.distributed as dist_mod
 
         dist = dist_mod

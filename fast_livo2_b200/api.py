@@ -95,6 +95,7 @@ def load_library():
     lib.esikf_comm_unique_id.argtypes = [C.c_char_p]
     lib.esikf_comm_init.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p]
     lib.esikf_comm_rank.argtypes = [vp, ip, ip]
+    lib.esikf_shard_range.argtypes = [C.c_int32, C.c_int32, C.c_int32, ip, ip]
     lib.esikf_profile_kernel.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, fp]
     lib.esikf_set_kernel_timing.argtypes = [vp, C.c_int32]
     lib.esikf_set_phase_stamps.argtypes = [vp, C.c_int32]
@@ -109,7 +110,7 @@ EXPORTED_SYMBOLS = [
     "esikf_set_extrinsics", "esikf_map_upload", "esikf_map_patch", "esikf_lio_set_scan", "esikf_lio_run", "esikf_lio_fetch",
     "esikf_lio_update", "esikf_lio_fetch_point_cov", "esikf_vio_set_camera", "esikf_vio_set_image", "esikf_vio_set_patches",
     "esikf_vio_run", "esikf_vio_fetch", "esikf_vio_update", "esikf_vio_get_image_patch", "esikf_vio_set_ref_images",
-    "esikf_vio_warp_patches", "esikf_comm_unique_id", "esikf_comm_init", "esikf_comm_rank", "esikf_profile_kernel", "esikf_set_kernel_timing", "esikf_get_kernel_timing", "esikf_set_phase_stamps", "esikf_get_phase_stamps",
+    "esikf_vio_warp_patches", "esikf_comm_unique_id", "esikf_comm_init", "esikf_comm_rank", "esikf_shard_range", "esikf_profile_kernel", "esikf_set_kernel_timing", "esikf_get_kernel_timing", "esikf_set_phase_stamps", "esikf_get_phase_stamps",
 ]
 
 
@@ -349,6 +350,14 @@ class Context:
         ms = C.c_float(0)
         self._ck(self.lib.esikf_profile_kernel(self.h, which, arg, reps, int(flush_l2), C.byref(ms)))
         return float(ms.value)
+
+
+def shard_range(n, rank, nranks):
+    lib = load_library()
+    b, c = C.c_int32(0), C.c_int32(0)
+    if lib.esikf_shard_range(n, rank, nranks, C.byref(b), C.byref(c)) != 0:
+        raise EsikfError("esikf_shard_range: bad argument")
+    return b.value, c.value
 
 
 def comm_unique_id() -> bytes:

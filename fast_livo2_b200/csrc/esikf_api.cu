@@ -780,6 +780,13 @@ int esikf_comm_init(esikf_ctx *ctx, int32_t rank, int32_t nranks, const char uni
   ctx->rank = rank, ctx->nranks = nranks;
   return ESIKF_OK;
 }
+int esikf_shard_range(int32_t n, int32_t rank, int32_t nranks, int32_t *begin, int32_t *count) {
+  if (n < 0 || nranks < 1 || rank < 0 || rank >= nranks || !begin || !count) return ESIKF_ERR_ARG;
+  int b, c;
+  shard_of(n, rank, nranks, b, c);
+  *begin = b, *count = c;
+  return ESIKF_OK;
+}
 int esikf_comm_rank(const esikf_ctx *ctx, int32_t *rank, int32_t *nranks) {
   if (!ctx) return ESIKF_ERR_ARG;
   if (rank) *rank = ctx->rank;

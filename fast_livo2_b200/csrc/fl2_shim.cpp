@@ -1,0 +1,358 @@
+// fl2_shim.cpp — see fl2_shim.hpp. Host C++ only (no CUDA here): fills the reference-shaped member fields from / into
+// the packed buffers of the C ABI (libesikf_b200.so, resolved at load time through the dynamic linker).
+#include "fl2_shim.hpp"
+
+#include <cmath>
+#include <cstring>
+
+namespace fl2b200 {
+
+StatesGroup::StatesGroup() {
+  for (int i = 0; i < 361; i++) cov[i] = 0.0;
+  for (int i = 0; i < 19; i++) cov[i * 19 + i] = 0.01;   // INIT_COV, include/common_lib.h:31,137
+  cov[6 * 19 + 6] = 0.00001;                              // :138
+  for (int i = 10; i < 19; i++) cov[i * 19 + i] = 0.00001;  // :139
+}
+void StatesGroup::pack(double *s) const {
+  memcpy(s, rot_end.m, 9 * sizeof(double));
+  memcpy(s + 9, pos_end.v, 3 * sizeof(double));
+  s[12] = inv_expo_time;
+  memcpy(s + 13, vel_end.v, 3 * sizeof(double));
+  memcpy(s + 16, bias_g.v, 3 * sizeof(double));
+  memcpy(s + 19, bias_a.v, 3 * sizeof(double));
+  memcpy(s + 22, gravity.v, 3 * sizeof(double));
+  memcpy(s + 25, cov, 361 * sizeof(double));
+}
+void StatesGroup::unpack(const double *s) {
+  memcpy(rot_end.m, s, 9 * sizeof(double));
+  memcpy(pos_end.v, s + 9, 3 * sizeof(double));
+  inv_expo_time = s[12];
+  memcpy(vel_end.v, s + 13, 3 * sizeof(double));
+  memcpy(bias_g.v, s + 16, 3 * sizeof(double));
+  memcpy(bias_a.v, s + 19, 3 * sizeof(double));
+  memcpy(gravity.v, s + 22, 3 * sizeof(double));
+  memcpy(cov, s + 25, 361 * sizeof(double));
+}
+
+pointWithVar::pointWithVar() {
+  for (int i = 0; i < 9; i++) var_nostate.m[i] = body_var.m[i] = var.m[i] = point_crossmat.m[i] = 0.0;
+}
+
+VoxelOctoTree::~VoxelOctoTree() {
+  for (int i = 0; i < 8; i++) delete leaves_[i];
+  delete plane_ptr_;
+}
+
+static void flatten_node(const VoxelOctoTree *node, int layer, int max_layer, int path, FlatVoxelMap &out) {
+  if (node->plane_ptr_ && node->plane_ptr_->is_plane_) {
+    const VoxelPlane &p = *node->plane_ptr_;
+    esikf_plane f;
+    memset(&f, 0, sizeof(f));
+    for (int k = 0; k < 3; k++) f.center[k] = p.center_[k], f.normal[k] = p.normal_[k];
+    int t = 0;
+    for (int i = 0; i < 6; i++)
+      for (int j = i; j < 6; j++) f.plane_var[t++] = p.plane_var_[i * 6 + j];
+    f.d = p.d_;
+    f.radius = p.radius_;
+    f.layer = layer;
+    f.path = path;
+    out.planes.push_back(f);
+    out.plane_src.push_back(&p);
+    return;
+  }
+  if (layer < max_layer)
+    for (int l = 0; l < 8; l++)
+      if (node->leaves_[l] != nullptr) flatten_node(node->leaves_[l], layer + 1, max_layer, path | (l << (3 * layer)), out);
+}
+
+bool FlattenVoxelMap(const VoxelMap &map, const VoxelMapConfig &cfg, FlatVoxelMap &out, std::string *err) {
+  out.keys.clear(), out.first.clear(), out.count.clear(), out.planes.clear(), out.plane_src.clear();
+  const float vs = (float)cfg.max_voxel_size_;
+  for (const auto &kv : map) {
+    const VoxelOctoTree *root = kv.second;
+    if (!root) continue;
+    // the device derives the root centre / quarter length from the key (src/voxel_map.cpp:578-581): check the host agrees
+    const double c[3] = {(0.5 + kv.first.x) * vs, (0.5 + kv.first.y) * vs, (0.5 + kv.first.z) * vs};
+    for (int k = 0; k < 3; k++)
+      if (root->voxel_center_[k] != c[k] || root->quater_length_ != vs / 4) {
+        if (err) *err = "root voxel centre / quarter length does not follow (0.5 + key) * voxel_size";
+        return false;
+      }
+    out.keys.push_back(kv.first.x), out.keys.push_back(kv.first.y), out.keys.push_back(kv.first.z);
+    out.first.push_back((int32_t)out.planes.size());
+    flatten_node(root, 0, cfg.max_layer_, 0, out);
+    out.count.push_back((int32_t)out.planes.size() - out.first.back());
+  }
+  return true;
+}
+
+VoxelMapManager::VoxelMapManager(VoxelMapConfig &config_setting, VoxelMap &voxel_map, int device) : config_setting_(config_setting), voxel_map_(voxel_map) {
+  last_status_ = esikf_create(&ctx_, device);
+  if (last_status_ != 0) last_error_ = "esikf_create failed (no sm_100 CUDA device?) — there is no CPU fallback";
+}
+VoxelMapManager::~VoxelMapManager() { esikf_destroy(ctx_); }
+
+void VoxelMapManager::SyncDeviceMap() {
+  if (!ctx_) return;
+  std::string err;
+  if (!FlattenVoxelMap(voxel_map_, config_setting_, flat_, &err)) {
+    last_status_ = ESIKF_ERR_ARG, last_error_ = err;
+    return;
+  }
+  last_status_ = esikf_map_upload(ctx_, flat_.keys.data(), flat_.first.data(), flat_.count.data(), (int32_t)flat_.first.size(), flat_.planes.data(),
+                                  (int32_t)flat_.planes.size(), config_setting_.max_voxel_size_);
+  if (last_status_) last_error_ = esikf_last_error(ctx_);
+  map_synced_ = (last_status_ == 0);
+}
+
+// include/voxel_map.h:229 / src/voxel_map.cpp:338-511
+void VoxelMapManager::StateEstimation(StatesGroup &state_propagat) {
+  if (!ctx_) return;
+  if (!map_synced_) SyncDeviceMap();
+  if (!map_synced_) return;
+  esikf_extrinsics ext;
+  memset(&ext, 0, sizeof(ext));
+  memcpy(ext.extR, extR_.m, sizeof(ext.extR));
+  memcpy(ext.extT, extT_.v, sizeof(ext.extT));
+  ext.Rcl[0] = ext.Rcl[4] = ext.Rcl[8] = 1.0;
+  if ((last_status_ = esikf_set_extrinsics(ctx_, &ext)) != 0) {
+    last_error_ = esikf_last_error(ctx_);
+    return;
+  }
+  const int n = feats_down_size_;
+  esikf_lio_cfg cfg;
+  cfg.voxel_size = config_setting_.max_voxel_size_, cfg.sigma_num = config_setting_.sigma_num_;
+  cfg.dept_err = config_setting_.dept_err_, cfg.beam_err = config_setting_.beam_err_;
+  cfg.max_layer = config_setting_.max_layer_, cfg.max_iterations = config_setting_.max_iterations_;
+  double sin[ESIKF_STATE_DOUBLES], sprop[ESIKF_STATE_DOUBLES], sout[ESIKF_STATE_DOUBLES];
+  state_.pack(sin);
+  state_propagat.pack(sprop);
+  std::vector<int32_t> match(n), normal(n);
+  std::vector<float> dis(n);
+  esikf_lio_stats stats;
+  static_assert(sizeof(PointXYZ) == 12, "xyz float32");
+  last_status_ = esikf_lio_update(ctx_, n ? &feats_down_body_[0].x : nullptr, n, sin, sprop, &cfg, sout, &stats, match.data(), normal.data(), dis.data());
+  if (last_status_) {
+    last_error_ = esikf_last_error(ctx_);
+    return;
+  }
+  state_.unpack(sout);                 // _state = voxelmap_manager->state_  (LIVMapper.cpp:371)
+  position_last_ = state_.pos_end;     // src/voxel_map.cpp:492
+  effct_feat_num_ = stats.iters > 0 ? stats.effct_feat_num[stats.iters - 1] : 0;
+  if (!fill_point_lists_) return;
+  // body_cov_list_ / cross_mat_list_ (LIVMapper.cpp:418-419), pv_list_ (:372) and ptpl_list_ (:446)
+  std::vector<double> bc((size_t)n * 9), cm((size_t)n * 9);
+  if ((last_status_ = esikf_lio_fetch_point_cov(ctx_, bc.data(), cm.data())) != 0) {
+    last_error_ = esikf_last_error(ctx_);
+    return;
+  }
+  body_cov_list_.assign(n, M3D()), cross_mat_list_.assign(n, M3D());
+  std::vector<pointWithVar>().swap(pv_list_);
+  pv_list_.resize(n);
+  ptpl_list_.clear();
+  const double *R = state_.rot_end.m;
+  for (int i = 0; i < n; i++) {
+    memcpy(body_cov_list_[i].m, &bc[(size_t)i * 9], 72);
+    memcpy(cross_mat_list_[i].m, &cm[(size_t)i * 9], 72);
+    pointWithVar &pv = pv_list_[i];
+    pv.point_b[0] = feats_down_body_[i].x, pv.point_b[1] = feats_down_body_[i].y, pv.point_b[2] = feats_down_body_[i].z;
+    pv.body_var = body_cov_list_[i];
+    // point_w / var are recomputed by the caller with the posterior state right after the call (LIVMapper.cpp:413-423);
+    // point_w is provided here with the posterior pose for convenience.
+    double pi[3], pw[3];
+    for (int r = 0; r < 3; r++) pi[r] = extR_.m[3 * r] * pv.point_b[0] + extR_.m[3 * r + 1] * pv.point_b[1] + extR_.m[3 * r + 2] * pv.point_b[2] + extT_[r];
+    for (int r = 0; r < 3; r++) pw[r] = R[3 * r] * pi[0] + R[3 * r + 1] * pi[1] + R[3 * r + 2] * pi[2] + state_.pos_end[r];
+    for (int r = 0; r < 3; r++) pv.point_w[r] = (double)(float)pw[r];
+    if (normal[i] >= 0) pv.normal = flat_.plane_src[normal[i]]->normal_;  // pv.normal (voxel_map.cpp:744), zero if never matched
+    if (match[i] >= 0) {
+      const VoxelPlane &pl = *flat_.plane_src[match[i]];
+      PointToPlane q;
+      q.point_b_ = pv.point_b, q.point_w_ = pv.point_w, q.normal_ = pl.normal_, q.center_ = pl.center_;
+      memcpy(q.plane_var_, pl.plane_var_, sizeof(q.plane_var_));
+      q.body_cov_ = pv.body_var;
+      q.layer_ = flat_.planes[match[i]].layer, q.d_ = pl.d_, q.is_valid_ = true, q.dis_to_plane_ = dis[i];
+      ptpl_list_.push_back(q);
+    }
+  }
+}
+
+VIOManager::VIOManager(esikf_ctx *shared_ctx) : ctx_(shared_ctx) {}
+
+void VIOManager::initializeVIO() {
+  if (!ctx_) return;
+  esikf_extrinsics ext;
+  memcpy(ext.extR, extR.m, sizeof(ext.extR));
+  memcpy(ext.extT, extT.v, sizeof(ext.extT));
+  memcpy(ext.Rcl, Rcl.m, sizeof(ext.Rcl));
+  memcpy(ext.Pcl, Pcl.v, sizeof(ext.Pcl));
+  last_status_ = esikf_set_extrinsics(ctx_, &ext);
+  esikf_vio_cfg cfg;
+  cfg.img_point_cov = img_point_cov, cfg.patch_pyrimid_level = patch_pyrimid_level, cfg.max_iterations = max_iterations;
+  cfg.exposure_estimate_en = exposure_estimate_en ? 1 : 0, cfg.pad_ = 0;
+  if (!last_status_) last_status_ = esikf_vio_set_camera(ctx_, &cam, &cfg);
+  if (last_status_) last_error_ = esikf_last_error(ctx_);
+}
+
+// include/vio.h:153 / src/vio.cpp:784-802
+void VIOManager::computeJacobianAndUpdateEKF(const GrayImage &img) {
+  if (!ctx_ || !state || !state_propagat || !visual_submap) return;
+  if (total_points == 0) return;  // src/vio.cpp:786
+  const int n = total_points, L = patch_pyrimid_level;
+  std::vector<double> pos((size_t)n * 3);
+  std::vector<float> wp((size_t)n * 64 * L);
+  std::vector<int32_t> sl(n);
+  for (int i = 0; i < n; i++) {
+    for (int k = 0; k < 3; k++) pos[(size_t)3 * i + k] = visual_submap->voxel_points_pos[i][k];
+    memcpy(&wp[(size_t)i * 64 * L], visual_submap->warp_patch[i].data(), sizeof(float) * 64 * L);
+    sl[i] = visual_submap->search_levels[i];
+  }
+  double sin[ESIKF_STATE_DOUBLES], sprop[ESIKF_STATE_DOUBLES], sout[ESIKF_STATE_DOUBLES];
+  state->pack(sin);
+  state_propagat->pack(sprop);
+  visual_submap->errors.resize(n);
+  esikf_vio_stats stats;
+  last_status_ = esikf_vio_update(ctx_, img.data, img.cols, img.rows, pos.data(), wp.data(), sl.data(), visual_submap->inv_expo_list.data(), n, sin, sprop,
+                                  sout, &stats, visual_submap->errors.data());
+  if (last_status_) {
+    last_error_ = esikf_last_error(ctx_);
+    return;
+  }
+  state->unpack(sout);
+}
+
+}  // namespace fl2b200
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C entry points for the parity tests (Python / ctypes): rebuild a pointer octree from flat arrays, run the shim on it.
+using namespace fl2b200;
+
+static void build_tree(VoxelMap &map, const VoxelMapConfig &cfg, const int64_t *keys, const int32_t *first, const int32_t *count, int n_roots,
+                       const esikf_plane *planes) {
+  const float vs = (float)cfg.max_voxel_size_;
+  for (int r = 0; r < n_roots; r++) {
+    VOXEL_LOCATION loc(keys[3 * r], keys[3 * r + 1], keys[3 * r + 2]);
+    VoxelOctoTree *root = new VoxelOctoTree;
+    root->plane_ptr_ = new VoxelPlane;
+    root->quater_length_ = vs / 4;
+    root->voxel_center_[0] = (0.5 + loc.x) * vs, root->voxel_center_[1] = (0.5 + loc.y) * vs, root->voxel_center_[2] = (0.5 + loc.z) * vs;
+    root->init_octo_ = true;
+    map[loc] = root;
+    for (int c = 0; c < count[r]; c++) {
+      const esikf_plane &f = planes[first[r] + c];
+      VoxelOctoTree *node = root;
+      for (int l = 0; l < f.layer; l++) {
+        const int leaf = (f.path >> (3 * l)) & 7;
+        if (!node->leaves_[leaf]) {
+          VoxelOctoTree *ch = new VoxelOctoTree;
+          ch->plane_ptr_ = new VoxelPlane;
+          ch->layer_ = l + 1;
+          const int xyz[3] = {(leaf >> 2) & 1, (leaf >> 1) & 1, leaf & 1};
+          for (int k = 0; k < 3; k++) ch->voxel_center_[k] = node->voxel_center_[k] + (2 * xyz[k] - 1) * node->quater_length_;
+          ch->quater_length_ = node->quater_length_ / 2;
+          ch->init_octo_ = true;
+          node->leaves_[leaf] = ch;
+        }
+        node = node->leaves_[leaf];
+      }
+      VoxelPlane &p = *node->plane_ptr_;
+      for (int k = 0; k < 3; k++) p.center_[k] = f.center[k], p.normal_[k] = f.normal[k];
+      int t = 0;
+      for (int i = 0; i < 6; i++)
+        for (int j = i; j < 6; j++) p.plane_var_[i * 6 + j] = p.plane_var_[j * 6 + i] = f.plane_var[t++];
+      p.d_ = f.d, p.radius_ = f.radius, p.is_plane_ = true, p.is_init_ = true;
+    }
+  }
+}
+
+extern "C" {
+
+// CPU-only: flat arrays -> pointer octree -> FlattenVoxelMap -> flat arrays (sizes returned; buffers sized like the input).
+int fl2_shim_flatten_roundtrip(const int64_t *keys, const int32_t *first, const int32_t *count, int n_roots, const esikf_plane *planes, int n_planes,
+                               double voxel_size, int max_layer, int64_t *keys_out, int32_t *first_out, int32_t *count_out, esikf_plane *planes_out) {
+  VoxelMapConfig cfg;
+  cfg.max_voxel_size_ = voxel_size, cfg.max_layer_ = max_layer;
+  VoxelMap map;
+  build_tree(map, cfg, keys, first, count, n_roots, planes);
+  FlatVoxelMap out;
+  std::string err;
+  const bool ok = FlattenVoxelMap(map, cfg, out, &err);
+  for (auto &kv : map) delete kv.second;
+  if (!ok || (int)out.first.size() != n_roots || (int)out.planes.size() != n_planes) return -1;
+  memcpy(keys_out, out.keys.data(), out.keys.size() * sizeof(int64_t));
+  memcpy(first_out, out.first.data(), out.first.size() * sizeof(int32_t));
+  memcpy(count_out, out.count.data(), out.count.size() * sizeof(int32_t));
+  memcpy(planes_out, out.planes.data(), out.planes.size() * sizeof(esikf_plane));
+  return 0;
+}
+
+// GPU: VoxelMapManager::StateEstimation + VIOManager::computeJacobianAndUpdateEKF through the shim classes.
+// vio arrays may be null (LIO only). Returns 0 or the first failing esikf_status.
+int fl2_shim_run(const int64_t *keys, const int32_t *first, const int32_t *count, int n_roots, const esikf_plane *planes, int n_planes,
+                 const esikf_lio_cfg *lcfg, const esikf_extrinsics *ext, const float *pts, int n, const double *state_in, const double *state_prop,
+                 double *lio_state_out, int32_t *n_effective, int32_t *n_ptpl, double *normals_out /* n x 3 */, const esikf_camera *cam,
+                 const esikf_vio_cfg *vcfg, const uint8_t *img, int n_patches, const double *pos, const float *warp_patch, const int32_t *search_levels,
+                 const double *inv_expo, double *vio_state_out, float *errors_out) {
+  (void)n_planes;
+  VoxelMapConfig cfg;
+  cfg.max_voxel_size_ = lcfg->voxel_size, cfg.max_layer_ = lcfg->max_layer, cfg.max_iterations_ = lcfg->max_iterations;
+  cfg.beam_err_ = lcfg->beam_err, cfg.dept_err_ = lcfg->dept_err, cfg.sigma_num_ = lcfg->sigma_num;
+  VoxelMap map;
+  build_tree(map, cfg, keys, first, count, n_roots, planes);
+  int rc = 0;
+  {
+    VoxelMapManager mgr(cfg, map, 0);
+    if (mgr.last_status_) rc = mgr.last_status_;
+    memcpy(mgr.extR_.m, ext->extR, 72);
+    memcpy(mgr.extT_.v, ext->extT, 24);
+    mgr.feats_down_body_.resize(n);
+    memcpy(mgr.feats_down_body_.data(), pts, (size_t)n * 12);
+    mgr.feats_down_size_ = n;
+    mgr.state_.unpack(state_in);              // voxelmap_manager->state_ = _state  (LIVMapper.cpp:257)
+    StatesGroup prop;
+    prop.unpack(state_prop);
+    if (!rc) {
+      mgr.SyncDeviceMap();
+      mgr.StateEstimation(prop);              // LIVMapper.cpp:370
+      rc = mgr.last_status_;
+    }
+    if (!rc) {
+      mgr.state_.pack(lio_state_out);
+      *n_effective = mgr.effct_feat_num_;
+      *n_ptpl = (int32_t)mgr.ptpl_list_.size();
+      for (int i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) normals_out[3 * i + k] = mgr.pv_list_[i].normal[k];
+    }
+    if (!rc && cam && n_patches > 0) {
+      VIOManager vio(mgr.context());
+      StatesGroup st = mgr.state_, stp = mgr.state_;
+      SubSparseMap sub;
+      const int L = vcfg->patch_pyrimid_level;
+      for (int i = 0; i < n_patches; i++) {
+        V3D p;
+        for (int k = 0; k < 3; k++) p[k] = pos[3 * i + k];
+        sub.voxel_points_pos.push_back(p);
+        sub.warp_patch.emplace_back(warp_patch + (size_t)i * 64 * L, warp_patch + (size_t)(i + 1) * 64 * L);
+        sub.search_levels.push_back(search_levels[i]);
+        sub.inv_expo_list.push_back(inv_expo[i]);
+      }
+      vio.state = &st, vio.state_propagat = &stp, vio.visual_submap = &sub, vio.total_points = n_patches;
+      vio.patch_pyrimid_level = L, vio.max_iterations = vcfg->max_iterations, vio.img_point_cov = vcfg->img_point_cov;
+      vio.exposure_estimate_en = vcfg->exposure_estimate_en != 0;
+      vio.cam = *cam;
+      memcpy(vio.Rcl.m, ext->Rcl, 72), memcpy(vio.Pcl.v, ext->Pcl, 24), memcpy(vio.extR.m, ext->extR, 72), memcpy(vio.extT.v, ext->extT, 24);
+      vio.initializeVIO();
+      GrayImage im;
+      im.data = img, im.cols = cam->width, im.rows = cam->height;
+      if (!vio.last_status_) vio.computeJacobianAndUpdateEKF(im);
+      rc = vio.last_status_;
+      if (!rc) {
+        st.pack(vio_state_out);
+        for (int i = 0; i < n_patches; i++) errors_out[i] = sub.errors[i];
+      }
+    }
+  }
+  for (auto &kv : map) delete kv.second;
+  return rc;
+}
+
+}  // extern "C"

@@ -199,6 +199,8 @@ int esikf_vio_warp_patches(esikf_ctx *ctx, int32_t n, const int32_t *ref_img_ind
 int esikf_comm_unique_id(char out[128]);
 int esikf_comm_init(esikf_ctx *ctx, int32_t rank, int32_t nranks, const char unique_id[128]);
 int esikf_comm_rank(const esikf_ctx *ctx, int32_t *rank, int32_t *nranks);
+/* The contiguous slice [begin, begin+count) of n units owned by `rank` (host-only helper, no device needed). */
+int esikf_shard_range(int32_t n, int32_t rank, int32_t nranks, int32_t *begin, int32_t *count);
 
 /* ---------------------------------------------------------------- measurement hooks (bench.py)
  * Average device time (ms, CUDA events on esikf_stream) of `reps` back-to-back launches of one

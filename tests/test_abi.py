@@ -1,0 +1,71 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/esikf_b200.h declares
+(no compute calls without a GPU), struct layouts agree between the header and the ctypes binding, the context refuses
+to exist without a device (no CPU fallback), and the C++ shim's map flattener round-trips."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from fast_livo2_b200 import api
+from fast_livo2_b200 import synthetic as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "esikf_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(esikf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = api.load_library()
+    names = _header_functions()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/esikf_b200.h but not exported by libesikf_b200.so"
+    assert set(api.EXPORTED_SYMBOLS) <= set(names)
+
+
+def test_struct_layouts_match_header():
+    assert S.PLANE_DTYPE.itemsize == 256 and S.PLANE_DTYPE.fields["d"][1] == 216 and S.PLANE_DTYPE.fields["layer"][1] == 224
+    assert C.sizeof(api.LioCfgC) == 40 and C.sizeof(api.ExtrinsicsC) == 192 and C.sizeof(api.CameraC) == 88 and C.sizeof(api.VioCfgC) == 24
+    assert C.sizeof(api.LioStatsC) == 4 * 18 + 8 * (8 + 8 * 36 + 8 * 6 + 8 * 19)
+    assert C.sizeof(api.VioStatsC) == 4 * 18 + 4 * 64 + 8 * 64 * (49 + 7 + 19)
+    assert api.STATE_DOUBLES == 386 == S.STATE_PACK
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(api.EsikfError):
+        api.Context(0)
+
+
+def test_shim_flattener_roundtrip(small_frame):
+    """fl2_shim: flat arrays -> pointer octree (VoxelOctoTree mirrors) -> FlattenVoxelMap -> identical candidate lists."""
+    path = os.path.join(ROOT, "fast_livo2_b200", "libfl2_shim.so")
+    if not os.path.exists(path):
+        pytest.skip("shim not built")
+    api.load_library()
+    shim = C.CDLL(path)
+    m = small_frame["map"]
+    k, f, c, p = (np.ascontiguousarray(m["keys"]), np.ascontiguousarray(m["first"]), np.ascontiguousarray(m["count"]), np.ascontiguousarray(m["planes"]))
+    ko, fo, co, po = np.zeros_like(k), np.zeros_like(f), np.zeros_like(c), np.zeros_like(p)
+    rc = shim.fl2_shim_flatten_roundtrip(k.ctypes.data_as(C.c_void_p), f.ctypes.data_as(C.c_void_p), c.ctypes.data_as(C.c_void_p), len(f),
+                                         p.ctypes.data_as(C.c_void_p), len(p), C.c_double(0.5), 2, ko.ctypes.data_as(C.c_void_p),
+                                         fo.ctypes.data_as(C.c_void_p), co.ctypes.data_as(C.c_void_p), po.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    src = {tuple(kk): (ff, cc) for kk, ff, cc in zip(k.tolist(), f, c)}
+    assert len(src) == len(fo)
+    for kk, ff, cc in zip(ko.tolist(), fo, co):
+        f0, c0 = src[tuple(kk)]
+        assert cc == c0
+        for j in range(cc):
+            a, b = p[f0 + j], po[ff + j]
+            for name in ("center", "normal", "plane_var", "d", "radius", "layer", "path"):
+                assert np.array_equal(a[name], b[name]), name
