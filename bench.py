@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-baseline-frames", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"], help="N>1: in-kernel NVLink peer-memory all-reduce (default) or NCCL per iteration")
     return ap.parse_args()
 
 
@@ -205,9 +206,14 @@ def b200_arm(args, rank, world, local_rank):
     fr = make_workload(args)
     ctx = api.Context(local_rank)
     if world > 1:
-        uid = [api.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ctx.comm_init(rank, world, uid[0])
+        if args.comm == "p2p":
+            handles = [None] * world
+            dist.all_gather_object(handles, ctx.peer_export())
+            ctx.peer_attach(rank, world, handles)
+        else:
+            uid = [api.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            ctx.comm_init(rank, world, uid[0])
     ctx.set_extrinsics(fr["ext"])
     ctx.map_upload(fr["map"], fr["lio_cfg"].voxel_size)
     ctx.vio_set_camera(fr["cam_cfg"], fr["vio_cfg"])
@@ -307,9 +313,10 @@ def b200_arm(args, rank, world, local_rank):
     d2h = 2 * 386 * 8 + n * 12 + npatch * 4 + 1288 + 33096  # states + match/normal/dis + errors + stats structs
 
     # ---------------- per-kernel device times inside the loop (separate instrumented pass) -> roofline of the LIO residual kernel
-    ctx.set_kernel_timing(True)
+    per_iter_ok = (world == 1) or args.comm == "nccl"  # per-launch event timing uses the per-iteration launch path
+    ctx.set_kernel_timing(per_iter_ok)
     res_ms, patch_ms, solve_ms = [], [], []
-    for k in range(max(5, min(K, 10))):
+    for k in range(max(5, min(K, 10)) if per_iter_ok else 0):
         with torch.cuda.stream(ext_stream):
             flush.zero_()
         ctx.lio_run(prior_h, prior_h, fr["lio_cfg"])
@@ -322,9 +329,9 @@ def b200_arm(args, rank, world, local_rank):
             base = (L - 1 - lvl) * fr["vio_cfg"].max_iterations
             patch_ms += list(tm["vio_patch_ms"][base: base + rv["iters_per_level"][lvl]])
     ctx.set_kernel_timing(False)
-    k1_ms = float(np.mean(res_ms))
     k1_iso_ms = ctx.profile_kernel(0, reps=20, flush_l2=True)
     k1_iso_warm_ms = ctx.profile_kernel(0, reps=20, flush_l2=False)
+    k1_ms = float(np.mean(res_ms)) if res_ms else k1_iso_ms
     k2_iso_ms = ctx.profile_kernel(2, arg=0, reps=20, flush_l2=False)
     k3_iso_ms = ctx.profile_kernel(1, reps=20, flush_l2=False)
     peak, peak_src = measured_peak_hbm()
@@ -338,7 +345,8 @@ def b200_arm(args, rank, world, local_rank):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n_pts": n, "n_patches": npatch, "image": "640x512", "levels": L, "iters_per_step": iters_per_step,
                        "lio_iters": int(rl["iters"]), "vio_iters": int(rv["total_iters"]), "l2": "flushed between steps (256 MiB write, untimed)",
-                       "parallelism": f"points/patches sharded over {world} rank(s), 1 all-reduce of 72 doubles per iteration" if world > 1 else "single GPU",
+                       "parallelism": (f"points/patches sharded over {world} ranks, 72-double information buffer all-reduced per iteration " +
+                                       ("inside the persistent kernel over NVLink peer memory" if args.comm == "p2p" else "with ncclAllReduce")) if world > 1 else "single GPU",
                        "map_planes": int(len(fr["map"]["planes"])), "matched_points": int(rl["M"][-1])},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * float(t_e2e.item()) / K},
@@ -349,7 +357,7 @@ def b200_arm(args, rank, world, local_rank):
                          "bytes_per_point": LIO_BYTES_PER_POINT, "points_per_launch": shard_pts, "avg_launch_ms_in_loop": k1_ms,
                          "avg_launch_ms_isolated_l2_flushed": k1_iso_ms, "avg_launch_ms_isolated_l2_warm": k1_iso_warm_ms,
                          "vio_patch_kernel_ms_in_loop": float(np.mean(patch_ms)) if patch_ms else None, "vio_patch_kernel_ms_isolated": k2_iso_ms,
-                         "lio_solve_kernel_ms_in_loop": float(np.mean(solve_ms)), "lio_solve_kernel_ms_isolated": k3_iso_ms,
+                         "lio_solve_kernel_ms_in_loop": float(np.mean(solve_ms)) if solve_ms else None, "lio_solve_kernel_ms_isolated": k3_iso_ms,
                          "vio_achieved_gbs": (VIO_BYTES_PER_PATCH * npatch / world) / (float(np.mean(patch_ms)) * 1e-3) / 1e9 if patch_ms else None},
         }
         if world == 1 and not args.no_cpu_baseline:

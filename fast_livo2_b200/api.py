@@ -95,6 +95,8 @@ def load_library():
     lib.esikf_comm_unique_id.argtypes = [C.c_char_p]
     lib.esikf_comm_init.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p]
     lib.esikf_comm_rank.argtypes = [vp, ip, ip]
+    lib.esikf_peer_export.argtypes = [vp, C.c_char_p]
+    lib.esikf_peer_attach.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p]
     lib.esikf_shard_range.argtypes = [C.c_int32, C.c_int32, C.c_int32, ip, ip]
     lib.esikf_profile_kernel.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, fp]
     lib.esikf_set_kernel_timing.argtypes = [vp, C.c_int32]
@@ -110,7 +112,7 @@ EXPORTED_SYMBOLS = [
     "esikf_set_extrinsics", "esikf_map_upload", "esikf_map_patch", "esikf_lio_set_scan", "esikf_lio_run", "esikf_lio_fetch",
     "esikf_lio_update", "esikf_lio_fetch_point_cov", "esikf_vio_set_camera", "esikf_vio_set_image", "esikf_vio_set_patches",
     "esikf_vio_run", "esikf_vio_fetch", "esikf_vio_update", "esikf_vio_get_image_patch", "esikf_vio_set_ref_images",
-    "esikf_vio_warp_patches", "esikf_comm_unique_id", "esikf_comm_init", "esikf_comm_rank", "esikf_shard_range", "esikf_profile_kernel", "esikf_set_kernel_timing", "esikf_get_kernel_timing", "esikf_set_phase_stamps", "esikf_get_phase_stamps",
+    "esikf_vio_warp_patches", "esikf_comm_unique_id", "esikf_comm_init", "esikf_comm_rank", "esikf_shard_range", "esikf_peer_export", "esikf_peer_attach", "esikf_profile_kernel", "esikf_set_kernel_timing", "esikf_get_kernel_timing", "esikf_set_phase_stamps", "esikf_get_phase_stamps",
 ]
 
 
@@ -345,6 +347,15 @@ class Context:
         f = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
         self._ck(self.lib.esikf_get_kernel_timing(self.h, f(a), f(b), f(c), f(d)))
         return dict(lio_residual_ms=a, lio_solve_ms=b, vio_patch_ms=c, vio_solve_ms=d)
+
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.esikf_peer_export(self.h, buf))
+        return buf.raw
+
+    def peer_attach(self, rank, nranks, handles):
+        """handles: list of the 64-byte IPC handles of every rank, in rank order."""
+        self._ck(self.lib.esikf_peer_attach(self.h, rank, nranks, b"".join(handles)))
 
     def profile_kernel(self, which, arg=0, reps=20, flush_l2=True):
         ms = C.c_float(0)

@@ -145,6 +145,12 @@ struct esikf_ctx {
   // multi-GPU
   int rank = 0, nranks = 1;
   ncclComm_t comm = nullptr;
+  // NVLink peer-memory all-reduce inside the persistent kernels
+  double *mailbox = nullptr;             // own mailbox [2][nranks<=8][PEER_SLOT]
+  std::vector<double *> peer_ptrs;       // mailbox of every rank as mapped into this process
+  DevBuf<double *> peer_ptrs_dev;
+  bool p2p = false;
+  unsigned long long peer_seq = 0;
 
   // measurement
   bool timing = false;
@@ -256,6 +262,10 @@ void esikf_destroy(esikf_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+  for (size_t r = 0; r < ctx->peer_ptrs.size(); r++)
+    if ((int)r != ctx->rank && ctx->peer_ptrs[r]) cudaIpcCloseMemHandle(ctx->peer_ptrs[r]);
+  if (ctx->mailbox) cudaFree(ctx->mailbox);
+  ctx->peer_ptrs_dev.release();
   ctx->slots.release(), ctx->planes.release(), ctx->pts.release(), ctx->pre.release(), ctx->match_plane.release();
   ctx->normal_plane.release(), ctx->dis.release(), ctx->ext_dev.release(), ctx->state.release(), ctx->prop.release();
   ctx->info.release(), ctx->partials.release(), ctx->old_state.release(), ctx->G.release(), ctx->ctl_block.release();
@@ -392,8 +402,17 @@ static int lio_grid(const esikf_ctx *ctx, int count) {
   int g = tiles < ctx->partial_blocks ? tiles : ctx->partial_blocks;  // persistent: <= 2 CTAs per SM, equal slices
   return g < 1 ? 1 : g;
 }
+static PeerArgs peer_args(esikf_ctx *ctx) {
+  PeerArgs p;
+  p.mbox = ctx->p2p ? ctx->peer_ptrs_dev.p : nullptr;
+  p.rank = ctx->rank, p.nranks = ctx->p2p ? ctx->nranks : 1;
+  p.seq_base = ctx->peer_seq;
+  if (ctx->p2p) ctx->peer_seq += 128;  // > levels * max_iterations: flags stay monotonic across launches (same on every rank)
+  return p;
+}
 static int allreduce_info(esikf_ctx *ctx) {
   if (ctx->nranks <= 1) return ESIKF_OK;
+  if (!ctx->comm) return fail(ctx, ESIKF_ERR_STATE, "per-iteration launches with %d ranks need esikf_comm_init (NCCL)", ctx->nranks);
   int r = g_nccl.AllReduce(ctx->info.p, ctx->info.p, INFO_N, NCCL_FLOAT64, NCCL_SUM, ctx->comm, ctx->stream);
   if (r != 0) return fail(ctx, ESIKF_ERR_COMM, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   return ESIKF_OK;
@@ -425,12 +444,13 @@ int esikf_lio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   sa.state = ctx->state.p, sa.prop = ctx->prop.p, sa.info = ctx->info.p, sa.ctrl = ctx->ctrl.p;
   sa.max_iterations = cfg->max_iterations, sa.solve_mode = ctx->solve_mode, sa.lio_stats = ctx->lio_stats.p;
   const int grid = lio_grid(ctx, ka.count);
-  if (ctx->loop_mode == 1 && ctx->nranks == 1 && ctx->coop_ok && ctx->coop_lio > 0 && !ctx->timing) {
+  if (ctx->loop_mode == 1 && (ctx->nranks == 1 || ctx->p2p) && ctx->coop_ok && ctx->coop_lio > 0 && !ctx->timing) {
     unsigned int *bar = ctx->barrier.p;
     unsigned long long *stamps = ctx->want_stamps ? ctx->stamps.p : nullptr;
     if (stamps) CK(cudaMemsetAsync(stamps, 0, 64 * sizeof(unsigned long long), st));
     ka.dbg = sa.dbg = ctx->want_stamps ? ctx->stamps.p + 576 : nullptr;
-    void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&stamps};
+    PeerArgs peer = peer_args(ctx);
+    void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&stamps, (void *)&peer};
     CK(cudaLaunchCooperativeKernel((const void *)lio_update_kernel, dim3(grid), dim3(LIO_THREADS), kargs, sizeof(LioSmem), st));
     ctx->launches += 1;
     ctx->lio_timed = false;
@@ -611,11 +631,12 @@ int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   sa.max_iterations = ctx->vio_cfg.max_iterations, sa.solve_mode = ctx->solve_mode, sa.vio_stats = ctx->vio_stats.p;
   sa.old_state = ctx->old_state.p, sa.G = ctx->G.p, sa.img_point_cov = ctx->vio_cfg.img_point_cov;
   const int grid = vio_grid(ctx, ka.count);
-  if (ctx->loop_mode == 1 && ctx->nranks == 1 && ctx->coop_ok && ctx->coop_vio > 0 && !ctx->timing) {
+  if (ctx->loop_mode == 1 && (ctx->nranks == 1 || ctx->p2p) && ctx->coop_ok && ctx->coop_vio > 0 && !ctx->timing) {
     unsigned int *bar = ctx->barrier.p;
     unsigned long long *stamps = ctx->want_stamps ? ctx->stamps.p + 64 : nullptr;
     if (stamps) CK(cudaMemsetAsync(stamps, 0, 512 * sizeof(unsigned long long), st));
-    void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&stamps};
+    PeerArgs peer = peer_args(ctx);
+    void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&stamps, (void *)&peer};
     CK(cudaLaunchCooperativeKernel((const void *)vio_update_kernel, dim3(grid), dim3(VIO_THREADS), kargs, sizeof(VioSmem) + sizeof(FusedSolveSmem), st));
     ctx->launches += 1;
     ctx->vio_timed = false;
@@ -778,6 +799,41 @@ int esikf_comm_init(esikf_ctx *ctx, int32_t rank, int32_t nranks, const char uni
   int r = g_nccl.CommInitRank(&ctx->comm, nranks, id, rank);
   if (r != 0) return fail(ctx, ESIKF_ERR_COMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   ctx->rank = rank, ctx->nranks = nranks;
+  return ESIKF_OK;
+}
+int esikf_peer_export(esikf_ctx *ctx, char out[64]) {
+  if (!ctx || !out) return ESIKF_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->mailbox) {
+    CK(cudaMalloc(&ctx->mailbox, 2 * 8 * PEER_SLOT * sizeof(double)));
+    CK(cudaMemset(ctx->mailbox, 0, 2 * 8 * PEER_SLOT * sizeof(double)));
+  }
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, ctx->mailbox));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(out, &h, 64);
+  return ESIKF_OK;
+}
+int esikf_peer_attach(esikf_ctx *ctx, int32_t rank, int32_t nranks, const char *handles) {
+  if (!ctx || !handles || nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks) return fail(ctx, ESIKF_ERR_ARG, "peer_attach: bad argument (1..8 ranks)");
+  if (!ctx->mailbox) return fail(ctx, ESIKF_ERR_STATE, "peer_attach before peer_export");
+  CK(cudaSetDevice(ctx->device));
+  ctx->peer_ptrs.assign(nranks, nullptr);
+  for (int r = 0; r < nranks; r++) {
+    if (r == rank) {
+      ctx->peer_ptrs[r] = ctx->mailbox;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * (size_t)r, 64);
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(ctx, ESIKF_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+    ctx->peer_ptrs[r] = (double *)p;
+  }
+  CK(ctx->peer_ptrs_dev.reserve(nranks));
+  CK(cudaMemcpy(ctx->peer_ptrs_dev.p, ctx->peer_ptrs.data(), nranks * sizeof(double *), cudaMemcpyHostToDevice));
+  ctx->rank = rank, ctx->nranks = nranks, ctx->p2p = true, ctx->peer_seq = 0;
   return ESIKF_OK;
 }
 int esikf_shard_range(int32_t n, int32_t rank, int32_t nranks, int32_t *begin, int32_t *count) {

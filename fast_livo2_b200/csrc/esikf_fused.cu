@@ -23,6 +23,54 @@ __device__ __forceinline__ void stamp(unsigned long long *stamps, int &k) {
   k++;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// In-kernel all-reduce of the 72-double information buffer over NVLink peer memory (one process per GPU, mailboxes
+// exchanged with CUDA IPC). Every rank owns a mailbox [2 parities][nranks][PEER_SLOT doubles] in its own HBM. CTA 0 of
+// rank r stores its contribution into slot (parity, r) of EVERY rank's mailbox (plain stores through the NVLink
+// aperture), fences system-wide, then release-stores the sequence number into the slot's flag; it then acquire-spins on
+// the nranks flags of its OWN mailbox and sums the slots in rank order — every rank forms the bit-identical sum, no
+// broadcast, no NCCL call, no kernel boundary. Two parities suffice: a rank can only reach iteration k+2 after every peer
+// has consumed iteration k (their k+1 contribution is sent after they read k).
+#define PEER_SLOT 80  // 72 data doubles + flag (u64) + padding
+struct PeerArgs {
+  double *const *mbox;  // device array: mailbox base of every rank (own entry = local memory)
+  int rank, nranks;
+  unsigned long long seq_base;  // flags of this launch are seq_base + iteration + 1 (monotonic across launches)
+};
+
+__device__ __forceinline__ void peer_allreduce(double *info, const PeerArgs &p, unsigned int it) {
+  if (p.nranks <= 1) return;
+  const int tid = threadIdx.x;
+  const unsigned long long seq = p.seq_base + it + 1;
+  const int par = it & 1;
+  const size_t my_slot = (size_t)(par * p.nranks + p.rank) * PEER_SLOT;
+  if (tid < INFO_N) {
+    const double v = __ldcg(info + tid);
+    for (int r = 0; r < p.nranks; r++) p.mbox[r][my_slot + tid] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < p.nranks) {
+    unsigned long long *flag = reinterpret_cast<unsigned long long *>(p.mbox[tid] + my_slot + INFO_N);
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
+    // wait for rank `tid`'s contribution in my own mailbox
+    const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(p.mbox[p.rank] + (size_t)(par * p.nranks + tid) * PEER_SLOT + INFO_N);
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+    } while (v < seq);
+  }
+  __syncthreads();
+  if (tid < INFO_N) {
+    const double *own = p.mbox[p.rank] + (size_t)par * p.nranks * PEER_SLOT;
+    double s = 0.0;
+    for (int r = 0; r < p.nranks; r++) s += __ldcv(own + (size_t)r * PEER_SLOT + tid);
+    info[tid] = s;
+  }
+  __threadfence();
+  __syncthreads();
+}
+
 // Sense-free counting barrier over all CTAs of a cooperative launch. `counter` is zeroed by the host before the launch;
 // the k-th barrier (k = 0, 1, ...) completes when it reaches (k + 1) * gridDim.x.
 __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int &epoch) {
@@ -79,7 +127,7 @@ struct FusedSolveSmem {
   SolveIO io;
 };
 
-__global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_kernel(const LioKernelArgs a, const SolveArgs sa, unsigned int *barrier, unsigned long long *stamps) {
+__global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_kernel(const LioKernelArgs a, const SolveArgs sa, unsigned int *barrier, unsigned long long *stamps, const PeerArgs peer) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   LioSmem &sm = *reinterpret_cast<LioSmem *>(smem_raw);
   // CTA 0's solve scratch lives in the reduction scratch (free between the two barriers); only the literal-mode
@@ -112,6 +160,7 @@ __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_kernel(const LioKer
     if (blockIdx.x == 0) {
       dbg_stamp(a.dbg, 12);
       reduce_partials_block(a.partials, a.partial_stride, gridDim.x, a.info);
+      peer_allreduce(a.info, peer, (unsigned int)it);
       dbg_stamp(a.dbg, 13);
       stamp(stamps, sk);  // 4: partials summed
       if (threadIdx.x == 0) {
@@ -133,7 +182,7 @@ __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_kernel(const LioKer
   }
 }
 
-__global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKernelArgs a, SolveArgs sa, unsigned int *barrier, unsigned long long *stamps) {
+__global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKernelArgs a, SolveArgs sa, unsigned int *barrier, unsigned long long *stamps, const PeerArgs peer) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   VioSmem &sm = *reinterpret_cast<VioSmem *>(smem_raw);
   // the solve scratch has its own shared memory behind VioSmem (so the diagnostics can be written while the next
@@ -165,6 +214,7 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKer
       (void)last_of_level;
       if (blockIdx.x == 0) {
         reduce_partials_block(a.partials, a.partial_stride, gridDim.x, a.info);
+        peer_allreduce(a.info, peer, (unsigned int)((a.levels - 1 - level) * sa.max_iterations + it));
         stamp(stamps, sk);
         sa.level = level, sa.slot_iter = it, sa.last_slot = 0;
         if (threadIdx.x == 0) fs.sm.W = vf.lit.W, fs.sm.K = vf.lit.K;

@@ -199,6 +199,12 @@ int esikf_vio_warp_patches(esikf_ctx *ctx, int32_t n, const int32_t *ref_img_ind
 int esikf_comm_unique_id(char out[128]);
 int esikf_comm_init(esikf_ctx *ctx, int32_t rank, int32_t nranks, const char unique_id[128]);
 int esikf_comm_rank(const esikf_ctx *ctx, int32_t *rank, int32_t *nranks);
+/* NVLink peer-memory path (no NCCL in the loop): every rank exports a CUDA-IPC handle of its 72-double mailbox, the host
+ * side all-gathers the 64-byte handles, esikf_peer_attach maps the peers' mailboxes. The persistent update kernels then
+ * all-reduce the information buffer themselves (stores into every peer's mailbox + flag spin) and stay one launch per
+ * update. <= 8 ranks of one NVSwitch box; every rank must issue the same sequence of updates. */
+int esikf_peer_export(esikf_ctx *ctx, char out[64]);
+int esikf_peer_attach(esikf_ctx *ctx, int32_t rank, int32_t nranks, const char *handles /* nranks x 64 bytes */);
 /* The contiguous slice [begin, begin+count) of n units owned by `rank` (host-only helper, no device needed). */
 int esikf_shard_range(int32_t n, int32_t rank, int32_t nranks, int32_t *begin, int32_t *count);
 

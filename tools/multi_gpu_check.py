@@ -17,9 +17,15 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 fr = S.cached_frame(seed=4, n_pts=20000, n_map=150_000, n_patches=0, scene_scale=0.5)
 frv = S.cached_frame(seed=2, n_pts=2000, n_map=120_000, n_patches=150, scene_scale=0.5)
 ctx = api.Context(local)
-uid = [api.comm_unique_id() if rank == 0 else None]
-dist.broadcast_object_list(uid, src=0)
-ctx.comm_init(rank, world, uid[0])
+mode = os.environ.get("ESIKF_COMM", "p2p")
+if mode == "p2p":
+    handles = [None] * world
+    dist.all_gather_object(handles, ctx.peer_export())
+    ctx.peer_attach(rank, world, handles)
+else:
+    uid = [api.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx.comm_init(rank, world, uid[0])
 ctx.set_extrinsics(fr["ext"]); ctx.map_upload(fr["map"], fr["lio_cfg"].voxel_size)
 g = ctx.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"])
 # every rank holds the same posterior (redundant solve on identical all-reduced information)
@@ -50,6 +56,6 @@ if rank == 0:
     ov = vio.update(frv["img"], frv["vis_pos"], w["warp_patch"], w["search_levels"], frv["inv_ref_expo"], frv["state_prior"], frv["state_prior"])
     assert gv["total_iters"] == ov["total_iters"]
     assert_state_close(gv["state"], ov["state"], rot_tol=1e-8, pos_tol=1e-8, cov_tol=1e-6, rest_tol=1e-8)
-    print(f"MULTI_GPU_OK world={world} lio_iters={g['iters']} M={g['M'].tolist()} vio_iters={gv['total_iters']}")
+    print(f"MULTI_GPU_OK mode={mode} world={world} lio_iters={g['iters']} M={g['M'].tolist()} vio_iters={gv['total_iters']}")
 ctx.close()
 dist.barrier(); dist.destroy_process_group()
