@@ -146,11 +146,11 @@ struct esikf_ctx {
   int rank = 0, nranks = 1;
   ncclComm_t comm = nullptr;
   // NVLink peer-memory all-reduce inside the persistent kernels
-  double *mailbox = nullptr;             // own mailbox [2][nranks<=8][PEER_SLOT]
-  std::vector<double *> peer_ptrs;       // mailbox of every rank as mapped into this process
-  DevBuf<double *> peer_ptrs_dev;
+  unsigned long long *mailbox = nullptr;             // own mailbox [2][PEER_MAX_RANKS][PEER_SLOT_WORDS]
+  std::vector<unsigned long long *> peer_ptrs;       // mailbox of every rank as mapped into this process
+  DevBuf<unsigned long long *> peer_ptrs_dev;
   bool p2p = false;
-  unsigned long long peer_seq = 0;
+  unsigned int peer_seq = 0;
 
   // measurement
   bool timing = false;
@@ -805,8 +805,8 @@ int esikf_peer_export(esikf_ctx *ctx, char out[64]) {
   if (!ctx || !out) return ESIKF_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   if (!ctx->mailbox) {
-    CK(cudaMalloc(&ctx->mailbox, 2 * 8 * PEER_SLOT * sizeof(double)));
-    CK(cudaMemset(ctx->mailbox, 0, 2 * 8 * PEER_SLOT * sizeof(double)));
+    CK(cudaMalloc(&ctx->mailbox, 2 * PEER_MAX_RANKS * PEER_SLOT_WORDS * sizeof(unsigned long long)));
+    CK(cudaMemset(ctx->mailbox, 0, 2 * PEER_MAX_RANKS * PEER_SLOT_WORDS * sizeof(unsigned long long)));  // tag 0 is never sent
   }
   cudaIpcMemHandle_t h;
   CK(cudaIpcGetMemHandle(&h, ctx->mailbox));
@@ -815,7 +815,7 @@ int esikf_peer_export(esikf_ctx *ctx, char out[64]) {
   return ESIKF_OK;
 }
 int esikf_peer_attach(esikf_ctx *ctx, int32_t rank, int32_t nranks, const char *handles) {
-  if (!ctx || !handles || nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks) return fail(ctx, ESIKF_ERR_ARG, "peer_attach: bad argument (1..8 ranks)");
+  if (!ctx || !handles || nranks < 1 || nranks > PEER_MAX_RANKS || rank < 0 || rank >= nranks) return fail(ctx, ESIKF_ERR_ARG, "peer_attach: bad argument (1..8 ranks)");
   if (!ctx->mailbox) return fail(ctx, ESIKF_ERR_STATE, "peer_attach before peer_export");
   CK(cudaSetDevice(ctx->device));
   ctx->peer_ptrs.assign(nranks, nullptr);
@@ -829,10 +829,10 @@ int esikf_peer_attach(esikf_ctx *ctx, int32_t rank, int32_t nranks, const char *
     void *p = nullptr;
     cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
     if (e != cudaSuccess) return fail(ctx, ESIKF_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
-    ctx->peer_ptrs[r] = (double *)p;
+    ctx->peer_ptrs[r] = (unsigned long long *)p;
   }
   CK(ctx->peer_ptrs_dev.reserve(nranks));
-  CK(cudaMemcpy(ctx->peer_ptrs_dev.p, ctx->peer_ptrs.data(), nranks * sizeof(double *), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->peer_ptrs_dev.p, ctx->peer_ptrs.data(), nranks * sizeof(unsigned long long *), cudaMemcpyHostToDevice));
   ctx->rank = rank, ctx->nranks = nranks, ctx->p2p = true, ctx->peer_seq = 0;
   return ESIKF_OK;
 }

@@ -25,46 +25,47 @@ __device__ __forceinline__ void stamp(unsigned long long *stamps, int &k) {
 
 // ---------------------------------------------------------------------------------------------------------------------
 // In-kernel all-reduce of the 72-double information buffer over NVLink peer memory (one process per GPU, mailboxes
-// exchanged with CUDA IPC). Every rank owns a mailbox [2 parities][nranks][PEER_SLOT doubles] in its own HBM. CTA 0 of
-// rank r stores its contribution into slot (parity, r) of EVERY rank's mailbox (plain stores through the NVLink
-// aperture), fences system-wide, then release-stores the sequence number into the slot's flag; it then acquire-spins on
-// the nranks flags of its OWN mailbox and sums the slots in rank order — every rank forms the bit-identical sum, no
-// broadcast, no NCCL call, no kernel boundary. Two parities suffice: a rank can only reach iteration k+2 after every peer
-// has consumed iteration k (their k+1 contribution is sent after they read k).
-#define PEER_SLOT 80  // 72 data doubles + flag (u64) + padding
+// exchanged with CUDA IPC), low-latency flavour: no fence, no separate flag. Every rank owns a mailbox
+// [2 parities][nranks][72 elements][2 words] in its own HBM. A double travels as two 64-bit words {payload half | 32-bit
+// sequence tag}; aligned 64-bit stores are single-copy atomic, so a reader that sees the expected tag in both words has
+// the whole value — one NVLink one-way trip instead of store + system fence + flag. CTA 0 of rank r stores its 72
+// elements into slot (parity, r) of EVERY rank's mailbox; its threads then spin on the nranks slots of their OWN mailbox
+// and add them in rank order, so every rank forms the bit-identical sum with no broadcast, no NCCL call and no kernel
+// boundary. Two parities suffice: a rank reaches iteration k+2 only after every peer consumed iteration k.
+#define PEER_SLOT_WORDS (INFO_N * 2)  // u64 words per (parity, rank) slot
+#define PEER_MAX_RANKS 8
 struct PeerArgs {
-  double *const *mbox;  // device array: mailbox base of every rank (own entry = local memory)
+  unsigned long long *const *mbox;  // device array: mailbox base of every rank (own entry = local memory)
   int rank, nranks;
-  unsigned long long seq_base;  // flags of this launch are seq_base + iteration + 1 (monotonic across launches)
+  unsigned int seq_base;            // tags of this launch are seq_base + iteration + 1 (monotonic, never 0)
 };
 
 __device__ __forceinline__ void peer_allreduce(double *info, const PeerArgs &p, unsigned int it) {
   if (p.nranks <= 1) return;
   const int tid = threadIdx.x;
-  const unsigned long long seq = p.seq_base + it + 1;
+  const unsigned int tag = p.seq_base + it + 1u;
   const int par = it & 1;
-  const size_t my_slot = (size_t)(par * p.nranks + p.rank) * PEER_SLOT;
   if (tid < INFO_N) {
-    const double v = __ldcg(info + tid);
-    for (int r = 0; r < p.nranks; r++) p.mbox[r][my_slot + tid] = v;
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (tid < p.nranks) {
-    unsigned long long *flag = reinterpret_cast<unsigned long long *>(p.mbox[tid] + my_slot + INFO_N);
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
-    // wait for rank `tid`'s contribution in my own mailbox
-    const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(p.mbox[p.rank] + (size_t)(par * p.nranks + tid) * PEER_SLOT + INFO_N);
-    unsigned long long v;
-    do {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
-    } while (v < seq);
-  }
-  __syncthreads();
-  if (tid < INFO_N) {
-    const double *own = p.mbox[p.rank] + (size_t)par * p.nranks * PEER_SLOT;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(__ldcg(info + tid));
+    const unsigned long long w0 = (bits << 32) | tag;                       // low half | tag
+    const unsigned long long w1 = (bits & 0xffffffff00000000ull) | tag;     // high half | tag
+    const size_t off = (size_t)(par * p.nranks + p.rank) * PEER_SLOT_WORDS + 2 * tid;
+    for (int r = 0; r < p.nranks; r++) {
+      unsigned long long *dst = p.mbox[r] + off;
+      asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(w0) : "memory");
+      asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst + 1), "l"(w1) : "memory");
+    }
+    const unsigned long long *own = p.mbox[p.rank] + (size_t)par * p.nranks * PEER_SLOT_WORDS + 2 * tid;
     double s = 0.0;
-    for (int r = 0; r < p.nranks; r++) s += __ldcv(own + (size_t)r * PEER_SLOT + tid);
+    for (int r = 0; r < p.nranks; r++) {
+      const unsigned long long *src = own + (size_t)r * PEER_SLOT_WORDS;
+      unsigned long long a, b;
+      do {
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(a) : "l"(src) : "memory");
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(b) : "l"(src + 1) : "memory");
+      } while ((unsigned int)a != tag || (unsigned int)b != tag);
+      s += __longlong_as_double((long long)((b & 0xffffffff00000000ull) | (a >> 32)));
+    }
     info[tid] = s;
   }
   __threadfence();
