@@ -334,9 +334,10 @@ class Context:
         self._ck(self.lib.esikf_set_phase_stamps(self.h, int(enable)))
 
     def get_phase_stamps(self):
-        out = np.zeros(640, np.uint64)
+        out = np.zeros(800, np.uint64)
         self._ck(self.lib.esikf_get_phase_stamps(self.h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
-        self.debug_stamps = out[576:].copy()
+        self.debug_stamps = out[576:640].copy()
+        self.cta_stamps = out[640:].copy()
         return out[:576].reshape(72, 8)
 
     def set_kernel_timing(self, enable):

@@ -216,7 +216,7 @@ int esikf_create(esikf_ctx **out, int device) {
             ctx->ctl_block.reserve(sizeof(esikf_lio_stats) + sizeof(Ctrl) + 64 + sizeof(esikf_vio_stats)) == cudaSuccess && ctx->ext_dev.reserve(12) == cudaSuccess &&
             ctx->scratch_state.reserve(S_N) == cudaSuccess;
   ctx->partial_blocks = ctx->sm_count < 160 ? ctx->sm_count : 160;  // persistent residual kernels: one CTA per SM
-  ok = ok && ctx->partials.reserve((size_t)ctx->partial_blocks * INFO_N) == cudaSuccess && ctx->stamps.reserve(8 * 72 + 64) == cudaSuccess;
+  ok = ok && ctx->partials.reserve((size_t)ctx->partial_blocks * INFO_N) == cudaSuccess && ctx->stamps.reserve(8 * 72 + 64 + 160) == cudaSuccess;
   if (ok) {
     unsigned char *b = ctx->ctl_block.p;
     ctx->lio_stats.p = reinterpret_cast<esikf_lio_stats *>(b);
@@ -914,10 +914,10 @@ int esikf_set_phase_stamps(esikf_ctx *ctx, int32_t enable) {
   ctx->want_stamps = enable != 0;
   return ESIKF_OK;
 }
-int esikf_get_phase_stamps(esikf_ctx *ctx, uint64_t *out /* 640 */) {
+int esikf_get_phase_stamps(esikf_ctx *ctx, uint64_t *out /* 800 */) {
   if (!ctx || !out) return ESIKF_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  CK(cudaMemcpyAsync(out, ctx->stamps.p, 640 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out, ctx->stamps.p, 800 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return ESIKF_OK;
 }

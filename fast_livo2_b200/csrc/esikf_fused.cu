@@ -154,6 +154,11 @@ __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_kernel(const LioKer
     int cnt = 0;
     lio_process_range(a, sm, lo, hi, D0, D1, cnt, lc, it == 0);
     __syncthreads();
+    if (stamps && it == 3 && threadIdx.x == 0) {  // measurement only: when did every CTA finish its slice of iteration 3?
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      stamps[640 + blockIdx.x] = t;
+    }
     stamp(stamps, sk);  // 2: CTA 0 finished its slice
     store_partials<LIO_WARPS>(sm.red, D0, D1, (double)cnt, true, a.partials, a.partial_stride);
     grid_barrier(barrier, epoch);

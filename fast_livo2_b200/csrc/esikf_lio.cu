@@ -131,7 +131,30 @@ struct EvalOut {
 
 // build_single_residual's plane branch (src/voxel_map.cpp:721-768) for one candidate plane record `q` (shared or global
 // memory, 32 doubles). The probability (:740) is only needed to arbitrate between several candidates.
-__device__ __forceinline__ EvalOut eval_rec(const double *__restrict__ q, const double pw[3], const double var[6], double sigma_num,
+// n^T pv.var n without forming pv.var (voxel_map.cpp:385-388, 736):
+//   pv.var = R body_cov R^T + [c]x P_tt [c]x^T + P_pp  =>  n^T var n = m^T body_cov m + u^T P_tt u + n^T P_pp n,  m = R^T n, u = c x n.
+struct PointCovRef {
+  const double *pre;  // SoA element of this point: c(3) | body cov (6), stride `ns`
+  size_t ns;
+  const double *R, *Ptt, *Ppp;  // shared-memory copies of the current rotation / covariance blocks
+};
+__device__ __forceinline__ double n_var_n(const PointCovRef &pc, double n0, double n1, double n2) {
+  const double *R = pc.R;
+  const double m0 = R[0] * n0 + R[3] * n1 + R[6] * n2, m1 = R[1] * n0 + R[4] * n1 + R[7] * n2, m2 = R[2] * n0 + R[5] * n1 + R[8] * n2;
+  const double *pre = pc.pre;
+  const size_t ns = pc.ns;
+  const double bc[6] = {pre[3 * ns], pre[4 * ns], pre[5 * ns], pre[6 * ns], pre[7 * ns], pre[8 * ns]};
+  double s = quad3_sym(bc, m0, m1, m2);
+  const double cx = pre[0], cy = pre[ns], cz = pre[2 * ns];
+  const double u0 = cy * n2 - cz * n1, u1 = cz * n0 - cx * n2, u2 = cx * n1 - cy * n0;
+  const double *P = pc.Ptt;
+  s += (u0 * P[0] + u1 * P[3] + u2 * P[6]) * u0 + (u0 * P[1] + u1 * P[4] + u2 * P[7]) * u1 + (u0 * P[2] + u1 * P[5] + u2 * P[8]) * u2;
+  const double *Q = pc.Ppp;
+  s += (n0 * Q[0] + n1 * Q[3] + n2 * Q[6]) * n0 + (n0 * Q[1] + n1 * Q[4] + n2 * Q[7]) * n1 + (n0 * Q[2] + n1 * Q[5] + n2 * Q[8]) * n2;
+  return s;
+}
+
+__device__ __forceinline__ EvalOut eval_rec(const double *__restrict__ q, const double pw[3], const PointCovRef &pc, double sigma_num,
                                             bool need_prob) {
   EvalOut o;
   o.pass = false, o.prob = 0.0, o.dis = 0.f;
@@ -148,7 +171,7 @@ __device__ __forceinline__ EvalOut eval_rec(const double *__restrict__ q, const 
   if ((double)range_dis <= 3.0 * (double)dr.y) {  // NaN fails, as in the reference
     const double J[6] = {pw[0] - c0, pw[1] - c1, pw[2] - c2, -n0, -n1, -n2};
     double sigma_l = quad6(q + 6, J);
-    sigma_l += quad3_sym(var, n0, n1, n2);
+    sigma_l += n_var_n(pc, n0, n1, n2);
     if ((double)dis_to_plane < sigma_num * sqrt(sigma_l)) {
       o.pass = true;
       o.dis = (float)sd;
@@ -175,32 +198,66 @@ __device__ __forceinline__ bool probe(const HashSlot *__restrict__ slots, uint32
   }
 }
 
-// Candidates [first+1, first+count) of ONE point evaluated lane-parallel by the whole warp, arg-max with lowest-index tie
-// break (the recursion of build_single_residual keeps the first of equal probabilities, voxel_map.cpp:741). `src` is the lane
-// that owns the point; its pw / var are broadcast. Returns the winner to every lane (idx < 0: none passed).
-__device__ __forceinline__ Cand warp_eval_extra(const esikf_plane *__restrict__ planes, int src, const double pw[3], const double var[6],
-                                                uint32_t first, uint32_t count, double sigma_num, int lane) {
-  double bpw[3], bvar[6];
+// Extra candidates (sub-divided root voxels) of ALL lanes of the warp that have some, in one pass: the (owner lane,
+// candidate) pairs are laid out consecutively and dealt one per lane, so the scattered plane-record reads of every pending
+// point overlap instead of being paid once per pending lane (the slowest warp of the slowest CTA sets the grid barrier).
+// Winner per owner = arg-max probability with lowest-index tie break, merged with `best` by strict '>' — exactly the
+// order-dependent rule of the recursion (voxel_map.cpp:741: the first of equal probabilities is kept).
+__device__ __forceinline__ void warp_eval_extras(const esikf_plane *__restrict__ planes, bool pending, const double pw[3], const PointCovRef &pc,
+                                                 int point, uint32_t first, uint32_t count, double sigma_num, int lane, Cand &best) {
+  const unsigned mask = __ballot_sync(0xffffffffu, pending);
+  if (!mask) return;
+  const int npairs = pending ? (int)count - 1 : 0;
+  int scan = npairs;
 #pragma unroll
-  for (int k = 0; k < 3; k++) bpw[k] = __shfl_sync(0xffffffffu, pw[k], src);
-#pragma unroll
-  for (int k = 0; k < 6; k++) bvar[k] = __shfl_sync(0xffffffffu, var[k], src);
-  const uint32_t bfirst = __shfl_sync(0xffffffffu, first, src), bcount = __shfl_sync(0xffffffffu, count, src);
-  Cand my;
-  my.prob = -1.0, my.idx = 0x7fffffff, my.dis = 0.f;
-  for (uint32_t c = 1 + lane; c < bcount; c += 32) {
-    const EvalOut e = eval_rec(reinterpret_cast<const double *>(planes + bfirst + c), bpw, bvar, sigma_num, true);
-    if (e.pass && e.prob > my.prob) my.prob = e.prob, my.idx = (int)(bfirst + c), my.dis = e.dis;
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, scan, d);
+    if (lane >= d) scan += t;
   }
+  const int total = __shfl_sync(0xffffffffu, scan, 31);
+  const int excl = scan - npairs;
+  Cand acc;
+  acc.prob = -1.0, acc.idx = -1, acc.dis = 0.f;
+  for (int base = 0; base < total; base += 32) {
+    const int k = base + lane;
+    int owner = 0, cand = 0;
+    for (unsigned m = mask; m; m &= m - 1) {
+      const int jl = __ffs(m) - 1;
+      const int ej = __shfl_sync(0xffffffffu, excl, jl), nj = __shfl_sync(0xffffffffu, npairs, jl);
+      if (k >= ej && k < ej + nj) owner = jl, cand = k - ej + 1;
+    }
+    const bool have = k < total;
+    double opw[3];
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    const double op = __shfl_xor_sync(0xffffffffu, my.prob, off);
-    const int oi = __shfl_xor_sync(0xffffffffu, my.idx, off);
-    const float od = __shfl_xor_sync(0xffffffffu, my.dis, off);
-    if (op > my.prob || (op == my.prob && oi < my.idx)) my.prob = op, my.idx = oi, my.dis = od;
+    for (int c = 0; c < 3; c++) opw[c] = __shfl_sync(0xffffffffu, pw[c], owner);
+    const int opoint = __shfl_sync(0xffffffffu, point, owner);
+    const uint32_t ofirst = __shfl_sync(0xffffffffu, first, owner);
+    Cand my;
+    my.prob = -1.0, my.idx = 0x7fffffff, my.dis = 0.f;
+    if (have) {
+      PointCovRef opc = pc;
+      opc.pre += opoint - point;
+      const EvalOut e = eval_rec(reinterpret_cast<const double *>(planes + ofirst + cand), opw, opc, sigma_num, true);
+      if (e.pass) my.prob = e.prob, my.idx = (int)(ofirst + cand), my.dis = e.dis;
+    }
+    for (unsigned m = mask; m; m &= m - 1) {
+      const int jl = __ffs(m) - 1;
+      const bool mine = have && owner == jl && my.idx != 0x7fffffff;
+      double rp = mine ? my.prob : -1.0;
+      int ri = mine ? my.idx : 0x7fffffff;
+      float rd = mine ? my.dis : 0.f;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double op = __shfl_xor_sync(0xffffffffu, rp, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, ri, off);
+        const float od = __shfl_xor_sync(0xffffffffu, rd, off);
+        if (op > rp || (op == rp && oi < ri)) rp = op, ri = oi, rd = od;
+      }
+      // chunks are visited in increasing candidate order: a later chunk only replaces on strictly larger probability
+      if (lane == jl && ri != 0x7fffffff && rp > acc.prob) acc.prob = rp, acc.idx = ri, acc.dis = rd;
+    }
   }
-  if (my.idx == 0x7fffffff) my.idx = -1;
-  return my;
+  if (pending && acc.idx >= 0 && acc.prob > best.prob) best = acc;
 }
 
 #define REC_STRIDE 38  // doubles per lane slot (304 B = 19 x 16 B: conflict-free 128-bit reads at lane stride)
@@ -257,7 +314,7 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
     if (hi - lo > LIO_THREADS) lc.staged_idx = -1, lc.have_pt = false;  // several tiles share the lanes: nothing stays resident
     int midx = -1;
     float mdis = 0.f;
-    double pw[3] = {0, 0, 0}, var[6] = {0, 0, 0, 0, 0, 0};
+    double pw[3] = {0, 0, 0};
     float loc[3] = {0, 0, 0};
     uint32_t first = 0, count = 0;
     bool found = false;
@@ -326,49 +383,15 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
     // ---- phase 3: association
     Cand best;
     best.prob = 0.0, best.idx = -1, best.dis = 0.f;
-    if (found) {
-      // pv.var = R body_cov R^T + (-C) P_tt (-C)^T + P_pp   (voxel_map.cpp:385-388), symmetric 6
-      const size_t ns = (size_t)a.pre_stride;
-      const double *__restrict__ pre = a.pre + i;
-      const double cx = pre[0], cy = pre[ns], cz = pre[2 * ns];
-      const double b0 = pre[3 * ns], b1 = pre[4 * ns], b2 = pre[5 * ns], b3 = pre[6 * ns], b4 = pre[7 * ns], b5 = pre[8 * ns];
-      double T[9];
-#pragma unroll
-      for (int r = 0; r < 3; r++) {
-        const double r0 = sm.R[3 * r], r1 = sm.R[3 * r + 1], r2 = sm.R[3 * r + 2];
-        T[3 * r + 0] = r0 * b0 + r1 * b1 + r2 * b2;
-        T[3 * r + 1] = r0 * b1 + r1 * b3 + r2 * b4;
-        T[3 * r + 2] = r0 * b2 + r1 * b4 + r2 * b5;
-      }
-      double U[9];  // U = [c]x * Ptt
-#pragma unroll
-      for (int c = 0; c < 3; c++) {
-        const double p0 = sm.Ptt[c], p1 = sm.Ptt[3 + c], p2 = sm.Ptt[6 + c];
-        U[0 + c] = -cz * p1 + cy * p2;
-        U[3 + c] = cz * p0 - cx * p2;
-        U[6 + c] = -cy * p0 + cx * p1;
-      }
-      const double V00 = -U[1] * cz + U[2] * cy, V01 = U[0] * cz - U[2] * cx, V02 = -U[0] * cy + U[1] * cx;
-      const double V11 = U[3] * cz - U[5] * cx, V12 = -U[3] * cy + U[4] * cx;
-      const double V22 = -U[6] * cy + U[7] * cx;
-      var[0] = (T[0] * sm.R[0] + T[1] * sm.R[1] + T[2] * sm.R[2]) + V00 + sm.Ppp[0];
-      var[1] = (T[0] * sm.R[3] + T[1] * sm.R[4] + T[2] * sm.R[5]) + V01 + sm.Ppp[1];
-      var[2] = (T[0] * sm.R[6] + T[1] * sm.R[7] + T[2] * sm.R[8]) + V02 + sm.Ppp[2];
-      var[3] = (T[3] * sm.R[3] + T[4] * sm.R[4] + T[5] * sm.R[5]) + V11 + sm.Ppp[4];
-      var[4] = (T[3] * sm.R[6] + T[4] * sm.R[7] + T[5] * sm.R[8]) + V12 + sm.Ppp[5];
-      var[5] = (T[6] * sm.R[6] + T[7] * sm.R[7] + T[8] * sm.R[8]) + V22 + sm.Ppp[8];
-      if (count > 0) {
-        const EvalOut e = eval_rec(myrec, pw, var, a.sigma_num, count > 1);
-        if (e.pass) best.prob = e.prob, best.idx = (int)first, best.dis = e.dis;
-      }
+    PointCovRef pc;
+    pc.pre = a.pre + i, pc.ns = (size_t)a.pre_stride, pc.R = sm.R, pc.Ptt = sm.Ptt, pc.Ppp = sm.Ppp;
+    if (found && count > 0) {
+      const EvalOut e = eval_rec(myrec, pw, pc, a.sigma_num, count > 1);
+      if (e.pass) best.prob = e.prob, best.idx = (int)first, best.dis = e.dis;
     }
     if (first_tile) dbg_stamp(a.dbg, 3);
     // further candidates of sub-divided root voxels (rare): one point at a time, lane-parallel over its candidate list
-    for (unsigned more = __ballot_sync(0xffffffffu, found && count > 1); more; more &= more - 1) {
-      const int src = __ffs(more) - 1;
-      const Cand c = warp_eval_extra(a.planes, src, pw, var, first, count, a.sigma_num, lane);
-      if (lane == src && c.idx >= 0 && c.prob > best.prob) best = c;
-    }
+    warp_eval_extras(a.planes, found && count > 1, pw, pc, i, first, count, a.sigma_num, lane, best);
     if (first_tile) dbg_stamp(a.dbg, 4);
     // one neighbour voxel when the home voxel gave nothing (voxel_map.cpp:680-691). loc is in voxel units, centre / quarter
     // length in metres: reproduced literally.
@@ -387,15 +410,11 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
       }
       found2 = probe(a.slots, a.hash_mask, nk[0], nk[1], nk[2], f2, c2) && c2 > 0;
       if (found2) {
-        const EvalOut e = eval_rec(reinterpret_cast<const double *>(a.planes + f2), pw, var, a.sigma_num, c2 > 1);
+        const EvalOut e = eval_rec(reinterpret_cast<const double *>(a.planes + f2), pw, pc, a.sigma_num, c2 > 1);
         if (e.pass) best.prob = e.prob, best.idx = (int)f2, best.dis = e.dis;
       }
     }
-    for (unsigned more = __ballot_sync(0xffffffffu, found2 && c2 > 1); more; more &= more - 1) {
-      const int src = __ffs(more) - 1;
-      const Cand c = warp_eval_extra(a.planes, src, pw, var, f2, c2, a.sigma_num, lane);
-      if (lane == src && c.idx >= 0 && c.prob > best.prob) best = c;
-    }
+    warp_eval_extras(a.planes, found2 && c2 > 1, pw, pc, i, f2, c2, a.sigma_num, lane, best);
 
     if (first_tile) dbg_stamp(a.dbg, 5);
     // ---- phase 4: Jacobian / measurement-noise loop (voxel_map.cpp:414-458) for matched points

@@ -227,7 +227,7 @@ int esikf_get_kernel_timing(esikf_ctx *ctx, float *lio_residual_ms /* 8 */, floa
  * [start, consts loaded, slice done, all CTAs arrived, partials summed, solved, state published, spare];
  * slots 0..7 = LIO iterations, 8..71 = VIO (levels-1-level)*max_iterations + iteration. 0 = slot not executed. */
 int esikf_set_phase_stamps(esikf_ctx *ctx, int32_t enable);
-int esikf_get_phase_stamps(esikf_ctx *ctx, uint64_t *out /* 640: 576 phase stamps + 64 fine-grained debug stamps */);
+int esikf_get_phase_stamps(esikf_ctx *ctx, uint64_t *out /* 800: 576 phase stamps + 64 fine-grained debug stamps + 160 per-CTA slice-end stamps of LIO iteration 3 */);
 
 #ifdef __cplusplus
 }
