@@ -52,7 +52,8 @@ struct Ctrl {
   float last_error; // VIO (vio.cpp:1528)
   int has_G;        // VIO: G valid (at least one accepted update)
   unsigned int block_counter;  // last-block-done counter of the residual kernels
-  int pad[7];
+  int accepted_in_level;       // VIO: accepted updates of the current level (diagnostics)
+  int pad[6];
 };
 
 

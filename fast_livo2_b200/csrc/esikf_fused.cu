@@ -46,7 +46,7 @@ __device__ __forceinline__ void peer_allreduce(double *info, const PeerArgs &p, 
   const unsigned int tag = p.seq_base + it + 1u;
   const int par = it & 1;
   if (tid < INFO_N) {
-    const unsigned long long bits = (unsigned long long)__double_as_longlong(__ldcg(info + tid));
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(info[tid]);
     const unsigned long long w0 = (bits << 32) | tag;                       // low half | tag
     const unsigned long long w1 = (bits & 0xffffffff00000000ull) | tag;     // high half | tag
     const size_t off = (size_t)(par * p.nranks + p.rank) * PEER_SLOT_WORDS + 2 * tid;
@@ -126,6 +126,7 @@ __device__ __forceinline__ void store_partials(ReduceSmem<WARPS> &rs, double D0,
 struct FusedSolveSmem {
   SolveSmem sm;
   SolveIO io;
+  Ctrl ctrl;  // CTA 0's working copy of the loop-control block (published to global memory after every solve)
 };
 
 __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_kernel(const LioKernelArgs a, const SolveArgs sa, unsigned int *barrier, unsigned long long *stamps, const PeerArgs peer) {
@@ -133,8 +134,8 @@ __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_kernel(const LioKer
   LioSmem &sm = *reinterpret_cast<LioSmem *>(smem_raw);
   // CTA 0's solve scratch lives in the reduction scratch (free between the two barriers); only the literal-mode
   // workspace (solve_mode 1, parity checks) borrows the record slots and forces a re-stage.
-  FusedSolveSmem &fs = *reinterpret_cast<FusedSolveSmem *>(&sm.red);
-  static_assert(sizeof(FusedSolveSmem) <= sizeof(sm.red), "solve scratch must fit in the reduction scratch");
+  static_assert(sizeof(FusedSolveSmem) <= sizeof(sm.fs_raw), "solve scratch must fit");
+  FusedSolveSmem &fs = *reinterpret_cast<FusedSolveSmem *>(sm.fs_raw);  // resident for the whole update in CTA 0: P, poses and loop control are staged once
   static_assert(sizeof(SolveLiteralScratch) <= sizeof(sm.rec), "literal scratch must fit in the record slots");
   if (threadIdx.x == 0) {
     SolveLiteralScratch *lit = reinterpret_cast<SolveLiteralScratch *>(&sm.rec[0][0][0]);
@@ -165,8 +166,12 @@ __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_kernel(const LioKer
     stamp(stamps, sk);  // 3: all CTAs arrived
     if (blockIdx.x == 0) {
       dbg_stamp(a.dbg, 12);
-      reduce_partials_block(a.partials, a.partial_stride, gridDim.x, a.info);
-      peer_allreduce(a.info, peer, (unsigned int)it);
+      if (it == 0) {  // stage P / poses / loop control once; later iterations find them in shared memory
+        solve_load(fs.sm, fs.io, sa, false);
+        if (threadIdx.x == 0) fs.ctrl = *a.ctrl;
+      }
+      reduce_partials_block(a.partials, a.partial_stride, gridDim.x, fs.io.info);
+      peer_allreduce(fs.io.info, peer, (unsigned int)it);
       dbg_stamp(a.dbg, 13);
       stamp(stamps, sk);  // 4: partials summed
       if (threadIdx.x == 0) {
@@ -174,7 +179,8 @@ __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_kernel(const LioKer
         fs.sm.W = lit->W, fs.sm.K = lit->K;
       }
       __syncthreads();
-      lio_solve_block(sa, fs.sm, fs.io, true);
+      lio_solve_block(sa, fs.sm, fs.io, fs.ctrl, true, true);
+      if (threadIdx.x == 0) *a.ctrl = fs.ctrl;  // publish stop / iteration count
       if (sa.solve_mode == 1) lc.staged_idx = -1;  // the literal workspace borrowed CTA 0's record slots
     } else {
       sk++;
@@ -219,19 +225,24 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKer
       const bool last_of_level = false;
       (void)last_of_level;
       if (blockIdx.x == 0) {
-        reduce_partials_block(a.partials, a.partial_stride, gridDim.x, a.info);
-        peer_allreduce(a.info, peer, (unsigned int)((a.levels - 1 - level) * sa.max_iterations + it));
+        if (level == a.levels - 1 && it == 0) {
+          solve_load(fs.sm, fs.io, sa, false);
+          if (threadIdx.x == 0) fs.ctrl = *a.ctrl;
+        }
+        reduce_partials_block(a.partials, a.partial_stride, gridDim.x, fs.io.info);
+        peer_allreduce(fs.io.info, peer, (unsigned int)((a.levels - 1 - level) * sa.max_iterations + it));
         stamp(stamps, sk);
         sa.level = level, sa.slot_iter = it, sa.last_slot = 0;
         if (threadIdx.x == 0) fs.sm.W = vf.lit.W, fs.sm.K = vf.lit.K;
         __syncthreads();
-        vio_solve_block(sa, fs.sm, fs.io, true);
+        vio_solve_block(sa, fs.sm, fs.io, fs.ctrl, true, true);
+        if (threadIdx.x == 0) *a.ctrl = fs.ctrl;
       } else {
         sk++;
       }
       stamp(stamps, sk);
       grid_barrier(barrier, epoch);
-      if (blockIdx.x == 0) vio_write_stats(sa, fs.sm, fs.io);
+      if (blockIdx.x == 0) vio_write_stats(sa, fs.sm, fs.io, fs.ctrl);
       stamp(stamps, sk);
       level_done = __ldcg(&a.ctrl->level_done) != 0;
       if (level_done) break;  // EKF_end (:1685)
@@ -242,11 +253,12 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKer
     __syncthreads();
     sa.level = 0, sa.slot_iter = 1, sa.last_slot = 1;
     if (threadIdx.x == 0) {
-      a.ctrl->level_done = 1;
+      fs.ctrl.level_done = 1;
       fs.sm.W = vf.lit.W, fs.sm.K = vf.lit.K;
     }
     __syncthreads();
-    vio_solve_block(sa, fs.sm, fs.io, false);
+    vio_solve_block(sa, fs.sm, fs.io, fs.ctrl, false, true);
+    if (threadIdx.x == 0) *a.ctrl = fs.ctrl;
   }
 }
 

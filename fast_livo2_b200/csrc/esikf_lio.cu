@@ -279,6 +279,7 @@ struct __align__(128) LioSmem {
   double R[9], t[3], Ptt[9], Ppp[9];      // current state
   double Rp[9], tp[3], Mp[9];             // prior pose, Mp = Rp * extR
   ReduceSmem<LIO_WARPS> red;
+  unsigned char fs_raw[6400];             // CTA 0's resident solve scratch (FusedSolveSmem) in the persistent kernel
 };
 
 // Load the per-iteration constants (current pose / covariance blocks, prior pose) into shared memory.

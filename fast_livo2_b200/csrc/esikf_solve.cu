@@ -263,13 +263,14 @@ __device__ __forceinline__ void lio_write_stats(const SolveArgs &a, SolveSmem &s
 }
 
 // One LIO gain solve + state update (src/voxel_map.cpp:462-499) by the calling block. Returns EKF_stop_flg.
-__device__ __noinline__ bool lio_solve_block(const SolveArgs &a, SolveSmem &sm, SolveIO &io, bool defer_stats) {
-  Ctrl &ctrl = *a.ctrl;
+// `ctrl` is the loop-control block the routine reads and updates (global memory for the per-iteration kernels, CTA 0's
+// shared-memory copy inside the persistent kernel). `resident`: P / poses / info are already staged in sm / io.
+__device__ __noinline__ bool lio_solve_block(const SolveArgs &a, SolveSmem &sm, SolveIO &io, Ctrl &ctrl, bool defer_stats, bool resident) {
   const int tid = threadIdx.x, lane = tid & 31;
   const int iterCount = ctrl.iter;
   const int rematch0 = ctrl.rematch_num;
   dbg_stamp(a.dbg, 16);
-  solve_load(sm, io, a, false);
+  if (!resident) solve_load(sm, io, a, false);
   __syncthreads();
   dbg_stamp(a.dbg, 17);
   double x[6], g[6];
@@ -346,10 +347,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lio_solve_kernel(const Solve
   __shared__ SolveLiteralScratch lit;
   if (threadIdx.x == 0) sm.W = lit.W, sm.K = lit.K;
   __syncthreads();
-  lio_solve_block(a, sm, io, false);
+  lio_solve_block(a, sm, io, *a.ctrl, false, false);
 }
 
-__device__ __forceinline__ void vio_write_stats(const SolveArgs &a, SolveSmem &sm, SolveIO &io) {
+__device__ __forceinline__ void vio_write_stats(const SolveArgs &a, SolveSmem &sm, SolveIO &io, const Ctrl &ctrl) {
   const int tid = threadIdx.x, level = a.level, iteration = a.slot_iter;
   const bool accepted = io.flags[0] != 0, ran = io.flags[2] != 0;
   if (ran && a.vio_stats && level < 8) {
@@ -370,14 +371,13 @@ __device__ __forceinline__ void vio_write_stats(const SolveArgs &a, SolveSmem &s
 
 // One VIO accept/rollback + gain solve (src/vio.cpp:1636-1685) by the calling block; on the last slot also the final
 // covariance update (:800). Returns EKF_end of the level.
-__device__ __forceinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &sm, SolveIO &io, bool defer_stats) {
-  Ctrl &ctrl = *a.ctrl;
+__device__ __forceinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &sm, SolveIO &io, Ctrl &ctrl, bool defer_stats, bool resident) {
   const int tid = threadIdx.x, lane = tid & 31;
   const bool level_done_in = (a.slot_iter == 0) ? false : (ctrl.level_done != 0);   // entering a level: EKF_end = false (vio.cpp:1527)
   const float last_error_in = (a.slot_iter == 0) ? FLT_MAX : ctrl.last_error;       // :1528
   const int has_G_in = ctrl.has_G;
   if (level_done_in && !a.last_slot) return true;
-  solve_load(sm, io, a, a.slot_iter != 0);
+  if (!resident) solve_load(sm, io, a, a.slot_iter != 0);
   __syncthreads();
   if (a.slot_iter == 0)
     for (int t = tid; t < 25; t += blockDim.x) io.old[t] = io.st[t];  // old_state = *state at level entry (:1523)
@@ -443,7 +443,7 @@ __device__ __forceinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &s
     }
     if (accepted)
       for (int t = tid; t < 133; t += blockDim.x) a.G[t] = io.g[t / 7][t % 7];
-    if (!defer_stats) vio_write_stats(a, sm, io);
+    if (!defer_stats) vio_write_stats(a, sm, io, ctrl);
   }
   if (a.last_slot) {
     // state->cov -= G * state->cov   (vio.cpp:800) with the last accepted G (this slot's if accepted, else the stored one)
@@ -461,11 +461,13 @@ __device__ __forceinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &s
     if (ran) {
       ctrl.iter += 1;
       ctrl.last_error = reinterpret_cast<float *>(io.flags)[3];
-      if (accepted) ctrl.has_G = 1;
+      if (a.slot_iter == 0) ctrl.accepted_in_level = 0;
+      if (accepted) ctrl.has_G = 1, ctrl.accepted_in_level += 1;
     }
     ctrl.level_done = io.flags[1];
     if (a.last_slot) ctrl.stop = 1;
   }
+  __syncthreads();
   return io.flags[1] != 0;
 }
 
@@ -475,7 +477,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) vio_solve_kernel(const Solve
   __shared__ SolveLiteralScratch lit;
   if (threadIdx.x == 0) sm.W = lit.W, sm.K = lit.K;
   __syncthreads();
-  vio_solve_block(a, sm, io, false);
+  vio_solve_block(a, sm, io, *a.ctrl, false, false);
 }
 
 }  // namespace esikf
