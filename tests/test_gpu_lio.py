@@ -174,3 +174,17 @@ def test_persistent_and_per_iteration_loops_are_bit_identical(gpu_ctx, small_fra
     assert a["iters"] == b["iters"]
     assert np.array_equal(a["state"], b["state"]) and np.array_equal(a["HTH"], b["HTH"]) and np.array_equal(a["match_plane"], b["match_plane"])
     _compare(b, _oracle(fr))
+
+
+def test_config4_260k_points_several_tiles_per_cta(gpu_ctx):
+    """BASELINE config 4 size (NTU_VIRAL: 260 k points, LIO only, beam_err 0.01): more points than one round of 148 x 704
+    lanes, so every CTA walks several tiles and nothing stays resident in its slots."""
+    cfg = S.LioCfg(beam_err=0.01)
+    fr = get_frame(seed=12, n_pts=260_000, n_map=1_000_000, lio=cfg)
+    g, o = _gpu(gpu_ctx, fr), _oracle(fr)
+    assert o["M"][0] > 200_000
+    _compare(g, o)
+    gpu_ctx.set_loop_mode(0)
+    g0 = _gpu(gpu_ctx, fr)
+    gpu_ctx.set_loop_mode(1)
+    assert np.array_equal(g0["state"], g["state"]) and np.array_equal(g0["match_plane"], g["match_plane"])

@@ -184,3 +184,19 @@ def test_persistent_and_per_iteration_loops_are_bit_identical(gpu_ctx, small_vio
     assert np.array_equal(a["state"], b["state"]) and np.array_equal(a["HTH"], b["HTH"]) and np.array_equal(a["errors"], b["errors"])
     vio = O.OracleVIO(fr["cam_cfg"], fr["ext"], fr["vio_cfg"])
     _compare_vio(b, vio.update(*args), fr["vio_cfg"].levels)
+
+
+def test_config5_five_levels_4k_patches(gpu_ctx):
+    """BASELINE config 5 visual size (MARS_LVIG camera 612x512, 4 k patches, 5 pyramid levels, img_point_cov 1000):
+    two patches per warp and a coarsest stride of 16 pixels."""
+    cam = S.CamCfg(width=612, height=512, fx=612.0 * 0.72, fy=612.0 * 0.72, cx=306.0, cy=256.0)
+    vcfg = S.VioCfg(levels=5, img_point_cov=1000.0)
+    fr = get_frame(seed=13, n_pts=1000, n_map=300_000, n_patches=4000, scene_scale=0.7, cam=cam, vio=vcfg)
+    assert len(fr["vis_pos"]) > 3000
+    _setup(gpu_ctx, fr)
+    prior = _vio_prior(fr, 13)
+    w = _gpu_warp(gpu_ctx, fr, prior)
+    args = (fr["img"], fr["vis_pos"], w["warp_patch"], w["search_levels"], fr["inv_ref_expo"], prior, prior)
+    g = gpu_ctx.vio_update(*args)
+    vio = O.OracleVIO(fr["cam_cfg"], fr["ext"], fr["vio_cfg"])
+    _compare_vio(g, vio.update(*args), 5)
