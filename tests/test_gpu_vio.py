@@ -40,8 +40,9 @@ def _compare_vio(g, o, L):
     assert np.array_equal(g["accepted_per_level"], o["accepted_per_level"])
     for lvl in range(L):
         for it in range(o["iters_per_level"][lvl]):
-            # error: float in the reference (sequential float accumulation); fp64 tree sum here -> 1e-6 relative
-            assert abs(g["error_trace"][lvl][it] - o["error_trace"][lvl][it]) <= 2e-6 * o["error_trace"][lvl][it]
+            # error: a sequential FLOAT accumulation over n_meas terms in the reference (rounding error ~ sqrt(n) * 6e-8, and an
+            # unspecified OpenMP order); an fp64 fixed-order sum here -> compare at 1e-5 relative
+            assert abs(g["error_trace"][lvl][it] - o["error_trace"][lvl][it]) <= 1e-5 * o["error_trace"][lvl][it]
         for it in range(o["accepted_per_level"][lvl]):
             assert rel(g["HTH"][lvl][it], o["HTH"][lvl][it]) < 1e-9
             assert rel(g["HTz"][lvl][it], o["HTz"][lvl][it]) < 1e-7
