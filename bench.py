@@ -291,15 +291,13 @@ def b200_arm(args, rank, world, local_rank):
     m_h, nm_h = torch.empty(n, dtype=torch.int32).pin_memory(), torch.empty(n, dtype=torch.int32).pin_memory()
     d_h, err_h = torch.empty(n, dtype=torch.float32).pin_memory(), torch.empty(max(npatch, 1), dtype=torch.float32).pin_memory()
 
+    lio_cfg_c = api.lio_cfg_c(fr["lio_cfg"])
+
     def e2e_step():
-        ctx.lio_set_scan(pts_h)
-        ctx.lio_run(prior_h, prior_h, fr["lio_cfg"])
-        a = ctx.lio_fetch(state_out=st_out, match=m_h, normal=nm_h, dis=d_h)
-        ctx.vio_set_image(img_h)
-        ctx.vio_set_patches(pos_h, wp_h, sl_h, ie_h)
-        ctx.vio_run(st_out, st_out)
-        b = ctx.vio_fetch(state_out=st_out2, err=err_h)
-        return a["iters"] + b["total_iters"]
+        # exactly what the C++ shim does per tick pair: esikf_lio_update(host buffers) then esikf_vio_update(host buffers)
+        a = ctx.lio_update_into(pts_h, prior_h, prior_h, lio_cfg_c, st_out, m_h, nm_h, d_h)
+        b = ctx.vio_update_into(img_h, pos_h, wp_h, sl_h, ie_h, st_out, st_out, st_out2, err_h)
+        return a + b
 
     for _ in range(W):
         e2e_step()

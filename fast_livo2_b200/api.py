@@ -243,6 +243,24 @@ class Context:
                                            match.ctypes.data, normal.ctypes.data, dis.ctypes.data))
         return self._lio_result(out, st, match, normal, dis)
 
+    def lio_update_into(self, pts, state_in, state_prop, cfg, state_out, match, normal, dis):
+        """esikf_lio_update with caller-owned (e.g. pinned) input AND output buffers: one C call per LIO tick."""
+        n = int(pts.shape[0])
+        self.n_pts = n
+        st = LioStatsC()
+        cfgc = lio_cfg_c(cfg) if not isinstance(cfg, LioCfgC) else cfg
+        self._ck(self.lib.esikf_lio_update(self.h, _addr(pts), n, _addr(state_in), _addr(state_prop), C.byref(cfgc), _addr(state_out), C.byref(st),
+                                           _addr(match), _addr(normal), _addr(dis)))
+        return st.iters
+
+    def vio_update_into(self, img, pos, warp_patch, search_levels, inv_expo, state_in, state_prop, state_out, errors):
+        n = int(pos.shape[0])
+        self.n_patches = n
+        st = VioStatsC()
+        self._ck(self.lib.esikf_vio_update(self.h, _addr(img), int(img.shape[1]), int(img.shape[0]), _addr(pos), _addr(warp_patch), _addr(search_levels),
+                                           _addr(inv_expo), n, _addr(state_in), _addr(state_prop), _addr(state_out), C.byref(st), _addr(errors)))
+        return st.total_iters
+
     def lio_fetch_point_cov(self):
         bc = np.zeros((self.n_pts, 3, 3))
         cm = np.zeros((self.n_pts, 3, 3))

@@ -91,7 +91,7 @@ struct esikf_ctx {
   int loop_mode = 1;      // 1: persistent cooperative kernel per update (single GPU), 0: one residual + one solve launch per iteration
   int coop_ok = 0;
   int coop_lio = 0, coop_vio = 0;  // co-resident CTAs per SM of the persistent kernels
-  struct { unsigned int *p; } barrier;
+  DevBuf<unsigned int> barrier;       // two grid barriers {counter @ +0, release word @ +128 B}, 256 B apart; launches alternate
   DevBuf<unsigned long long> stamps;  // 8 per slot: 8 LIO slots then 64 VIO slots
   bool want_stamps = false;
   esikf_extrinsics ext{};
@@ -117,7 +117,15 @@ struct esikf_ctx {
   DevBuf<double> ext_dev;    // extR(9) extT(3)
 
   // shared update state
-  DevBuf<double> state, prop, info, partials, old_state, G;
+  DevBuf<double> state_prop;             // [state 386 | prop 386] contiguous: one H2D copy per update
+  struct { double *p; } state, prop;
+  DevBuf<double> info, partials, old_state, G;
+  // pinned staging ring for the two packed states of an update (slot reuse guarded by an event)
+  enum { STAGE_SLOTS = 16 };
+  double *stage = nullptr;
+  cudaEvent_t stage_ev[STAGE_SLOTS] = {};
+  unsigned stage_idx = 0;
+  unsigned launch_parity = 0;            // the persistent kernels alternate between two grid-barrier counters
   DevBuf<unsigned char> ctl_block;  // [esikf_lio_stats | Ctrl | barrier (64 B) | esikf_vio_stats], zeroed with one memset per update
   struct { Ctrl *p; } ctrl;
   struct { esikf_lio_stats *p; } lio_stats;
@@ -211,17 +219,23 @@ int esikf_create(esikf_ctx **out, int device) {
     delete ctx;
     return ESIKF_ERR_CUDA;
   }
-  bool ok = ctx->state.reserve(S_N) == cudaSuccess && ctx->prop.reserve(S_N) == cudaSuccess && ctx->info.reserve(INFO_N) == cudaSuccess &&
+  bool ok = ctx->state_prop.reserve(2 * S_N) == cudaSuccess && ctx->info.reserve(INFO_N) == cudaSuccess &&
+            cudaMallocHost(&ctx->stage, (size_t)esikf_ctx::STAGE_SLOTS * 2 * S_N * sizeof(double)) == cudaSuccess &&
             ctx->old_state.reserve(32) == cudaSuccess && ctx->G.reserve(19 * 7) == cudaSuccess &&
             ctx->ctl_block.reserve(sizeof(esikf_lio_stats) + sizeof(Ctrl) + 64 + sizeof(esikf_vio_stats)) == cudaSuccess && ctx->ext_dev.reserve(12) == cudaSuccess &&
             ctx->scratch_state.reserve(S_N) == cudaSuccess;
   ctx->partial_blocks = ctx->sm_count < 160 ? ctx->sm_count : 160;  // persistent residual kernels: one CTA per SM
-  ok = ok && ctx->partials.reserve((size_t)ctx->partial_blocks * INFO_N) == cudaSuccess && ctx->stamps.reserve(8 * 72 + 64 + 160) == cudaSuccess;
+  ok = ok && ctx->partials.reserve((size_t)ctx->partial_blocks * INFO_N) == cudaSuccess && ctx->stamps.reserve(8 * 72 + 64 + 160) == cudaSuccess &&
+       ctx->barrier.reserve(128) == cudaSuccess;
+  if (ok) cudaMemsetAsync(ctx->barrier.p, 0, 128 * sizeof(unsigned int), ctx->stream);
+  if (ok) {
+    ctx->state.p = ctx->state_prop.p, ctx->prop.p = ctx->state_prop.p + S_N;
+    for (int i = 0; i < esikf_ctx::STAGE_SLOTS; i++) ok = ok && cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming) == cudaSuccess;
+  }
   if (ok) {
     unsigned char *b = ctx->ctl_block.p;
     ctx->lio_stats.p = reinterpret_cast<esikf_lio_stats *>(b);
     ctx->ctrl.p = reinterpret_cast<Ctrl *>(b + sizeof(esikf_lio_stats));
-    ctx->barrier.p = reinterpret_cast<unsigned int *>(b + sizeof(esikf_lio_stats) + sizeof(Ctrl));
     ctx->vio_stats.p = reinterpret_cast<esikf_vio_stats *>(b + sizeof(esikf_lio_stats) + sizeof(Ctrl) + 64);
     cudaMemsetAsync(b, 0, ctx->ctl_block.cap, ctx->stream);
   }
@@ -267,9 +281,12 @@ void esikf_destroy(esikf_ctx *ctx) {
   if (ctx->mailbox) cudaFree(ctx->mailbox);
   ctx->peer_ptrs_dev.release();
   ctx->slots.release(), ctx->planes.release(), ctx->pts.release(), ctx->pre.release(), ctx->match_plane.release();
-  ctx->normal_plane.release(), ctx->dis.release(), ctx->ext_dev.release(), ctx->state.release(), ctx->prop.release();
+  ctx->normal_plane.release(), ctx->dis.release(), ctx->ext_dev.release(), ctx->state_prop.release();
+  if (ctx->stage) cudaFreeHost(ctx->stage);
+  for (int i = 0; i < esikf_ctx::STAGE_SLOTS; i++)
+    if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
   ctx->info.release(), ctx->partials.release(), ctx->old_state.release(), ctx->G.release(), ctx->ctl_block.release();
-  ctx->stamps.release(), ctx->img.release(), ctx->vis_pos.release(), ctx->inv_expo.release();
+  ctx->stamps.release(), ctx->barrier.release(), ctx->img.release(), ctx->vis_pos.release(), ctx->inv_expo.release();
   ctx->warp_patch.release(), ctx->errors.release(), ctx->search_levels.release(), ctx->ref_img_ptrs.release(), ctx->ref_idx.release();
   ctx->px_ref.release(), ctx->pos_w.release(), ctx->normal_w.release(), ctx->T_ref.release(), ctx->T_cur.release();
   ctx->A_cur_ref.release(), ctx->pc_buf.release(), ctx->patch_buf.release(), ctx->flush.release(), ctx->scratch_state.release();
@@ -402,6 +419,17 @@ static int lio_grid(const esikf_ctx *ctx, int count) {
   int g = tiles < ctx->partial_blocks ? tiles : ctx->partial_blocks;  // persistent: <= 2 CTAs per SM, equal slices
   return g < 1 ? 1 : g;
 }
+// Stage the two packed states of an update in pinned memory and upload them with ONE copy ([state | prop] is contiguous).
+static int upload_states(esikf_ctx *ctx, const double *state_in, const double *state_prop) {
+  const unsigned slot = ctx->stage_idx++ % esikf_ctx::STAGE_SLOTS;
+  CK(cudaEventSynchronize(ctx->stage_ev[slot]));  // the copy that last used this slot has been consumed
+  double *h = ctx->stage + (size_t)slot * 2 * S_N;
+  memcpy(h, state_in, S_N * sizeof(double));
+  memcpy(h + S_N, state_prop, S_N * sizeof(double));
+  CK(cudaMemcpyAsync(ctx->state_prop.p, h, 2 * S_N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaEventRecord(ctx->stage_ev[slot], ctx->stream));
+  return ESIKF_OK;
+}
 static PeerArgs peer_args(esikf_ctx *ctx) {
   PeerArgs p;
   p.mbox = ctx->p2p ? ctx->peer_ptrs_dev.p : nullptr;
@@ -426,9 +454,13 @@ int esikf_lio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   CK(cudaSetDevice(ctx->device));
   ctx->lio_cfg = *cfg;
   cudaStream_t st = ctx->stream;
-  CK(cudaMemcpyAsync(ctx->state.p, state_in, S_N * sizeof(double), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(ctx->prop.p, state_prop, S_N * sizeof(double), cudaMemcpyHostToDevice, st));
-  CK(cudaMemsetAsync(ctx->lio_stats.p, 0, sizeof(esikf_lio_stats) + sizeof(Ctrl) + 64, st));  // stats + loop control + grid barrier
+  {
+    int rc = upload_states(ctx, state_in, state_prop);
+    if (rc) return rc;
+  }
+  const bool fused_lio = ctx->loop_mode == 1 && (ctx->nranks == 1 || ctx->p2p) && ctx->coop_ok && ctx->coop_lio > 0 && !ctx->timing;
+  // the persistent kernel initialises its own loop control / stats / barrier; the per-iteration path needs them zeroed
+  if (!fused_lio) CK(cudaMemsetAsync(ctx->lio_stats.p, 0, sizeof(esikf_lio_stats) + sizeof(Ctrl) + 64, st));
   const int n = ctx->n_pts;
   if (ctx->scan_fresh) {
     if (n > 0) {
@@ -444,13 +476,14 @@ int esikf_lio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   sa.state = ctx->state.p, sa.prop = ctx->prop.p, sa.info = ctx->info.p, sa.ctrl = ctx->ctrl.p;
   sa.max_iterations = cfg->max_iterations, sa.solve_mode = ctx->solve_mode, sa.lio_stats = ctx->lio_stats.p;
   const int grid = lio_grid(ctx, ka.count);
-  if (ctx->loop_mode == 1 && (ctx->nranks == 1 || ctx->p2p) && ctx->coop_ok && ctx->coop_lio > 0 && !ctx->timing) {
-    unsigned int *bar = ctx->barrier.p;
+  if (fused_lio) {
+    const unsigned par = ctx->launch_parity++ & 1;
+    unsigned int *bar = ctx->barrier.p + 64 * par, *bar_next = ctx->barrier.p + 64 * (par ^ 1);  // this launch's barrier / the next launch's (zeroed by the kernel)
     unsigned long long *stamps = ctx->want_stamps ? ctx->stamps.p : nullptr;
     if (stamps) CK(cudaMemsetAsync(stamps, 0, 64 * sizeof(unsigned long long), st));
     ka.dbg = sa.dbg = ctx->want_stamps ? ctx->stamps.p + 576 : nullptr;
     PeerArgs peer = peer_args(ctx);
-    void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&stamps, (void *)&peer};
+    void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&peer};
     CK(cudaLaunchCooperativeKernel((const void *)lio_update_kernel, dim3(grid), dim3(LIO_THREADS), kargs, sizeof(LioSmem), st));
     ctx->launches += 1;
     ctx->lio_timed = false;
@@ -619,9 +652,15 @@ int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   if (ctx->img_w == 0) return fail(ctx, ESIKF_ERR_STATE, "vio_run before vio_set_image");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  CK(cudaMemcpyAsync(ctx->state.p, state_in, S_N * sizeof(double), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(ctx->prop.p, state_prop, S_N * sizeof(double), cudaMemcpyHostToDevice, st));
-  CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl) + 64 + sizeof(esikf_vio_stats), st));  // loop control + grid barrier + stats
+  {
+    int rc = upload_states(ctx, state_in, state_prop);
+    if (rc) return rc;
+  }
+  const bool fused_vio = ctx->n_patches > 0 && ctx->loop_mode == 1 && (ctx->nranks == 1 || ctx->p2p) && ctx->coop_ok && ctx->coop_vio > 0 && !ctx->timing;
+  if (!fused_vio) {
+    CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), st));
+    CK(cudaMemsetAsync(ctx->vio_stats.p, 0, sizeof(esikf_vio_stats), st));
+  }
   if (ctx->n_patches == 0) return ESIKF_OK;  // total_points == 0: early return (vio.cpp:786)
   VioKernelArgs ka;
   vio_fill_args(ctx, ka, ctx->state.p);
@@ -631,12 +670,13 @@ int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   sa.max_iterations = ctx->vio_cfg.max_iterations, sa.solve_mode = ctx->solve_mode, sa.vio_stats = ctx->vio_stats.p;
   sa.old_state = ctx->old_state.p, sa.G = ctx->G.p, sa.img_point_cov = ctx->vio_cfg.img_point_cov;
   const int grid = vio_grid(ctx, ka.count);
-  if (ctx->loop_mode == 1 && (ctx->nranks == 1 || ctx->p2p) && ctx->coop_ok && ctx->coop_vio > 0 && !ctx->timing) {
-    unsigned int *bar = ctx->barrier.p;
+  if (fused_vio) {
+    const unsigned par = ctx->launch_parity++ & 1;
+    unsigned int *bar = ctx->barrier.p + 64 * par, *bar_next = ctx->barrier.p + 64 * (par ^ 1);
     unsigned long long *stamps = ctx->want_stamps ? ctx->stamps.p + 64 : nullptr;
     if (stamps) CK(cudaMemsetAsync(stamps, 0, 512 * sizeof(unsigned long long), st));
     PeerArgs peer = peer_args(ctx);
-    void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&stamps, (void *)&peer};
+    void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&peer};
     CK(cudaLaunchCooperativeKernel((const void *)vio_update_kernel, dim3(grid), dim3(VIO_THREADS), kargs, sizeof(VioSmem) + sizeof(FusedSolveSmem), st));
     ctx->launches += 1;
     ctx->vio_timed = false;

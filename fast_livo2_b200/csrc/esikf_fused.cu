@@ -72,8 +72,10 @@ __device__ __forceinline__ void peer_allreduce(double *info, const PeerArgs &p, 
   __syncthreads();
 }
 
-// Sense-free counting barrier over all CTAs of a cooperative launch. `counter` is zeroed by the host before the launch;
-// the k-th barrier (k = 0, 1, ...) completes when it reaches (k + 1) * gridDim.x.
+// Counting grid barrier over all CTAs of a cooperative launch: arrivals are atomic increments, everybody polls the same
+// counter; the k-th barrier (k = 0, 1, ...) completes when it reaches (k + 1) * gridDim.x. The counter is zeroed for this
+// launch by the previous launch (launches alternate between two counters). A variant with a separate release word written
+// by the last arriver was measured and is ~1 us SLOWER per barrier (extra L2 hop), see profiles/README.md.
 __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int &epoch) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -129,7 +131,8 @@ struct FusedSolveSmem {
   Ctrl ctrl;  // CTA 0's working copy of the loop-control block (published to global memory after every solve)
 };
 
-__global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_kernel(const LioKernelArgs a, const SolveArgs sa, unsigned int *barrier, unsigned long long *stamps, const PeerArgs peer) {
+__global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_kernel(const LioKernelArgs a, const SolveArgs sa, unsigned int *barrier, unsigned int *barrier_next, unsigned long long *stamps,
+                                                                     const PeerArgs peer) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   LioSmem &sm = *reinterpret_cast<LioSmem *>(smem_raw);
   // CTA 0's solve scratch lives in the reduction scratch (free between the two barriers); only the literal-mode
@@ -144,6 +147,19 @@ __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_kernel(const LioKer
   unsigned int epoch = 0;
   int lo, hi;
   lio_block_range(a.count, lo, hi);
+  if (blockIdx.x == 0) {
+    // CTA 0 owns the loop control for the whole update: initialise it, the diagnostics and the NEXT launch's barrier
+    // counter here (no host-side memset per update). `barrier` alternates between two counters from launch to launch.
+    if (threadIdx.x == 0) {
+      Ctrl z;
+      memset(&z, 0, sizeof(z));
+      fs.ctrl = z;
+      barrier_next[0] = 0u, barrier_next[32] = 0u;
+    }
+    if (sa.lio_stats)
+      for (int t = threadIdx.x; t < (int)(sizeof(esikf_lio_stats) / 4); t += blockDim.x) reinterpret_cast<int *>(sa.lio_stats)[t] = 0;
+    __syncthreads();
+  }
   int sk = 0;
   LaneCache lc;  // what stays with this lane's point across iterations (registers + its shared-memory slot)
   lc.staged_idx = -1, lc.have_pt = false, lc.px = lc.py = lc.pz = 0.f;
@@ -168,7 +184,6 @@ __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_kernel(const LioKer
       dbg_stamp(a.dbg, 12);
       if (it == 0) {  // stage P / poses / loop control once; later iterations find them in shared memory
         solve_load(fs.sm, fs.io, sa, false);
-        if (threadIdx.x == 0) fs.ctrl = *a.ctrl;
       }
       reduce_partials_block(a.partials, a.partial_stride, gridDim.x, fs.io.info);
       peer_allreduce(fs.io.info, peer, (unsigned int)it);
@@ -194,7 +209,8 @@ __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_kernel(const LioKer
   }
 }
 
-__global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKernelArgs a, SolveArgs sa, unsigned int *barrier, unsigned long long *stamps, const PeerArgs peer) {
+__global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKernelArgs a, SolveArgs sa, unsigned int *barrier, unsigned int *barrier_next, unsigned long long *stamps,
+                                                                     const PeerArgs peer) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   VioSmem &sm = *reinterpret_cast<VioSmem *>(smem_raw);
   // the solve scratch has its own shared memory behind VioSmem (so the diagnostics can be written while the next
@@ -208,6 +224,17 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKer
   unsigned int epoch = 0;
   int lo, hi;
   vio_block_range(a.count, lo, hi);
+  if (blockIdx.x == 0) {
+    if (threadIdx.x == 0) {
+      Ctrl z;
+      memset(&z, 0, sizeof(z));
+      fs.ctrl = z;
+      barrier_next[0] = 0u, barrier_next[32] = 0u;
+    }
+    if (sa.vio_stats)
+      for (int t = threadIdx.x; t < (int)(sizeof(esikf_vio_stats) / 4); t += blockDim.x) reinterpret_cast<int *>(sa.vio_stats)[t] = 0;
+    __syncthreads();
+  }
   for (int level = a.levels - 1; level >= 0; level--) {      // vio.cpp:790
     for (int it = 0; it < sa.max_iterations; it++) {          // :1536
       int sk = 8 * ((a.levels - 1 - level) * sa.max_iterations + it);
@@ -227,7 +254,6 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKer
       if (blockIdx.x == 0) {
         if (level == a.levels - 1 && it == 0) {
           solve_load(fs.sm, fs.io, sa, false);
-          if (threadIdx.x == 0) fs.ctrl = *a.ctrl;
         }
         reduce_partials_block(a.partials, a.partial_stride, gridDim.x, fs.io.info);
         peer_allreduce(fs.io.info, peer, (unsigned int)((a.levels - 1 - level) * sa.max_iterations + it));
