@@ -195,7 +195,9 @@ int esikf_vio_warp_patches(esikf_ctx *ctx, int32_t n, const int32_t *ref_img_ind
  * packed information buffer [HTH upper | HTz | M | sum|d| ...] and every rank solves redundantly.
  * esikf_comm_unique_id: rank 0 creates the NCCL id, the host side broadcasts it (torch.distributed).
  * esikf_comm_init     : ncclCommInitRank on this context. shard = [begin, begin+count) of the scan /
- *                       patch arrays given to set_scan / set_patches (all ranks pass the full arrays). */
+ *                       patch arrays given to set_scan / set_patches (all ranks pass the full arrays).
+ * With more than one rank the per-point / per-patch outputs of a rank (match_plane, normal_plane, dis_to_plane,
+ * errors) are valid on that rank's esikf_shard_range slice only; the state and the stats are identical on every rank. */
 int esikf_comm_unique_id(char out[128]);
 int esikf_comm_init(esikf_ctx *ctx, int32_t rank, int32_t nranks, const char unique_id[128]);
 int esikf_comm_rank(const esikf_ctx *ctx, int32_t *rank, int32_t *nranks);

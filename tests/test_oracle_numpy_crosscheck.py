@@ -1,0 +1,195 @@
+"""Second, independent restatement (plain numpy, written against the reference text, not against oracle/) of ONE LIO
+iteration: TransformLidar + per-point covariance (voxel_map.cpp:376-390), voxel key / neighbour rule (:665-691), plane gate
+and max-probability choice (:721-754), Jacobian / R^-1 (:414-458) and the information sums (:464-466). The C++ oracle must
+agree with it point by point — this is what stands in for the golden vectors the reference does not ship."""
+import numpy as np
+
+import oracle_bind as O
+from fast_livo2_b200 import synthetic as S
+
+f32 = np.float32
+
+
+def _body_cov(p, dept, beam):
+    p = p.copy()
+    if p[2] == 0:
+        p[2] = 0.0001
+    rng = f32(np.sqrt(p @ p))
+    rv = f32(dept) * f32(dept)
+    dv = np.sin(float(f32(beam)) * 0.017453293) ** 2
+    d = p / np.linalg.norm(p)
+    b1 = np.array([1.0, 1.0, -(d[0] + d[1]) / d[2]])
+    b1 /= np.linalg.norm(b1)
+    b2 = np.cross(b1, d)
+    b2 /= np.linalg.norm(b2)
+    A = float(rng) * S.skew(d) @ np.stack([b1, b2], 1)
+    return np.outer(d, d) * float(rv) + A @ (np.eye(2) * dv) @ A.T
+
+
+def _key(pw, vs):
+    loc = np.zeros(3, f32)
+    for j in range(3):
+        loc[j] = f32(pw[j] / vs)
+        if loc[j] < 0:
+            loc[j] = f32(float(loc[j]) - 1.0)
+    return loc, tuple(int(np.trunc(float(x))) for x in loc)
+
+
+def _eval(pl, pw, var, sigma_num):
+    n, c = pl["normal"], pl["center"]
+    pv = np.zeros((6, 6))
+    iu = np.triu_indices(6)
+    pv[iu] = pl["plane_var"]
+    pv = pv + pv.T - np.diag(np.diag(pv))
+    sd = n @ pw + float(pl["d"])
+    dtp = f32(abs(sd))
+    dtc = f32(((c - pw) ** 2).sum())
+    with np.errstate(invalid="ignore"):
+        rd = np.sqrt(f32(dtc - f32(dtp * dtp)))
+    if not (float(rd) <= 3.0 * float(pl["radius"])):
+        return None
+    J = np.concatenate([pw - c, -n])
+    sig = J @ pv @ J + n @ var @ n
+    if not (float(dtp) < sigma_num * np.sqrt(sig)):
+        return None
+    return 1.0 / np.sqrt(sig) * np.exp(-0.5 * float(dtp) * float(dtp) / sig), f32(sd)
+
+
+def test_numpy_restatement_agrees_with_cpp_oracle(small_frame):
+    fr = small_frame
+    cfg, ext, vm = fr["lio_cfg"], fr["ext"], fr["map"]
+    st = S.unpack_state(fr["state_prior"])
+    R, t, P = st["R"], st["p"], st["cov"]
+    roots = {tuple(k): (f, c) for k, f, c in zip(vm["keys"].tolist(), vm["first"], vm["count"])}
+    vsf = float(f32(cfg.voxel_size))
+    ql = float(f32(f32(cfg.voxel_size) / f32(4)))
+    pts = fr["pts"][:700]
+    lio = O.OracleLIO(cfg, ext)
+    lio.set_map(vm)
+    sp = lio.single_pass(pts, fr["state_prior"], fr["state_prior"])
+    HTH, HTz, n_match, n_neigh, n_multi = np.zeros((6, 6)), np.zeros(6), 0, 0, 0
+    for i, pb in enumerate(pts.astype(np.float64)):
+        pz = pb.copy()
+        if pz[2] == 0:
+            pz[2] = 0.001
+        bc = _body_cov(pz, cfg.dept_err, cfg.beam_err)
+        cm = S.skew(ext.extR @ pz + ext.extT)
+        pi = ext.extR @ pb + ext.extT
+        pw = (R @ pi + t).astype(f32).astype(np.float64)
+        var = R @ bc @ R.T + (-cm) @ P[0:3, 0:3] @ (-cm).T + P[3:6, 3:6]
+        np.testing.assert_allclose(sp["point_w"][i], pw, rtol=0, atol=0)
+        np.testing.assert_allclose(sp["var"][i], var, rtol=1e-11, atol=1e-18)
+        loc, key = _key(pw, cfg.voxel_size)
+        best = None
+        if key in roots:
+            f, c = roots[key]
+            n_multi += c > 1
+            for j in range(f, f + c):
+                e = _eval(vm["planes"][j], pw, var, cfg.sigma_num)
+                if e is not None and (best is None or e[0] > best[0]):
+                    best = (e[0], j, e[1])
+            if best is None:
+                nk = list(key)
+                for a in range(3):
+                    center = (0.5 + key[a]) * vsf
+                    if float(loc[a]) > center + ql:
+                        nk[a] += 1
+                    elif float(loc[a]) < center - ql:
+                        nk[a] -= 1
+                if tuple(nk) in roots:
+                    f, c = roots[tuple(nk)]
+                    for j in range(f, f + c):
+                        e = _eval(vm["planes"][j], pw, var, cfg.sigma_num)
+                        if e is not None and (best is None or e[0] > best[0]):
+                            best = (e[0], j, e[1])
+                    n_neigh += best is not None
+        if best is None:
+            assert sp["plane"][i] == -1
+            continue
+        n_match += 1
+        assert sp["plane"][i] == best[1] and sp["dis"][i] == best[2]
+        pl = vm["planes"][best[1]]
+        n, c = pl["normal"], pl["center"]
+        pv = np.zeros((6, 6))
+        iu = np.triu_indices(6)
+        pv[iu] = pl["plane_var"]
+        pv = pv + pv.T - np.diag(np.diag(pv))
+        J = np.concatenate([R @ pi + t - c, -n])  # prior pose == current pose in this single pass
+        RE = R @ ext.extR
+        rinv = 1.0 / (0.001 + J @ pv @ J + n @ (RE @ bc @ RE.T) @ n)
+        A = S.skew(pi) @ R.T @ n
+        H = np.concatenate([A, n])
+        np.testing.assert_allclose(sp["H"][i], H, rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(sp["R_inv"][i], rinv, rtol=1e-11)
+        HTH += rinv * np.outer(H, H)
+        HTz += rinv * H * (-float(best[2]))
+    assert n_match > 500 and n_multi > 0
+    # the full oracle's first-iteration information matrix over the same points
+    r = lio.state_estimation(pts, fr["state_prior"], fr["state_prior"])
+    assert r["M"][0] == n_match
+    np.testing.assert_allclose(r["HTH"][0], HTH, rtol=1e-11)
+    np.testing.assert_allclose(r["HTz"][0], HTz, rtol=1e-9, atol=1e-9)
+
+
+def test_numpy_restatement_of_one_vio_iteration(small_vio_frame):
+    """First iteration of updateState at the coarsest level (vio.cpp:1540-1634, 1660-1662) restated in numpy with the
+    reference's float / double narrowing points; the oracle's H^T H, H^T z and mean squared error must agree."""
+    fr = small_vio_frame
+    ext, cam, vcfg = fr["ext"], fr["cam_cfg"], fr["vio_cfg"]
+    w = O.oracle_warp_patches(fr, fr["state_prior"])
+    n = 40
+    pos, wp, sl = fr["vis_pos"][:n], w["warp_patch"][:n], w["search_levels"][:n]
+    st = S.unpack_state(fr["state_prior"])
+    Rli, Pli = ext.extR.T, -ext.extR.T @ ext.extT
+    Rci = ext.Rcl @ Rli
+    Pci = ext.Rcl @ Pli + ext.Pcl
+    Pic = -Rci.T @ Pci
+    Jdp_dR = -Rci @ S.skew(Pic)
+    Rcw = Rci @ st["R"].T
+    Pcw = -Rci @ st["R"].T @ st["p"] + Pci
+    level = vcfg.levels - 1
+    img = fr["img"].astype(np.int64)
+    width = cam.width
+    flat = img.reshape(-1)
+    HTH, HTz, err, nm = np.zeros((7, 7)), np.zeros(7), f32(0), 0
+    for i in range(n):
+        scale = 1 << (level + int(sl[i]))
+        inv_scale = f32(1.0) / f32(scale)
+        pf = Rcw @ pos[i] + Pcw
+        pc = np.array([cam.fx * pf[0] / pf[2] + cam.cx, cam.fy * pf[1] / pf[2] + cam.cy])
+        zi = 1.0 / pf[2]
+        Jdpi = np.array([[cam.fx * zi, 0, -cam.fx * pf[0] * zi * zi], [0, cam.fy * zi, -cam.fy * pf[1] * zi * zi]])
+        u_ref, v_ref = f32(pc[0]), f32(pc[1])
+        u_i = int(np.floor(f32(pc[0] / scale)) * scale)
+        v_i = int(np.floor(f32(pc[1] / scale)) * scale)
+        su, sv = f32((u_ref - f32(u_i)) / f32(scale)), f32((v_ref - f32(v_i)) / f32(scale))
+        wtl, wtr = f32((1.0 - float(su)) * (1.0 - float(sv))), f32(float(su) * (1.0 - float(sv)))
+        wbl, wbr = f32((1.0 - float(su)) * float(sv)), f32(su * sv)
+        bil = lambda a, b, c, d: f32(f32(f32(wtl * f32(a)) + f32(wtr * f32(b))) + f32(wbl * f32(c))) + f32(wbr * f32(d))
+        perr = f32(0)
+        for x in range(8):
+            for y in range(8):
+                b = (v_i + x * scale - 4 * scale) * width + u_i - 4 * scale + y * scale
+                sw = scale * width
+                T = lambda o: flat[b + o]
+                du = f32(0.5) * f32(bil(T(scale), T(2 * scale), T(sw + scale), T(sw + 2 * scale)) - bil(T(-scale), T(0), T(sw - scale), T(sw)))
+                dv = f32(0.5) * f32(bil(T(sw), T(scale + sw), T(2 * sw), T(2 * sw + scale)) - bil(T(-sw), T(-sw + scale), T(0), T(scale)))
+                Jimg = np.array([float(du), float(dv)]) * st["inv_expo"] * float(inv_scale)
+                Jdphi = Jimg @ Jdpi @ S.skew(pf)
+                Jdp = -Jimg @ Jdpi
+                JdR = Jdphi @ Rci + Jdp @ Jdp_dR
+                Jdt = Jdp @ Rcw
+                cur = float(bil(T(0), T(scale), T(sw), T(sw + scale)))
+                res = st["inv_expo"] * cur - 1.0 * float(wp[i][64 * level + x * 8 + y])
+                h = np.concatenate([JdR, Jdt, [cur]])
+                HTH += np.outer(h, h)
+                HTz += h * res
+                perr = f32(float(perr) + res * res)
+                nm += 1
+        err = f32(err + perr)
+    err = f32(err / f32(nm))
+    vio = O.OracleVIO(cam, ext, vcfg)
+    o = vio.update(fr["img"], pos, wp, sl, np.ones(n), fr["state_prior"], fr["state_prior"])
+    np.testing.assert_allclose(o["HTH"][level][0], HTH, rtol=1e-11)
+    np.testing.assert_allclose(o["HTz"][level][0], HTz, rtol=1e-10, atol=1e-8)
+    assert o["error_trace"][level][0] == err
