@@ -68,7 +68,6 @@ __device__ __forceinline__ void peer_allreduce(double *info, const PeerArgs &p, 
     }
     info[tid] = s;
   }
-  __threadfence();
   __syncthreads();
 }
 
@@ -80,13 +79,13 @@ __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned int target = (epoch + 1) * gridDim.x;
-    __threadfence();
-    atomicAdd(counter, 1u);
+    // release-increment: orders this CTA's earlier writes (made visible to thread 0 by the CTA barrier above) before the
+    // arrival, without a separate membar; the acquire poll orders the other CTAs' writes before everything after it.
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     unsigned int v;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
     } while (v < target);
-    __threadfence();
   }
   epoch++;
   __syncthreads();
@@ -97,8 +96,7 @@ __device__ __forceinline__ void reduce_partials_block(const double *partials, in
   const int tid = threadIdx.x;
   sum_partials(partials, partial_stride, nb, info, blockDim.x >> 5);
   if (tid >= 66 && tid < INFO_N) info[tid] = 0.0;
-  __threadfence();
-  __syncthreads();
+  __syncthreads();  // `info` is CTA 0's shared-memory copy: no fence needed
 }
 
 // Per-CTA partial block -> global (entry-major), same layout / order as reduce_info.
