@@ -12,13 +12,7 @@
 
 #include "esikf_dev.cuh"
 
-namespace esikf {
-// kernels (defined in the other translation units of this library)
-struct LioKernelArgs;
-struct VioKernelArgs;
-struct SolveArgs;
-}  // namespace esikf
-
+// single translation unit: the kernels are included so the whole library builds with one nvcc invocation
 #include "esikf_lio.cu"
 #include "esikf_solve.cu"
 #include "esikf_vio.cu"
@@ -126,7 +120,8 @@ struct esikf_ctx {
   cudaEvent_t stage_ev[STAGE_SLOTS] = {};
   unsigned stage_idx = 0;
   unsigned launch_parity = 0;            // the persistent kernels alternate between two grid-barrier counters
-  DevBuf<unsigned char> ctl_block;  // [esikf_lio_stats | Ctrl | barrier (64 B) | esikf_vio_stats], zeroed with one memset per update
+  DevBuf<unsigned char> ctl_block;  // [esikf_lio_stats | Ctrl | 64 B pad | esikf_vio_stats]; initialised by CTA 0 of the persistent kernels,
+                                    // by a memset on the per-iteration launch path
   struct { Ctrl *p; } ctrl;
   struct { esikf_lio_stats *p; } lio_stats;
   struct { esikf_vio_stats *p; } vio_stats;

@@ -5,10 +5,13 @@
 //                           covariance, :643-786 voxel probe + plane association, :414-458 Jacobian / R^-1) fused with the
 //                           H^T R^-1 H, H^T R^-1 z reduction (:464-466). No PointToPlane is ever materialised.
 //
-// Mapping: one thread per LiDAR point (fp64 work per point is ~600 flop and sequential; a warp per point would idle 31/32 of
-// the fp64 pipe), 32 points per warp. The per-warp contraction sum_i a_i (w_i a_i)^T, a = [H_i(6), z_i, 1], runs on the fp64
-// tensor-core path (mma.sync.m8n8k4.f64, SASS DMMA) out of shared-memory staged rows; partial 8x8 blocks are combined in a
-// fixed order (warp -> block -> grid) so the result is bit-reproducible run to run.
+// Mapping: one thread per LiDAR point (the ~600 fp64 operations per point are sequential; a warp per point would idle 31/32
+// of the fp64 pipe), 22 warps per CTA, one CTA per SM (148 x 704 = 104 k points in one round). The warp is the cooperation
+// unit: (i) the 32 first-candidate plane records of a warp are staged into shared memory with coalesced half-warp copies
+// and stay resident across the iterations of the persistent kernel; (ii) the rare extra candidates of sub-divided root
+// voxels of ALL lanes are evaluated lane-parallel in one pass; (iii) the per-warp contraction sum_i a_i (w_i a_i)^T,
+// a = [H_i(6), z_i, 1], runs on the fp64 tensor-core path (mma.sync.m8n8k4.f64, SASS DMMA) out of the shared-memory rows.
+// Partial 8x8 blocks are combined in a fixed order (warp -> CTA -> grid), so results are bit-reproducible run to run.
 #include "esikf_dev.cuh"
 
 namespace esikf {
