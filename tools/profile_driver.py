@@ -8,6 +8,8 @@ from fast_livo2_b200 import api, synthetic as S
 n_pts = int(os.environ.get("N_PTS", 100000)); n_patch = int(os.environ.get("N_PATCH", 2000)); steps = int(os.environ.get("STEPS", 3))
 fr = S.cached_frame(seed=0, n_pts=n_pts, n_map=int(os.environ.get("N_MAP", 1000000)), n_patches=n_patch)
 ctx = api.Context(0)
+if os.environ.get("ESIKF_LOOP") is not None:
+    ctx.set_loop_mode(int(os.environ["ESIKF_LOOP"]))  # 0: per-iteration launches (profiles the stand-alone residual kernels)
 ctx.set_extrinsics(fr["ext"]); ctx.map_upload(fr["map"], fr["lio_cfg"].voxel_size); ctx.vio_set_camera(fr["cam_cfg"], fr["vio_cfg"])
 r = ctx.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"])
 st = S.unpack_state(r["state"])
