@@ -117,3 +117,53 @@ def test_vio_rollback_semantics(small_vio_frame):
         assert all(tr[k + 1] <= tr[k] for k in range(acc - 1))  # accepted errors are non-increasing
         if acc == it - 1:
             assert tr[it - 1] > tr[it - 2]
+
+
+def test_vio_jacobian_rows_match_finite_differences(small_vio_frame):
+    """Finite-difference pin of the geometric Jacobian chain (vio.cpp:1574-1629: Jdpi, [pf]x, Jdphi_dR, Jdp_dR, Jdp_dt).
+    On an integer-slope ramp image the bilinear sample and the central-difference gradient are exact, so every one of
+    the 64 rows of a patch is d(inv_expo * I(pi(Rcw p + Pcw)))/d(dtheta, dp) and H^T H[:6,:6] = 64 j j^T."""
+    import dataclasses
+
+    fr = small_vio_frame
+    ext, cam = fr["ext"], fr["cam_cfg"]
+    assert cam.model == 0 and not any(cam.d)
+    vcfg = dataclasses.replace(fr["vio_cfg"], levels=1, max_iterations=1)
+    st = S.unpack_state(fr["state_prior"])
+    pos = fr["vis_pos"][3]
+
+    def project(state):
+        s = S.unpack_state(state)
+        Rcw, Pcw = S.camera_pose(ext, s["R"], s["p"])
+        pf = Rcw @ pos + Pcw
+        return np.array([cam.fx * pf[0] / pf[2] + cam.cx, cam.fy * pf[1] / pf[2] + cam.cy])
+
+    pc0 = project(fr["state_prior"])
+    uc, vc = int(round(pc0[0])), int(round(pc0[1]))
+    a, b = 2, -1  # integer slopes: the u8 image is an exact plane around the patch
+    uu, vv = np.meshgrid(np.arange(cam.width), np.arange(cam.height))
+    img = np.clip(127 + a * (uu - uc) + b * (vv - vc), 0, 255).astype(np.uint8)
+
+    vio = O.OracleVIO(cam, ext, vcfg)
+    o = vio.update(img, pos[None], np.zeros((1, 64), np.float32), np.zeros(1, np.int32), np.ones(1), fr["state_prior"], fr["state_prior"])
+    HTH = o["HTH"][0][0]
+
+    lib = O.load()
+
+    def boxplus(state, d):
+        out = np.zeros_like(state)
+        lib.orc_boxplus(O.dptr(O.c64(state)), O.dptr(O.c64(d)), O.dptr(out))
+        return out
+
+    h = 1e-4  # above Exp()'s 1e-5 identity threshold (so3_math.h:44-66)
+    j = np.zeros(6)
+    for k in range(6):
+        d = np.zeros(19)
+        d[k] = h
+        pp, pm = project(boxplus(fr["state_prior"], d)), project(boxplus(fr["state_prior"], -d))
+        j[k] = st["inv_expo"] * (a * (pp[0] - pm[0]) + b * (pp[1] - pm[1])) / (2 * h)
+    # float32 bilinear weights carry ~1e-7 relative error into du, dv
+    np.testing.assert_allclose(HTH[:6, :6], 64.0 * np.outer(j, j), rtol=2e-5, atol=1e-6 * np.abs(j).max() ** 2 * 64)
+    # 7th column: the sampled intensity itself (vio.cpp:1626); sum over the ramp patch = 64*127 + offsets
+    cur_sum = HTH[:6, 6] / j
+    assert np.allclose(cur_sum, cur_sum[0], rtol=1e-4)
