@@ -30,6 +30,7 @@ struct SolveArgs {
   double *G;            // 19 x 7 last accepted gain block
   double img_point_cov;
   int level, slot_iter, last_slot;
+  int no_publish;       // replicated-solve kernels: every CTA solves, only CTA 0 writes the results to global memory
   unsigned long long *dbg;  // measurement only
 };
 
@@ -317,8 +318,9 @@ __device__ __noinline__ bool lio_solve_block(const SolveArgs &a, SolveSmem &sm, 
   }
   __syncthreads();
   const bool stop = io.flags[2] != 0;
-  for (int t = tid; t < 25; t += blockDim.x) a.state[t] = io.st[t];
-  if (stop) {
+  if (!a.no_publish)
+    for (int t = tid; t < 25; t += blockDim.x) a.state[t] = io.st[t];
+  if (stop && !a.no_publish) {
     // cov = (I - G) cov   (:489-490); G only has its first 6 columns
     for (int t = tid; t < 361; t += blockDim.x) {
       const int r = t / 19, c = t - 19 * r;
@@ -436,7 +438,7 @@ __device__ __forceinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &s
   }
   __syncthreads();
   const bool accepted = io.flags[0] != 0, ran = io.flags[2] != 0;
-  if (ran) {
+  if (ran && !a.no_publish) {
     for (int t = tid; t < 25; t += blockDim.x) {
       a.state[t] = io.st[t];
       a.old_state[t] = io.old[t];

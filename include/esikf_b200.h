@@ -125,7 +125,10 @@ int64_t esikf_launch_count(const esikf_ctx *ctx);
  * partial-pivot inversions as at src/voxel_map.cpp:468 / src/vio.cpp:1661. */
 int esikf_set_solve_mode(esikf_ctx *ctx, int mode);
 /* loop_mode: 1 (default) = one persistent cooperative kernel runs the whole iteration loop of an update (single GPU);
- * 0 = one residual + one solve launch per iteration (also used when a communicator is attached or timing is on). */
+ * 0 = one residual + one solve launch per iteration (also used when a communicator is attached or timing is on);
+ * 2 = persistent kernel with the gain solve replicated in every CTA (single GPU; one grid barrier per iteration instead
+ * of two, no state round trip through global memory); 3 = as 2 with the per-CTA partial blocks exchanged as tagged
+ * 64-bit words (no grid barrier at all). Results of all modes are bit-identical. */
 int esikf_set_loop_mode(esikf_ctx *ctx, int mode);
 int esikf_set_extrinsics(esikf_ctx *ctx, const esikf_extrinsics *ext);
 
