@@ -542,7 +542,8 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_repl_kernel(const V
   __syncthreads();
   int slot = 0;
   for (int level = a.levels - 1; level >= 0; level--) {      // vio.cpp:790
-    for (int it = 0; it < sa.max_iterations; it++, slot++) {  // :1536
+    for (int it = 0; it < sa.max_iterations; it++) {          // :1536
+      const int cur = slot++;  // counts executed iterations (a level may end early): buffer parity and tag follow it
       int sk = 8 * ((a.levels - 1 - level) * sa.max_iterations + it);
       stamp(stamps, sk);
       vio_consts_from_resident(sm, a, fs);
@@ -552,13 +553,13 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_repl_kernel(const V
       __syncthreads();
       stamp(stamps, sk);
       if (LL) {
-        const unsigned int tag = ll.seq_base + (unsigned int)slot + 1u;
-        unsigned long long *const w = ll.words + (size_t)(slot & 1) * 66 * a.partial_stride * 2;
+        const unsigned int tag = ll.seq_base + (unsigned int)cur + 1u;
+        unsigned long long *const w = ll.words + (size_t)(cur & 1) * 66 * a.partial_stride * 2;
         ll_store_partials<VIO_WARPS>(sm.red, D0, D1, n_meas, false, w, a.partial_stride, tag);
         stamp(stamps, sk);
         ll_reduce_partials_block<false, (58 + VIO_WARPS - 1) / VIO_WARPS>(w, a.partial_stride, gridDim.x, fs.io.info, tag);
       } else {
-        double *const part = a.partials + (size_t)(slot & 1) * partial_parity_stride;
+        double *const part = a.partials + (size_t)(cur & 1) * partial_parity_stride;
         store_partials<VIO_WARPS>(sm.red, D0, D1, n_meas, false, part, a.partial_stride);
         grid_barrier(barrier, epoch);
         stamp(stamps, sk);
