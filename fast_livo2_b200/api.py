@@ -107,6 +107,8 @@ def load_library():
     return lib
 
 
+DEFAULT_LOOP_MODE = 2  # esikf_set_loop_mode: 2 replicated-solve persistent kernel, 1 CTA-0 solve, 0 per-iteration launches
+
 EXPORTED_SYMBOLS = [
     "esikf_create", "esikf_destroy", "esikf_last_error", "esikf_stream", "esikf_synchronize", "esikf_launch_count", "esikf_set_solve_mode", "esikf_set_loop_mode",
     "esikf_set_extrinsics", "esikf_map_upload", "esikf_map_patch", "esikf_lio_set_scan", "esikf_lio_run", "esikf_lio_fetch",

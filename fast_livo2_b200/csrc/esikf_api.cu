@@ -82,13 +82,12 @@ struct esikf_ctx {
   std::string err;
   int64_t launches = 0;
   int solve_mode = 0;
-  int loop_mode = 1;      // 1: persistent cooperative kernel per update, 0: one residual + one solve launch per iteration,
-                          // 2: persistent kernel with the solve replicated in every CTA (single GPU; one grid barrier per iteration)
+  int loop_mode = 2;      // 2: persistent cooperative kernel per update, solve replicated in every CTA (one grid barrier per
+                          //    iteration; with peers attached it runs as mode 1), 1: persistent kernel with the solve on CTA 0
+                          //    (two barriers; carries the NVLink peer all-reduce), 0: one residual + one solve launch per iteration
   int coop_ok = 0;
   int coop_lio = 0, coop_vio = 0;  // co-resident CTAs per SM of the persistent kernels
   bool coop_repl = false;          // the replicated-solve variants fit as well
-  DevBuf<unsigned long long> ll_words;  // loop_mode 3: tagged partial words [2][66][partial_blocks][2]
-  unsigned int ll_seq = 0;
   DevBuf<unsigned int> barrier;       // two grid barriers {counter @ +0, release word @ +128 B}, 256 B apart; launches alternate
   DevBuf<unsigned long long> stamps;  // 8 per slot: 8 LIO slots then 64 VIO slots
   bool want_stamps = false;
@@ -224,10 +223,9 @@ int esikf_create(esikf_ctx **out, int device) {
             ctx->ctl_block.reserve(sizeof(esikf_lio_stats) + sizeof(Ctrl) + 64 + sizeof(esikf_vio_stats)) == cudaSuccess && ctx->ext_dev.reserve(12) == cudaSuccess &&
             ctx->scratch_state.reserve(S_N) == cudaSuccess;
   ctx->partial_blocks = ctx->sm_count < 160 ? ctx->sm_count : 160;  // persistent residual kernels: one CTA per SM
-  ok = ok && ctx->partials.reserve((size_t)2 * ctx->partial_blocks * INFO_N) == cudaSuccess && ctx->ll_words.reserve((size_t)2 * 66 * ctx->partial_blocks * 2) == cudaSuccess && ctx->stamps.reserve(8 * 72 + 64 + 160) == cudaSuccess &&
+  ok = ok && ctx->partials.reserve((size_t)2 * ctx->partial_blocks * INFO_N) == cudaSuccess && ctx->stamps.reserve(8 * 72 + 64 + 160) == cudaSuccess &&
        ctx->barrier.reserve(128) == cudaSuccess;
   if (ok) cudaMemsetAsync(ctx->barrier.p, 0, 128 * sizeof(unsigned int), ctx->stream);
-  if (ok) cudaMemsetAsync(ctx->ll_words.p, 0, ctx->ll_words.cap * sizeof(unsigned long long), ctx->stream);
   if (ok) {
     ctx->state.p = ctx->state_prop.p, ctx->prop.p = ctx->state_prop.p + S_N;
     for (int i = 0; i < esikf_ctx::STAGE_SLOTS; i++) ok = ok && cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming) == cudaSuccess;
@@ -248,10 +246,8 @@ int esikf_create(esikf_ctx **out, int device) {
   cudaFuncSetAttribute(vio_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VioSmem));
   cudaError_t ea = cudaFuncSetAttribute(lio_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
   cudaError_t eb = cudaFuncSetAttribute(vio_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(VioSmem) + sizeof(FusedSolveSmem)));
-  cudaFuncSetAttribute(lio_update_repl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
-  cudaFuncSetAttribute(vio_update_repl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(VioSmem) + sizeof(FusedSolveSmem)));
-  cudaFuncSetAttribute(lio_update_repl_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
-  cudaFuncSetAttribute(vio_update_repl_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(VioSmem) + sizeof(FusedSolveSmem)));
+  cudaFuncSetAttribute(lio_update_repl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
+  cudaFuncSetAttribute(vio_update_repl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(VioSmem) + sizeof(FusedSolveSmem)));
   // the persistent kernels need every CTA co-resident: check what the device can hold
   int occ_l = 0, occ_v = 0, occ_r = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, lio_update_kernel, LIO_THREADS, sizeof(LioSmem));
@@ -259,12 +255,10 @@ int esikf_create(esikf_ctx **out, int device) {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, lio_residual_kernel, LIO_THREADS, sizeof(LioSmem));
   ctx->coop_lio = occ_l, ctx->coop_vio = occ_v;
   {
-    int occ_lr = 0, occ_vr = 0, occ_ll = 0, occ_vl = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lr, lio_update_repl_kernel<false>, LIO_THREADS, sizeof(LioSmem));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_vr, vio_update_repl_kernel<false>, VIO_THREADS, sizeof(VioSmem) + sizeof(FusedSolveSmem));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ll, lio_update_repl_kernel<true>, LIO_THREADS, sizeof(LioSmem));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_vl, vio_update_repl_kernel<true>, VIO_THREADS, sizeof(VioSmem) + sizeof(FusedSolveSmem));
-    ctx->coop_repl = occ_lr > 0 && occ_vr > 0 && occ_ll > 0 && occ_vl > 0;
+    int occ_lr = 0, occ_vr = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lr, lio_update_repl_kernel, LIO_THREADS, sizeof(LioSmem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_vr, vio_update_repl_kernel, VIO_THREADS, sizeof(VioSmem) + sizeof(FusedSolveSmem));
+    ctx->coop_repl = occ_lr > 0 && occ_vr > 0;
   }
   if (getenv("ESIKF_DEBUG"))
     fprintf(stderr, "[esikf] SMs=%d smem LIO=%zu VIO=%zu attr=%d/%d occupancy: lio_update=%d vio_update=%d lio_residual=%d coop=%d\n", ctx->sm_count, sizeof(LioSmem),
@@ -297,7 +291,7 @@ void esikf_destroy(esikf_ctx *ctx) {
   if (ctx->stage) cudaFreeHost(ctx->stage);
   for (int i = 0; i < esikf_ctx::STAGE_SLOTS; i++)
     if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
-  ctx->info.release(), ctx->partials.release(), ctx->ll_words.release(), ctx->old_state.release(), ctx->G.release(), ctx->ctl_block.release();
+  ctx->info.release(), ctx->partials.release(), ctx->old_state.release(), ctx->G.release(), ctx->ctl_block.release();
   ctx->stamps.release(), ctx->barrier.release(), ctx->img.release(), ctx->vis_pos.release(), ctx->inv_expo.release();
   ctx->warp_patch.release(), ctx->errors.release(), ctx->search_levels.release(), ctx->ref_img_ptrs.release(), ctx->ref_idx.release();
   ctx->px_ref.release(), ctx->pos_w.release(), ctx->normal_w.release(), ctx->T_ref.release(), ctx->T_cur.release();
@@ -323,7 +317,7 @@ int esikf_set_solve_mode(esikf_ctx *ctx, int mode) {
   return ESIKF_OK;
 }
 int esikf_set_loop_mode(esikf_ctx *ctx, int mode) {
-  if (!ctx || mode < 0 || mode > 3) return ESIKF_ERR_ARG;
+  if (!ctx || mode < 0 || mode > 2) return ESIKF_ERR_ARG;
   ctx->loop_mode = mode;
   return ESIKF_OK;
 }
@@ -450,13 +444,6 @@ static PeerArgs peer_args(esikf_ctx *ctx) {
   if (ctx->p2p) ctx->peer_seq += 128;  // > levels * max_iterations: flags stay monotonic across launches (same on every rank)
   return p;
 }
-static LLArgs ll_args(esikf_ctx *ctx) {
-  LLArgs l;
-  l.words = ctx->ll_words.p;
-  l.seq_base = ctx->ll_seq;
-  ctx->ll_seq += 128;  // > levels * max_iterations: tags stay monotonic across launches
-  return l;
-}
 static int allreduce_info(esikf_ctx *ctx) {
   if (ctx->nranks <= 1) return ESIKF_OK;
   if (!ctx->comm) return fail(ctx, ESIKF_ERR_STATE, "per-iteration launches with %d ranks need esikf_comm_init (NCCL)", ctx->nranks);
@@ -501,12 +488,10 @@ int esikf_lio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
     unsigned long long *stamps = ctx->want_stamps ? ctx->stamps.p : nullptr;
     if (stamps) CK(cudaMemsetAsync(stamps, 0, 64 * sizeof(unsigned long long), st));
     ka.dbg = sa.dbg = ctx->want_stamps ? ctx->stamps.p + 576 : nullptr;
-    if (ctx->loop_mode >= 2 && ctx->nranks == 1 && ctx->coop_repl) {
+    if (ctx->loop_mode == 2 && ctx->nranks == 1 && ctx->coop_repl) {
       size_t parity_stride = (size_t)ctx->partial_blocks * INFO_N;
-      LLArgs ll = ll_args(ctx);
-      void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride, (void *)&ll};
-      const void *fn = ctx->loop_mode == 3 ? (const void *)lio_update_repl_kernel<true> : (const void *)lio_update_repl_kernel<false>;
-      CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(LIO_THREADS), kargs, sizeof(LioSmem), st));
+      void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride};
+      CK(cudaLaunchCooperativeKernel((const void *)lio_update_repl_kernel, dim3(grid), dim3(LIO_THREADS), kargs, sizeof(LioSmem), st));
     } else {
       PeerArgs peer = peer_args(ctx);
       void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&peer};
@@ -702,12 +687,10 @@ int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
     unsigned int *bar = ctx->barrier.p + 64 * par, *bar_next = ctx->barrier.p + 64 * (par ^ 1);
     unsigned long long *stamps = ctx->want_stamps ? ctx->stamps.p + 64 : nullptr;
     if (stamps) CK(cudaMemsetAsync(stamps, 0, 512 * sizeof(unsigned long long), st));
-    if (ctx->loop_mode >= 2 && ctx->nranks == 1 && ctx->coop_repl) {
+    if (ctx->loop_mode == 2 && ctx->nranks == 1 && ctx->coop_repl) {
       size_t parity_stride = (size_t)ctx->partial_blocks * INFO_N;
-      LLArgs ll = ll_args(ctx);
-      void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride, (void *)&ll};
-      const void *fn = ctx->loop_mode == 3 ? (const void *)vio_update_repl_kernel<true> : (const void *)vio_update_repl_kernel<false>;
-      CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(VIO_THREADS), kargs, sizeof(VioSmem) + sizeof(FusedSolveSmem), st));
+      void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride};
+      CK(cudaLaunchCooperativeKernel((const void *)vio_update_repl_kernel, dim3(grid), dim3(VIO_THREADS), kargs, sizeof(VioSmem) + sizeof(FusedSolveSmem), st));
     } else {
       PeerArgs peer = peer_args(ctx);
       void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&peer};

@@ -287,118 +287,16 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKer
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Barrier-free exchange of the per-CTA partial blocks (loop_mode 3), the on-chip analogue of peer_allreduce: a partial
-// travels as two 64-bit words {payload half | 32-bit sequence tag} written with one 16-byte store; a reader that finds the
-// expected tag in both words has the value, so "all partials of this iteration are present" needs no counter, no fence and
-// no separate round trip — every CTA polls the words it is going to add anyway. Layout [2 parities][66 entries][stride
-// blocks][2 words]; the sum order is exactly sum_partials' (lane l adds blocks l, l+32, ... then the xor-shuffle tree).
-struct LLArgs {
-  unsigned long long *words;  // device buffer, zero-initialised once; tags are monotonic over the life of the context
-  unsigned int seq_base;      // tags of this launch: seq_base + slot + 1
-};
-
-__device__ __forceinline__ void ll_put(unsigned long long *words, int stride, int e, double val, unsigned int tag) {
-  const unsigned long long bits = (unsigned long long)__double_as_longlong(val);
-  const unsigned long long w0 = (bits << 32) | tag;
-  const unsigned long long w1 = (bits & 0xffffffff00000000ull) | tag;
-  unsigned long long *dst = words + ((size_t)e * stride + blockIdx.x) * 2;
-  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
-}
-
-template <int WARPS>
-__device__ __forceinline__ void ll_store_partials(ReduceSmem<WARPS> &rs, double D0, double D1, double cnt, bool abs_in_77, unsigned long long *words, int stride,
-                                                  unsigned int tag) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  {
-    const int g = lane >> 2, t = lane & 3;
-    rs.warpD[warp][g * 8 + 2 * t] = D0;
-    rs.warpD[warp][g * 8 + 2 * t + 1] = D1;
-    if (lane == 0) rs.warpD[warp][64] = cnt;
-  }
-  __syncthreads();
-  if (tid < 65) {
-    double s = rs.warpD[0][tid];
-#pragma unroll
-    for (int w = 1; w < WARPS; w++) s += rs.warpD[w][tid];
-    int e = tid;
-    if (tid == 64) e = INFO_COUNT;
-    if (abs_in_77 && tid == 63) e = INFO_ABS;
-    ll_put(words, stride, e, s, tag);
-    if (tid == 63) ll_put(words, stride, abs_in_77 ? 63 : INFO_ABS, 0.0, tag);
-  }
-}
-
-// Entries of info[] the solve actually reads (the tensor-core block is 8 x 8, the information block 6 x 6 / 7 x 7):
-//   LIO: rows 0..5 x cols 0..6 (H^T R^-1 H | H^T R^-1 z), the matched count and sum|d|             -> 44 of 66
-//   VIO: rows 0..6 x cols 0..7 (H^T H | H^T z), [7][7] = sum res^2 and the measurement count        -> 58 of 66
-template <bool LIO> __device__ __forceinline__ int ll_entry(int q) {
-  if (LIO) return q < 42 ? (q / 7) * 8 + (q % 7) : (q == 42 ? INFO_COUNT : INFO_ABS);
-  return q < 56 ? q : (q == 56 ? 63 : INFO_COUNT);
-}
-template <bool LIO> struct LLCount { static constexpr int value = LIO ? 44 : 58; };
-
-// Fixed-order sum of the needed entries over all CTAs' tagged partials into info[] by the calling CTA: warp w adds the
-// entries q = w, w + nwarps, ... (KE per warp); lane l adds blocks l, l+32, ... then the xor-shuffle tree — sum_partials'
-// order. All loads of a poll are issued before the first tag check; only words that have not arrived are polled again.
-template <bool LIO, int KE>
-__device__ __forceinline__ void ll_reduce_partials_block(const unsigned long long *words, int stride, int nb, double *info, unsigned int tag) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  constexpr int NQ = LLCount<LIO>::value;
-  if (tid < INFO_N) info[tid] = 0.0;  // entries nobody reads stay defined
-  __syncthreads();
-  double v[KE][SUM_MAXC];
-  unsigned int pending = 0;
-#pragma unroll
-  for (int k = 0; k < KE; k++)
-#pragma unroll
-    for (int c = 0; c < SUM_MAXC; c++) {
-      v[k][c] = 0.0;
-      if (warp + k * nwarps < NQ && lane + 32 * c < nb) pending |= 1u << (k * SUM_MAXC + c);
-    }
-  while (pending) {
-    unsigned long long w0[KE][SUM_MAXC], w1[KE][SUM_MAXC];
-#pragma unroll
-    for (int k = 0; k < KE; k++)
-#pragma unroll
-      for (int c = 0; c < SUM_MAXC; c++)
-        if ((pending >> (k * SUM_MAXC + c)) & 1u) {
-          const int e = ll_entry<LIO>(warp + k * nwarps), b = lane + 32 * c;
-          const unsigned long long *src = words + ((size_t)e * stride + b) * 2;
-          asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[k][c]), "=l"(w1[k][c]) : "l"(src) : "memory");
-        }
-#pragma unroll
-    for (int k = 0; k < KE; k++)
-#pragma unroll
-      for (int c = 0; c < SUM_MAXC; c++)
-        if ((pending >> (k * SUM_MAXC + c)) & 1u) {
-          if ((unsigned int)w0[k][c] == tag && (unsigned int)w1[k][c] == tag) {
-            v[k][c] = __longlong_as_double((long long)((w1[k][c] & 0xffffffff00000000ull) | (w0[k][c] >> 32)));
-            pending &= ~(1u << (k * SUM_MAXC + c));
-          }
-        }
-  }
-  __syncwarp();
-#pragma unroll
-  for (int k = 0; k < KE; k++) {
-    const int q = warp + k * nwarps;
-    double s = v[k][0];
-#pragma unroll
-    for (int c = 1; c < SUM_MAXC; c++) s += v[k][c];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if (lane == 0 && q < NQ) info[ll_entry<LIO>(q)] = s;
-  }
-  __syncthreads();
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Replicated-solve variants (loop_mode 2, single GPU). Every CTA keeps its own copy of P, the poses and the loop control
+// Replicated-solve variants (loop_mode 2, the default on a single GPU). Every CTA keeps its own copy of P, the poses and the loop control
 // in shared memory, sums the per-CTA partials itself after the one grid barrier of the iteration and runs the same m x m
 // solve — same instructions on the same inputs in the same order, so all copies stay bit-identical and equal to what
 // CTA 0 computes in the kernels above. That removes the second grid barrier, the publication of the state through global
 // memory and the reload of the pose / covariance blocks from every iteration; only CTA 0 writes results and diagnostics.
 // The partial blocks are double-buffered by iteration parity: a CTA can overwrite buffer p again only two iterations
-// later, after a barrier that every reader of iteration k has already passed.
+// later, after a barrier that every reader of iteration k has already passed. Measured on config 2: 61.4 k it/s against
+// 55.1 k for the CTA-0 solve (profiles/loop_modes_r01_mode2.txt). Exchanging the partials as tagged 64-bit words polled
+// by every CTA instead of the barrier was also built and measured: bit-identical but slower (49.3 k it/s, the polling
+// of 148 CTAs saturates L2; profiles/loop_modes_r01_mode3_ll.txt) and removed again.
 __device__ __forceinline__ void lio_consts_from_resident(LioSmem &sm, const FusedSolveSmem &fs) {
   const int tid = threadIdx.x;
   if (tid < 9) {
@@ -412,9 +310,8 @@ __device__ __forceinline__ void lio_consts_from_resident(LioSmem &sm, const Fuse
   __syncthreads();
 }
 
-template <bool LL>
 __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_repl_kernel(const LioKernelArgs a, const SolveArgs sa_in, unsigned int *barrier, unsigned int *barrier_next,
-                                                                          unsigned long long *stamps, size_t partial_parity_stride, const LLArgs ll) {
+                                                                          unsigned long long *stamps, size_t partial_parity_stride) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   LioSmem &sm = *reinterpret_cast<LioSmem *>(smem_raw);
   FusedSolveSmem &fs = *reinterpret_cast<FusedSolveSmem *>(sm.fs_raw);
@@ -464,19 +361,11 @@ __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_repl_kernel(const L
       stamps[640 + blockIdx.x] = t;
     }
     stamp(stamps, sk);  // 2: CTA 0 finished its slice
-    if (LL) {
-      const unsigned int tag = ll.seq_base + (unsigned int)it + 1u;
-      unsigned long long *const w = ll.words + (size_t)(it & 1) * 66 * a.partial_stride * 2;
-      ll_store_partials<LIO_WARPS>(sm.red, D0, D1, (double)cnt, true, w, a.partial_stride, tag);
-      stamp(stamps, sk);  // 3: own partials on their way
-      ll_reduce_partials_block<true, (44 + LIO_WARPS - 1) / LIO_WARPS>(w, a.partial_stride, gridDim.x, fs.io.info, tag);
-    } else {
-      double *const part = a.partials + (size_t)(it & 1) * partial_parity_stride;
-      store_partials<LIO_WARPS>(sm.red, D0, D1, (double)cnt, true, part, a.partial_stride);
-      grid_barrier(barrier, epoch);
-      stamp(stamps, sk);  // 3: all CTAs arrived
-      reduce_partials_block(part, a.partial_stride, gridDim.x, fs.io.info);
-    }
+    double *const part = a.partials + (size_t)(it & 1) * partial_parity_stride;
+    store_partials<LIO_WARPS>(sm.red, D0, D1, (double)cnt, true, part, a.partial_stride);
+    grid_barrier(barrier, epoch);
+    stamp(stamps, sk);  // 3: all CTAs arrived
+    reduce_partials_block(part, a.partial_stride, gridDim.x, fs.io.info);
     stamp(stamps, sk);  // 4: partials summed
     if (threadIdx.x == 0) {
       SolveLiteralScratch *lit = reinterpret_cast<SolveLiteralScratch *>(&sm.rec[0][0][0]);
@@ -517,9 +406,8 @@ __device__ __forceinline__ void vio_consts_from_resident(VioSmem &sm, const VioK
   __syncthreads();
 }
 
-template <bool LL>
 __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_repl_kernel(const VioKernelArgs a, SolveArgs sa, unsigned int *barrier, unsigned int *barrier_next,
-                                                                          unsigned long long *stamps, size_t partial_parity_stride, const LLArgs ll) {
+                                                                          unsigned long long *stamps, size_t partial_parity_stride) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   VioSmem &sm = *reinterpret_cast<VioSmem *>(smem_raw);
   FusedSolveSmem &fs = *reinterpret_cast<FusedSolveSmem *>(smem_raw + sizeof(VioSmem));
@@ -543,7 +431,7 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_repl_kernel(const V
   int slot = 0;
   for (int level = a.levels - 1; level >= 0; level--) {      // vio.cpp:790
     for (int it = 0; it < sa.max_iterations; it++) {          // :1536
-      const int cur = slot++;  // counts executed iterations (a level may end early): buffer parity and tag follow it
+      const int cur = slot++;  // counts executed iterations (a level may end early): the partial-buffer parity follows it
       int sk = 8 * ((a.levels - 1 - level) * sa.max_iterations + it);
       stamp(stamps, sk);
       vio_consts_from_resident(sm, a, fs);
@@ -552,19 +440,11 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_repl_kernel(const V
       vio_process_range(a, sm, level, lo, hi, D0, D1, n_meas);
       __syncthreads();
       stamp(stamps, sk);
-      if (LL) {
-        const unsigned int tag = ll.seq_base + (unsigned int)cur + 1u;
-        unsigned long long *const w = ll.words + (size_t)(cur & 1) * 66 * a.partial_stride * 2;
-        ll_store_partials<VIO_WARPS>(sm.red, D0, D1, n_meas, false, w, a.partial_stride, tag);
-        stamp(stamps, sk);
-        ll_reduce_partials_block<false, (58 + VIO_WARPS - 1) / VIO_WARPS>(w, a.partial_stride, gridDim.x, fs.io.info, tag);
-      } else {
-        double *const part = a.partials + (size_t)(cur & 1) * partial_parity_stride;
-        store_partials<VIO_WARPS>(sm.red, D0, D1, n_meas, false, part, a.partial_stride);
-        grid_barrier(barrier, epoch);
-        stamp(stamps, sk);
-        reduce_partials_block(part, a.partial_stride, gridDim.x, fs.io.info);
-      }
+      double *const part = a.partials + (size_t)(cur & 1) * partial_parity_stride;
+      store_partials<VIO_WARPS>(sm.red, D0, D1, n_meas, false, part, a.partial_stride);
+      grid_barrier(barrier, epoch);
+      stamp(stamps, sk);
+      reduce_partials_block(part, a.partial_stride, gridDim.x, fs.io.info);
       stamp(stamps, sk);
       sa.level = level, sa.slot_iter = it, sa.last_slot = 0;
       if (threadIdx.x == 0) fs.sm.W = lit.W, fs.sm.K = lit.K;

@@ -124,11 +124,13 @@ int64_t esikf_launch_count(const esikf_ctx *ctx);
 /* solve_mode: 0 = Woodbury 6x6/7x7 form of (H^T H + P^-1)^-1 (default), 1 = literal two 19x19
  * partial-pivot inversions as at src/voxel_map.cpp:468 / src/vio.cpp:1661. */
 int esikf_set_solve_mode(esikf_ctx *ctx, int mode);
-/* loop_mode: 1 (default) = one persistent cooperative kernel runs the whole iteration loop of an update (single GPU);
- * 0 = one residual + one solve launch per iteration (also used when a communicator is attached or timing is on);
- * 2 = persistent kernel with the gain solve replicated in every CTA (single GPU; one grid barrier per iteration instead
- * of two, no state round trip through global memory); 3 = as 2 with the per-CTA partial blocks exchanged as tagged
- * 64-bit words (no grid barrier at all). Results of all modes are bit-identical. */
+/* loop_mode: how the iteration loop of an update is driven. Results of all modes are bit-identical.
+ *   2 (default) = one persistent cooperative kernel per update; every CTA sums the per-CTA partial blocks and runs the
+ *       gain solve itself, so an iteration costs one grid barrier and the state never goes through global memory.
+ *       With peer GPUs attached (esikf_peer_attach) the update runs as mode 1.
+ *   1 = one persistent cooperative kernel per update, gain solve on CTA 0 (two grid barriers per iteration); carries
+ *       the in-kernel NVLink all-reduce of the information buffer.
+ *   0 = one residual + one solve launch per iteration (also used with an NCCL communicator or kernel timing on). */
 int esikf_set_loop_mode(esikf_ctx *ctx, int mode);
 int esikf_set_extrinsics(esikf_ctx *ctx, const esikf_extrinsics *ext);
 

@@ -4,6 +4,7 @@ import pytest
 
 import oracle_bind as O
 from conftest import get_frame
+from fast_livo2_b200 import api
 from fast_livo2_b200 import synthetic as S
 from parity_util import INFO_RTOL, assert_state_close, rel
 
@@ -164,15 +165,21 @@ def test_full_size_properties(gpu_ctx):
 
 
 def test_persistent_and_per_iteration_loops_are_bit_identical(gpu_ctx, small_frame):
-    """loop_mode 1 (one cooperative kernel for the whole update) vs loop_mode 0 (residual + solve launch per iteration)."""
+    """loop_mode 2 / 1 (one cooperative kernel for the whole update, solve in every CTA / on CTA 0) vs loop_mode 0
+    (residual + solve launch per iteration)."""
     fr = get_frame(seed=4, n_pts=20000, n_map=150_000, scene_scale=0.5)
-    gpu_ctx.set_loop_mode(1)
-    a = _gpu(gpu_ctx, fr)
-    gpu_ctx.set_loop_mode(0)
-    b = _gpu(gpu_ctx, fr)
-    gpu_ctx.set_loop_mode(1)
-    assert a["iters"] == b["iters"]
-    assert np.array_equal(a["state"], b["state"]) and np.array_equal(a["HTH"], b["HTH"]) and np.array_equal(a["match_plane"], b["match_plane"])
+    try:
+        gpu_ctx.set_loop_mode(2)
+        a2 = _gpu(gpu_ctx, fr)
+        gpu_ctx.set_loop_mode(1)
+        a = _gpu(gpu_ctx, fr)
+        gpu_ctx.set_loop_mode(0)
+        b = _gpu(gpu_ctx, fr)
+    finally:
+        gpu_ctx.set_loop_mode(api.DEFAULT_LOOP_MODE)
+    for x in (a, a2):
+        assert x["iters"] == b["iters"]
+        assert np.array_equal(x["state"], b["state"]) and np.array_equal(x["HTH"], b["HTH"]) and np.array_equal(x["match_plane"], b["match_plane"])
     _compare(b, _oracle(fr))
 
 
@@ -184,7 +191,9 @@ def test_config4_260k_points_several_tiles_per_cta(gpu_ctx):
     g, o = _gpu(gpu_ctx, fr), _oracle(fr)
     assert o["M"][0] > 200_000
     _compare(g, o)
-    gpu_ctx.set_loop_mode(0)
-    g0 = _gpu(gpu_ctx, fr)
-    gpu_ctx.set_loop_mode(1)
+    try:
+        gpu_ctx.set_loop_mode(0)
+        g0 = _gpu(gpu_ctx, fr)
+    finally:
+        gpu_ctx.set_loop_mode(api.DEFAULT_LOOP_MODE)
     assert np.array_equal(g0["state"], g["state"]) and np.array_equal(g0["match_plane"], g["match_plane"])

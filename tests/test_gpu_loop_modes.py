@@ -1,11 +1,12 @@
-"""GPU: the replicated-solve persistent kernels (loop_mode 2: every CTA sums the partials and runs the gain solve itself,
-one grid barrier per iteration; loop_mode 3: the same with the partials exchanged as tagged words, no grid barrier at all)
-must reproduce loop_mode 1 bit for bit — states, associations and per-iteration diagnostics — in both solve modes, across
-repeated launches (barrier counters, partial buffers and tag sequences alternate / advance)."""
+"""GPU: the replicated-solve persistent kernels (loop_mode 2, the default: every CTA sums the partials and runs the gain
+solve itself, one grid barrier per iteration) must reproduce loop_mode 1 (solve on CTA 0) bit for bit — states,
+associations and per-iteration diagnostics — in both solve modes, across repeated launches (barrier counters and partial
+buffers alternate)."""
 import numpy as np
 import pytest
 
 from conftest import get_frame
+from fast_livo2_b200 import api
 from test_gpu_vio import _gpu_warp, _setup, _vio_prior
 
 pytestmark = pytest.mark.gpu
@@ -25,17 +26,17 @@ def test_lio_replicated_solve_is_bit_identical(gpu_ctx, solve_mode):
     gpu_ctx.set_solve_mode(solve_mode)
     try:
         out = {}
-        for mode in (1, 2, 3, 3, 2, 1):
+        for mode in (1, 2, 2, 1, 2):
             gpu_ctx.set_loop_mode(mode)
             r = gpu_ctx.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"])
             out.setdefault(mode, []).append(r)
     finally:
-        gpu_ctx.set_loop_mode(1)
+        gpu_ctx.set_loop_mode(api.DEFAULT_LOOP_MODE)
         gpu_ctx.set_solve_mode(0)
     ref = out[1][0]
     assert ref["iters"] >= 3
     keys = ("state", "match_plane", "normal_plane", "dis_to_plane", "M", "HTH", "HTz", "solution", "total_residual", "converged")
-    for r in out[2] + out[3] + out[1][1:]:
+    for r in out[2] + out[1][1:]:
         assert r["iters"] == ref["iters"]
         _bits_equal(ref, r, keys)
 
@@ -50,15 +51,12 @@ def test_lio_replicated_solve_several_tiles_per_cta(gpu_ctx):
     try:
         gpu_ctx.set_loop_mode(1)
         a = gpu_ctx.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"])
-        outs = []
-        for mode in (2, 3):
-            gpu_ctx.set_loop_mode(mode)
-            outs.append(gpu_ctx.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"]))
+        gpu_ctx.set_loop_mode(2)
+        b = gpu_ctx.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"])
     finally:
-        gpu_ctx.set_loop_mode(1)
-    for b in outs:
-        assert a["iters"] == b["iters"]
-        _bits_equal(a, b, ("state", "match_plane", "normal_plane", "dis_to_plane", "M", "HTH"))
+        gpu_ctx.set_loop_mode(api.DEFAULT_LOOP_MODE)
+    assert a["iters"] == b["iters"]
+    _bits_equal(a, b, ("state", "match_plane", "normal_plane", "dis_to_plane", "M", "HTH"))
 
 
 @pytest.mark.parametrize("solve_mode", [0, 1])
@@ -71,15 +69,15 @@ def test_vio_replicated_solve_is_bit_identical(gpu_ctx, small_vio_frame, solve_m
     gpu_ctx.set_solve_mode(solve_mode)
     try:
         out = {}
-        for mode in (1, 2, 3, 3, 2, 1):
+        for mode in (1, 2, 2, 1, 2):
             gpu_ctx.set_loop_mode(mode)
             out.setdefault(mode, []).append(gpu_ctx.vio_update(*args))
     finally:
-        gpu_ctx.set_loop_mode(1)
+        gpu_ctx.set_loop_mode(api.DEFAULT_LOOP_MODE)
         gpu_ctx.set_solve_mode(0)
     ref = out[1][0]
     assert ref["total_iters"] >= 4
     keys = ("state", "errors", "iters_per_level", "accepted_per_level", "error_trace", "HTH", "HTz", "solution")
-    for r in out[2] + out[3] + out[1][1:]:
+    for r in out[2] + out[1][1:]:
         assert r["total_iters"] == ref["total_iters"]
         _bits_equal(ref, r, keys)

@@ -176,13 +176,18 @@ def test_persistent_and_per_iteration_loops_are_bit_identical(gpu_ctx, small_vio
     prior = _vio_prior(fr)
     w = _gpu_warp(gpu_ctx, fr, prior)
     args = (fr["img"], fr["vis_pos"], w["warp_patch"], w["search_levels"], fr["inv_ref_expo"], prior, prior)
-    gpu_ctx.set_loop_mode(1)
-    a = gpu_ctx.vio_update(*args)
-    gpu_ctx.set_loop_mode(0)
-    b = gpu_ctx.vio_update(*args)
-    gpu_ctx.set_loop_mode(1)
-    assert a["total_iters"] == b["total_iters"]
-    assert np.array_equal(a["state"], b["state"]) and np.array_equal(a["HTH"], b["HTH"]) and np.array_equal(a["errors"], b["errors"])
+    try:
+        gpu_ctx.set_loop_mode(2)
+        a2 = gpu_ctx.vio_update(*args)
+        gpu_ctx.set_loop_mode(1)
+        a = gpu_ctx.vio_update(*args)
+        gpu_ctx.set_loop_mode(0)
+        b = gpu_ctx.vio_update(*args)
+    finally:
+        gpu_ctx.set_loop_mode(api.DEFAULT_LOOP_MODE)
+    for x in (a, a2):
+        assert x["total_iters"] == b["total_iters"]
+        assert np.array_equal(x["state"], b["state"]) and np.array_equal(x["HTH"], b["HTH"]) and np.array_equal(x["errors"], b["errors"])
     vio = O.OracleVIO(fr["cam_cfg"], fr["ext"], fr["vio_cfg"])
     _compare_vio(b, vio.update(*args), fr["vio_cfg"].levels)
 

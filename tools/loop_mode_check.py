@@ -1,4 +1,4 @@
-"""Checks the three loop modes of the update against each other (bit-identical states / associations / diagnostics) on a
+"""Checks the loop modes of the update against each other (bit-identical states / associations / diagnostics) on a
 small frame and on the BASELINE config-2 frame, and times the resident LIO + VIO update per mode (CUDA events, L2 flushed
 between steps). Run on the GPU box:  timeout 170 python tools/loop_mode_check.py"""
 import os
@@ -12,7 +12,7 @@ import torch  # noqa: E402
 
 from fast_livo2_b200 import api, synthetic as S  # noqa: E402
 
-MODES = [int(m) for m in os.environ.get("MODES", "1,0,2,3").split(",")]
+MODES = [int(m) for m in os.environ.get("MODES", "2,1,0").split(",")]
 STEPS = int(os.environ.get("STEPS", 30))
 
 
