@@ -353,12 +353,16 @@ def b200_arm(args, rank, world, local_rank):
                        "lio_iters": int(rl["iters"]), "vio_iters": int(rv["total_iters"]), "l2": "flushed between steps (256 MiB write, untimed)",
                        "parallelism": (f"points/patches sharded over {world} ranks, 72-double information buffer all-reduced per iteration " +
                                        ("inside the persistent kernel over NVLink peer memory" if args.comm == "p2p" else "with ncclAllReduce")) if world > 1 else "single GPU",
-                       "map_planes": int(len(fr["map"]["planes"])), "matched_points": int(rl["M"][-1])},
+                       "map_planes": int(len(fr["map"]["planes"])), "matched_points": int(rl["M"][-1]),
+                       "loop": "one persistent cooperative kernel per update" + (", gain solve replicated in every CTA (loop_mode 2)" if world == 1 else ", solve on CTA 0 (loop_mode 1)")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * float(t_e2e.item()) / K},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "lio_update_kernel (persistent: all LIO iterations of a step in one launch)", "bound": "hbm", "achieved": achieved,
+            "roofline": {"kernel": ("lio_update_repl_kernel" if world == 1 else "lio_update_kernel") + " (persistent: all LIO iterations of a step in one launch)",
+                         "traffic_note": "dram bytes per launch from the ncu --set full capture of lio_update_kernel (profiles/ncu_summary.json); the replicated-solve "
+                                         "variant runs the same slice code, its own capture is pending",
+                         "bound": "hbm", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_point": LIO_BYTES_PER_POINT, "points_per_launch": shard_pts,
                          "iterations_per_launch": int(rl["iters"]), "avg_launch_ms_in_timed_region": lio_ms, "vio_update_ms_in_timed_region": vio_ms,
