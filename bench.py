@@ -159,7 +159,21 @@ def run_cpu_reference(fr, threads, frames, warm=1, kind="baseline"):
                 t_v += v["secs"]
                 it_v += v["total_iters"]
     return dict(value=(it_l + it_v) / (t_l + t_v), lio_iters_per_s=it_l / t_l if t_l else None, vio_iters_per_s=it_v / t_v if t_v else None,
-                ms_per_frame=1e3 * (t_l + t_v) / frames, iters_per_frame=(it_l + it_v) / frames, seconds=t_l + t_v)
+                ms_per_frame=1e3 * (t_l + t_v) / frames, iters_per_frame=(it_l + it_v) / frames, seconds=t_l + t_v,
+                lio_state=r["state"], lio_M=[int(m) for m in r["M"]], vio_state=v["state"] if w is not None else None)
+
+
+def state_error(s, ref):
+    """Pose / covariance error of a packed state against the oracle's: rotation angle of R_ref^T R [rad],
+    |p - p_ref| / |p_ref|, max |cov - cov_ref| / max |cov_ref|."""
+    from fast_livo2_b200 import synthetic as S
+
+    a, b = S.unpack_state(np.asarray(s, dtype=np.float64)), S.unpack_state(np.asarray(ref, dtype=np.float64))
+    dR = b["R"].T @ a["R"]
+    rot = float(np.linalg.norm(dR - dR.T) / (2.0 * np.sqrt(2.0)))  # = sin(angle), exact to first order where acos() loses digits
+    pos = float(np.linalg.norm(a["p"] - b["p"]) / max(np.linalg.norm(b["p"]), 1e-12))
+    cov = float(np.abs(a["cov"] - b["cov"]).max() / np.abs(b["cov"]).max())
+    return {"rot_rad": rot, "pos_rel": pos, "cov_rel_to_max": cov}
 
 
 def reference_arm(args, rank, world):
@@ -354,7 +368,8 @@ def b200_arm(args, rank, world, local_rank):
                        "parallelism": (f"points/patches sharded over {world} ranks, 72-double information buffer all-reduced per iteration " +
                                        ("inside the persistent kernel over NVLink peer memory" if args.comm == "p2p" else "with ncclAllReduce")) if world > 1 else "single GPU",
                        "map_planes": int(len(fr["map"]["planes"])), "matched_points": int(rl["M"][-1]),
-                       "loop": "one persistent cooperative kernel per update" + (", gain solve replicated in every CTA (loop_mode 2)" if world == 1 else ", solve on CTA 0 (loop_mode 1)")},
+                       "loop": ("residual + all-reduce + solve launches per iteration (loop_mode 0)" if (world > 1 and args.comm == "nccl") else
+                                "one persistent cooperative kernel per update" + (", gain solve replicated in every CTA (loop_mode 2)" if world == 1 else ", solve on CTA 0 (loop_mode 1)"))},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * float(t_e2e.item()) / K},
             "gpu_launches": int(launches),
@@ -381,6 +396,12 @@ def b200_arm(args, rank, world, local_rank):
                                    "sample": f"{frames} frames of the same workload ({cb['seconds']:.1f} s of CPU work); oracle restatement compiled with the "
                                              f"reference's flags, OpenMP capped at 4 threads like the reference (CMakeLists.txt:46-58); host has {os.cpu_count()} logical cores",
                                    "lio_iters_per_s": cb["lio_iters_per_s"], "vio_iters_per_s": cb["vio_iters_per_s"], "ms_per_frame": cb["ms_per_frame"]}
+            try:  # pose error of this run's CUDA result against the CPU restatement on the same frame (north star: <= 1e-5)
+                out["parity_vs_oracle"] = {"lio": state_error(rl["state"], cb["lio_state"]), "vio": state_error(rv["state"], cb["vio_state"]),
+                                           "matched_points_equal": [int(m) for m in rl["M"]] == cb["lio_M"], "tolerance": 1e-5,
+                                           "note": "oracle built with the reference's -O3 -march=native flags (FMA contraction on); the bit-exact association checks are in tests/"}
+            except Exception as e:  # never lose the bench line over the cross-check
+                out["parity_vs_oracle"] = {"error": repr(e)}
         print(json.dumps(out), flush=True)
     ctx.close()
     if dist is not None:
