@@ -92,6 +92,7 @@ def load_library():
     lib.esikf_vio_get_image_patch.argtypes = [vp, vp, C.c_int32, C.c_int32, vp]
     lib.esikf_vio_set_ref_images.argtypes = [vp, C.POINTER(vp), C.c_int32, C.c_int32, C.c_int32]
     lib.esikf_vio_warp_patches.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int32]
+    lib.esikf_vio_warp_affine.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp]
     lib.esikf_comm_unique_id.argtypes = [C.c_char_p]
     lib.esikf_comm_init.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p]
     lib.esikf_comm_rank.argtypes = [vp, ip, ip]
@@ -114,7 +115,7 @@ EXPORTED_SYMBOLS = [
     "esikf_set_extrinsics", "esikf_map_upload", "esikf_map_patch", "esikf_lio_set_scan", "esikf_lio_run", "esikf_lio_fetch",
     "esikf_lio_update", "esikf_lio_fetch_point_cov", "esikf_vio_set_camera", "esikf_vio_set_image", "esikf_vio_set_patches",
     "esikf_vio_run", "esikf_vio_fetch", "esikf_vio_update", "esikf_vio_get_image_patch", "esikf_vio_set_ref_images",
-    "esikf_vio_warp_patches", "esikf_comm_unique_id", "esikf_comm_init", "esikf_comm_rank", "esikf_shard_range", "esikf_peer_export", "esikf_peer_attach", "esikf_profile_kernel", "esikf_set_kernel_timing", "esikf_get_kernel_timing", "esikf_set_phase_stamps", "esikf_get_phase_stamps",
+    "esikf_vio_warp_patches", "esikf_vio_warp_affine", "esikf_comm_unique_id", "esikf_comm_init", "esikf_comm_rank", "esikf_shard_range", "esikf_peer_export", "esikf_peer_attach", "esikf_profile_kernel", "esikf_set_kernel_timing", "esikf_get_kernel_timing", "esikf_set_phase_stamps", "esikf_get_phase_stamps",
 ]
 
 
@@ -347,6 +348,15 @@ class Context:
         return dict(A_cur_ref=A, search_levels=sl, warp_patch=wp)
 
     # ------------------------------------------------------------------ multi-GPU / measurement
+    def vio_warp_affine(self, ref_idx, px_ref, A_cur_ref, search_levels):
+        """warpAffine alone (esikf_vio_warp_affine): caller-provided 2x2 matrices and search levels -> (n, levels*64) float32."""
+        n = len(px_ref)
+        ref_idx, sl = _c(ref_idx, np.int32), _c(search_levels, np.int32)
+        px_ref, A = _c(px_ref, np.float64), _c(A_cur_ref, np.float64).reshape(n, 4)
+        wp = np.zeros((n, 64 * self.levels), np.float32)
+        self._ck(self.lib.esikf_vio_warp_affine(self.h, n, ref_idx.ctypes.data, px_ref.ctypes.data, A.ctypes.data, sl.ctypes.data, wp.ctypes.data))
+        return wp
+
     def comm_init(self, rank, nranks, unique_id: bytes):
         self._ck(self.lib.esikf_comm_init(self.h, rank, nranks, unique_id))
 

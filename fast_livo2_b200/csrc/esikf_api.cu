@@ -139,6 +139,8 @@ struct esikf_ctx {
   DevBuf<double> vis_pos, inv_expo;
   DevBuf<float> warp_patch, errors;
   DevBuf<int32_t> search_levels;
+  DevBuf<float> warp_out;        // esikf_vio_warp_affine scratch (does not disturb the installed patches)
+  DevBuf<int32_t> warp_levels;
   int n_patches = 0;
   // warp producers
   std::vector<uint8_t *> ref_imgs;
@@ -295,6 +297,7 @@ void esikf_destroy(esikf_ctx *ctx) {
   ctx->stamps.release(), ctx->barrier.release(), ctx->img.release(), ctx->vis_pos.release(), ctx->inv_expo.release();
   ctx->warp_patch.release(), ctx->errors.release(), ctx->search_levels.release(), ctx->ref_img_ptrs.release(), ctx->ref_idx.release();
   ctx->px_ref.release(), ctx->pos_w.release(), ctx->normal_w.release(), ctx->T_ref.release(), ctx->T_cur.release();
+  ctx->warp_out.release(), ctx->warp_levels.release();
   ctx->A_cur_ref.release(), ctx->pc_buf.release(), ctx->patch_buf.release(), ctx->flush.release(), ctx->scratch_state.release();
   for (uint8_t *p : ctx->ref_imgs) cudaFree(p);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
@@ -832,6 +835,40 @@ int esikf_vio_warp_patches(esikf_ctx *ctx, int32_t n, const int32_t *ref_img_ind
     ctx->n_patches = n;
   }
   CK(cudaStreamSynchronize(st));
+  return ESIKF_OK;
+}
+
+int esikf_vio_warp_affine(esikf_ctx *ctx, int32_t n, const int32_t *ref_img_index, const double *px_ref, const double *A_cur_ref,
+                          const int32_t *search_level, float *warp_patch_out) {
+  if (!ctx || n < 0 || (n > 0 && (!ref_img_index || !px_ref || !A_cur_ref || !search_level || !warp_patch_out)))
+    return fail(ctx, ESIKF_ERR_ARG, "warp_affine: bad argument");
+  if (!ctx->have_cam) return fail(ctx, ESIKF_ERR_STATE, "warp_affine before vio_set_camera");
+  if (ctx->ref_imgs.empty()) return fail(ctx, ESIKF_ERR_STATE, "warp_affine before set_ref_images");
+  for (int i = 0; i < n; i++) {
+    if (ref_img_index[i] < 0 || ref_img_index[i] >= (int)ctx->ref_imgs.size()) return fail(ctx, ESIKF_ERR_ARG, "warp_affine: ref image index %d", ref_img_index[i]);
+    if (search_level[i] < 0 || search_level[i] > 8) return fail(ctx, ESIKF_ERR_ARG, "warp_affine: search level %d", search_level[i]);
+  }
+  if (n == 0) return ESIKF_OK;
+  CK(cudaSetDevice(ctx->device));
+  const int L = ctx->vio_cfg.patch_pyrimid_level;
+  cudaStream_t st = ctx->stream;
+  CK(ctx->ref_idx.reserve(n));
+  CK(ctx->px_ref.reserve((size_t)n * 2));
+  CK(ctx->A_cur_ref.reserve((size_t)n * 4));
+  CK(ctx->warp_levels.reserve(n + 1));
+  CK(ctx->warp_out.reserve((size_t)n * 64 * L + 64));
+  CK(cudaMemcpyAsync(ctx->ref_idx.p, ref_img_index, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->px_ref.p, px_ref, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->A_cur_ref.p, A_cur_ref, (size_t)n * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->warp_levels.p, search_level, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  // separate scratch: the patches / search levels installed by set_patches (or warp_patches with keep_on_device) stay untouched
+  CK(cudaMemsetAsync(ctx->warp_out.p, 0, (size_t)n * 64 * L * sizeof(float), st));
+  warp_affine_kernel<<<(n * L * 64 + 255) / 256, 256, 0, st>>>(ctx->ref_img_ptrs.p, ctx->ref_idx.p, ctx->ref_w, ctx->ref_h, n, L, ctx->A_cur_ref.p,
+                                                              ctx->px_ref.p, ctx->warp_levels.p, ctx->warp_out.p);
+  ctx->launches += 1;
+  CK(cudaMemcpyAsync(warp_patch_out, ctx->warp_out.p, (size_t)n * 64 * L * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
   return ESIKF_OK;
 }
 

@@ -220,6 +220,48 @@ void VIOManager::computeJacobianAndUpdateEKF(const GrayImage &img) {
   state->unpack(sout);
 }
 
+// include/vio.h:151 / src/vio.cpp:203-225: writes patch_tmp[patch_size_total * level + row * patch_size + col]
+void VIOManager::getImagePatch(const GrayImage &img, const double pc[2], float *patch_tmp, int level) {
+  if (!ctx_ || !img.data || !pc || !patch_tmp) return;
+  last_status_ = esikf_vio_set_image(ctx_, img.data, img.cols, img.rows);
+  float out[64];
+  if (!last_status_) last_status_ = esikf_vio_get_image_patch(ctx_, pc, 1, level, out);
+  if (last_status_) {
+    last_error_ = esikf_last_error(ctx_);
+    return;
+  }
+  memcpy(patch_tmp + 64 * level, out, sizeof(out));
+}
+
+// include/vio.h:161-162 / src/vio.cpp:292-318: writes patch[patch_size_total * pyramid_level + y * patch_size + x].
+// level_ref is unused by the reference as well; halfpatch_size must be 4 (patch_size 8).
+void VIOManager::warpAffine(const double A_cur_ref[4], const GrayImage &img_ref, const double px_ref[2], int level_ref, int search_level, int pyramid_level,
+                            int halfpatch_size, float *patch) {
+  (void)level_ref;
+  if (!ctx_ || !img_ref.data || !A_cur_ref || !px_ref || !patch) return;
+  if (halfpatch_size != 4 || pyramid_level < 0 || pyramid_level >= patch_pyrimid_level) {
+    last_status_ = ESIKF_ERR_ARG;
+    last_error_ = "warpAffine: halfpatch_size must be 4 and pyramid_level inside the pyramid";
+    return;
+  }
+  const uint8_t *imgs[1] = {img_ref.data};
+  last_status_ = esikf_vio_set_ref_images(ctx_, imgs, 1, img_ref.cols, img_ref.rows);
+  std::vector<float> all((size_t)64 * patch_pyrimid_level);
+  const int32_t idx = 0, sl = search_level;
+  if (!last_status_) last_status_ = esikf_vio_warp_affine(ctx_, 1, &idx, px_ref, A_cur_ref, &sl, all.data());
+  if (last_status_) {
+    last_error_ = esikf_last_error(ctx_);
+    return;
+  }
+  // a singular A leaves the patch untouched in the reference (vio.cpp:297-301); the kernel writes zeros into its own
+  // scratch in that case, so only copy when A is invertible
+  const double det = A_cur_ref[0] * A_cur_ref[3] - A_cur_ref[1] * A_cur_ref[2];
+  const double inv_det = 1.0 / det;
+  const float inv00 = (float)(A_cur_ref[3] * inv_det);  // same expression as the kernel's A_ref_cur(0, 0)
+  if (inv00 != inv00) return;
+  memcpy(patch + 64 * pyramid_level, all.data() + 64 * pyramid_level, sizeof(float) * 64);
+}
+
 }  // namespace fl2b200
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -352,6 +394,34 @@ int fl2_shim_run(const int64_t *keys, const int32_t *first, const int32_t *count
     }
   }
   for (auto &kv : map) delete kv.second;
+  return rc;
+}
+
+// GPU: VIOManager::getImagePatch / VIOManager::warpAffine through the shim class (one patch each).
+int fl2_shim_patch_helpers(const esikf_camera *cam, const esikf_vio_cfg *vcfg, const uint8_t *img, int cols, int rows, const double *pc, int level,
+                           float *patch_tmp /* levels*64, only `level` written */, const double *A_cur_ref, const uint8_t *img_ref, const double *px_ref,
+                           int search_level, int pyramid_level, float *warp_patch /* levels*64, only `pyramid_level` written */) {
+  esikf_ctx *ctx = nullptr;
+  int rc = esikf_create(&ctx, 0);
+  if (rc) return rc;
+  {
+    VIOManager vio(ctx);
+    vio.cam = *cam;
+    vio.patch_pyrimid_level = vcfg->patch_pyrimid_level, vio.max_iterations = vcfg->max_iterations, vio.img_point_cov = vcfg->img_point_cov;
+    vio.exposure_estimate_en = vcfg->exposure_estimate_en != 0;
+    vio.initializeVIO();
+    rc = vio.last_status_;
+    GrayImage g{img, cols, rows}, gr{img_ref, cols, rows};
+    if (!rc) {
+      vio.getImagePatch(g, pc, patch_tmp, level);
+      rc = vio.last_status_;
+    }
+    if (!rc) {
+      vio.warpAffine(A_cur_ref, gr, px_ref, 0, search_level, pyramid_level, 4, warp_patch);
+      rc = vio.last_status_;
+    }
+  }
+  esikf_destroy(ctx);
   return rc;
 }
 

@@ -173,6 +173,11 @@ class VIOManager {
   explicit VIOManager(esikf_ctx *shared_ctx);  // shares the device context (and stream) of the VoxelMapManager
   void initializeVIO();                         // src/vio.cpp:41-160 (the parts the update needs)
   void computeJacobianAndUpdateEKF(const GrayImage &img);  // include/vio.h:153
+  // Per-patch helpers with the reference's signatures (include/vio.h:151, 161-162; V2D / Matrix2d as plain arrays). They
+  // upload the image on every call: use the batched esikf_vio_get_image_patch / esikf_vio_warp_patches on the frame path.
+  void getImagePatch(const GrayImage &img, const double pc[2], float *patch_tmp, int level);
+  void warpAffine(const double A_cur_ref[4] /* row-major 2x2 */, const GrayImage &img_ref, const double px_ref[2], int level_ref, int search_level,
+                  int pyramid_level, int halfpatch_size, float *patch);
 
  private:
   esikf_ctx *ctx_ = nullptr;

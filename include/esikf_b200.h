@@ -194,6 +194,12 @@ int esikf_vio_warp_patches(esikf_ctx *ctx, int32_t n, const int32_t *ref_img_ind
                            const double *T_cur_w /* 12: new_frame_->T_f_w_ */, double *A_cur_ref_out /* n x 4, nullable */,
                            int32_t *search_level_out /* n */, float *warp_patch_out /* n x levels*64 */,
                            int32_t keep_on_device /* 1: also install as the patches of set_patches */);
+/* warp_affine    : batched warpAffine alone (src/vio.cpp:292-318, include/vio.h:161-162) with caller-provided affine
+ *                  matrices A_cur_ref (n x 4, row-major [a00 a01 a10 a11]) and search levels; writes all pyramid levels,
+ *                  patch i level l at warp_patch_out[(i*levels + l)*64 ...] like visual_submap->warp_patch[i]. */
+int esikf_vio_warp_affine(esikf_ctx *ctx, int32_t n, const int32_t *ref_img_index, const double *px_ref /* n x 2 */,
+                          const double *A_cur_ref /* n x 4 */, const int32_t *search_level /* n */,
+                          float *warp_patch_out /* n x levels*64 */);
 
 /* ---------------------------------------------------------------- multi-GPU (one process per GPU)
  * The residual point / patch set is sharded by contiguous blocks; each iteration all-reduces the
