@@ -371,7 +371,9 @@ __global__ void warp_affine_kernel(const uint8_t *const *__restrict__ ref_imgs, 
   const float px0 = __fadd_rn(__fadd_rn(__fmul_rn(A00, pp0), __fmul_rn(A01, pp1)), (float)px_ref[2 * i]);
   const float px1 = __fadd_rn(__fadd_rn(__fmul_rn(A10, pp0), __fmul_rn(A11, pp1)), (float)px_ref[2 * i + 1]);
   float val = 0.0f;
-  if (!(px0 < 0 || px1 < 0 || px0 >= (float)(cols - 1) || px1 >= (float)(rows - 1))) {
+  // in-frame test of :312 written so that a NaN position (singular A with zero entries: inf * 0) counts as outside; the
+  // reference would hand NaN to vk::interpolateMat_8u and read out of bounds
+  if (px0 >= 0 && px1 >= 0 && px0 < (float)(cols - 1) && px1 < (float)(rows - 1)) {
     // vk::interpolateMat_8u
     const uint8_t *__restrict__ img = ref_imgs[ref_idx[i]];
     const int xi = (int)floorf(px0), yi = (int)floorf(px1);

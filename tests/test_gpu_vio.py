@@ -211,7 +211,7 @@ def test_config5_five_levels_4k_patches(gpu_ctx):
 def test_warp_affine_alone_with_caller_matrices(gpu_ctx, small_vio_frame):
     """esikf_vio_warp_affine (include/vio.h:161-162): the same kernel as warp_patches fed with caller-provided matrices —
     identical to the batched producer for its own matrices, and equal to the oracle's warpAffine for arbitrary ones
-    (rotation + anisotropic scale, search level 1; a singular matrix leaves zeros)."""
+    (rotation + anisotropic scale, search levels 0 / 1; a zero matrix leaves zeros)."""
     fr = small_vio_frame
     _setup(gpu_ctx, fr)
     prior = _vio_prior(fr)
@@ -223,7 +223,7 @@ def test_warp_affine_alone_with_caller_matrices(gpu_ctx, small_vio_frame):
     rng = np.random.default_rng(5)
     ang = rng.uniform(-0.6, 0.6, m)
     A = np.stack([np.stack([1.3 * np.cos(ang), -0.8 * np.sin(ang)], 1), np.stack([1.3 * np.sin(ang), 0.8 * np.cos(ang)], 1)], 1)  # (m, 2, 2)
-    A[-1] = [[1.0, 2.0], [2.0, 4.0]]  # singular
+    A[-1] = 0.0  # singular with A_ref_cur(0, 0) = NaN: the patch is left untouched (vio.cpp:297-301)
     sl = (np.arange(m) % 2).astype(np.int32)
     out = gpu_ctx.vio_warp_affine(np.zeros(m, np.int32), fr["px_ref"][:m], A, sl)
     vio = O.OracleVIO(fr["cam_cfg"], fr["ext"], fr["vio_cfg"])
