@@ -310,6 +310,8 @@ __device__ __forceinline__ void lio_consts_from_resident(LioSmem &sm, const Fuse
   __syncthreads();
 }
 
+// DEAL: 32-point chunks dealt round-robin over the CTAs instead of one contiguous block per CTA (see lio_process_range).
+template <bool DEAL>
 __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_repl_kernel(const LioKernelArgs a, const SolveArgs sa_in, unsigned int *barrier, unsigned int *barrier_next,
                                                                           unsigned long long *stamps, size_t partial_parity_stride) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -320,7 +322,10 @@ __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_repl_kernel(const L
   if (blockIdx.x != 0) sa.dbg = nullptr;
   unsigned int epoch = 0;
   int lo, hi;
-  lio_block_range(a.count, lo, hi);
+  if (DEAL)
+    lo = 0, hi = a.count;
+  else
+    lio_block_range(a.count, lo, hi);
   if (threadIdx.x == 0) {
     Ctrl z;
     memset(&z, 0, sizeof(z));
@@ -353,7 +358,7 @@ __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_repl_kernel(const L
     stamp(stamps, sk);  // 1: constants in place
     double D0 = 0.0, D1 = 0.0;
     int cnt = 0;
-    lio_process_range(a, sm, lo, hi, D0, D1, cnt, lc, it == 0);
+    lio_process_range<DEAL>(a, sm, lo, hi, D0, D1, cnt, lc, it == 0);
     __syncthreads();
     if (stamps && it == 3 && threadIdx.x == 0) {
       unsigned long long t;

@@ -307,15 +307,22 @@ __device__ __forceinline__ void lio_load_consts(LioSmem &sm, const LioKernelArgs
 
 // Residual / Jacobian build over the points [lo, hi) of this rank's shard (indices local to the shard), accumulated into
 // the calling warp's 8x8 tensor-core block (D0, D1) and matched-point count.
+// DEAL = false: the CTA owns the contiguous block [lo, hi) and walks it in tiles of LIO_THREADS points.
+// DEAL = true (lo = 0, hi = points of the shard): 32-point chunks are dealt round-robin over the CTAs — chunk
+// (t * LIO_WARPS + warp) * gridDim.x + blockIdx.x belongs to this warp in tile t — so a CTA samples the whole scan instead
+// of inheriting the local structure (sub-divided voxels, unmatched regions) of one stretch of it. Loads stay coalesced per
+// warp; only the fixed summation order differs between the two schedules.
+template <bool DEAL = false>
 __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSmem &sm, int lo, int hi, double &D0, double &D1, int &cnt,
                                                   LaneCache &lc, bool init_normal) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double *const myrec = &sm.rec[warp][lane][0];
-  for (int base = lo; base < hi; base += LIO_THREADS) {
-    const int li = base + tid;
+  const int tile_pts = DEAL ? (int)(LIO_THREADS * gridDim.x) : LIO_THREADS;
+  for (int base = lo; base < hi; base += tile_pts) {
+    const int li = DEAL ? base + (warp * (int)gridDim.x + (int)blockIdx.x) * 32 + lane : base + tid;
     const bool valid = li < hi;
     const int i = a.begin + li;
-    if (hi - lo > LIO_THREADS) lc.staged_idx = -1, lc.have_pt = false;  // several tiles share the lanes: nothing stays resident
+    if (hi - lo > tile_pts) lc.staged_idx = -1, lc.have_pt = false;  // several tiles share the lanes: nothing stays resident
     int midx = -1;
     float mdis = 0.f;
     double pw[3] = {0, 0, 0};
@@ -329,7 +336,7 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
     if (valid) {
       if (!lc.have_pt) {
         lc.px = a.pts[3 * (size_t)i], lc.py = a.pts[3 * (size_t)i + 1], lc.pz = a.pts[3 * (size_t)i + 2];
-        lc.have_pt = (hi - lo <= LIO_THREADS);
+        lc.have_pt = (hi - lo <= tile_pts);
       }
       const double px = lc.px, py = lc.py, pz = lc.pz;
       // p_imu = extR p + extT ; p_w = R p_imu + t, narrowed to float (TransformLidar, voxel_map.cpp:522-526). No FMA contraction

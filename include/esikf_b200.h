@@ -132,6 +132,11 @@ int esikf_set_solve_mode(esikf_ctx *ctx, int mode);
  *       the in-kernel NVLink all-reduce of the information buffer.
  *   0 = one residual + one solve launch per iteration (also used with an NCCL communicator or kernel timing on). */
 int esikf_set_loop_mode(esikf_ctx *ctx, int mode);
+/* lio_schedule: how the points of a scan are assigned to the CTAs of the persistent LIO kernel (loop_mode 2, one GPU).
+ *   0 (default) = one contiguous block of points per CTA;
+ *   1 = 32-point chunks dealt round-robin over all SMs (evens out sub-divided / unmatched regions of the scan).
+ * Both are deterministic; they differ in the fixed summation order of H^T R^-1 H (last bits), not in the association. */
+int esikf_set_lio_schedule(esikf_ctx *ctx, int schedule);
 int esikf_set_extrinsics(esikf_ctx *ctx, const esikf_extrinsics *ext);
 
 /* ---------------------------------------------------------------- voxel map mirror
