@@ -193,3 +193,34 @@ def test_numpy_restatement_of_one_vio_iteration(small_vio_frame):
     np.testing.assert_allclose(o["HTH"][level][0], HTH, rtol=1e-11)
     np.testing.assert_allclose(o["HTz"][level][0], HTz, rtol=1e-10, atol=1e-8)
     assert o["error_trace"][level][0] == err
+
+
+def _numpy_gain_solution(HTH_m, HTz_m, P, sign):
+    """K_1 = (H^T H + P^-1)^-1 with the information block zero-padded to 19 x 19; first-iteration solution (vec = 0):
+    sign * K_1[:, :m] H^T z   (voxel_map.cpp:462-472 with sign +1, vio.cpp:1660-1667 with sign -1)."""
+    m = len(HTz_m)
+    H = np.zeros((19, 19))
+    H[:m, :m] = HTH_m
+    K1 = np.linalg.inv(H + np.linalg.inv(P))
+    return sign * K1[:, :m] @ HTz_m
+
+
+def test_first_iteration_solutions_match_numpy_gain_formula(small_frame, small_vio_frame):
+    """The gain algebra (a7 / a9) restated with numpy's LAPACK inverses instead of the oracle's own 19 x 19 elimination."""
+    fr = small_frame
+    lio = O.OracleLIO(fr["lio_cfg"], fr["ext"])
+    lio.set_map(fr["map"])
+    r = lio.state_estimation(fr["pts"], fr["state_prior"], fr["state_prior"])
+    P = S.unpack_state(fr["state_prior"])["cov"]
+    want = _numpy_gain_solution(r["HTH"][0], r["HTz"][0], P, +1.0)
+    np.testing.assert_allclose(r["solution"][0], want, rtol=1e-7, atol=1e-10 * np.abs(want).max())
+
+    fv = small_vio_frame
+    w = O.oracle_warp_patches(fv, fv["state_prior"])
+    vio = O.OracleVIO(fv["cam_cfg"], fv["ext"], fv["vio_cfg"])
+    o = vio.update(fv["img"], fv["vis_pos"], w["warp_patch"], w["search_levels"], fv["inv_ref_expo"], fv["state_prior"], fv["state_prior"])
+    top = fv["vio_cfg"].levels - 1
+    assert o["accepted_per_level"][top] >= 1
+    Pv = S.unpack_state(fv["state_prior"])["cov"] / fv["vio_cfg"].img_point_cov
+    want = _numpy_gain_solution(o["HTH"][top][0], o["HTz"][top][0], Pv, -1.0)
+    np.testing.assert_allclose(o["solution"][top][0], want, rtol=1e-7, atol=1e-10 * np.abs(want).max())
