@@ -75,7 +75,7 @@ def load_library():
     lib.esikf_launch_count.restype = C.c_int64
     lib.esikf_set_solve_mode.argtypes = [vp, C.c_int]
     lib.esikf_set_loop_mode.argtypes = [vp, C.c_int]
-    lib.esikf_set_lio_schedule.argtypes = [vp, C.c_int]
+    lib.esikf_set_tuning.argtypes = [vp, C.c_uint32]
     lib.esikf_set_extrinsics.argtypes = [vp, C.POINTER(ExtrinsicsC)]
     lib.esikf_map_upload.argtypes = [vp, i64p, ip, ip, C.c_int32, vp, C.c_int32, C.c_double]
     lib.esikf_map_patch.argtypes = [vp, ip, vp, C.c_int32]
@@ -109,10 +109,11 @@ def load_library():
     return lib
 
 
+TUNE_DEAL_POINTS, TUNE_DEFER_DIAGNOSTICS = 1, 2  # esikf_set_tuning flags
 DEFAULT_LOOP_MODE = 2  # esikf_set_loop_mode: 2 replicated-solve persistent kernel, 1 CTA-0 solve, 0 per-iteration launches
 
 EXPORTED_SYMBOLS = [
-    "esikf_create", "esikf_destroy", "esikf_last_error", "esikf_stream", "esikf_synchronize", "esikf_launch_count", "esikf_set_solve_mode", "esikf_set_loop_mode", "esikf_set_lio_schedule",
+    "esikf_create", "esikf_destroy", "esikf_last_error", "esikf_stream", "esikf_synchronize", "esikf_launch_count", "esikf_set_solve_mode", "esikf_set_loop_mode", "esikf_set_tuning",
     "esikf_set_extrinsics", "esikf_map_upload", "esikf_map_patch", "esikf_lio_set_scan", "esikf_lio_run", "esikf_lio_fetch",
     "esikf_lio_update", "esikf_lio_fetch_point_cov", "esikf_vio_set_camera", "esikf_vio_set_image", "esikf_vio_set_patches",
     "esikf_vio_run", "esikf_vio_fetch", "esikf_vio_update", "esikf_vio_get_image_patch", "esikf_vio_set_ref_images",
@@ -182,8 +183,9 @@ class Context:
     def set_loop_mode(self, mode):
         self._ck(self.lib.esikf_set_loop_mode(self.h, mode))
 
-    def set_lio_schedule(self, schedule):
-        self._ck(self.lib.esikf_set_lio_schedule(self.h, schedule))
+    def set_tuning(self, flags):
+        """OR of TUNE_DEAL_POINTS / TUNE_DEFER_DIAGNOSTICS (opt-in variants of the default kernels); 0 = none."""
+        self._ck(self.lib.esikf_set_tuning(self.h, flags))
 
     def set_extrinsics(self, ext):
         e = ExtrinsicsC()

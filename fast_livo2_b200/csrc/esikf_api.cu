@@ -88,8 +88,8 @@ struct esikf_ctx {
   int coop_ok = 0;
   int coop_lio = 0, coop_vio = 0;  // co-resident CTAs per SM of the persistent kernels
   bool coop_repl = false;          // the replicated-solve variants fit as well
-  bool coop_deal = false;
-  int lio_schedule = 0;            // 0: contiguous block of points per CTA, 1: 32-point chunks dealt round-robin over the CTAs (loop_mode 2 only)
+  bool coop_tuned = false;         // ... and so do their opt-in variants
+  uint32_t tuning = 0;             // ESIKF_TUNE_* flags (opt-in variants of the loop_mode 2 kernels)
   DevBuf<unsigned int> barrier;       // two grid barriers {counter @ +0, release word @ +128 B}, 256 B apart; launches alternate
   DevBuf<unsigned long long> stamps;  // 8 per slot: 8 LIO slots then 64 VIO slots
   bool want_stamps = false;
@@ -250,9 +250,12 @@ int esikf_create(esikf_ctx **out, int device) {
   cudaFuncSetAttribute(vio_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VioSmem));
   cudaError_t ea = cudaFuncSetAttribute(lio_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
   cudaError_t eb = cudaFuncSetAttribute(vio_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(VioSmem) + sizeof(FusedSolveSmem)));
-  cudaFuncSetAttribute(lio_update_repl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
-  cudaFuncSetAttribute(lio_update_repl_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
-  cudaFuncSetAttribute(vio_update_repl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(VioSmem) + sizeof(FusedSolveSmem)));
+  cudaFuncSetAttribute(lio_update_repl_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
+  cudaFuncSetAttribute(lio_update_repl_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
+  cudaFuncSetAttribute(lio_update_repl_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
+  cudaFuncSetAttribute(lio_update_repl_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
+  cudaFuncSetAttribute(vio_update_repl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(VioSmem) + sizeof(FusedSolveSmem)));
+  cudaFuncSetAttribute(vio_update_repl_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(VioSmem) + sizeof(FusedSolveSmem)));
   // the persistent kernels need every CTA co-resident: check what the device can hold
   int occ_l = 0, occ_v = 0, occ_r = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, lio_update_kernel, LIO_THREADS, sizeof(LioSmem));
@@ -261,11 +264,14 @@ int esikf_create(esikf_ctx **out, int device) {
   ctx->coop_lio = occ_l, ctx->coop_vio = occ_v;
   {
     int occ_lr = 0, occ_vr = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lr, lio_update_repl_kernel<false>, LIO_THREADS, sizeof(LioSmem));
-    int occ_ld = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ld, lio_update_repl_kernel<true>, LIO_THREADS, sizeof(LioSmem));
-    ctx->coop_deal = occ_ld > 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_vr, vio_update_repl_kernel, VIO_THREADS, sizeof(VioSmem) + sizeof(FusedSolveSmem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lr, lio_update_repl_kernel<false, false>, LIO_THREADS, sizeof(LioSmem));
+    int occ_a = 0, occ_b = 0, occ_c = 0, occ_d = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, lio_update_repl_kernel<true, false>, LIO_THREADS, sizeof(LioSmem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, lio_update_repl_kernel<false, true>, LIO_THREADS, sizeof(LioSmem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, lio_update_repl_kernel<true, true>, LIO_THREADS, sizeof(LioSmem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_d, vio_update_repl_kernel<true>, VIO_THREADS, sizeof(VioSmem) + sizeof(FusedSolveSmem));
+    ctx->coop_tuned = occ_a > 0 && occ_b > 0 && occ_c > 0 && occ_d > 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_vr, vio_update_repl_kernel<false>, VIO_THREADS, sizeof(VioSmem) + sizeof(FusedSolveSmem));
     ctx->coop_repl = occ_lr > 0 && occ_vr > 0;
   }
   if (getenv("ESIKF_DEBUG"))
@@ -330,9 +336,9 @@ int esikf_set_loop_mode(esikf_ctx *ctx, int mode) {
   ctx->loop_mode = mode;
   return ESIKF_OK;
 }
-int esikf_set_lio_schedule(esikf_ctx *ctx, int schedule) {
-  if (!ctx || schedule < 0 || schedule > 1) return ESIKF_ERR_ARG;
-  ctx->lio_schedule = schedule;
+int esikf_set_tuning(esikf_ctx *ctx, uint32_t flags) {
+  if (!ctx || (flags & ~(uint32_t)(ESIKF_TUNE_DEAL_POINTS | ESIKF_TUNE_DEFER_DIAGNOSTICS))) return ESIKF_ERR_ARG;
+  ctx->tuning = flags;
   return ESIKF_OK;
 }
 int esikf_set_extrinsics(esikf_ctx *ctx, const esikf_extrinsics *ext) {
@@ -505,13 +511,17 @@ int esikf_lio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
     if (ctx->loop_mode == 2 && ctx->nranks == 1 && ctx->coop_repl) {
       size_t parity_stride = (size_t)ctx->partial_blocks * INFO_N;
       void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride};
-      if (ctx->lio_schedule == 1 && ctx->coop_deal) {
+      const uint32_t tune = ctx->coop_tuned ? ctx->tuning : 0u;
+      const bool defer = (tune & ESIKF_TUNE_DEFER_DIAGNOSTICS) != 0;
+      if (tune & ESIKF_TUNE_DEAL_POINTS) {
         int chunks = (ka.count + 31) / 32;  // dealt schedule: every SM takes part as soon as there is a chunk for it
         int gd = chunks < ctx->partial_blocks ? chunks : ctx->partial_blocks;
         if (gd < 1) gd = 1;
-        CK(cudaLaunchCooperativeKernel((const void *)lio_update_repl_kernel<true>, dim3(gd), dim3(LIO_THREADS), kargs, sizeof(LioSmem), st));
+        const void *fn = defer ? (const void *)lio_update_repl_kernel<true, true> : (const void *)lio_update_repl_kernel<true, false>;
+        CK(cudaLaunchCooperativeKernel(fn, dim3(gd), dim3(LIO_THREADS), kargs, sizeof(LioSmem), st));
       } else {
-        CK(cudaLaunchCooperativeKernel((const void *)lio_update_repl_kernel<false>, dim3(grid), dim3(LIO_THREADS), kargs, sizeof(LioSmem), st));
+        const void *fn = defer ? (const void *)lio_update_repl_kernel<false, true> : (const void *)lio_update_repl_kernel<false, false>;
+        CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(LIO_THREADS), kargs, sizeof(LioSmem), st));
       }
     } else {
       PeerArgs peer = peer_args(ctx);
@@ -711,7 +721,9 @@ int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
     if (ctx->loop_mode == 2 && ctx->nranks == 1 && ctx->coop_repl) {
       size_t parity_stride = (size_t)ctx->partial_blocks * INFO_N;
       void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride};
-      CK(cudaLaunchCooperativeKernel((const void *)vio_update_repl_kernel, dim3(grid), dim3(VIO_THREADS), kargs, sizeof(VioSmem) + sizeof(FusedSolveSmem), st));
+      const bool defer = ctx->coop_tuned && (ctx->tuning & ESIKF_TUNE_DEFER_DIAGNOSTICS);
+      const void *fn = defer ? (const void *)vio_update_repl_kernel<true> : (const void *)vio_update_repl_kernel<false>;
+      CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(VIO_THREADS), kargs, sizeof(VioSmem) + sizeof(FusedSolveSmem), st));
     } else {
       PeerArgs peer = peer_args(ctx);
       void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&peer};

@@ -247,8 +247,6 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKer
       grid_barrier(barrier, epoch);
       stamp(stamps, sk);
       bool level_done;
-      const bool last_of_level = false;
-      (void)last_of_level;
       if (blockIdx.x == 0) {
         if (level == a.levels - 1 && it == 0) {
           solve_load(fs.sm, fs.io, sa, false);
@@ -297,6 +295,62 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKer
 // 55.1 k for the CTA-0 solve (profiles/loop_modes_r01_mode2.txt). Exchanging the partials as tagged 64-bit words polled
 // by every CTA instead of the barrier was also built and measured: bit-identical but slower (49.3 k it/s, the polling
 // of 148 CTAs saturates L2; profiles/loop_modes_r01_mode3_ll.txt) and removed again.
+// grid_barrier whose waiting time does useful work: thread 0 arrives and polls as in grid_barrier, the other threads run
+// `work` (global writes nobody reads inside the kernel) meanwhile. Same counter protocol, so both forms can be mixed.
+template <class F> __device__ __forceinline__ void grid_barrier_overlap(unsigned int *counter, unsigned int &epoch, F work) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int target = (epoch + 1) * gridDim.x;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+  } else {
+    work();
+  }
+  epoch++;
+  __syncthreads();
+}
+
+// Diagnostics of the last solved iteration written by ONE warp (lane-strided) — the deferred form of lio_write_stats /
+// vio_write_stats + the control-block publication, run by warp 1 of CTA 0 inside the next barrier wait.
+__device__ __forceinline__ void lio_write_stats_warp(const SolveArgs &a, const SolveSmem &sm, const SolveIO &io, const Ctrl &ctrl, Ctrl *ctrl_out, int lane) {
+  const int iterCount = io.flags[3];
+  if (lane < (int)(sizeof(Ctrl) / 4)) reinterpret_cast<int *>(ctrl_out)[lane] = reinterpret_cast<const int *>(&ctrl)[lane];
+  if (a.lio_stats && iterCount < 8) {
+    esikf_lio_stats &S = *a.lio_stats;
+    for (int t = lane; t < 36; t += 32) S.HTH[iterCount][t] = sm.A[t];
+    if (lane < 6) S.HTz[iterCount][lane] = sm.HTz[lane];
+    if (lane < 19) S.solution[iterCount][lane] = sm.sol[lane];
+    if (lane == 31) {
+      S.iters = iterCount + 1;
+      S.effct_feat_num[iterCount] = (int)io.info[INFO_COUNT];
+      S.total_residual[iterCount] = io.info[INFO_ABS];
+      S.converged[iterCount] = io.flags[0];
+    }
+  }
+}
+__device__ __forceinline__ void vio_write_stats_warp(const SolveArgs &a, int level, int iteration, const SolveSmem &sm, const SolveIO &io, const Ctrl &ctrl,
+                                                     Ctrl *ctrl_out, int lane) {
+  const bool accepted = io.flags[0] != 0, ran = io.flags[2] != 0;
+  if (lane < (int)(sizeof(Ctrl) / 4)) reinterpret_cast<int *>(ctrl_out)[lane] = reinterpret_cast<const int *>(&ctrl)[lane];
+  if (ran && a.vio_stats && level < 8) {
+    esikf_vio_stats &S = *a.vio_stats;
+    if (accepted && iteration < 8) {
+      for (int t = lane; t < 49; t += 32) S.HTH[level][iteration][t] = sm.A[t];
+      if (lane < 7) S.HTz[level][iteration][lane] = sm.HTz[lane];
+      if (lane < 19) S.solution[level][iteration][lane] = sm.sol[lane];
+    }
+    if (lane == 31) {
+      if (iteration < 8) S.error_trace[level][iteration] = reinterpret_cast<const float *>(io.flags)[4];
+      S.iters_per_level[level] = iteration + 1;
+      if (accepted) S.accepted_per_level[level] += 1;
+      S.total_iters += 1;
+    }
+  }
+}
+
 __device__ __forceinline__ void lio_consts_from_resident(LioSmem &sm, const FusedSolveSmem &fs) {
   const int tid = threadIdx.x;
   if (tid < 9) {
@@ -311,7 +365,10 @@ __device__ __forceinline__ void lio_consts_from_resident(LioSmem &sm, const Fuse
 }
 
 // DEAL: 32-point chunks dealt round-robin over the CTAs instead of one contiguous block per CTA (see lio_process_range).
-template <bool DEAL>
+// DEFER: CTA 0 writes the diagnostics / control block of iteration k while it waits at the grid barrier of iteration k + 1
+// (warp 1, while thread 0 polls) instead of right after the solve, where it delays CTA 0's next slice — and with it the
+// whole grid — by the ~1 us the "publish" phase takes in profiles/loop_modes_r01_mode2.txt.
+template <bool DEAL, bool DEFER>
 __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_repl_kernel(const LioKernelArgs a, const SolveArgs sa_in, unsigned int *barrier, unsigned int *barrier_next,
                                                                           unsigned long long *stamps, size_t partial_parity_stride) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -368,7 +425,12 @@ __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_repl_kernel(const L
     stamp(stamps, sk);  // 2: CTA 0 finished its slice
     double *const part = a.partials + (size_t)(it & 1) * partial_parity_stride;
     store_partials<LIO_WARPS>(sm.red, D0, D1, (double)cnt, true, part, a.partial_stride);
-    grid_barrier(barrier, epoch);
+    if (DEFER && blockIdx.x == 0 && it > 0)
+      grid_barrier_overlap(barrier, epoch, [&]() {
+        if ((threadIdx.x >> 5) == 1) lio_write_stats_warp(sa, fs.sm, fs.io, fs.ctrl, a.ctrl, threadIdx.x & 31);
+      });
+    else
+      grid_barrier(barrier, epoch);
     stamp(stamps, sk);  // 3: all CTAs arrived
     reduce_partials_block(part, a.partial_stride, gridDim.x, fs.io.info);
     stamp(stamps, sk);  // 4: partials summed
@@ -381,7 +443,8 @@ __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_repl_kernel(const L
     if (sa.solve_mode == 1) lc.staged_idx = -1;  // the literal workspace borrowed the record slots
     stamp(stamps, sk);  // 5: solved
     __syncthreads();    // fs.ctrl (written by thread 0) is read by everybody below
-    if (blockIdx.x == 0) {
+    const bool last = fs.ctrl.stop || it == sa.max_iterations - 1;
+    if (blockIdx.x == 0 && (!DEFER || last)) {
       if (threadIdx.x == 0) *a.ctrl = fs.ctrl;
       lio_write_stats(sa, fs.sm, fs.io);
     }
@@ -411,6 +474,7 @@ __device__ __forceinline__ void vio_consts_from_resident(VioSmem &sm, const VioK
   __syncthreads();
 }
 
+template <bool DEFER>
 __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_repl_kernel(const VioKernelArgs a, SolveArgs sa, unsigned int *barrier, unsigned int *barrier_next,
                                                                           unsigned long long *stamps, size_t partial_parity_stride) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -434,6 +498,7 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_repl_kernel(const V
   solve_load(fs.sm, fs.io, sa, false);
   __syncthreads();
   int slot = 0;
+  int pend_level = -1, pend_it = 0;  // DEFER: iteration whose diagnostics CTA 0 still has to write
   for (int level = a.levels - 1; level >= 0; level--) {      // vio.cpp:790
     for (int it = 0; it < sa.max_iterations; it++) {          // :1536
       const int cur = slot++;  // counts executed iterations (a level may end early): the partial-buffer parity follows it
@@ -447,7 +512,14 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_repl_kernel(const V
       stamp(stamps, sk);
       double *const part = a.partials + (size_t)(cur & 1) * partial_parity_stride;
       store_partials<VIO_WARPS>(sm.red, D0, D1, n_meas, false, part, a.partial_stride);
-      grid_barrier(barrier, epoch);
+      if (DEFER && blockIdx.x == 0 && pend_level >= 0) {
+        grid_barrier_overlap(barrier, epoch, [&]() {
+          if ((threadIdx.x >> 5) == 1) vio_write_stats_warp(sa, pend_level, pend_it, fs.sm, fs.io, fs.ctrl, a.ctrl, threadIdx.x & 31);
+        });
+        pend_level = -1;
+      } else {
+        grid_barrier(barrier, epoch);
+      }
       stamp(stamps, sk);
       reduce_partials_block(part, a.partial_stride, gridDim.x, fs.io.info);
       stamp(stamps, sk);
@@ -457,12 +529,21 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_repl_kernel(const V
       vio_solve_block(sa, fs.sm, fs.io, fs.ctrl, true, true);  // ends with a CTA barrier: fs.ctrl is current for everybody
       stamp(stamps, sk);
       if (blockIdx.x == 0) {
-        if (threadIdx.x == 0) *a.ctrl = fs.ctrl;
-        vio_write_stats(sa, fs.sm, fs.io, fs.ctrl);
+        if (DEFER) {
+          pend_level = level, pend_it = it;
+        } else {
+          if (threadIdx.x == 0) *a.ctrl = fs.ctrl;
+          vio_write_stats(sa, fs.sm, fs.io, fs.ctrl);
+        }
       }
       stamp(stamps, sk);
       if (fs.ctrl.level_done) break;  // EKF_end (:1685)
     }
+  }
+  if (DEFER && blockIdx.x == 0 && pend_level >= 0) {  // the last iteration's diagnostics: nothing left to hide them behind
+    sa.level = pend_level, sa.slot_iter = pend_it;
+    if (threadIdx.x == 0) *a.ctrl = fs.ctrl;
+    vio_write_stats(sa, fs.sm, fs.io, fs.ctrl);
   }
   // state->cov -= G * state->cov (vio.cpp:800): a last-slot pass of the solve routine with the level already finished
   if (blockIdx.x == 0) {

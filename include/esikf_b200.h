@@ -132,11 +132,16 @@ int esikf_set_solve_mode(esikf_ctx *ctx, int mode);
  *       the in-kernel NVLink all-reduce of the information buffer.
  *   0 = one residual + one solve launch per iteration (also used with an NCCL communicator or kernel timing on). */
 int esikf_set_loop_mode(esikf_ctx *ctx, int mode);
-/* lio_schedule: how the points of a scan are assigned to the CTAs of the persistent LIO kernel (loop_mode 2, one GPU).
- *   0 (default) = one contiguous block of points per CTA;
- *   1 = 32-point chunks dealt round-robin over all SMs (evens out sub-divided / unmatched regions of the scan).
- * Both are deterministic; they differ in the fixed summation order of H^T R^-1 H (last bits), not in the association. */
-int esikf_set_lio_schedule(esikf_ctx *ctx, int schedule);
+/* Opt-in variants of the default (loop_mode 2, one GPU) kernels, OR-ed flags; 0 = none (default). They change when / in
+ * which order work is done, not the algorithm: every combination is deterministic and keeps the association bit-identical.
+ *   ESIKF_TUNE_DEAL_POINTS       : LIO points assigned to CTAs as 32-point chunks dealt round-robin over all SMs instead of
+ *                                  one contiguous block per CTA (evens out sub-divided / unmatched regions of the scan;
+ *                                  the fixed summation order of H^T R^-1 H — its last bits — follows the assignment).
+ *   ESIKF_TUNE_DEFER_DIAGNOSTICS : CTA 0 writes the per-iteration diagnostics while it waits at the next grid barrier
+ *                                  instead of right after the solve (same values, off the critical path). */
+#define ESIKF_TUNE_DEAL_POINTS 1u
+#define ESIKF_TUNE_DEFER_DIAGNOSTICS 2u
+int esikf_set_tuning(esikf_ctx *ctx, uint32_t flags);
 int esikf_set_extrinsics(esikf_ctx *ctx, const esikf_extrinsics *ext);
 
 /* ---------------------------------------------------------------- voxel map mirror

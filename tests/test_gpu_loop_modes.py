@@ -85,9 +85,12 @@ def test_vio_replicated_solve_is_bit_identical(gpu_ctx, small_vio_frame, solve_m
         _bits_equal(ref, r, keys)
 
 
-@pytest.mark.skipif(os.environ.get("ESIKF_EXPERIMENTAL") != "1",
-                    reason="dealt point schedule (esikf_set_lio_schedule 1): built at the end of round 1 without GPU time left to run it; "
-                           "ESIKF_EXPERIMENTAL=1 enables the check")
+EXPERIMENTAL = pytest.mark.skipif(os.environ.get("ESIKF_EXPERIMENTAL") != "1",
+                                  reason="opt-in kernel variants (esikf_set_tuning) were written at the end of round 1 with no GPU time left to run "
+                                         "them; ESIKF_EXPERIMENTAL=1 enables these checks")
+
+
+@EXPERIMENTAL
 @pytest.mark.parametrize("seed,n_pts,n_map,scale", [(4, 20000, 150_000, 0.5), (12, 260_000, 1_000_000, 1.0)])
 def test_lio_dealt_schedule_matches_contiguous_and_oracle(gpu_ctx, seed, n_pts, n_map, scale):
     """32-point chunks dealt round-robin over the CTAs: the association is identical, the state agrees to the summation-
@@ -101,13 +104,13 @@ def test_lio_dealt_schedule_matches_contiguous_and_oracle(gpu_ctx, seed, n_pts, 
     gpu_ctx.set_extrinsics(fr["ext"])
     gpu_ctx.map_upload(fr["map"], fr["lio_cfg"].voxel_size)
     try:
-        gpu_ctx.set_lio_schedule(0)
+        gpu_ctx.set_tuning(0)
         a = gpu_ctx.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"])
-        gpu_ctx.set_lio_schedule(1)
+        gpu_ctx.set_tuning(api.TUNE_DEAL_POINTS)
         b = gpu_ctx.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"])
         b2 = gpu_ctx.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"])
     finally:
-        gpu_ctx.set_lio_schedule(0)
+        gpu_ctx.set_tuning(0)
     assert a["iters"] == b["iters"]
     _bits_equal(a, b, ("match_plane", "normal_plane", "dis_to_plane", "M", "converged"))
     _bits_equal(b, b2, ("state", "HTH", "HTz", "match_plane"))  # deterministic
@@ -117,3 +120,32 @@ def test_lio_dealt_schedule_matches_contiguous_and_oracle(gpu_ctx, seed, n_pts, 
     o = lio.state_estimation(fr["pts"], fr["state_prior"], fr["state_prior"])
     assert np.array_equal(b["match_plane"], o["match_plane"])
     assert_state_close(b["state"], o["state"])
+
+
+@EXPERIMENTAL
+def test_deferred_diagnostics_are_bit_identical(gpu_ctx, small_vio_frame):
+    """ESIKF_TUNE_DEFER_DIAGNOSTICS only moves CTA 0's diagnostics writes into the next barrier wait: every output of the
+    LIO and VIO updates, diagnostics included, must be bit-identical to the default."""
+    fr = get_frame(seed=4, n_pts=20000, n_map=150_000, scene_scale=0.5)
+    gpu_ctx.set_extrinsics(fr["ext"])
+    gpu_ctx.map_upload(fr["map"], fr["lio_cfg"].voxel_size)
+    fv = small_vio_frame
+    lio_keys = ("state", "match_plane", "normal_plane", "dis_to_plane", "M", "HTH", "HTz", "solution", "total_residual", "converged")
+    vio_keys = ("state", "errors", "iters_per_level", "accepted_per_level", "error_trace", "HTH", "HTz", "solution")
+    out = []
+    try:
+        for flags in (0, api.TUNE_DEFER_DIAGNOSTICS, api.TUNE_DEFER_DIAGNOSTICS):
+            gpu_ctx.set_tuning(flags)
+            gpu_ctx.set_extrinsics(fr["ext"])
+            r = gpu_ctx.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"])
+            _setup(gpu_ctx, fv)
+            prior = _vio_prior(fv)
+            w = _gpu_warp(gpu_ctx, fv, prior)
+            v = gpu_ctx.vio_update(fv["img"], fv["vis_pos"], w["warp_patch"], w["search_levels"], fv["inv_ref_expo"], prior, prior)
+            out.append((r, v))
+    finally:
+        gpu_ctx.set_tuning(0)
+    for r, v in out[1:]:
+        assert r["iters"] == out[0][0]["iters"] and v["total_iters"] == out[0][1]["total_iters"]
+        _bits_equal(out[0][0], r, lio_keys)
+        _bits_equal(out[0][1], v, vio_keys)

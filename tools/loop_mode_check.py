@@ -80,10 +80,10 @@ def check(fr, label, time_it):
         ctx.lio_set_scan(pin(fr["pts"]))
         ctx.vio_set_patches(pin(fr["vis_pos"]), pin(w["warp_patch"]), pin(w["search_levels"]), pin(fr["inv_ref_expo"]))
         iters = int(ref[0]["iters"] + ref[1]["total_iters"])
-        runs = [(m, 0) for m in MODES] + ([(2, 1)] if os.environ.get("SCHEDULE1") else [])  # (loop mode, lio schedule)
+        runs = [(m, 0) for m in MODES] + [(2, int(f)) for f in os.environ.get("TUNING", "").split(",") if f]  # (loop mode, esikf_set_tuning flags)
         for mode, sched in runs:
             ctx.set_loop_mode(mode)
-            ctx.set_lio_schedule(sched)
+            ctx.set_tuning(sched)
             evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(STEPS)]
             for k in range(-3, STEPS):
                 with torch.cuda.stream(ext_stream):
@@ -101,8 +101,8 @@ def check(fr, label, time_it):
             torch.cuda.synchronize()
             lio = np.mean([a.elapsed_time(b) for a, b, _ in evs]) * 1e3
             vio = np.mean([b.elapsed_time(c) for _, b, c in evs]) * 1e3
-            print(f"[{label}] mode {mode} schedule {sched}: LIO {lio:.1f} us  VIO {vio:.1f} us  step {lio + vio:.1f} us  -> {iters / ((lio + vio) * 1e-6):.0f} it/s resident", flush=True)
-        ctx.set_lio_schedule(0)
+            print(f"[{label}] mode {mode} tuning {sched}: LIO {lio:.1f} us  VIO {vio:.1f} us  step {lio + vio:.1f} us  -> {iters / ((lio + vio) * 1e-6):.0f} it/s resident", flush=True)
+        ctx.set_tuning(0)
         if os.environ.get("STAMPS"):
             ctx.set_loop_mode(MODES[-1])
             ctx.set_phase_stamps(True)
