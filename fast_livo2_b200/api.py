@@ -109,7 +109,7 @@ def load_library():
     return lib
 
 
-TUNE_DEAL_POINTS, TUNE_DEFER_DIAGNOSTICS = 1, 2  # esikf_set_tuning flags
+TUNE_DEAL_POINTS, TUNE_DEFER_DIAGNOSTICS, TUNE_VIO_FAST_PATH = 1, 2, 4  # esikf_set_tuning flags
 DEFAULT_LOOP_MODE = 2  # esikf_set_loop_mode: 2 replicated-solve persistent kernel, 1 CTA-0 solve, 0 per-iteration launches
 
 EXPORTED_SYMBOLS = [
@@ -184,7 +184,7 @@ class Context:
         self._ck(self.lib.esikf_set_loop_mode(self.h, mode))
 
     def set_tuning(self, flags):
-        """OR of TUNE_DEAL_POINTS / TUNE_DEFER_DIAGNOSTICS (opt-in variants of the default kernels); 0 = none."""
+        """OR of TUNE_DEAL_POINTS / TUNE_DEFER_DIAGNOSTICS / TUNE_VIO_FAST_PATH (opt-in variants of the default kernels); 0 = none."""
         self._ck(self.lib.esikf_set_tuning(self.h, flags))
 
     def set_extrinsics(self, ext):

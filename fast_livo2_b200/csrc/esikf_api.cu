@@ -75,6 +75,8 @@ template <typename T> struct DevBuf {
   }
 };
 
+#define VIO_FAST_SMEM (sizeof(VioSmem) + sizeof(FusedSolveSmem) + VIO_WARPS * sizeof(VioPatchSlot))
+
 struct esikf_ctx {
   int device = 0;
   int sm_count = 148;
@@ -254,8 +256,10 @@ int esikf_create(esikf_ctx **out, int device) {
   cudaFuncSetAttribute(lio_update_repl_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
   cudaFuncSetAttribute(lio_update_repl_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
   cudaFuncSetAttribute(lio_update_repl_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
-  cudaFuncSetAttribute(vio_update_repl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(VioSmem) + sizeof(FusedSolveSmem)));
-  cudaFuncSetAttribute(vio_update_repl_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(VioSmem) + sizeof(FusedSolveSmem)));
+  cudaFuncSetAttribute(vio_update_repl_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(VioSmem) + sizeof(FusedSolveSmem)));
+  cudaFuncSetAttribute(vio_update_repl_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(VioSmem) + sizeof(FusedSolveSmem)));
+  cudaFuncSetAttribute(vio_update_repl_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VIO_FAST_SMEM);
+  cudaFuncSetAttribute(vio_update_repl_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VIO_FAST_SMEM);
   // the persistent kernels need every CTA co-resident: check what the device can hold
   int occ_l = 0, occ_v = 0, occ_r = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, lio_update_kernel, LIO_THREADS, sizeof(LioSmem));
@@ -269,9 +273,12 @@ int esikf_create(esikf_ctx **out, int device) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, lio_update_repl_kernel<true, false>, LIO_THREADS, sizeof(LioSmem));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, lio_update_repl_kernel<false, true>, LIO_THREADS, sizeof(LioSmem));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, lio_update_repl_kernel<true, true>, LIO_THREADS, sizeof(LioSmem));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_d, vio_update_repl_kernel<true>, VIO_THREADS, sizeof(VioSmem) + sizeof(FusedSolveSmem));
-    ctx->coop_tuned = occ_a > 0 && occ_b > 0 && occ_c > 0 && occ_d > 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_vr, vio_update_repl_kernel<false>, VIO_THREADS, sizeof(VioSmem) + sizeof(FusedSolveSmem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_d, vio_update_repl_kernel<true, false>, VIO_THREADS, sizeof(VioSmem) + sizeof(FusedSolveSmem));
+    int occ_e = 0, occ_f = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, vio_update_repl_kernel<false, true>, VIO_THREADS, VIO_FAST_SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, vio_update_repl_kernel<true, true>, VIO_THREADS, VIO_FAST_SMEM);
+    ctx->coop_tuned = occ_a > 0 && occ_b > 0 && occ_c > 0 && occ_d > 0 && occ_e > 0 && occ_f > 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_vr, vio_update_repl_kernel<false, false>, VIO_THREADS, sizeof(VioSmem) + sizeof(FusedSolveSmem));
     ctx->coop_repl = occ_lr > 0 && occ_vr > 0;
   }
   if (getenv("ESIKF_DEBUG"))
@@ -337,7 +344,7 @@ int esikf_set_loop_mode(esikf_ctx *ctx, int mode) {
   return ESIKF_OK;
 }
 int esikf_set_tuning(esikf_ctx *ctx, uint32_t flags) {
-  if (!ctx || (flags & ~(uint32_t)(ESIKF_TUNE_DEAL_POINTS | ESIKF_TUNE_DEFER_DIAGNOSTICS))) return ESIKF_ERR_ARG;
+  if (!ctx || (flags & ~(uint32_t)(ESIKF_TUNE_DEAL_POINTS | ESIKF_TUNE_DEFER_DIAGNOSTICS | ESIKF_TUNE_VIO_FAST_PATH))) return ESIKF_ERR_ARG;
   ctx->tuning = flags;
   return ESIKF_OK;
 }
@@ -722,8 +729,10 @@ int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
       size_t parity_stride = (size_t)ctx->partial_blocks * INFO_N;
       void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride};
       const bool defer = ctx->coop_tuned && (ctx->tuning & ESIKF_TUNE_DEFER_DIAGNOSTICS);
-      const void *fn = defer ? (const void *)vio_update_repl_kernel<true> : (const void *)vio_update_repl_kernel<false>;
-      CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(VIO_THREADS), kargs, sizeof(VioSmem) + sizeof(FusedSolveSmem), st));
+      const bool fast = ctx->coop_tuned && (ctx->tuning & ESIKF_TUNE_VIO_FAST_PATH);
+      const void *fn = fast ? (defer ? (const void *)vio_update_repl_kernel<true, true> : (const void *)vio_update_repl_kernel<false, true>)
+                            : (defer ? (const void *)vio_update_repl_kernel<true, false> : (const void *)vio_update_repl_kernel<false, false>);
+      CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(VIO_THREADS), kargs, fast ? VIO_FAST_SMEM : sizeof(VioSmem) + sizeof(FusedSolveSmem), st));
     } else {
       PeerArgs peer = peer_args(ctx);
       void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&peer};

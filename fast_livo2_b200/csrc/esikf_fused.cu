@@ -128,6 +128,7 @@ struct FusedSolveSmem {
   SolveIO io;
   Ctrl ctrl;  // CTA 0's working copy of the loop-control block (published to global memory after every solve)
 };
+static_assert(sizeof(FusedSolveSmem) % 8 == 0, "what follows it in shared memory holds doubles");
 
 __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_kernel(const LioKernelArgs a, const SolveArgs sa, unsigned int *barrier, unsigned int *barrier_next, unsigned long long *stamps,
                                                                      const PeerArgs peer) {
@@ -474,12 +475,17 @@ __device__ __forceinline__ void vio_consts_from_resident(VioSmem &sm, const VioK
   __syncthreads();
 }
 
-template <bool DEFER>
+// FAST: per-patch inputs cached across iterations + exact-reciprocal tap-stride arithmetic (vio_process_range<true>) and
+// the boxminus overlapped with the gain elimination (vio_solve_block<true>); bit-identical results.
+template <bool DEFER, bool FAST>
 __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_repl_kernel(const VioKernelArgs a, SolveArgs sa, unsigned int *barrier, unsigned int *barrier_next,
                                                                           unsigned long long *stamps, size_t partial_parity_stride) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   VioSmem &sm = *reinterpret_cast<VioSmem *>(smem_raw);
   FusedSolveSmem &fs = *reinterpret_cast<FusedSolveSmem *>(smem_raw + sizeof(VioSmem));
+  VioPatchSlot *const slots = reinterpret_cast<VioPatchSlot *>(smem_raw + sizeof(VioSmem) + sizeof(FusedSolveSmem));  // FAST launches only
+  VioLaneCache lc;
+  lc.Pv = make_float2(0.f, 0.f), lc.level = -1, lc.have = false;
   SolveLiteralScratch &lit = *reinterpret_cast<SolveLiteralScratch *>(&sm.rows[0][0][0]);
   static_assert(sizeof(SolveLiteralScratch) <= sizeof(sm.rows), "literal scratch must fit in the row staging area");
   sa.no_publish = (blockIdx.x != 0);
@@ -507,7 +513,10 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_repl_kernel(const V
       vio_consts_from_resident(sm, a, fs);
       stamp(stamps, sk);
       double D0 = 0.0, D1 = 0.0, n_meas = 0.0;
-      vio_process_range(a, sm, level, lo, hi, D0, D1, n_meas);
+      if (FAST)
+        vio_process_range<true>(a, sm, level, lo, hi, D0, D1, n_meas, slots, &lc);
+      else
+        vio_process_range(a, sm, level, lo, hi, D0, D1, n_meas);
       __syncthreads();
       stamp(stamps, sk);
       double *const part = a.partials + (size_t)(cur & 1) * partial_parity_stride;
@@ -526,7 +535,7 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_repl_kernel(const V
       sa.level = level, sa.slot_iter = it, sa.last_slot = 0;
       if (threadIdx.x == 0) fs.sm.W = lit.W, fs.sm.K = lit.K;
       __syncthreads();
-      vio_solve_block(sa, fs.sm, fs.io, fs.ctrl, true, true);  // ends with a CTA barrier: fs.ctrl is current for everybody
+      vio_solve_block<FAST>(sa, fs.sm, fs.io, fs.ctrl, true, true);  // ends with a CTA barrier: fs.ctrl is current for everybody
       stamp(stamps, sk);
       if (blockIdx.x == 0) {
         if (DEFER) {

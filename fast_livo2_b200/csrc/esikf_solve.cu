@@ -373,6 +373,9 @@ __device__ __forceinline__ void vio_write_stats(const SolveArgs &a, SolveSmem &s
 
 // One VIO accept/rollback + gain solve (src/vio.cpp:1636-1685) by the calling block; on the last slot also the final
 // covariance update (:800). Returns EKF_end of the level.
+// OVERLAP (opt-in, same arithmetic): warp 1's boxminus runs concurrently with warp 0's accept test and gain elimination;
+// the two warps meet at a named barrier right before the solution needs `vec`, instead of a CTA barrier after the boxminus.
+template <bool OVERLAP = false>
 __device__ __forceinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &sm, SolveIO &io, Ctrl &ctrl, bool defer_stats, bool resident) {
   const int tid = threadIdx.x, lane = tid & 31;
   const bool level_done_in = (a.slot_iter == 0) ? false : (ctrl.level_done != 0);   // entering a level: EKF_end = false (vio.cpp:1527)
@@ -386,8 +389,11 @@ __device__ __forceinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &s
   __syncthreads();
   const int level = a.level, iteration = a.slot_iter;
   // vec = state_propagat (-) state on warp 1 while warp 0 decides accept / rollback and runs the gain solve (:1664)
-  if (tid >= 32 && tid < 64 && !level_done_in) boxminus_warp(io.pr, io.st, sm.vec, lane);
-  __syncthreads();
+  if (tid >= 32 && tid < 64 && !level_done_in) {
+    boxminus_warp(io.pr, io.st, sm.vec, lane);
+    if (OVERLAP) asm volatile("bar.sync 1, 64;" ::: "memory");  // meets warp 0 below
+  }
+  if (!OVERLAP) __syncthreads();
   if (tid < 32) {
     bool accepted = false, ekf_end = level_done_in;
     float error = 0.f, last_error = last_error_in;
@@ -405,6 +411,7 @@ __device__ __forceinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &s
         __syncwarp();
         double x[7];
         gain_rows<7>(sm, 1.0 / a.img_point_cov, a.solve_mode, lane, x);
+        if (OVERLAP) asm volatile("bar.sync 1, 64;" ::: "memory");  // vec = state_propagat (-) state is complete
         double g[7];
 #pragma unroll
         for (int j = 0; j < 7; j++) {
@@ -426,6 +433,7 @@ __device__ __forceinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &s
         // :1675 (float constants 57.3f / 100.0f / 0.001f promote to double against the double norm)
         ekf_end = (warp_norm3(sm.sol) * (double)57.3f < (double)0.001f) && (warp_norm3(sm.sol + 3) * (double)100.0f < (double)0.001f);
       } else {
+        if (OVERLAP) asm volatile("bar.sync 1, 64;" ::: "memory");  // warp 1 still reads io.st for the (unused) boxminus
         if (lane < 25) io.st[lane] = io.old[lane];  // *state = old_state  (:1679)
         ekf_end = true;
       }

@@ -139,22 +139,58 @@ __device__ __forceinline__ void vio_load_consts(VioSmem &sm, const VioKernelArgs
   __syncthreads();
 }
 
+// What a warp keeps about ITS patch across the iterations of a persistent update (FAST variant, one patch per warp): the
+// iteration-invariant inputs in shared memory (one slot per warp) and the lane's two reference-patch values of the current
+// pyramid level in registers — an L2 round trip per iteration that the default path spends at the top of the loop.
+struct VioPatchSlot {
+  double X, Y, Z, inv_ref_expo;
+  int search_level, pad;
+};
+struct VioLaneCache {
+  float2 Pv;
+  int level;   // pyramid level Pv belongs to (-1: none)
+  bool have;   // the warp's slot is filled
+};
+
 // Photometric residual / Jacobian build of the patches [lo, hi) of this rank's shard at pyramid level `level`.
+// FAST (opt-in, bit-identical results): per-patch inputs cached across iterations (slots / lc), and the divisions by the
+// power-of-two tap stride replaced by multiplications with its exact reciprocal (same quotient bit for bit).
+template <bool FAST = false>
 __device__ __forceinline__ void vio_process_range(const VioKernelArgs &a, VioSmem &sm, int level, int lo, int hi, double &D0, double &D1,
-                                                  double &n_meas) {
+                                                  double &n_meas, VioPatchSlot *slots = nullptr, VioLaneCache *lc = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long npix = (long)a.cam.width * a.cam.height;
   const int width = a.cam.width;
   const double inv_expo = sm.inv_expo;
   float *const sT = sm.taps[warp];
   float *const sG = sm.grid[warp];
+  const bool single = FAST && (hi - lo <= VIO_WARPS);  // one patch per warp: it is the same patch in every iteration
   for (int lp = lo + warp; lp < hi; lp += VIO_WARPS) {
     const int i = a.begin + lp;
-    const int search_level = a.search_levels[i];
+    int search_level;
+    double X, Y, Z, inv_ref_expo_c = 0.0;
+    if (FAST && single && lc->have) {
+      const VioPatchSlot &ps = slots[warp];
+      search_level = ps.search_level, X = ps.X, Y = ps.Y, Z = ps.Z, inv_ref_expo_c = ps.inv_ref_expo;
+    } else {
+      search_level = a.search_levels[i];
+      X = a.pos[3 * (size_t)i], Y = a.pos[3 * (size_t)i + 1], Z = a.pos[3 * (size_t)i + 2];
+      if (FAST) {
+        inv_ref_expo_c = a.inv_expo_list[i];
+        if (single) {
+          if (lane == 0) {
+            VioPatchSlot &ps = slots[warp];
+            ps.search_level = search_level, ps.X = X, ps.Y = Y, ps.Z = Z, ps.inv_ref_expo = inv_ref_expo_c;
+          }
+          lc->have = true;
+        }
+      }
+    }
     const int pyramid_level = level + search_level;
     const int scale = 1 << pyramid_level;
-    const float inv_scale = 1.0f / (float)scale;
-    const double X = a.pos[3 * (size_t)i], Y = a.pos[3 * (size_t)i + 1], Z = a.pos[3 * (size_t)i + 2];
+    // 2^-pyramid_level assembled from its exponent bits (FAST) — the value 1.0f / (float)scale has
+    const float inv_scale = FAST ? __int_as_float((127 - pyramid_level) << 23) : 1.0f / (float)scale;
+    const double inv_scale_d = FAST ? __longlong_as_double((long long)(1023 - pyramid_level) << 52) : 0.0;
     const double pf0 = sm.Rcw[0] * X + sm.Rcw[1] * Y + sm.Rcw[2] * Z + sm.Pcw[0];
     const double pf1 = sm.Rcw[3] * X + sm.Rcw[4] * Y + sm.Rcw[5] * Z + sm.Pcw[1];
     const double pf2 = sm.Rcw[6] * X + sm.Rcw[7] * Y + sm.Rcw[8] * Z + sm.Pcw[2];
@@ -162,10 +198,11 @@ __device__ __forceinline__ void vio_process_range(const VioKernelArgs &a, VioSme
     world2cam(a.cam, pf0, pf1, pf2, pcu, pcv);
     // bilinear weights (:1580-1589) — float, via double (1.0 - subpix)
     const float u_ref = (float)pcu, v_ref = (float)pcv;
-    const int u_ref_i = (int)(floorf((float)(pcu / scale)) * scale);
-    const int v_ref_i = (int)(floorf((float)(pcv / scale)) * scale);
-    const float subpix_u = (u_ref - (float)u_ref_i) / (float)scale;
-    const float subpix_v = (v_ref - (float)v_ref_i) / (float)scale;
+    // x / 2^k == x * 2^-k exactly (no rounding in either), so the FAST forms give the same floats
+    const int u_ref_i = (int)(floorf(FAST ? (float)(pcu * inv_scale_d) : (float)(pcu / scale)) * scale);
+    const int v_ref_i = (int)(floorf(FAST ? (float)(pcv * inv_scale_d) : (float)(pcv / scale)) * scale);
+    const float subpix_u = FAST ? __fmul_rn(u_ref - (float)u_ref_i, inv_scale) : (u_ref - (float)u_ref_i) / (float)scale;
+    const float subpix_v = FAST ? __fmul_rn(v_ref - (float)v_ref_i, inv_scale) : (v_ref - (float)v_ref_i) / (float)scale;
     const float w_tl = (float)((1.0 - subpix_u) * (1.0 - subpix_v));
     const float w_tr = (float)(subpix_u * (1.0 - subpix_v));
     const float w_bl = (float)((1.0 - subpix_u) * subpix_v);
@@ -200,8 +237,14 @@ __device__ __forceinline__ void vio_process_range(const VioKernelArgs &a, VioSme
       WT[0][c] = -sc * (J00 * sm.Rcw[c] + J02 * sm.Rcw[6 + c]);
       WT[1][c] = -sc * (J11 * sm.Rcw[3 + c] + J12 * sm.Rcw[6 + c]);
     }
-    const double inv_ref_expo = a.inv_expo_list[i];
-    const float2 Pv = *reinterpret_cast<const float2 *>(a.warp_patch + (size_t)i * 64 * a.levels + 64 * level + 2 * lane);
+    const double inv_ref_expo = FAST ? inv_ref_expo_c : a.inv_expo_list[i];
+    float2 Pv;
+    if (FAST && single && lc->level == level) {
+      Pv = lc->Pv;
+    } else {
+      Pv = *reinterpret_cast<const float2 *>(a.warp_patch + (size_t)i * 64 * a.levels + 64 * level + 2 * lane);
+      if (FAST && single) lc->Pv = Pv, lc->level = level;
+    }
     __syncwarp();
     // bilinear value grid: G(a,b) = cur_value of patch pixel (a-1, b-1), a,b in 0..9 (same float op order as :1619-1620)
 #pragma unroll

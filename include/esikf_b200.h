@@ -138,9 +138,13 @@ int esikf_set_loop_mode(esikf_ctx *ctx, int mode);
  *                                  one contiguous block per CTA (evens out sub-divided / unmatched regions of the scan;
  *                                  the fixed summation order of H^T R^-1 H — its last bits — follows the assignment).
  *   ESIKF_TUNE_DEFER_DIAGNOSTICS : CTA 0 writes the per-iteration diagnostics while it waits at the next grid barrier
- *                                  instead of right after the solve (same values, off the critical path). */
+ *                                  instead of right after the solve (same values, off the critical path).
+ *   ESIKF_TUNE_VIO_FAST_PATH     : VIO keeps the iteration-invariant inputs of a warp's patch on chip across iterations,
+ *                                  replaces divisions by the power-of-two tap stride with exact multiplications and
+ *                                  overlaps the boxminus with the gain elimination (bit-identical results). */
 #define ESIKF_TUNE_DEAL_POINTS 1u
 #define ESIKF_TUNE_DEFER_DIAGNOSTICS 2u
+#define ESIKF_TUNE_VIO_FAST_PATH 4u
 int esikf_set_tuning(esikf_ctx *ctx, uint32_t flags);
 int esikf_set_extrinsics(esikf_ctx *ctx, const esikf_extrinsics *ext);
 

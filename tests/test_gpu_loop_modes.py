@@ -123,29 +123,61 @@ def test_lio_dealt_schedule_matches_contiguous_and_oracle(gpu_ctx, seed, n_pts, 
 
 
 @EXPERIMENTAL
-def test_deferred_diagnostics_are_bit_identical(gpu_ctx, small_vio_frame):
-    """ESIKF_TUNE_DEFER_DIAGNOSTICS only moves CTA 0's diagnostics writes into the next barrier wait: every output of the
-    LIO and VIO updates, diagnostics included, must be bit-identical to the default."""
+def test_bit_identical_tuning_variants(gpu_ctx, small_vio_frame):
+    """ESIKF_TUNE_DEFER_DIAGNOSTICS only moves CTA 0's diagnostics writes into the next barrier wait and
+    ESIKF_TUNE_VIO_FAST_PATH only caches per-patch inputs / replaces power-of-two divisions / overlaps the boxminus: every
+    output of the LIO and VIO updates, diagnostics included, must be bit-identical to the default, in any combination."""
     fr = get_frame(seed=4, n_pts=20000, n_map=150_000, scene_scale=0.5)
-    gpu_ctx.set_extrinsics(fr["ext"])
-    gpu_ctx.map_upload(fr["map"], fr["lio_cfg"].voxel_size)
     fv = small_vio_frame
     lio_keys = ("state", "match_plane", "normal_plane", "dis_to_plane", "M", "HTH", "HTz", "solution", "total_residual", "converged")
     vio_keys = ("state", "errors", "iters_per_level", "accepted_per_level", "error_trace", "HTH", "HTz", "solution")
+    D, F = api.TUNE_DEFER_DIAGNOSTICS, api.TUNE_VIO_FAST_PATH
     out = []
     try:
-        for flags in (0, api.TUNE_DEFER_DIAGNOSTICS, api.TUNE_DEFER_DIAGNOSTICS):
+        for flags in (0, D, F, D | F, D | F):
             gpu_ctx.set_tuning(flags)
             gpu_ctx.set_extrinsics(fr["ext"])
+            gpu_ctx.map_upload(fr["map"], fr["lio_cfg"].voxel_size)
             r = gpu_ctx.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"])
             _setup(gpu_ctx, fv)
             prior = _vio_prior(fv)
             w = _gpu_warp(gpu_ctx, fv, prior)
-            v = gpu_ctx.vio_update(fv["img"], fv["vis_pos"], w["warp_patch"], w["search_levels"], fv["inv_ref_expo"], prior, prior)
-            out.append((r, v))
+            args = (fv["img"], fv["vis_pos"], w["warp_patch"], w["search_levels"], fv["inv_ref_expo"], prior, prior)
+            v = gpu_ctx.vio_update(*args)
+            gpu_ctx.set_solve_mode(1)
+            v_lit = gpu_ctx.vio_update(*args)
+            gpu_ctx.set_solve_mode(0)
+            out.append((r, v, v_lit))
     finally:
         gpu_ctx.set_tuning(0)
-    for r, v in out[1:]:
+        gpu_ctx.set_solve_mode(0)
+    for r, v, v_lit in out[1:]:
         assert r["iters"] == out[0][0]["iters"] and v["total_iters"] == out[0][1]["total_iters"]
         _bits_equal(out[0][0], r, lio_keys)
         _bits_equal(out[0][1], v, vio_keys)
+        _bits_equal(out[0][2], v_lit, vio_keys)
+
+
+@EXPERIMENTAL
+def test_vio_fast_path_with_two_patches_per_warp_and_search_levels(gpu_ctx):
+    """More patches than warps (nothing stays cached) and non-zero search levels / a distorted camera through the FAST path."""
+    from fast_livo2_b200 import synthetic as S
+
+    cam = S.CamCfg(width=612, height=512, fx=612.0 * 0.72, fy=612.0 * 0.72, cx=306.0, cy=256.0)
+    vcfg = S.VioCfg(levels=5, img_point_cov=1000.0)
+    fr = get_frame(seed=13, n_pts=1000, n_map=300_000, n_patches=4000, scene_scale=0.7, cam=cam, vio=vcfg)
+    _setup(gpu_ctx, fr)
+    prior = _vio_prior(fr, 13)
+    w = _gpu_warp(gpu_ctx, fr, prior)
+    sl = (np.arange(len(fr["vis_pos"])) % 2).astype(np.int32)  # exercise search_level 1 as well
+    args = (fr["img"], fr["vis_pos"], w["warp_patch"], sl, fr["inv_ref_expo"], prior, prior)
+    keys = ("state", "errors", "iters_per_level", "accepted_per_level", "error_trace", "HTH", "HTz", "solution")
+    try:
+        gpu_ctx.set_tuning(0)
+        a = gpu_ctx.vio_update(*args)
+        gpu_ctx.set_tuning(api.TUNE_VIO_FAST_PATH | api.TUNE_DEFER_DIAGNOSTICS)
+        b = gpu_ctx.vio_update(*args)
+    finally:
+        gpu_ctx.set_tuning(0)
+    assert a["total_iters"] == b["total_iters"]
+    _bits_equal(a, b, keys)
