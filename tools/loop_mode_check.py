@@ -102,9 +102,10 @@ def check(fr, label, time_it):
             lio = np.mean([a.elapsed_time(b) for a, b, _ in evs]) * 1e3
             vio = np.mean([b.elapsed_time(c) for _, b, c in evs]) * 1e3
             print(f"[{label}] mode {mode} tuning {sched}: LIO {lio:.1f} us  VIO {vio:.1f} us  step {lio + vio:.1f} us  -> {iters / ((lio + vio) * 1e-6):.0f} it/s resident", flush=True)
-        ctx.set_tuning(0)
         if os.environ.get("STAMPS"):
-            ctx.set_loop_mode(MODES[-1])
+            ctx.set_loop_mode(runs[-1][0])
+            ctx.set_tuning(runs[-1][1])
+            print(f"[{label}] phase stamps of mode {runs[-1][0]} tuning {runs[-1][1]}", flush=True)
             ctx.set_phase_stamps(True)
             for rep in range(2):
                 ctx.lio_run(prior_h, prior_h, fr["lio_cfg"])
@@ -118,6 +119,7 @@ def check(fr, label, time_it):
                 d = np.diff(s[slot, :7])
                 print(("LIO" if slot < 8 else "VIO"), slot if slot < 8 else slot - 8, " ".join(f"{n}={x / 1000:.2f}us" for n, x in zip(names, d)),
                       f"total={(s[slot, 6] - s[slot, 0]) / 1000:.2f}us", flush=True)
+        ctx.set_tuning(0)
     ctx.close()
     return ok
 
