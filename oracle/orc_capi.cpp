@@ -304,6 +304,34 @@ double orc_vio_update(void *h, const uint8_t *img, int n_pts, const double *pos,
   return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// Inverse-compositional variant: per-point reference-feature data (kept by pointer for the images: the caller keeps them alive)
+// and the switch the reference reads from vio/inverse_composition_en.
+void orc_vio_set_inverse_refs(void *h, const uint8_t *const *imgs, int n_imgs, int n_pts, const int32_t *ref_img_index, const double *ref_px,
+                              const double *ref_f, const double *ref_R, const double *ref_pos) {
+  VIOManager *v = (VIOManager *)h;
+  v->ref_imgs.resize(n_imgs);
+  for (int k = 0; k < n_imgs; k++) v->ref_imgs[k].data = imgs[k], v->ref_imgs[k].cols = v->width, v->ref_imgs[k].rows = v->height;
+  v->ref_img_index.assign(ref_img_index, ref_img_index + n_pts);
+  v->ref_px.assign(ref_px, ref_px + 2 * (size_t)n_pts);
+  v->ref_f.assign(ref_f, ref_f + 3 * (size_t)n_pts);
+  v->ref_R.assign(ref_R, ref_R + 9 * (size_t)n_pts);
+  v->ref_pos.assign(ref_pos, ref_pos + 3 * (size_t)n_pts);
+}
+void orc_vio_set_inverse(void *h, int enable) { ((VIOManager *)h)->inverse_composition_en = enable != 0; }
+// H_sub_inv of the LAST level processed (level 0 after a full update): (n_pts*64) x 6
+int orc_vio_get_h_sub_inv(void *h, double *out, int max_doubles) {
+  VIOManager *v = (VIOManager *)h;
+  int n = (int)v->H_sub_inv.size();
+  if (out && n <= max_doubles) memcpy(out, v->H_sub_inv.data(), sizeof(double) * n);
+  return n;
+}
+void orc_vio_precompute_reference_patches(void *h, int n_pts, const double *pos, int level) {
+  VIOManager *v = (VIOManager *)h;
+  v->total_points = n_pts;
+  v->pos.assign(pos, pos + 3 * (size_t)n_pts);
+  v->precomputeReferencePatches(level);
+}
+
 void orc_vio_get_image_patch(void *h, const uint8_t *img, const double *pc, int level, float *patch_out /* levels*64 */) {
   VIOManager *v = (VIOManager *)h;
   Image im;

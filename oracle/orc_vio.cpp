@@ -227,7 +227,14 @@ int VIOManager::getBestSearchLevel(const M2 &A_cur_ref, const int max_level) {
 void VIOManager::computeJacobianAndUpdateEKF(const Image &img) {
   memset(&stats_, 0, sizeof(stats_));
   if (total_points == 0) return;
-  for (int level = patch_pyrimid_level - 1; level >= 0; level--) updateState(img, level);
+  for (int level = patch_pyrimid_level - 1; level >= 0; level--) {  // :790-798
+    if (inverse_composition_en) {
+      has_ref_patch_cache = false;
+      updateStateInverse(img, level);
+    } else {
+      updateState(img, level);
+    }
+  }
   state->cov = state->cov - G * state->cov;  // :800
   // updateFrameState(*state) :801 / :1690-1697
   M3 Rwi = state->rot_end;
@@ -378,6 +385,172 @@ void VIOManager::updateState(const Image &img, int level) {
       V3 t_add = block<3, 1>(solution, 3, 0);
       if (level < 8) stats_.accepted_per_level[level]++;
       if ((norm(rot_add) * 57.3f < 0.001f) && (norm(t_add) * 100.0f < 0.001f)) EKF_end = true;  // :1675
+    } else {
+      (*state) = old_state;
+      EKF_end = true;
+    }
+    if (iteration == max_iterations || EKF_end) break;
+  }
+}
+
+// src/vio.cpp:1327-1396 — Jacobian rows of every reference patch pixel w.r.t. the WORLD-frame pose perturbation, from the
+// gradients of the reference image (the pyramid level only sets the tap stride; search levels are not used here).
+void VIOManager::precomputeReferencePatches(int level) {
+  if (total_points == 0) return;
+  const int H_DIM = total_points * patch_size_total;
+  H_sub_inv.assign((size_t)H_DIM * 6, 0.0);
+  for (int i = 0; i < total_points; i++) {
+    const int scale = (1 << level);
+    const Image &img = ref_imgs[ref_img_index[i]];
+    V3 pt_pos = v3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+    V3 rp = v3(ref_pos[3 * i], ref_pos[3 * i + 1], ref_pos[3 * i + 2]);
+    double depth = norm(pt_pos - rp);
+    V3 pf = v3(ref_f[3 * i], ref_f[3 * i + 1], ref_f[3 * i + 2]) * depth;
+    V2 pc;
+    pc[0] = ref_px[2 * i], pc[1] = ref_px[2 * i + 1];
+    M3 R_ref_w;
+    for (int k = 0; k < 9; k++) R_ref_w.a[k] = ref_R[9 * (size_t)i + k];
+    Mat<2, 3> Jdpi;
+    computeProjectionJacobian(pf, Jdpi);
+    M3 p_w_hat = skew(pt_pos);
+
+    const float u_ref = pc[0];
+    const float v_ref = pc[1];
+    const int u_ref_i = floorf(pc[0] / scale) * scale;
+    const int v_ref_i = floorf(pc[1] / scale) * scale;
+    const float subpix_u_ref = (u_ref - u_ref_i) / scale;
+    const float subpix_v_ref = (v_ref - v_ref_i) / scale;
+    const float w_ref_tl = (1.0 - subpix_u_ref) * (1.0 - subpix_v_ref);
+    const float w_ref_tr = subpix_u_ref * (1.0 - subpix_v_ref);
+    const float w_ref_bl = (1.0 - subpix_u_ref) * subpix_v_ref;
+    const float w_ref_br = subpix_u_ref * subpix_v_ref;
+    const int w = img.cols;  // the reference indexes the reference image with the manager's `width`; same size here
+    for (int x = 0; x < patch_size; x++) {
+      long b = (long)(v_ref_i + x * scale - patch_size_half * scale) * w + u_ref_i - patch_size_half * scale;
+      const long sw = (long)scale * w;
+      for (int y = 0; y < patch_size; ++y, b += scale) {
+        float du = 0.5f * ((w_ref_tl * pix(img, b + scale) + w_ref_tr * pix(img, b + scale * 2) + w_ref_bl * pix(img, b + sw + scale) +
+                            w_ref_br * pix(img, b + sw + scale * 2)) -
+                           (w_ref_tl * pix(img, b - scale) + w_ref_tr * pix(img, b) + w_ref_bl * pix(img, b + sw - scale) + w_ref_br * pix(img, b + sw)));
+        float dv = 0.5f * ((w_ref_tl * pix(img, b + sw) + w_ref_tr * pix(img, b + scale + sw) + w_ref_bl * pix(img, b + 2 * sw) +
+                            w_ref_br * pix(img, b + 2 * sw + scale)) -
+                           (w_ref_tl * pix(img, b - sw) + w_ref_tr * pix(img, b - sw + scale) + w_ref_bl * pix(img, b) + w_ref_br * pix(img, b + scale)));
+        Mat<1, 2> Jimg;
+        Jimg(0, 0) = du, Jimg(0, 1) = dv;
+        Jimg = Jimg * (1.0 / scale);
+        Mat<1, 3> JdR = ((Jimg * Jdpi) * R_ref_w) * p_w_hat;  // :1387
+        Mat<1, 3> Jdt = ((-Jimg) * Jdpi) * R_ref_w;           // :1388
+        double *h = &H_sub_inv[((size_t)i * patch_size_total + x * patch_size + y) * 6];
+        h[0] = JdR(0, 0), h[1] = JdR(0, 1), h[2] = JdR(0, 2), h[3] = Jdt(0, 0), h[4] = Jdt(0, 1), h[5] = Jdt(0, 2);
+      }
+    }
+  }
+  has_ref_patch_cache = true;
+}
+
+// src/vio.cpp:1398-1518 — serial in the reference (no OpenMP); 6-column H (no exposure column, no exposure factors in the
+// residual); the residual is formed in FLOAT (bilinear sum minus the float reference value) and then widened (:1466-1468).
+void VIOManager::updateStateInverse(const Image &img, int level) {
+  if (total_points == 0) return;
+  StatesGroup old_state = (*state);
+  bool EKF_end = false;
+  float last_error = std::numeric_limits<float>::max();
+  const int H_DIM = total_points * patch_size_total;
+  std::vector<double> z(H_DIM, 0.0);
+  std::vector<double> H_sub((size_t)H_DIM * 6, 0.0);
+  errors.resize(total_points);
+
+  for (int iteration = 0; iteration < max_iterations; iteration++) {
+    if (has_ref_patch_cache == false) precomputeReferencePatches(level);
+    int n_meas = 0;
+    float error = 0.0;
+    M3 Rwi = state->rot_end;
+    V3 Pwi = state->pos_end;
+    M3 P_wi_hat = skew(Pwi);
+    Rcw = Rci * T(Rwi);
+    Pcw = -((Rci * T(Rwi)) * Pwi) + Pci;
+
+    for (int i = 0; i < total_points; i++) {
+      float patch_error = 0.0;
+      const int scale = (1 << level);
+      V3 pt_pos = v3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+      V3 pf = Rcw * pt_pos + Pcw;
+      V2 pc = cam.world2cam(pf);
+
+      const float u_ref = pc[0];
+      const float v_ref = pc[1];
+      const int u_ref_i = floorf(pc[0] / scale) * scale;
+      const int v_ref_i = floorf(pc[1] / scale) * scale;
+      const float subpix_u_ref = (u_ref - u_ref_i) / scale;
+      const float subpix_v_ref = (v_ref - v_ref_i) / scale;
+      const float w_ref_tl = (1.0 - subpix_u_ref) * (1.0 - subpix_v_ref);
+      const float w_ref_tr = subpix_u_ref * (1.0 - subpix_v_ref);
+      const float w_ref_bl = (1.0 - subpix_u_ref) * subpix_v_ref;
+      const float w_ref_br = subpix_u_ref * subpix_v_ref;
+
+      const float *P = &warp_patch[(size_t)i * patch_size_total * patch_pyrimid_level];
+      for (int x = 0; x < patch_size; x++) {
+        long b = (long)(v_ref_i + x * scale - patch_size_half * scale) * width + u_ref_i - patch_size_half * scale;
+        const long sw = (long)scale * width;
+        for (int y = 0; y < patch_size; ++y, b += scale) {
+          double res = w_ref_tl * pix(img, b) + w_ref_tr * pix(img, b + scale) + w_ref_bl * pix(img, b + sw) + w_ref_br * pix(img, b + sw + scale) -
+                       P[patch_size_total * level + x * patch_size + y];
+          const size_t row = (size_t)i * patch_size_total + x * patch_size + y;
+          z[row] = res;
+          patch_error += res * res;
+          Mat<1, 3> J_dR, J_dt;
+          const double *hi = &H_sub_inv[row * 6];
+          J_dR(0, 0) = hi[0], J_dR(0, 1) = hi[1], J_dR(0, 2) = hi[2];
+          J_dt(0, 0) = hi[3], J_dt(0, 1) = hi[4], J_dt(0, 2) = hi[5];
+          Mat<1, 3> JdR = J_dR * Rwi + (J_dt * P_wi_hat) * Rwi;  // :1471
+          Mat<1, 3> Jdt = J_dt * Rwi;                            // :1472
+          double *h = &H_sub[row * 6];
+          h[0] = JdR(0, 0), h[1] = JdR(0, 1), h[2] = JdR(0, 2), h[3] = Jdt(0, 0), h[4] = Jdt(0, 1), h[5] = Jdt(0, 2);
+          n_meas++;
+        }
+      }
+      errors[i] = patch_error;
+      error += patch_error;
+    }
+    error = error / n_meas;
+    if (level < 8 && iteration < 8) stats_.error_trace[level][iteration] = error;
+    if (level < 8) stats_.iters_per_level[level] = iteration + 1;
+    stats_.total_iters++;
+
+    if (error <= last_error) {
+      old_state = (*state);
+      last_error = error;
+      H_T_H = M19::Zero();
+      G = M19::Zero();
+      Mat<6, 6> HTH6 = Mat<6, 6>::Zero();
+      Mat<6, 1> HTz = Mat<6, 1>::Zero();
+      for (int r = 0; r < H_DIM; r++) {
+        const double *h = &H_sub[(size_t)r * 6];
+        for (int a = 0; a < 6; a++) {
+          HTz[a] += h[a] * z[r];
+          for (int b = 0; b < 6; b++) HTH6(a, b) += h[a] * h[b];
+        }
+      }
+      set_block(H_T_H, 0, 0, HTH6);
+      M19 K_1 = inverse_pplu(H_T_H + inverse_pplu(state->cov / img_point_cov));  // :1492
+      V19 vec = state_propagat->boxminus(*state);
+      Mat<19, 6> K16 = block<19, 6>(K_1, 0, 0);
+      Mat<19, 6> G6 = K16 * HTH6;  // :1495
+      set_block(G, 0, 0, G6);
+      V19 solution = (-K16) * HTz + vec - G6 * block<6, 1>(vec, 0, 0);  // :1496
+      if (level < 8 && iteration < 8) {
+        // diagnostics share the 7 x 7 / 7-vector slots of the forward variant (last row / column zero)
+        for (int a = 0; a < 6; a++) {
+          stats_.HTz[level][iteration][a] = HTz[a];
+          for (int b = 0; b < 6; b++) stats_.HTH[level][iteration][a * 7 + b] = HTH6(a, b);
+        }
+        memcpy(stats_.solution[level][iteration], solution.a, sizeof(double) * 19);
+      }
+      state->boxplus(solution);
+      V3 rot_add = block<3, 1>(solution, 0, 0);
+      V3 t_add = block<3, 1>(solution, 3, 0);
+      if (level < 8) stats_.accepted_per_level[level]++;
+      if ((norm(rot_add) * 57.3f < 0.001f) && (norm(t_add) * 100.0f < 0.001f)) EKF_end = true;  // :1501
     } else {
       (*state) = old_state;
       EKF_end = true;

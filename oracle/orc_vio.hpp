@@ -72,6 +72,16 @@ class VIOManager {  // include/vio.h (hot-path subset)
   std::vector<float> errors;           // Np (out)
   M19 G, H_T_H;
   VioStats stats_;
+  // inverse-compositional variant (vio/inverse_composition_en, LIVMapper.cpp:60,140): what it reads of every point's
+  // reference feature (include/feature.h: img_, px_, f_, T_f_w_), flattened
+  bool inverse_composition_en = false, has_ref_patch_cache = false;
+  std::vector<Image> ref_imgs;         // Feature::img_ (one per reference frame)
+  std::vector<int> ref_img_index;      // Np
+  std::vector<double> ref_px;          // Np*2  ref_patch->px_
+  std::vector<double> ref_f;           // Np*3  ref_patch->f_ (unit bearing)
+  std::vector<double> ref_R;           // Np*9  ref_patch->T_f_w_.rotation_matrix()
+  std::vector<double> ref_pos;         // Np*3  ref_patch->pos() = T_f_w_.inverse().translation()
+  std::vector<double> H_sub_inv;       // (Np*64) x 6
 
   void setImuToLidarExtrinsic(const V3 &transl, const M3 &rot);
   void setLidarToCameraExtrinsic(const M3 &R, const V3 &P);
@@ -85,6 +95,8 @@ class VIOManager {  // include/vio.h (hot-path subset)
   int getBestSearchLevel(const M2 &A_cur_ref, const int max_level);
   void computeJacobianAndUpdateEKF(const Image &img);
   void updateState(const Image &img, int level);
+  void precomputeReferencePatches(int level);
+  void updateStateInverse(const Image &img, int level);
 };
 
 }  // namespace orc

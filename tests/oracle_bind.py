@@ -44,6 +44,11 @@ def load(kind="parity"):
     lib.orc_vio_update.restype = C.c_double
     lib.orc_vio_update.argtypes = [vp, u8p, C.c_int, dp, fp, ip, dp, dp, dp, dp, fp, dp]
     lib.orc_vio_get_image_patch.argtypes = [vp, u8p, dp, C.c_int, fp]
+    lib.orc_vio_set_inverse_refs.argtypes = [vp, vp, C.c_int, C.c_int, ip, dp, dp, dp, dp]
+    lib.orc_vio_set_inverse.argtypes = [vp, C.c_int]
+    lib.orc_vio_get_h_sub_inv.restype = C.c_int
+    lib.orc_vio_get_h_sub_inv.argtypes = [vp, dp, C.c_int]
+    lib.orc_vio_precompute_reference_patches.argtypes = [vp, C.c_int, dp, C.c_int]
     lib.orc_vio_warp_affine.argtypes = [vp, u8p, C.c_int, C.c_int, dp, dp, C.c_int, fp]
     lib.orc_vio_warp_matrix.restype = C.c_int
     lib.orc_vio_warp_matrix.argtypes = [vp, dp, dp, dp, dp, dp, dp, dp, dp]
@@ -174,6 +179,27 @@ class OracleVIO:
                     HTH=stats[81:3217].reshape(8, 8, 7, 7), HTz=stats[3217:3665].reshape(8, 8, 7), solution=stats[3665:4881].reshape(8, 8, 19),
                     secs=secs)
 
+    def set_inverse_refs(self, ref_imgs, ref_img_index, ref_px, ref_f, ref_R, ref_pos):
+        """Reference-feature data of the inverse-compositional variant (Feature::img_, px_, f_, T_f_w_ rotation, pos())."""
+        self._ref_imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in ref_imgs]
+        arr = (C.c_void_p * len(self._ref_imgs))(*[im.ctypes.data for im in self._ref_imgs])
+        idx = np.ascontiguousarray(ref_img_index, dtype=np.int32)
+        n = len(idx)
+        self.lib.orc_vio_set_inverse_refs(self.h, arr, len(self._ref_imgs), n, iptr(idx), dptr(c64(ref_px)), dptr(c64(ref_f)),
+                                          dptr(c64(np.asarray(ref_R).reshape(n, 9))), dptr(c64(ref_pos)))
+
+    def set_inverse(self, enable):
+        self.lib.orc_vio_set_inverse(self.h, int(bool(enable)))
+
+    def precompute_reference_patches(self, pos, level):
+        pos = c64(pos)
+        n = len(pos)
+        self.lib.orc_vio_precompute_reference_patches(self.h, n, dptr(pos), level)
+        out = np.zeros(n * 64 * 6)
+        got = self.lib.orc_vio_get_h_sub_inv(self.h, dptr(out), out.size)
+        assert got == out.size
+        return out.reshape(n, 64, 6)
+
     def get_image_patch(self, img, pc, level):
         img = np.ascontiguousarray(img, dtype=np.uint8)
         out = np.zeros(64 * self.cfg.levels, np.float32)
@@ -229,3 +255,14 @@ def rot_err(Ra, Rb):
     v = np.zeros(3)
     load().orc_log(dptr(c64(Ra.T @ Rb)), dptr(v))
     return float(np.linalg.norm(v))
+
+
+def inverse_refs_from_frame(fr):
+    """Reference-feature arrays of the inverse-compositional variant for a synthetic frame (one reference frame):
+    T_f_w_ = (Rcw_ref, Pcw_ref), pos() = -R^T t, f_ = unit bearing of the point in the reference camera."""
+    R, t = fr["T_ref"]
+    n = len(fr["vis_pos"])
+    pc = fr["vis_pos"] @ R.T + t
+    f = pc / np.linalg.norm(pc, axis=1, keepdims=True)
+    return dict(ref_imgs=[fr["img_ref"]], ref_img_index=np.zeros(n, np.int32), ref_px=np.ascontiguousarray(fr["px_ref"], dtype=np.float64),
+                ref_f=np.ascontiguousarray(f), ref_R=np.tile(R.reshape(1, 9), (n, 1)), ref_pos=np.tile(-R.T @ t, (n, 1)))

@@ -224,3 +224,88 @@ def test_first_iteration_solutions_match_numpy_gain_formula(small_frame, small_v
     Pv = S.unpack_state(fv["state_prior"])["cov"] / fv["vio_cfg"].img_point_cov
     want = _numpy_gain_solution(o["HTH"][top][0], o["HTz"][top][0], Pv, -1.0)
     np.testing.assert_allclose(o["solution"][top][0], want, rtol=1e-7, atol=1e-10 * np.abs(want).max())
+
+
+def test_numpy_restatement_of_the_inverse_compositional_variant(small_vio_frame):
+    """precomputeReferencePatches (vio.cpp:1327-1396) and the first iteration of updateStateInverse (:1398-1518) restated in
+    numpy: reference-image gradients -> world-frame Jacobian rows, float residual, 6 x 6 information block."""
+    fr = small_vio_frame
+    ext, cam, vcfg = fr["ext"], fr["cam_cfg"], fr["vio_cfg"]
+    n = 24
+    w = O.oracle_warp_patches(fr, fr["state_prior"])
+    pos, wp = fr["vis_pos"][:n], w["warp_patch"][:n]
+    refs = O.inverse_refs_from_frame(fr)
+    refs = {k: (v if k == "ref_imgs" else v[:n]) for k, v in refs.items()}
+    vio = O.OracleVIO(cam, ext, vcfg)
+    vio.set_inverse_refs(**refs)
+    level = vcfg.levels - 1
+    scale = 1 << level
+    H_inv = vio.precompute_reference_patches(pos, level)
+
+    def taps(img_flat, width, pc):
+        u_i = int(np.floor(f32(pc[0] / scale)) * scale)
+        v_i = int(np.floor(f32(pc[1] / scale)) * scale)
+        su = f32((f32(pc[0]) - f32(u_i)) / f32(scale))
+        sv = f32((f32(pc[1]) - f32(v_i)) / f32(scale))
+        wts = (f32((1.0 - float(su)) * (1.0 - float(sv))), f32(float(su) * (1.0 - float(sv))), f32((1.0 - float(su)) * float(sv)), f32(su * sv))
+        bil = lambda a, b, c, d: f32(f32(f32(wts[0] * f32(a)) + f32(wts[1] * f32(b))) + f32(wts[2] * f32(c))) + f32(wts[3] * f32(d))
+        return u_i, v_i, bil
+
+    width = cam.width
+    ref_flat = fr["img_ref"].astype(np.int64).reshape(-1)
+    R_ref = fr["T_ref"][0]
+    for i in range(n):
+        depth = np.linalg.norm(pos[i] - refs["ref_pos"][i])
+        pf = refs["ref_f"][i] * depth
+        zi = 1.0 / pf[2]
+        Jdpi = np.array([[cam.fx * zi, 0, -cam.fx * pf[0] * zi * zi], [0, cam.fy * zi, -cam.fy * pf[1] * zi * zi]])
+        u_i, v_i, bil = taps(ref_flat, width, refs["ref_px"][i])
+        sw = scale * width
+        for x in (0, 3, 7):
+            for y in (0, 4, 7):
+                b = (v_i + x * scale - 4 * scale) * width + u_i - 4 * scale + y * scale
+                T = lambda o: ref_flat[b + o]
+                du = f32(0.5) * f32(bil(T(scale), T(2 * scale), T(sw + scale), T(sw + 2 * scale)) - bil(T(-scale), T(0), T(sw - scale), T(sw)))
+                dv = f32(0.5) * f32(bil(T(sw), T(scale + sw), T(2 * sw), T(2 * sw + scale)) - bil(T(-sw), T(-sw + scale), T(0), T(scale)))
+                Jimg = np.array([float(du), float(dv)]) * (1.0 / scale)
+                JdR = Jimg @ Jdpi @ R_ref @ S.skew(pos[i])
+                Jdt = -Jimg @ Jdpi @ R_ref
+                np.testing.assert_allclose(H_inv[i, x * 8 + y], np.concatenate([JdR, Jdt]), rtol=1e-12, atol=1e-12)
+
+    # first iteration at the coarsest level: H rows rotated into the current IMU frame, float residual, H^T H / H^T z / error
+    st = S.unpack_state(fr["state_prior"])
+    Rwi, Pwi = st["R"], st["p"]
+    Rcw, Pcw = S.camera_pose(ext, Rwi, Pwi)
+    cur_flat = fr["img"].astype(np.int64).reshape(-1)
+    HTH, HTz, err, nm = np.zeros((6, 6)), np.zeros(6), f32(0), 0
+    for i in range(n):
+        pf = Rcw @ pos[i] + Pcw
+        pc = np.array([cam.fx * pf[0] / pf[2] + cam.cx, cam.fy * pf[1] / pf[2] + cam.cy])
+        u_i, v_i, bil = taps(cur_flat, width, pc)
+        sw = scale * width
+        perr = f32(0)
+        for x in range(8):
+            for y in range(8):
+                b = (v_i + x * scale - 4 * scale) * width + u_i - 4 * scale + y * scale
+                T = lambda o: cur_flat[b + o]
+                res = float(f32(bil(T(0), T(scale), T(sw), T(sw + scale)) - f32(wp[i][64 * level + x * 8 + y])))
+                J_dR, J_dt = H_inv[i, x * 8 + y, :3], H_inv[i, x * 8 + y, 3:]
+                h = np.concatenate([J_dR @ Rwi + (J_dt @ S.skew(Pwi)) @ Rwi, J_dt @ Rwi])
+                HTH += np.outer(h, h)
+                HTz += h * res
+                perr = f32(float(perr) + res * res)
+                nm += 1
+        err = f32(err + perr)
+    err = f32(err / f32(nm))
+    vio.set_inverse(True)
+    o = vio.update(fr["img"], pos, wp, np.zeros(n, np.int32), np.ones(n), fr["state_prior"], fr["state_prior"])
+    np.testing.assert_allclose(o["HTH"][level][0][:6, :6], HTH, rtol=1e-10, atol=1e-10 * np.abs(HTH).max())
+    np.testing.assert_allclose(o["HTz"][level][0][:6], HTz, rtol=1e-9, atol=1e-9 * np.abs(HTz).max())
+    assert not o["HTH"][level][0][6].any() and not o["HTH"][level][0][:, 6].any()
+    assert o["error_trace"][level][0] == err
+    P = S.unpack_state(fr["state_prior"])["cov"] / vcfg.img_point_cov
+    want = _numpy_gain_solution(HTH, HTz, P, -1.0)
+    np.testing.assert_allclose(o["solution"][level][0], want, rtol=1e-6, atol=1e-9 * np.abs(want).max())
+    vio.set_inverse(False)
+    fwd = vio.update(fr["img"], pos, wp, np.zeros(n, np.int32), np.ones(n), fr["state_prior"], fr["state_prior"])
+    assert fwd["HTH"][level][0][6, 6] > 0  # the forward variant is untouched by the switch

@@ -167,3 +167,35 @@ def test_vio_jacobian_rows_match_finite_differences(small_vio_frame):
     # 7th column: the sampled intensity itself (vio.cpp:1626); sum over the ramp patch = 64*127 + offsets
     cur_sum = HTH[:6, 6] / j
     assert np.allclose(cur_sum, cur_sum[0], rtol=1e-4)
+
+
+def test_inverse_compositional_variant_converges_like_the_forward_one(small_vio_frame):
+    """vio/inverse_composition_en (vio.cpp:792-795): gradients of the reference patch instead of the current image. On the
+    synthetic frame it must pull the prior to the truth about as well as the forward variant, with a 6-column H."""
+    fr = small_vio_frame
+    rng = np.random.default_rng(3)
+    t = S.unpack_state(fr["state_true"])
+    prior = S.pack_state(t["R"] @ S.so3_exp(rng.normal(0, np.deg2rad(0.15), 3)), t["p"] + rng.normal(0, 0.01, 3), 1.0, t["v"], g=t["g"],
+                         cov=S.random_prior_cov(rng, scale=0.2))
+    w = O.oracle_warp_patches(fr, prior)
+    vio = O.OracleVIO(fr["cam_cfg"], fr["ext"], fr["vio_cfg"])
+    vio.set_inverse_refs(**O.inverse_refs_from_frame(fr))
+    n = len(fr["vis_pos"])
+    args = (fr["img"], fr["vis_pos"], w["warp_patch"], w["search_levels"], np.ones(n), prior, prior)
+    vio.set_inverse(True)
+    inv = vio.update(*args)
+    vio.set_inverse(False)
+    fwd = vio.update(*args)
+
+    def err(s):
+        a = S.unpack_state(s)
+        return O.rot_err(a["R"], t["R"]), np.linalg.norm(a["p"] - t["p"])
+
+    e0, ei, ef = err(prior), err(inv["state"]), err(fwd["state"])
+    assert inv["total_iters"] >= fr["vio_cfg"].levels and inv["accepted_per_level"][: fr["vio_cfg"].levels].min() >= 1
+    assert ei[0] < 0.2 * e0[0] and ei[1] < 0.5 * e0[1]
+    assert ei[0] < 5 * ef[0] + 1e-4 and ei[1] < 5 * ef[1] + 1e-3
+    Pi = S.unpack_state(inv["state"])["cov"]
+    assert np.linalg.eigvalsh(0.5 * (Pi + Pi.T)).min() > 0
+    top = fr["vio_cfg"].levels - 1
+    assert not inv["HTH"][top][0][6].any() and S.unpack_state(inv["state"])["inv_expo"] != 0
