@@ -36,7 +36,7 @@ class CameraC(C.Structure):
 
 class VioCfgC(C.Structure):
     _fields_ = [("img_point_cov", C.c_double), ("patch_pyrimid_level", C.c_int32), ("max_iterations", C.c_int32),
-                ("exposure_estimate_en", C.c_int32), ("pad_", C.c_int32)]
+                ("exposure_estimate_en", C.c_int32), ("inverse_composition_en", C.c_int32)]
 
 
 class LioStatsC(C.Structure):
@@ -94,6 +94,7 @@ def load_library():
     lib.esikf_vio_set_ref_images.argtypes = [vp, C.POINTER(vp), C.c_int32, C.c_int32, C.c_int32]
     lib.esikf_vio_warp_patches.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int32]
     lib.esikf_vio_warp_affine.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp]
+    lib.esikf_vio_set_inverse_refs.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp]
     lib.esikf_comm_unique_id.argtypes = [C.c_char_p]
     lib.esikf_comm_init.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p]
     lib.esikf_comm_rank.argtypes = [vp, ip, ip]
@@ -117,7 +118,7 @@ EXPORTED_SYMBOLS = [
     "esikf_set_extrinsics", "esikf_map_upload", "esikf_map_patch", "esikf_lio_set_scan", "esikf_lio_run", "esikf_lio_fetch",
     "esikf_lio_update", "esikf_lio_fetch_point_cov", "esikf_vio_set_camera", "esikf_vio_set_image", "esikf_vio_set_patches",
     "esikf_vio_run", "esikf_vio_fetch", "esikf_vio_update", "esikf_vio_get_image_patch", "esikf_vio_set_ref_images",
-    "esikf_vio_warp_patches", "esikf_vio_warp_affine", "esikf_comm_unique_id", "esikf_comm_init", "esikf_comm_rank", "esikf_shard_range", "esikf_peer_export", "esikf_peer_attach", "esikf_profile_kernel", "esikf_set_kernel_timing", "esikf_get_kernel_timing", "esikf_set_phase_stamps", "esikf_get_phase_stamps",
+    "esikf_vio_warp_patches", "esikf_vio_warp_affine", "esikf_vio_set_inverse_refs", "esikf_comm_unique_id", "esikf_comm_init", "esikf_comm_rank", "esikf_shard_range", "esikf_peer_export", "esikf_peer_attach", "esikf_profile_kernel", "esikf_set_kernel_timing", "esikf_get_kernel_timing", "esikf_set_phase_stamps", "esikf_get_phase_stamps",
 ]
 
 
@@ -280,7 +281,7 @@ class Context:
     def vio_set_camera(self, cam, vio):
         c = CameraC(cam.model, cam.width, cam.height, 0, cam.fx, cam.fy, cam.cx, cam.cy)
         c.d[:] = list(cam.d)
-        v = VioCfgC(vio.img_point_cov, vio.levels, vio.max_iterations, int(vio.exposure_estimate_en), 0)
+        v = VioCfgC(vio.img_point_cov, vio.levels, vio.max_iterations, int(vio.exposure_estimate_en), int(getattr(vio, "inverse_composition_en", False)))
         self._ck(self.lib.esikf_vio_set_camera(self.h, C.byref(c), C.byref(v)))
         self.levels = vio.levels
 
@@ -354,6 +355,13 @@ class Context:
         return dict(A_cur_ref=A, search_levels=sl, warp_patch=wp)
 
     # ------------------------------------------------------------------ multi-GPU / measurement
+    def vio_set_inverse_refs(self, ref_img_index, ref_px, ref_f, ref_R, ref_pos):
+        """Reference-feature data of the inverse-compositional variant (esikf_vio_set_inverse_refs); images via vio_set_ref_images."""
+        idx = _c(ref_img_index, np.int32)
+        n = len(idx)
+        px, f, R, pos = _c(ref_px, np.float64), _c(ref_f, np.float64), _c(np.asarray(ref_R).reshape(n, 9), np.float64), _c(ref_pos, np.float64)
+        self._ck(self.lib.esikf_vio_set_inverse_refs(self.h, n, idx.ctypes.data, px.ctypes.data, f.ctypes.data, R.ctypes.data, pos.ctypes.data))
+
     def vio_warp_affine(self, ref_idx, px_ref, A_cur_ref, search_levels):
         """warpAffine alone (esikf_vio_warp_affine): caller-provided 2x2 matrices and search levels -> (n, levels*64) float32."""
         n = len(px_ref)

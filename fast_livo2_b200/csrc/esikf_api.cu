@@ -143,6 +143,9 @@ struct esikf_ctx {
   DevBuf<double> vis_pos, inv_expo;
   DevBuf<float> warp_patch, errors;
   DevBuf<int32_t> search_levels;
+  DevBuf<double> inv_ref_px, inv_ref_f, inv_ref_R, inv_ref_pos, H_sub_inv;  // inverse-compositional variant
+  DevBuf<int32_t> inv_ref_idx;
+  int n_inv_refs = 0;
   DevBuf<float> warp_out;        // esikf_vio_warp_affine scratch (does not disturb the installed patches)
   DevBuf<int32_t> warp_levels;
   int n_patches = 0;
@@ -250,6 +253,7 @@ int esikf_create(esikf_ctx **out, int device) {
   }
   cudaFuncSetAttribute(lio_residual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
   cudaFuncSetAttribute(vio_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VioSmem));
+  cudaFuncSetAttribute(vio_inverse_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VioSmem));
   cudaError_t ea = cudaFuncSetAttribute(lio_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
   cudaError_t eb = cudaFuncSetAttribute(vio_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(VioSmem) + sizeof(FusedSolveSmem)));
   cudaFuncSetAttribute(lio_update_repl_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
@@ -317,6 +321,7 @@ void esikf_destroy(esikf_ctx *ctx) {
   ctx->warp_patch.release(), ctx->errors.release(), ctx->search_levels.release(), ctx->ref_img_ptrs.release(), ctx->ref_idx.release();
   ctx->px_ref.release(), ctx->pos_w.release(), ctx->normal_w.release(), ctx->T_ref.release(), ctx->T_cur.release();
   ctx->warp_out.release(), ctx->warp_levels.release();
+  ctx->inv_ref_px.release(), ctx->inv_ref_f.release(), ctx->inv_ref_R.release(), ctx->inv_ref_pos.release(), ctx->H_sub_inv.release(), ctx->inv_ref_idx.release();
   ctx->A_cur_ref.release(), ctx->pc_buf.release(), ctx->patch_buf.release(), ctx->flush.release(), ctx->scratch_state.release();
   for (uint8_t *p : ctx->ref_imgs) cudaFree(p);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
@@ -706,7 +711,12 @@ int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
     int rc = upload_states(ctx, state_in, state_prop);
     if (rc) return rc;
   }
-  const bool fused_vio = ctx->n_patches > 0 && ctx->loop_mode >= 1 && (ctx->nranks == 1 || ctx->p2p) && ctx->coop_ok && ctx->coop_vio > 0 && !ctx->timing;
+  const bool inverse = ctx->vio_cfg.inverse_composition_en != 0;
+  if (inverse && ctx->n_patches > 0) {
+    if (ctx->n_inv_refs != ctx->n_patches) return fail(ctx, ESIKF_ERR_STATE, "vio_run: inverse_composition_en needs esikf_vio_set_inverse_refs for the %d patches (have %d)", ctx->n_patches, ctx->n_inv_refs);
+    if (ctx->ref_w != ctx->cam.width || ctx->ref_h != ctx->cam.height) return fail(ctx, ESIKF_ERR_STATE, "vio_run: reference images must have the camera's size");
+  }
+  const bool fused_vio = !inverse && ctx->n_patches > 0 && ctx->loop_mode >= 1 && (ctx->nranks == 1 || ctx->p2p) && ctx->coop_ok && ctx->coop_vio > 0 && !ctx->timing;
   if (!fused_vio) {
     CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), st));
     CK(cudaMemsetAsync(ctx->vio_stats.p, 0, sizeof(esikf_vio_stats), st));
@@ -744,13 +754,28 @@ int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   }
   ctx->vio_timed = ctx->timing;
   ctx->vio_slots = ctx->vio_cfg.patch_pyrimid_level * ctx->vio_cfg.max_iterations;
+  VioInvArgs iv;
+  memset(&iv, 0, sizeof(iv));
+  if (inverse) {
+    CK(ctx->H_sub_inv.reserve((size_t)ka.count * 64 * 6 + 8));
+    iv.ref_imgs = ctx->ref_img_ptrs.p, iv.ref_idx = ctx->inv_ref_idx.p, iv.ref_px = ctx->inv_ref_px.p, iv.ref_f = ctx->inv_ref_f.p;
+    iv.ref_R = ctx->inv_ref_R.p, iv.ref_pos = ctx->inv_ref_pos.p, iv.H_sub_inv = ctx->H_sub_inv.p;
+    iv.ref_w = ctx->ref_w, iv.ref_h = ctx->ref_h, iv.fx = ctx->cam.fx, iv.fy = ctx->cam.fy;
+  }
   int slot = 0;
   for (int level = ctx->vio_cfg.patch_pyrimid_level - 1; level >= 0; level--) {
+    if (inverse) {  // has_ref_patch_cache = false at every level (vio.cpp:794): H_sub_inv of this level's tap stride
+      vio_inverse_precompute_kernel<<<(ka.count + 7) / 8, 256, 0, st>>>(ka, iv, level);
+      ctx->launches++;
+    }
     for (int it = 0; it < ctx->vio_cfg.max_iterations; it++, slot++) {
       ka.level = level, ka.slot_iter = it;
       cudaEvent_t *e = ctx->timing ? timing_events(ctx, EV_VIO_BASE, slot) : nullptr;
       if (e) cudaEventRecord(e[0], st);
-      vio_patch_kernel<<<grid, VIO_THREADS, sizeof(VioSmem), st>>>(ka);
+      if (inverse)
+        vio_inverse_patch_kernel<<<grid, VIO_THREADS, sizeof(VioSmem), st>>>(ka, iv);
+      else
+        vio_patch_kernel<<<grid, VIO_THREADS, sizeof(VioSmem), st>>>(ka);
       if (e) cudaEventRecord(e[1], st);
       int rc = allreduce_info(ctx);
       if (rc) return rc;
@@ -874,6 +899,31 @@ int esikf_vio_warp_patches(esikf_ctx *ctx, int32_t n, const int32_t *ref_img_ind
     ctx->n_patches = n;
   }
   CK(cudaStreamSynchronize(st));
+  return ESIKF_OK;
+}
+
+int esikf_vio_set_inverse_refs(esikf_ctx *ctx, int32_t n, const int32_t *ref_img_index, const double *ref_px, const double *ref_f, const double *ref_R,
+                               const double *ref_pos) {
+  if (!ctx || n < 0 || (n > 0 && (!ref_img_index || !ref_px || !ref_f || !ref_R || !ref_pos))) return fail(ctx, ESIKF_ERR_ARG, "set_inverse_refs: bad argument");
+  if (ctx->ref_imgs.empty() && n > 0) return fail(ctx, ESIKF_ERR_STATE, "set_inverse_refs before set_ref_images");
+  for (int i = 0; i < n; i++)
+    if (ref_img_index[i] < 0 || ref_img_index[i] >= (int)ctx->ref_imgs.size()) return fail(ctx, ESIKF_ERR_ARG, "set_inverse_refs: ref image index %d", ref_img_index[i]);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CK(ctx->inv_ref_idx.reserve(n + 1));
+  CK(ctx->inv_ref_px.reserve((size_t)n * 2 + 2));
+  CK(ctx->inv_ref_f.reserve((size_t)n * 3 + 3));
+  CK(ctx->inv_ref_R.reserve((size_t)n * 9 + 9));
+  CK(ctx->inv_ref_pos.reserve((size_t)n * 3 + 3));
+  if (n > 0) {
+    CK(cudaMemcpyAsync(ctx->inv_ref_idx.p, ref_img_index, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->inv_ref_px.p, ref_px, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->inv_ref_f.p, ref_f, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->inv_ref_R.p, ref_R, (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->inv_ref_pos.p, ref_pos, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // the caller's arrays may go away
+  }
+  ctx->n_inv_refs = n;
   return ESIKF_OK;
 }
 

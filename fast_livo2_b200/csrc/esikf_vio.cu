@@ -429,4 +429,163 @@ __global__ void warp_affine_kernel(const uint8_t *const *__restrict__ ref_imgs, 
   out[gid] = val;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Inverse-compositional variant (vio/inverse_composition_en, src/vio.cpp:792-795, 1327-1518): the Jacobian rows come from the
+// gradients of each point's REFERENCE image, computed once per pyramid level in the world frame (H_sub_inv) and rotated into
+// the current IMU frame every iteration; the residual has no exposure factors and H has 6 columns. First CUDA form: one
+// launch per (level, iteration) like the per-iteration forward path; the solve is vio_solve_kernel unchanged (with a zero
+// 7th column the 7 x 7 gain elimination reproduces the 6 x 6 one exactly).
+struct VioInvArgs {
+  const uint8_t *const *ref_imgs;  // registered reference images (Feature::img_)
+  const int32_t *ref_idx;          // [n] image of point i
+  const double *ref_px;            // [n][2] Feature::px_
+  const double *ref_f;             // [n][3] Feature::f_
+  const double *ref_R;             // [n][9] Feature::T_f_w_ rotation
+  const double *ref_pos;           // [n][3] Feature::pos()
+  double *H_sub_inv;               // [n][64][6] rows of the level being processed
+  int ref_w, ref_h;
+  double fx, fy;
+};
+
+// precomputeReferencePatches (:1327-1396) for one level: one warp per point, two pixels per lane.
+__global__ void vio_inverse_precompute_kernel(const VioKernelArgs a, const VioInvArgs v, int level) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lp = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (lp >= a.count) return;
+  const int i = a.begin + lp;
+  const int scale = 1 << level;
+  const uint8_t *__restrict__ img = v.ref_imgs[v.ref_idx[i]];
+  const long npix = (long)v.ref_w * v.ref_h;
+  const int width = v.ref_w;
+  const double X = a.pos[3 * (size_t)i], Y = a.pos[3 * (size_t)i + 1], Z = a.pos[3 * (size_t)i + 2];
+  const double dx = X - v.ref_pos[3 * (size_t)i], dy = Y - v.ref_pos[3 * (size_t)i + 1], dz = Z - v.ref_pos[3 * (size_t)i + 2];
+  const double depth = sqrt(dx * dx + dy * dy + dz * dz);
+  const double pf0 = v.ref_f[3 * (size_t)i] * depth, pf1 = v.ref_f[3 * (size_t)i + 1] * depth, pf2 = v.ref_f[3 * (size_t)i + 2] * depth;
+  const double z_inv = 1. / pf2, z_inv_2 = z_inv * z_inv;
+  const double J00 = v.fx * z_inv, J02 = -v.fx * pf0 * z_inv_2, J11 = v.fy * z_inv, J12 = -v.fy * pf1 * z_inv_2;
+  const double *R = v.ref_R + 9 * (size_t)i;
+  // B = Jdpi * R_ref_w (2 x 3); C = B * [pos]x (2 x 3): per pixel JdR = Jimg C, Jdt = -Jimg B with Jimg = [du dv] / scale
+  double B[2][3], Cm[2][3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    B[0][c] = J00 * R[c] + J02 * R[6 + c];
+    B[1][c] = J11 * R[3 + c] + J12 * R[6 + c];
+  }
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    Cm[r][0] = B[r][1] * Z - B[r][2] * Y;   // B * skew(pos): column 0 = B1 * Z + B2 * (-Y)
+    Cm[r][1] = -B[r][0] * Z + B[r][2] * X;
+    Cm[r][2] = B[r][0] * Y - B[r][1] * X;
+  }
+  const double pcu = v.ref_px[2 * (size_t)i], pcv = v.ref_px[2 * (size_t)i + 1];
+  const float u_ref = (float)pcu, v_ref = (float)pcv;
+  const int u_ref_i = (int)(floorf((float)(pcu / scale)) * scale);
+  const int v_ref_i = (int)(floorf((float)(pcv / scale)) * scale);
+  const float subpix_u = (u_ref - (float)u_ref_i) / (float)scale;
+  const float subpix_v = (v_ref - (float)v_ref_i) / (float)scale;
+  const float w_tl = (float)((1.0 - subpix_u) * (1.0 - subpix_v));
+  const float w_tr = (float)(subpix_u * (1.0 - subpix_v));
+  const float w_bl = (float)((1.0 - subpix_u) * subpix_v);
+  const float w_br = subpix_u * subpix_v;
+  const double inv_scale = 1.0 / scale;
+  const long sw = (long)scale * width;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const int pix = 2 * lane + k, x = pix >> 3, y = pix & 7;
+    const long b = (long)(v_ref_i + x * scale - 4 * scale) * width + (u_ref_i - 4 * scale) + (long)y * scale;
+    const float du = __fmul_rn(0.5f, __fsub_rn(bil(w_tl, w_tr, w_bl, w_br, tap(img, b + scale, npix), tap(img, b + 2 * scale, npix), tap(img, b + sw + scale, npix),
+                                                 tap(img, b + sw + 2 * scale, npix)),
+                                             bil(w_tl, w_tr, w_bl, w_br, tap(img, b - scale, npix), tap(img, b, npix), tap(img, b + sw - scale, npix), tap(img, b + sw, npix))));
+    const float dv = __fmul_rn(0.5f, __fsub_rn(bil(w_tl, w_tr, w_bl, w_br, tap(img, b + sw, npix), tap(img, b + scale + sw, npix), tap(img, b + 2 * sw, npix),
+                                                 tap(img, b + 2 * sw + scale, npix)),
+                                             bil(w_tl, w_tr, w_bl, w_br, tap(img, b - sw, npix), tap(img, b - sw + scale, npix), tap(img, b, npix), tap(img, b + scale, npix))));
+    const double ju = (double)du * inv_scale, jv = (double)dv * inv_scale;
+    double *h = v.H_sub_inv + ((size_t)lp * 64 + pix) * 6;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      h[c] = ju * Cm[0][c] + jv * Cm[1][c];
+      h[3 + c] = -(ju * B[0][c] + jv * B[1][c]);
+    }
+  }
+}
+
+// One iteration of updateStateInverse's measurement build (:1420-1480) at pyramid level a.level: residual / rows of this
+// rank's patches contracted on the tensor-core path into the same 8 x 8 block layout as the forward kernel
+// (H^T H in [0..5][0..5], row / column 6 zero, H^T z in column 7, sum res^2 in [7][7]).
+__global__ void __launch_bounds__(VIO_THREADS, 1) vio_inverse_patch_kernel(const VioKernelArgs a, const VioInvArgs v) {
+  if (a.slot_iter > 0 && a.ctrl->level_done) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  VioSmem &sm = *reinterpret_cast<VioSmem *>(smem_raw);
+  __shared__ double Rwi[9], Pwi[3];
+  vio_load_consts(sm, a);
+  if (threadIdx.x < 9) Rwi[threadIdx.x] = __ldcg(a.state + S_R + threadIdx.x);
+  if (threadIdx.x < 3) Pwi[threadIdx.x] = __ldcg(a.state + S_P + threadIdx.x);
+  __syncthreads();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int level = a.level, scale = 1 << level;
+  const long npix = (long)a.cam.width * a.cam.height;
+  const int width = a.cam.width;
+  double D0 = 0.0, D1 = 0.0, n_meas = 0.0;
+  int lo, hi;
+  vio_block_range(a.count, lo, hi);
+  for (int lp = lo + warp; lp < hi; lp += VIO_WARPS) {
+    const int i = a.begin + lp;
+    const double X = a.pos[3 * (size_t)i], Y = a.pos[3 * (size_t)i + 1], Z = a.pos[3 * (size_t)i + 2];
+    const double pf0 = sm.Rcw[0] * X + sm.Rcw[1] * Y + sm.Rcw[2] * Z + sm.Pcw[0];
+    const double pf1 = sm.Rcw[3] * X + sm.Rcw[4] * Y + sm.Rcw[5] * Z + sm.Pcw[1];
+    const double pf2 = sm.Rcw[6] * X + sm.Rcw[7] * Y + sm.Rcw[8] * Z + sm.Pcw[2];
+    double pcu, pcv;
+    world2cam(a.cam, pf0, pf1, pf2, pcu, pcv);
+    const float u_ref = (float)pcu, v_ref = (float)pcv;
+    const int u_ref_i = (int)(floorf((float)(pcu / scale)) * scale);
+    const int v_ref_i = (int)(floorf((float)(pcv / scale)) * scale);
+    const float subpix_u = (u_ref - (float)u_ref_i) / (float)scale;
+    const float subpix_v = (v_ref - (float)v_ref_i) / (float)scale;
+    const float w_tl = (float)((1.0 - subpix_u) * (1.0 - subpix_v));
+    const float w_tr = (float)(subpix_u * (1.0 - subpix_v));
+    const float w_bl = (float)((1.0 - subpix_u) * subpix_v);
+    const float w_br = subpix_u * subpix_v;
+    const float2 Pv = *reinterpret_cast<const float2 *>(a.warp_patch + (size_t)i * 64 * a.levels + 64 * level + 2 * lane);
+    const long sw = (long)scale * width;
+    double sq = 0.0;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const int pix = 2 * lane + k, x = pix >> 3, y = pix & 7;
+      const long b = (long)(v_ref_i + x * scale - 4 * scale) * width + (u_ref_i - 4 * scale) + (long)y * scale;
+      const float cur = bil(w_tl, w_tr, w_bl, w_br, tap(a.img, b, npix), tap(a.img, b + scale, npix), tap(a.img, b + sw, npix), tap(a.img, b + sw + scale, npix));
+      const double res = (double)__fsub_rn(cur, k == 0 ? Pv.x : Pv.y);  // float residual, then widened (:1466-1468)
+      const double *hi6 = v.H_sub_inv + ((size_t)lp * 64 + pix) * 6;
+      const double r0 = hi6[0], r1 = hi6[1], r2 = hi6[2], t0 = hi6[3], t1 = hi6[4], t2 = hi6[5];
+      // q = J_dt * [Pwi]x ; JdR = J_dR * Rwi + q * Rwi ; Jdt = J_dt * Rwi   (:1471-1472, same association)
+      const double q0 = t1 * Pwi[2] - t2 * Pwi[1], q1 = -t0 * Pwi[2] + t2 * Pwi[0], q2 = t0 * Pwi[1] - t1 * Pwi[0];
+      double row[8];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        row[c] = (r0 * Rwi[c] + r1 * Rwi[3 + c] + r2 * Rwi[6 + c]) + (q0 * Rwi[c] + q1 * Rwi[3 + c] + q2 * Rwi[6 + c]);
+        row[3 + c] = t0 * Rwi[c] + t1 * Rwi[3 + c] + t2 * Rwi[6 + c];
+      }
+      row[6] = 0.0, row[7] = res;
+      double4 *dst = reinterpret_cast<double4 *>(&sm.rows[warp][pix][0]);
+      dst[0] = make_double4(row[0], row[1], row[2], row[3]);
+      dst[1] = make_double4(row[4], row[5], row[6], row[7]);
+      sq += res * res;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (lane == 0) a.errors[i] = (float)sq;
+    n_meas += 64.0;
+    __syncwarp();
+    {
+      const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+      for (int s = 0; s < 16; s++) {
+        const double val = sm.rows[warp][4 * s + t][g];
+        dmma_m8n8k4(D0, D1, val, val);
+      }
+    }
+    __syncwarp();
+  }
+  reduce_info<VIO_WARPS>(sm.red, D0, D1, n_meas, false, a.partials, a.partial_stride, a.info, a.ctrl);
+}
+
 }  // namespace esikf

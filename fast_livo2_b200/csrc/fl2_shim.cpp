@@ -188,7 +188,7 @@ void VIOManager::initializeVIO() {
   last_status_ = esikf_set_extrinsics(ctx_, &ext);
   esikf_vio_cfg cfg;
   cfg.img_point_cov = img_point_cov, cfg.patch_pyrimid_level = patch_pyrimid_level, cfg.max_iterations = max_iterations;
-  cfg.exposure_estimate_en = exposure_estimate_en ? 1 : 0, cfg.pad_ = 0;
+  cfg.exposure_estimate_en = exposure_estimate_en ? 1 : 0, cfg.inverse_composition_en = 0;
   if (!last_status_) last_status_ = esikf_vio_set_camera(ctx_, &cam, &cfg);
   if (last_status_) last_error_ = esikf_last_error(ctx_);
 }

@@ -70,6 +70,7 @@ class VioCfg:
     max_iterations: int = 5
     img_point_cov: float = 100.0
     exposure_estimate_en: bool = True
+    inverse_composition_en: bool = False  # vio/inverse_composition_en (LIVMapper.cpp:60); false in every shipped config
 
     def as_array(self):
         return np.array([self.levels, self.max_iterations, self.img_point_cov, float(self.exposure_estimate_en)], dtype=np.float64)

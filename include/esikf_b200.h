@@ -86,7 +86,8 @@ typedef struct esikf_vio_cfg {
   int32_t patch_pyrimid_level; /* <= 8 */
   int32_t max_iterations;      /* <= 8 */
   int32_t exposure_estimate_en;
-  int32_t pad_;
+  int32_t inverse_composition_en; /* vio/inverse_composition_en (LIVMapper.cpp:60): updateStateInverse instead of updateState;
+                                     needs esikf_vio_set_inverse_refs. 0 in every shipped config. */
 } esikf_vio_cfg;
 
 /* Per-call diagnostics (what the reference prints at src/voxel_map.cpp:404-405). */
@@ -208,6 +209,11 @@ int esikf_vio_warp_patches(esikf_ctx *ctx, int32_t n, const int32_t *ref_img_ind
                            const double *T_cur_w /* 12: new_frame_->T_f_w_ */, double *A_cur_ref_out /* n x 4, nullable */,
                            int32_t *search_level_out /* n */, float *warp_patch_out /* n x levels*64 */,
                            int32_t keep_on_device /* 1: also install as the patches of set_patches */);
+/* set_inverse_refs: what the inverse-compositional variant (src/vio.cpp:1327-1518) reads of every visual point's reference
+ *                  feature (include/feature.h): image (index into set_ref_images), px_, f_ (unit bearing), the rotation
+ *                  of T_f_w_ (row-major) and pos() = T_f_w_.inverse().translation(). n must equal the n of set_patches. */
+int esikf_vio_set_inverse_refs(esikf_ctx *ctx, int32_t n, const int32_t *ref_img_index, const double *ref_px /* n x 2 */,
+                               const double *ref_f /* n x 3 */, const double *ref_R /* n x 9 */, const double *ref_pos /* n x 3 */);
 /* warp_affine    : batched warpAffine alone (src/vio.cpp:292-318, include/vio.h:161-162) with caller-provided affine
  *                  matrices A_cur_ref (n x 4, row-major [a00 a01 a10 a11]) and search levels; writes all pyramid levels,
  *                  patch i level l at warp_patch_out[(i*levels + l)*64 ...] like visual_submap->warp_patch[i]. */
