@@ -58,36 +58,3 @@ def test_shim_lio_and_vio_match_oracle(gpu_ctx, small_vio_frame):
     ov = vio.update(img, pos, wp, sl, ie, lio_out, lio_out)
     assert_state_close(vio_out, ov["state"], rot_tol=1e-8, pos_tol=1e-8, cov_tol=1e-6, rest_tol=1e-8)
     np.testing.assert_allclose(errs, ov["errors"], rtol=2e-6, atol=1e-3)
-
-
-def test_shim_patch_helpers_match_oracle(small_vio_frame):
-    """VIOManager::getImagePatch / VIOManager::warpAffine mirrors (include/vio.h:151, 161-162): one patch each through the
-    shim class; only the addressed pyramid level of the caller's buffer is written."""
-    import torch
-
-    if not torch.cuda.is_available():
-        pytest.skip("no CUDA device")
-    fr = small_vio_frame
-    shim = C.CDLL(os.path.join(ROOT, "fast_livo2_b200", "libfl2_shim.so"))
-    L = fr["vio_cfg"].levels
-    cam = api.CameraC(fr["cam_cfg"].model, fr["cam_cfg"].width, fr["cam_cfg"].height, 0, fr["cam_cfg"].fx, fr["cam_cfg"].fy, fr["cam_cfg"].cx, fr["cam_cfg"].cy)
-    cam.d[:] = list(fr["cam_cfg"].d)
-    vcfg = api.VioCfgC(fr["vio_cfg"].img_point_cov, L, fr["vio_cfg"].max_iterations, int(fr["vio_cfg"].exposure_estimate_en), 0)
-    img, img_ref = np.ascontiguousarray(fr["img"]), np.ascontiguousarray(fr["img_ref"])
-    vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    vio = O.OracleVIO(fr["cam_cfg"], fr["ext"], fr["vio_cfg"])
-    pc = np.array([301.37, 222.81])
-    A = np.array([[1.1, -0.2], [0.15, 0.9]])
-    px_ref = np.ascontiguousarray(fr["px_ref"][0], dtype=np.float64)
-    for level, search_level in ((0, 0), (2, 1), (L - 1, 0)):
-        patch = np.full(64 * L, -7.0, np.float32)
-        warp = np.full(64 * L, -7.0, np.float32)
-        rc = shim.fl2_shim_patch_helpers(C.byref(cam), C.byref(vcfg), vp(img), img.shape[1], img.shape[0], vp(pc), level, vp(patch), vp(A), vp(img_ref), vp(px_ref),
-                                         search_level, level, vp(warp))
-        assert rc == 0
-        sel = slice(64 * level, 64 * level + 64)
-        assert np.array_equal(patch[sel], vio.get_image_patch(img, pc, level))
-        np.testing.assert_allclose(warp[sel], vio.warp_affine(img_ref, A, px_ref, search_level)[sel], atol=2e-3)
-        untouched = np.ones(64 * L, bool)
-        untouched[sel] = False
-        assert (patch[untouched] == -7.0).all() and (warp[untouched] == -7.0).all()

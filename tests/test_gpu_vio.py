@@ -206,31 +206,3 @@ def test_config5_five_levels_4k_patches(gpu_ctx):
     g = gpu_ctx.vio_update(*args)
     vio = O.OracleVIO(fr["cam_cfg"], fr["ext"], fr["vio_cfg"])
     _compare_vio(g, vio.update(*args), 5)
-
-
-def test_warp_affine_alone_with_caller_matrices(gpu_ctx, small_vio_frame):
-    """esikf_vio_warp_affine (include/vio.h:161-162): the same kernel as warp_patches fed with caller-provided matrices —
-    identical to the batched producer for its own matrices, and equal to the oracle's warpAffine for arbitrary ones
-    (rotation + anisotropic scale, search levels 0 / 1; a zero matrix leaves zeros)."""
-    fr = small_vio_frame
-    _setup(gpu_ctx, fr)
-    prior = _vio_prior(fr)
-    g = _gpu_warp(gpu_ctx, fr, prior)
-    n = len(fr["vis_pos"])
-    again = gpu_ctx.vio_warp_affine(np.zeros(n, np.int32), fr["px_ref"], g["A_cur_ref"], g["search_levels"])
-    assert np.array_equal(again, g["warp_patch"])
-    m = 24
-    rng = np.random.default_rng(5)
-    ang = rng.uniform(-0.6, 0.6, m)
-    A = np.stack([np.stack([1.3 * np.cos(ang), -0.8 * np.sin(ang)], 1), np.stack([1.3 * np.sin(ang), 0.8 * np.cos(ang)], 1)], 1)  # (m, 2, 2)
-    A[-1] = 0.0  # singular with A_ref_cur(0, 0) = NaN: the patch is left untouched (vio.cpp:297-301)
-    sl = (np.arange(m) % 2).astype(np.int32)
-    out = gpu_ctx.vio_warp_affine(np.zeros(m, np.int32), fr["px_ref"][:m], A, sl)
-    vio = O.OracleVIO(fr["cam_cfg"], fr["ext"], fr["vio_cfg"])
-    exact = 0
-    for i in range(m - 1):
-        ref = vio.warp_affine(fr["img_ref"], A[i], fr["px_ref"][i], sl[i])
-        np.testing.assert_allclose(out[i], ref, atol=2e-3)
-        exact += np.array_equal(out[i], ref)
-    assert exact >= m // 2  # float products without contraction on both sides: mostly bit-exact
-    assert not out[-1].any()
