@@ -38,6 +38,18 @@ def main():
         inv_ref_expo=fr["inv_ref_expo"], warp_patch=w["warp_patch"], search_levels=w["search_levels"], A_cur_ref=w["A_cur_ref"],
         vio_state=v["state"], vio_total_iters=v["total_iters"], vio_iters_per_level=v["iters_per_level"], vio_errors=v["errors"], vio_error_trace=v["error_trace"])
     print("written", os.path.getsize(os.path.join(HERE, "esikf_golden.npz")) // 1024, "KiB; LIO iters", o["iters"], "M", o["M"], "VIO iters", v["total_iters"])
+    # inverse-compositional variant (vio/inverse_composition_en) on the same inputs: only the extra inputs and the outputs
+    refs = O.inverse_refs_from_frame(fr)
+    vio.set_inverse_refs(**refs)
+    vio.set_inverse(True)
+    n = len(fr["vis_pos"])
+    vi = vio.update(fr["img"], fr["vis_pos"], w["warp_patch"], w["search_levels"], np.ones(n), o["state"], o["state"])
+    Hinv = vio.precompute_reference_patches(fr["vis_pos"], 1)
+    np.savez_compressed(os.path.join(HERE, "esikf_golden_inverse.npz"), ref_img_index=refs["ref_img_index"], ref_px=refs["ref_px"], ref_f=refs["ref_f"],
+                        ref_R=refs["ref_R"], ref_pos=refs["ref_pos"], vio_state=vi["state"], vio_total_iters=vi["total_iters"],
+                        vio_iters_per_level=vi["iters_per_level"], vio_accepted_per_level=vi["accepted_per_level"], vio_errors=vi["errors"],
+                        vio_error_trace=vi["error_trace"], H_sub_inv_level1=Hinv[:8])
+    print("inverse variant: VIO iters", vi["total_iters"], vi["iters_per_level"][:4])
 
 
 if __name__ == "__main__":

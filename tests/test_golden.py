@@ -39,6 +39,24 @@ def test_oracle_reproduces_golden_vectors():
     assert np.array_equal(v["state"], g["vio_state"]) and np.array_equal(v["errors"], g["vio_errors"])
 
 
+def test_oracle_reproduces_inverse_variant_golden_vectors():
+    """Same inputs, vio/inverse_composition_en on (tests/golden/esikf_golden_inverse.npz)."""
+    import oracle_bind as O
+
+    g, lio_cfg, vio_cfg, cam, ext, vmap = _load()
+    gi = np.load(os.path.join(HERE, "golden", "esikf_golden_inverse.npz"))
+    vio = O.OracleVIO(cam, ext, vio_cfg)
+    vio.set_inverse_refs([g["img_ref"]], gi["ref_img_index"], gi["ref_px"], gi["ref_f"], gi["ref_R"], gi["ref_pos"])
+    vio.set_inverse(True)
+    n = len(g["vis_pos"])
+    v = vio.update(g["img"], g["vis_pos"], g["warp_patch"], g["search_levels"], np.ones(n), g["lio_state"], g["lio_state"])
+    assert v["total_iters"] == int(gi["vio_total_iters"]) and np.array_equal(v["iters_per_level"], gi["vio_iters_per_level"])
+    assert np.array_equal(v["accepted_per_level"], gi["vio_accepted_per_level"])
+    assert np.array_equal(v["state"], gi["vio_state"]) and np.array_equal(v["errors"], gi["vio_errors"])
+    assert np.array_equal(v["error_trace"], gi["vio_error_trace"])
+    assert np.array_equal(vio.precompute_reference_patches(g["vis_pos"], 1)[:8], gi["H_sub_inv_level1"])
+
+
 @pytest.mark.gpu
 def test_cuda_path_matches_golden_vectors(gpu_ctx):
     from fast_livo2_b200 import api
