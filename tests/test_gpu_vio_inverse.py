@@ -57,3 +57,25 @@ def test_inverse_variant_needs_its_reference_data(gpu_ctx, small_vio_frame):
             gpu_ctx.vio_update(fr["img"], fr["vis_pos"], w["warp_patch"], w["search_levels"], np.ones(len(fr["vis_pos"])), prior, prior)
     finally:
         gpu_ctx.vio_set_camera(fr["cam_cfg"], fr["vio_cfg"])
+
+
+def test_inverse_variant_matches_golden_vectors(gpu_ctx):
+    """tests/golden/esikf_golden_inverse.npz: the CUDA path without the oracle in the loop."""
+    from parity_util import assert_state_close
+    from test_golden import HERE, _load
+
+    g, lio_cfg, vio_cfg, cam, ext, vmap = _load()
+    gi = np.load(os.path.join(HERE, "golden", "esikf_golden_inverse.npz"))
+    n = len(g["vis_pos"])
+    try:
+        gpu_ctx.set_extrinsics(ext)
+        gpu_ctx.vio_set_camera(cam, dataclasses.replace(vio_cfg, inverse_composition_en=True))
+        gpu_ctx.vio_set_ref_images([g["img_ref"]])
+        gpu_ctx.vio_set_inverse_refs(gi["ref_img_index"], gi["ref_px"], gi["ref_f"], gi["ref_R"], gi["ref_pos"])
+        v = gpu_ctx.vio_update(g["img"], g["vis_pos"], g["warp_patch"], g["search_levels"], np.ones(n), g["lio_state"], g["lio_state"])
+    finally:
+        gpu_ctx.vio_set_camera(cam, vio_cfg)
+    assert v["total_iters"] == int(gi["vio_total_iters"]) and np.array_equal(v["iters_per_level"], gi["vio_iters_per_level"])
+    assert np.array_equal(v["accepted_per_level"], gi["vio_accepted_per_level"])
+    assert_state_close(v["state"], gi["vio_state"], rot_tol=1e-8, pos_tol=1e-8, cov_tol=1e-6, rest_tol=1e-8)
+    np.testing.assert_allclose(v["errors"], gi["vio_errors"], rtol=2e-6, atol=1e-3)
