@@ -173,7 +173,7 @@ struct esikf_ctx {
   int lio_slots = 0, vio_slots = 0;
   bool lio_timed = false, vio_timed = false;
   DevBuf<uint8_t> flush;
-  DevBuf<double> scratch_state;
+  DevBuf<double> scratch_state, point_cov_tmp;
 };
 
 static int fail(esikf_ctx *c, int code, const char *fmt, ...) {
@@ -322,7 +322,7 @@ void esikf_destroy(esikf_ctx *ctx) {
   ctx->px_ref.release(), ctx->pos_w.release(), ctx->normal_w.release(), ctx->T_ref.release(), ctx->T_cur.release();
   ctx->warp_out.release(), ctx->warp_levels.release();
   ctx->inv_ref_px.release(), ctx->inv_ref_f.release(), ctx->inv_ref_R.release(), ctx->inv_ref_pos.release(), ctx->H_sub_inv.release(), ctx->inv_ref_idx.release();
-  ctx->A_cur_ref.release(), ctx->pc_buf.release(), ctx->patch_buf.release(), ctx->flush.release(), ctx->scratch_state.release();
+  ctx->A_cur_ref.release(), ctx->pc_buf.release(), ctx->patch_buf.release(), ctx->flush.release(), ctx->scratch_state.release(), ctx->point_cov_tmp.release();
   for (uint8_t *p : ctx->ref_imgs) cudaFree(p);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -376,7 +376,6 @@ int esikf_map_upload(esikf_ctx *ctx, const int64_t *keys, const int32_t *first, 
   while (cap < (uint32_t)n_roots * 2u) cap <<= 1;
   std::vector<HashSlot> table(cap);
   for (auto &s : table) s.key = ESIKF_KEY_EMPTY, s.first = 0, s.count = 0;
-  const float vsf = (float)voxel_size;
   for (int r = 0; r < n_roots; r++) {
     long long x = keys[3 * r], y = keys[3 * r + 1], z = keys[3 * r + 2];
     if (!key_in_range(x, y, z)) return fail(ctx, ESIKF_ERR_ARG, "map_upload: voxel key (%lld,%lld,%lld) outside +-2^20", x, y, z);
@@ -389,7 +388,6 @@ int esikf_map_upload(esikf_ctx *ctx, const int64_t *keys, const int32_t *first, 
     }
     table[s].key = k, table[s].first = (uint32_t)first[r], table[s].count = (uint32_t)count[r];
   }
-  (void)vsf;
   CK(ctx->slots.reserve(cap));
   CK(ctx->planes.reserve((size_t)n_planes + 1));
   CK(cudaMemcpyAsync(ctx->slots.p, table.data(), cap * sizeof(HashSlot), cudaMemcpyHostToDevice, ctx->stream));
@@ -606,14 +604,13 @@ int esikf_lio_fetch_point_cov(esikf_ctx *ctx, double *body_cov9, double *cross_m
   CK(cudaSetDevice(ctx->device));
   const int n = ctx->n_pts;
   if (n == 0) return ESIKF_OK;
-  DevBuf<double> tmp;
+  DevBuf<double> &tmp = ctx->point_cov_tmp;  // context-owned scratch: no allocation per tick once it has grown
   CK(tmp.reserve((size_t)n * 18));
   expand_point_cov_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->pre.p, ctx->pre_stride, n, body_cov9 ? tmp.p : nullptr, cross_mat9 ? tmp.p + 9 * (size_t)n : nullptr);
   ctx->launches++;
   if (body_cov9) CK(cudaMemcpyAsync(body_cov9, tmp.p, (size_t)n * 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (cross_mat9) CK(cudaMemcpyAsync(cross_mat9, tmp.p + 9 * (size_t)n, (size_t)n * 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  tmp.release();
   return ESIKF_OK;
 }
 
