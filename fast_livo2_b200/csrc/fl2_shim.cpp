@@ -86,6 +86,16 @@ bool FlattenVoxelMap(const VoxelMap &map, const VoxelMapConfig &cfg, FlatVoxelMa
   return true;
 }
 
+bool DiffFlatVoxelMaps(const FlatVoxelMap &synced, const FlatVoxelMap &now, std::vector<int32_t> &changed_ids) {
+  changed_ids.clear();
+  if (synced.keys != now.keys || synced.first != now.first || synced.count != now.count || synced.planes.size() != now.planes.size()) return false;
+  for (size_t i = 0; i < now.planes.size(); i++) {
+    // layer / path are part of the record: a plane that moved inside its octree changes them and is patched like a refit
+    if (memcmp(&synced.planes[i], &now.planes[i], sizeof(esikf_plane)) != 0) changed_ids.push_back((int32_t)i);
+  }
+  return true;
+}
+
 VoxelMapManager::VoxelMapManager(VoxelMapConfig &config_setting, VoxelMap &voxel_map, int device) : config_setting_(config_setting), voxel_map_(voxel_map) {
   last_status_ = esikf_create(&ctx_, device);
   if (last_status_ != 0) last_error_ = "esikf_create failed (no sm_100 CUDA device?) — there is no CPU fallback";
@@ -95,13 +105,30 @@ VoxelMapManager::~VoxelMapManager() { esikf_destroy(ctx_); }
 void VoxelMapManager::SyncDeviceMap() {
   if (!ctx_) return;
   std::string err;
-  if (!FlattenVoxelMap(voxel_map_, config_setting_, flat_, &err)) {
+  FlatVoxelMap now;
+  if (!FlattenVoxelMap(voxel_map_, config_setting_, now, &err)) {
     last_status_ = ESIKF_ERR_ARG, last_error_ = err;
     return;
   }
-  last_status_ = esikf_map_upload(ctx_, flat_.keys.data(), flat_.first.data(), flat_.count.data(), (int32_t)flat_.first.size(), flat_.planes.data(),
-                                  (int32_t)flat_.planes.size(), config_setting_.max_voxel_size_);
-  if (last_status_) last_error_ = esikf_last_error(ctx_);
+  std::vector<int32_t> ids;
+  if (device_has_map_ && DiffFlatVoxelMaps(flat_, now, ids)) {
+    // same roots and candidate lists as on the device: only the refitted records travel
+    std::vector<esikf_plane> recs(ids.size());
+    for (size_t k = 0; k < ids.size(); k++) recs[k] = now.planes[ids[k]];
+    last_status_ = ids.empty() ? 0 : esikf_map_patch(ctx_, ids.data(), recs.data(), (int32_t)ids.size());
+    last_sync_patched_ = (int)ids.size();
+  } else {
+    last_status_ = esikf_map_upload(ctx_, now.keys.data(), now.first.data(), now.count.data(), (int32_t)now.first.size(), now.planes.data(),
+                                    (int32_t)now.planes.size(), config_setting_.max_voxel_size_);
+    last_sync_patched_ = -1;
+  }
+  if (last_status_) {
+    last_error_ = esikf_last_error(ctx_);
+    device_has_map_ = false;  // unknown device state: the next sync uploads everything
+  } else {
+    flat_.keys.swap(now.keys), flat_.first.swap(now.first), flat_.count.swap(now.count), flat_.planes.swap(now.planes), flat_.plane_src.swap(now.plane_src);
+    device_has_map_ = true;
+  }
   map_synced_ = (last_status_ == 0);
 }
 
@@ -391,6 +418,82 @@ int fl2_shim_run(const int64_t *keys, const int32_t *first, const int32_t *count
         st.pack(vio_state_out);
         for (int i = 0; i < n_patches; i++) errors_out[i] = sub.errors[i];
       }
+    }
+  }
+  for (auto &kv : map) delete kv.second;
+  return rc;
+}
+
+// CPU-only: DiffFlatVoxelMaps on two flat maps given as arrays (same root arrays for both unless keys_b is non-null).
+// Returns -1 if the structure differs, else the number of changed plane ids written to ids_out (capacity n_planes_a).
+int fl2_shim_diff(const int64_t *keys_a, const int32_t *first_a, const int32_t *count_a, int n_roots_a, const esikf_plane *planes_a, int n_planes_a,
+                  const int64_t *keys_b, const int32_t *first_b, const int32_t *count_b, int n_roots_b, const esikf_plane *planes_b, int n_planes_b,
+                  int32_t *ids_out) {
+  FlatVoxelMap a, b;
+  a.keys.assign(keys_a, keys_a + 3 * (size_t)n_roots_a), a.first.assign(first_a, first_a + n_roots_a), a.count.assign(count_a, count_a + n_roots_a);
+  a.planes.assign(planes_a, planes_a + n_planes_a);
+  b.keys.assign(keys_b, keys_b + 3 * (size_t)n_roots_b), b.first.assign(first_b, first_b + n_roots_b), b.count.assign(count_b, count_b + n_roots_b);
+  b.planes.assign(planes_b, planes_b + n_planes_b);
+  std::vector<int32_t> ids;
+  if (!DiffFlatVoxelMaps(a, b, ids)) return -1;
+  for (size_t k = 0; k < ids.size(); k++) ids_out[k] = ids[k];
+  return (int)ids.size();
+}
+
+// GPU: map refresh through the shim. Builds the octree of map A, syncs (full upload), overwrites the plane fits with map B's
+// (same structure: an UpdateVoxelMap that only refitted planes), syncs again (incremental: esikf_map_patch of the changed
+// records) and runs StateEstimation. The caller compares with a run on a fresh manager holding map B.
+int fl2_shim_resync_run(const int64_t *keys, const int32_t *first, const int32_t *count, int n_roots, const esikf_plane *planes_a, const esikf_plane *planes_b,
+                        int n_planes, const esikf_lio_cfg *lcfg, const esikf_extrinsics *ext, const float *pts, int n, const double *state_in,
+                        double *state_out, int32_t *n_patched) {
+  (void)n_planes;
+  VoxelMapConfig cfg;
+  cfg.max_voxel_size_ = lcfg->voxel_size, cfg.max_layer_ = lcfg->max_layer, cfg.max_iterations_ = lcfg->max_iterations;
+  cfg.beam_err_ = lcfg->beam_err, cfg.dept_err_ = lcfg->dept_err, cfg.sigma_num_ = lcfg->sigma_num;
+  VoxelMap map;
+  build_tree(map, cfg, keys, first, count, n_roots, planes_a);
+  int rc = 0;
+  {
+    VoxelMapManager mgr(cfg, map, 0);
+    rc = mgr.last_status_;
+    memcpy(mgr.extR_.m, ext->extR, 72);
+    memcpy(mgr.extT_.v, ext->extT, 24);
+    if (!rc) {
+      mgr.SyncDeviceMap();
+      rc = mgr.last_status_;
+    }
+    if (!rc) {
+      // the host map changes under the manager: same octree, new plane fits
+      for (int r = 0; r < n_roots; r++) {
+        VOXEL_LOCATION loc(keys[3 * r], keys[3 * r + 1], keys[3 * r + 2]);
+        for (int c = 0; c < count[r]; c++) {
+          const esikf_plane &f = planes_b[first[r] + c];
+          VoxelOctoTree *node = map[loc];
+          for (int l = 0; l < f.layer; l++) node = node->leaves_[(f.path >> (3 * l)) & 7];
+          VoxelPlane &p = *node->plane_ptr_;
+          for (int k = 0; k < 3; k++) p.center_[k] = f.center[k], p.normal_[k] = f.normal[k];
+          int t = 0;
+          for (int i = 0; i < 6; i++)
+            for (int j = i; j < 6; j++) p.plane_var_[i * 6 + j] = p.plane_var_[j * 6 + i] = f.plane_var[t++];
+          p.d_ = f.d, p.radius_ = f.radius;
+        }
+      }
+      mgr.MarkMapDirty();
+      mgr.SyncDeviceMap();
+      rc = mgr.last_status_;
+      *n_patched = mgr.last_sync_patched_;
+    }
+    if (!rc) {
+      mgr.feats_down_body_.resize(n);
+      memcpy(mgr.feats_down_body_.data(), pts, (size_t)n * 12);
+      mgr.feats_down_size_ = n;
+      mgr.fill_point_lists_ = false;
+      mgr.state_.unpack(state_in);
+      StatesGroup prop;
+      prop.unpack(state_in);
+      mgr.StateEstimation(prop);
+      rc = mgr.last_status_;
+      if (!rc) mgr.state_.pack(state_out);
     }
   }
   for (auto &kv : map) delete kv.second;

@@ -111,6 +111,10 @@ struct FlatVoxelMap {
 // DFS of every root in leaf order 0..7, plane nodes terminate their branch: exactly what build_single_residual visits
 // (src/voxel_map.cpp:721, 771-784). Throws nothing; returns false with `err` set on inconsistent roots.
 bool FlattenVoxelMap(const VoxelMap &map, const VoxelMapConfig &cfg, FlatVoxelMap &out, std::string *err);
+// What changed between two flattenings of the same map: false if the structure differs (roots added / removed, a candidate
+// list grew or shrank or moved — needs a full upload), true with the ids of the plane records whose content changed
+// (refitted planes: what esikf_map_patch takes). is_update_ is not used: the reference sets it on every fit and never clears it.
+bool DiffFlatVoxelMaps(const FlatVoxelMap &synced, const FlatVoxelMap &now, std::vector<int32_t> &changed_ids);
 
 class VoxelMapManager {
  public:
@@ -132,15 +136,18 @@ class VoxelMapManager {
 
   VoxelMapManager(VoxelMapConfig &config_setting, VoxelMap &voxel_map, int device = 0);
   ~VoxelMapManager();
-  // call after BuildVoxelMap / UpdateVoxelMap / mapSliding changed voxel_map_ (is_update_ planes): re-flatten + upload
+  // call after BuildVoxelMap / UpdateVoxelMap / mapSliding changed voxel_map_: re-flatten, then patch the refitted plane
+  // records in place (esikf_map_patch) when the candidate lists kept their shape, full upload (esikf_map_upload) otherwise
   void SyncDeviceMap();
+  void MarkMapDirty() { map_synced_ = false; }
+  int last_sync_patched_ = -1;     // planes patched by the last SyncDeviceMap, -1 = it was a full upload
   void StateEstimation(StatesGroup &state_propagat);  // include/voxel_map.h:229
   esikf_ctx *context() { return ctx_; }
 
  private:
   esikf_ctx *ctx_ = nullptr;
   FlatVoxelMap flat_;
-  bool map_synced_ = false;
+  bool map_synced_ = false, device_has_map_ = false;
 };
 
 // include/vio.h:26-57 restated over flat storage

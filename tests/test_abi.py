@@ -69,3 +69,33 @@ def test_shim_flattener_roundtrip(small_frame):
             a, b = p[f0 + j], po[ff + j]
             for name in ("center", "normal", "plane_var", "d", "radius", "layer", "path"):
                 assert np.array_equal(a[name], b[name]), name
+
+
+def test_shim_map_diff_finds_refitted_planes_and_structure_changes(small_frame):
+    """fl2_shim DiffFlatVoxelMaps: what VoxelMapManager::SyncDeviceMap uses to choose between esikf_map_patch (same roots and
+    candidate lists, some refitted plane records) and a full esikf_map_upload."""
+    path = os.path.join(ROOT, "fast_livo2_b200", "libfl2_shim.so")
+    shim = C.CDLL(path)
+    m = small_frame["map"]
+    k, f, c = (np.ascontiguousarray(m["keys"], dtype=np.int64), np.ascontiguousarray(m["first"], dtype=np.int32), np.ascontiguousarray(m["count"], dtype=np.int32))
+    pa = np.ascontiguousarray(m["planes"]).copy()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    ids = np.zeros(len(pa), np.int32)
+
+    def diff(k2, f2, c2, pb):
+        return shim.fl2_shim_diff(vp(k), vp(f), vp(c), len(f), vp(pa), len(pa), vp(k2), vp(f2), vp(c2), len(f2), vp(pb), len(pb), vp(ids))
+
+    assert diff(k, f, c, pa.copy()) == 0
+    pb = pa.copy()
+    touched = [0, 7, len(pb) - 1]
+    pb["d"][touched[0]] += np.float32(0.25)
+    pb["normal"][touched[1]] = -pb["normal"][touched[1]]
+    pb["plane_var"][touched[2], 3] *= 1.5
+    assert diff(k, f, c, pb) == 3 and ids[:3].tolist() == touched
+    # a candidate list that grew / a new root voxel / a missing root: structure change -> full upload
+    c2 = c.copy()
+    c2[0] += 1
+    assert diff(k, f, c2, pa) == -1
+    k2 = np.concatenate([k.reshape(-1, 3), [[9999, 9999, 9999]]]).astype(np.int64)
+    assert diff(np.ascontiguousarray(k2), np.append(f, 0).astype(np.int32), np.append(c, 0).astype(np.int32), pa) == -1
+    assert diff(np.ascontiguousarray(k.reshape(-1, 3)[:-1]), f[:-1].copy(), c[:-1].copy(), pa) == -1

@@ -74,3 +74,77 @@ def test_shim_patch_helpers_match_oracle(small_vio_frame):
         untouched = np.ones(64 * L, bool)
         untouched[sel] = False
         assert (patch[untouched] == -7.0).all() and (warp[untouched] == -7.0).all()
+
+
+def _refit(planes, rng, frac=0.05):
+    """Planes as UpdateVoxelMap would leave them after refitting a few: nudged offsets / normals, same structure."""
+    out = planes.copy()
+    ids = np.sort(rng.choice(len(out), max(3, int(frac * len(out))), replace=False))
+    out["d"][ids] += rng.normal(0, 0.01, len(ids)).astype(np.float32)
+    out["center"][ids] += rng.normal(0, 0.005, (len(ids), 3))
+    out["plane_var"][ids] *= 1.1
+    return out, ids
+
+
+def test_map_patch_equals_full_upload(small_frame):
+    """esikf_map_patch: patching the refitted plane records in place gives the same update, bit for bit, as uploading the
+    whole modified map into a fresh context."""
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    fr = small_frame
+    m = fr["map"]
+    rng = np.random.default_rng(8)
+    planes_b, ids = _refit(np.ascontiguousarray(m["planes"]), rng)
+    a = api.Context(0)
+    b = api.Context(0)
+    try:
+        for ctx in (a, b):
+            ctx.set_extrinsics(fr["ext"])
+        a.map_upload(m, fr["lio_cfg"].voxel_size)
+        before = a.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"])
+        a.map_patch(ids.astype(np.int32), planes_b[ids])
+        ra = a.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"])
+        b.map_upload(dict(m, planes=planes_b), fr["lio_cfg"].voxel_size)
+        rb = b.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"])
+    finally:
+        a.close()
+        b.close()
+    assert not np.array_equal(before["state"], ra["state"])  # the refit matters
+    for key in ("state", "match_plane", "normal_plane", "dis_to_plane", "M", "HTH"):
+        assert np.array_equal(np.asarray(ra[key]), np.asarray(rb[key])), key
+
+
+def test_shim_incremental_map_sync_equals_fresh_upload(small_frame):
+    """VoxelMapManager::SyncDeviceMap after the host map was refitted under it: the changed records are patched (no full
+    upload) and StateEstimation matches a fresh manager built on the refitted map."""
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    fr = small_frame
+    shim = C.CDLL(os.path.join(ROOT, "fast_livo2_b200", "libfl2_shim.so"))
+    m = fr["map"]
+    k, f, c = (np.ascontiguousarray(m["keys"], dtype=np.int64), np.ascontiguousarray(m["first"], dtype=np.int32), np.ascontiguousarray(m["count"], dtype=np.int32))
+    pa = np.ascontiguousarray(m["planes"])
+    pb, ids = _refit(pa, np.random.default_rng(9))
+    lcfg = api.lio_cfg_c(fr["lio_cfg"])
+    ext = api.ExtrinsicsC()
+    ext.extR[:] = fr["ext"].extR.reshape(9)
+    ext.extT[:] = fr["ext"].extT
+    ext.Rcl[:] = fr["ext"].Rcl.reshape(9)
+    ext.Pcl[:] = fr["ext"].Pcl
+    pts = np.ascontiguousarray(fr["pts"])
+    sp = np.ascontiguousarray(fr["state_prior"])
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    out_inc, out_fresh = np.zeros(386), np.zeros(386)
+    npatched = C.c_int32(-2)
+    rc = shim.fl2_shim_resync_run(vp(k), vp(f), vp(c), len(f), vp(pa), vp(pb), len(pa), C.byref(lcfg), C.byref(ext), vp(pts), len(pts), vp(sp), vp(out_inc),
+                                  C.byref(npatched))
+    assert rc == 0 and npatched.value == len(ids)
+    n2 = C.c_int32(-2)
+    rc = shim.fl2_shim_resync_run(vp(k), vp(f), vp(c), len(f), vp(pb), vp(pb), len(pb), C.byref(lcfg), C.byref(ext), vp(pts), len(pts), vp(sp), vp(out_fresh),
+                                  C.byref(n2))
+    assert rc == 0 and n2.value == 0  # nothing changed between the two syncs
+    assert np.array_equal(out_inc, out_fresh)
