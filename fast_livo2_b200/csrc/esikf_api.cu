@@ -404,9 +404,13 @@ int esikf_map_patch(esikf_ctx *ctx, const int32_t *plane_ids, const esikf_plane 
   if (!ctx || n < 0 || (n > 0 && (!plane_ids || !planes))) return fail(ctx, ESIKF_ERR_ARG, "map_patch: bad argument");
   if (!ctx->have_map) return fail(ctx, ESIKF_ERR_STATE, "map_patch before map_upload");
   CK(cudaSetDevice(ctx->device));
-  for (int i = 0; i < n; i++) {
+  for (int i = 0; i < n; i++)
     if (plane_ids[i] < 0 || plane_ids[i] >= ctx->n_planes) return fail(ctx, ESIKF_ERR_ARG, "map_patch: plane id %d", plane_ids[i]);
-    CK(cudaMemcpyAsync(ctx->planes.p + plane_ids[i], planes + i, sizeof(esikf_plane), cudaMemcpyHostToDevice, ctx->stream));
+  for (int i = 0; i < n;) {
+    int j = i + 1;
+    while (j < n && plane_ids[j] == plane_ids[j - 1] + 1) j++;  // a run of consecutive ids travels as one copy
+    CK(cudaMemcpyAsync(ctx->planes.p + plane_ids[i], planes + i, (size_t)(j - i) * sizeof(esikf_plane), cudaMemcpyHostToDevice, ctx->stream));
+    i = j;
   }
   CK(cudaStreamSynchronize(ctx->stream));
   return ESIKF_OK;
