@@ -2,8 +2,6 @@
 solve itself, one grid barrier per iteration) must reproduce loop_mode 1 (solve on CTA 0) bit for bit — states,
 associations and per-iteration diagnostics — in both solve modes, across repeated launches (barrier counters and partial
 buffers alternate)."""
-import os
-
 import numpy as np
 import pytest
 
@@ -85,12 +83,6 @@ def test_vio_replicated_solve_is_bit_identical(gpu_ctx, small_vio_frame, solve_m
         _bits_equal(ref, r, keys)
 
 
-EXPERIMENTAL = pytest.mark.skipif(os.environ.get("ESIKF_EXPERIMENTAL") != "1",
-                                  reason="opt-in kernel variants (esikf_set_tuning) were written at the end of round 1 with no GPU time left to run "
-                                         "them; ESIKF_EXPERIMENTAL=1 enables these checks")
-
-
-@EXPERIMENTAL
 @pytest.mark.parametrize("seed,n_pts,n_map,scale", [(4, 20000, 150_000, 0.5), (12, 260_000, 1_000_000, 1.0)])
 def test_lio_dealt_schedule_matches_contiguous_and_oracle(gpu_ctx, seed, n_pts, n_map, scale):
     """32-point chunks dealt round-robin over the CTAs: the association is identical, the state agrees to the summation-
@@ -122,7 +114,6 @@ def test_lio_dealt_schedule_matches_contiguous_and_oracle(gpu_ctx, seed, n_pts, 
     assert_state_close(b["state"], o["state"])
 
 
-@EXPERIMENTAL
 def test_bit_identical_tuning_variants(gpu_ctx, small_vio_frame):
     """ESIKF_TUNE_DEFER_DIAGNOSTICS only moves CTA 0's diagnostics writes into the next barrier wait and
     ESIKF_TUNE_VIO_FAST_PATH only caches per-patch inputs / replaces power-of-two divisions / overlaps the boxminus: every
@@ -158,7 +149,6 @@ def test_bit_identical_tuning_variants(gpu_ctx, small_vio_frame):
         _bits_equal(out[0][2], v_lit, vio_keys)
 
 
-@EXPERIMENTAL
 def test_vio_fast_path_with_two_patches_per_warp_and_search_levels(gpu_ctx):
     """More patches than warps (nothing stays cached) and non-zero search levels / a distorted camera through the FAST path."""
     from fast_livo2_b200 import synthetic as S

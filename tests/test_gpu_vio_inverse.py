@@ -1,6 +1,5 @@
 """GPU parity of the inverse-compositional VIO variant (vio/inverse_composition_en, src/vio.cpp:792-795, 1327-1518) against
-the oracle. The CUDA kernels were written at the end of round 1 with no GPU time left to run them, so the checks are
-opt-in (ESIKF_EXPERIMENTAL=1) until they have passed on a B200 once."""
+the oracle and the golden vectors (first GPU run: profiles/gpu_tests_r01_new_paths.txt)."""
 import dataclasses
 import os
 
@@ -10,8 +9,7 @@ import pytest
 import oracle_bind as O
 from test_gpu_vio import _compare_vio, _gpu_warp, _setup, _vio_prior
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ESIKF_EXPERIMENTAL") != "1", reason="inverse-compositional CUDA path not yet run on a GPU (ESIKF_EXPERIMENTAL=1)")]
+pytestmark = pytest.mark.gpu
 
 
 def test_inverse_variant_matches_oracle(gpu_ctx, small_vio_frame):

@@ -1,7 +1,6 @@
 """GPU: entry points added (or first tested) at the end of round 1 — esikf_vio_warp_affine, the shim's per-patch
-getImagePatch / warpAffine mirrors, esikf_map_patch and the shim's incremental map refresh. They reuse kernels that the other
-GPU tests cover, but this host plumbing was written after the round's GPU budget was spent and has not run on a GPU yet, so
-the checks are opt-in (ESIKF_EXPERIMENTAL=1, tools/validate_tuning.sh) until they have passed once."""
+getImagePatch / warpAffine mirrors, esikf_map_patch and the shim's incremental map refresh (first GPU run:
+profiles/gpu_tests_r01_new_paths.txt)."""
 import ctypes as C
 import os
 
@@ -12,8 +11,7 @@ import oracle_bind as O
 from fast_livo2_b200 import api
 from test_gpu_vio import _gpu_warp, _setup, _vio_prior
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ESIKF_EXPERIMENTAL") != "1", reason="not yet run on a GPU (ESIKF_EXPERIMENTAL=1 enables)")]
+pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
