@@ -110,7 +110,7 @@ def load_library():
     return lib
 
 
-TUNE_DEAL_POINTS, TUNE_DEFER_DIAGNOSTICS, TUNE_VIO_FAST_PATH = 1, 2, 4  # esikf_set_tuning flags
+TUNE_DEAL_POINTS, TUNE_DEFER_DIAGNOSTICS, TUNE_VIO_FAST_PATH, TUNE_PEER_REPLICATED = 1, 2, 4, 8  # esikf_set_tuning flags
 DEFAULT_LOOP_MODE = 2  # esikf_set_loop_mode: 2 replicated-solve persistent kernel, 1 CTA-0 solve, 0 per-iteration launches
 
 EXPORTED_SYMBOLS = [

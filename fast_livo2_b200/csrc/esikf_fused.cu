@@ -71,6 +71,49 @@ __device__ __forceinline__ void peer_allreduce(double *info, const PeerArgs &p, 
   __syncthreads();
 }
 
+// The same exchange split for the replicated-solve kernels: CTA 0 pushes the rank's (locally reduced) buffer into every
+// rank's mailbox — its own included —, EVERY CTA pulls the nranks slots of the local mailbox and adds them in rank order.
+// `seq` counts executed iterations (tag and parity follow it). Two parities suffice: a rank's CTA 0 writes exchange k + 2
+// only after it received every peer's k + 1, which a peer's CTA 0 sends after its own grid barrier k + 1 — and every CTA of
+// that peer passes that barrier only after it finished pulling exchange k.
+__device__ __forceinline__ void peer_push(const double *info, const PeerArgs &p, unsigned int seq) {
+  const int tid = threadIdx.x;
+  const unsigned int tag = p.seq_base + seq + 1u;
+  const int par = seq & 1;
+  if (tid < INFO_N) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(info[tid]);
+    const unsigned long long w0 = (bits << 32) | tag;
+    const unsigned long long w1 = (bits & 0xffffffff00000000ull) | tag;
+    const size_t off = (size_t)(par * p.nranks + p.rank) * PEER_SLOT_WORDS + 2 * tid;
+    for (int r = 0; r < p.nranks; r++) {
+      unsigned long long *dst = p.mbox[r] + off;
+      asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(w0) : "memory");
+      asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst + 1), "l"(w1) : "memory");
+    }
+  }
+}
+__device__ __forceinline__ void peer_pull(double *info, const PeerArgs &p, unsigned int seq) {
+  const int tid = threadIdx.x;
+  const unsigned int tag = p.seq_base + seq + 1u;
+  const int par = seq & 1;
+  __syncthreads();  // everybody is done reading the local sum (CTA 0's pushers read it too)
+  if (tid < INFO_N) {
+    const unsigned long long *own = p.mbox[p.rank] + (size_t)par * p.nranks * PEER_SLOT_WORDS + 2 * tid;
+    double s = 0.0;
+    for (int r = 0; r < p.nranks; r++) {
+      const unsigned long long *src = own + (size_t)r * PEER_SLOT_WORDS;
+      unsigned long long a, b;
+      do {
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(a) : "l"(src) : "memory");
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(b) : "l"(src + 1) : "memory");
+      } while ((unsigned int)a != tag || (unsigned int)b != tag);
+      s += __longlong_as_double((long long)((b & 0xffffffff00000000ull) | (a >> 32)));
+    }
+    info[tid] = s;
+  }
+  __syncthreads();
+}
+
 // Counting grid barrier over all CTAs of a cooperative launch: arrivals are atomic increments, everybody polls the same
 // counter; the k-th barrier (k = 0, 1, ...) completes when it reaches (k + 1) * gridDim.x. The counter is zeroed for this
 // launch by the previous launch (launches alternate between two counters). A variant with a separate release word written
@@ -369,9 +412,10 @@ __device__ __forceinline__ void lio_consts_from_resident(LioSmem &sm, const Fuse
 // DEFER: CTA 0 writes the diagnostics / control block of iteration k while it waits at the grid barrier of iteration k + 1
 // (warp 1, while thread 0 polls) instead of right after the solve, where it delays CTA 0's next slice — and with it the
 // whole grid — by the ~1 us the "publish" phase takes in profiles/loop_modes_r01_mode2.txt.
-template <bool DEAL, bool DEFER>
+// PEER: every CTA pulls the peer-reduced information buffer from the local NVLink mailbox (CTA 0 pushed it), see peer_push.
+template <bool DEAL, bool DEFER, bool PEER = false>
 __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_repl_kernel(const LioKernelArgs a, const SolveArgs sa_in, unsigned int *barrier, unsigned int *barrier_next,
-                                                                          unsigned long long *stamps, size_t partial_parity_stride) {
+                                                                          unsigned long long *stamps, size_t partial_parity_stride, const PeerArgs peer) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   LioSmem &sm = *reinterpret_cast<LioSmem *>(smem_raw);
   FusedSolveSmem &fs = *reinterpret_cast<FusedSolveSmem *>(sm.fs_raw);
@@ -434,6 +478,10 @@ __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_repl_kernel(const L
       grid_barrier(barrier, epoch);
     stamp(stamps, sk);  // 3: all CTAs arrived
     reduce_partials_block(part, a.partial_stride, gridDim.x, fs.io.info);
+    if (PEER && peer.nranks > 1) {
+      if (blockIdx.x == 0) peer_push(fs.io.info, peer, (unsigned int)it);
+      peer_pull(fs.io.info, peer, (unsigned int)it);
+    }
     stamp(stamps, sk);  // 4: partials summed
     if (threadIdx.x == 0) {
       SolveLiteralScratch *lit = reinterpret_cast<SolveLiteralScratch *>(&sm.rec[0][0][0]);
@@ -477,9 +525,9 @@ __device__ __forceinline__ void vio_consts_from_resident(VioSmem &sm, const VioK
 
 // FAST: per-patch inputs cached across iterations + exact-reciprocal tap-stride arithmetic (vio_process_range<true>) and
 // the boxminus overlapped with the gain elimination (vio_solve_block<true>); bit-identical results.
-template <bool DEFER, bool FAST>
+template <bool DEFER, bool FAST, bool PEER = false>
 __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_repl_kernel(const VioKernelArgs a, SolveArgs sa, unsigned int *barrier, unsigned int *barrier_next,
-                                                                          unsigned long long *stamps, size_t partial_parity_stride) {
+                                                                          unsigned long long *stamps, size_t partial_parity_stride, const PeerArgs peer) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   VioSmem &sm = *reinterpret_cast<VioSmem *>(smem_raw);
   FusedSolveSmem &fs = *reinterpret_cast<FusedSolveSmem *>(smem_raw + sizeof(VioSmem));
@@ -531,6 +579,10 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_repl_kernel(const V
       }
       stamp(stamps, sk);
       reduce_partials_block(part, a.partial_stride, gridDim.x, fs.io.info);
+      if (PEER && peer.nranks > 1) {
+        if (blockIdx.x == 0) peer_push(fs.io.info, peer, (unsigned int)cur);
+        peer_pull(fs.io.info, peer, (unsigned int)cur);
+      }
       stamp(stamps, sk);
       sa.level = level, sa.slot_iter = it, sa.last_slot = 0;
       if (threadIdx.x == 0) fs.sm.W = lit.W, fs.sm.K = lit.K;

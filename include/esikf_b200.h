@@ -142,10 +142,14 @@ int esikf_set_loop_mode(esikf_ctx *ctx, int mode);
  *                                  instead of right after the solve (same values, off the critical path).
  *   ESIKF_TUNE_VIO_FAST_PATH     : VIO keeps the iteration-invariant inputs of a warp's patch on chip across iterations,
  *                                  replaces divisions by the power-of-two tap stride with exact multiplications and
- *                                  overlaps the boxminus with the gain elimination (bit-identical results). */
+ *                                  overlaps the boxminus with the gain elimination (bit-identical results).
+ *   ESIKF_TUNE_PEER_REPLICATED   : with peer GPUs attached, keep the replicated-solve kernels: CTA 0 pushes the rank's
+ *                                  information buffer into every rank's mailbox and EVERY CTA pulls the rank-ordered sum
+ *                                  from the local one (same sum as loop_mode 1's exchange, one grid barrier per iteration). */
 #define ESIKF_TUNE_DEAL_POINTS 1u
 #define ESIKF_TUNE_DEFER_DIAGNOSTICS 2u
 #define ESIKF_TUNE_VIO_FAST_PATH 4u
+#define ESIKF_TUNE_PEER_REPLICATED 8u
 int esikf_set_tuning(esikf_ctx *ctx, uint32_t flags);
 int esikf_set_extrinsics(esikf_ctx *ctx, const esikf_extrinsics *ext);
 

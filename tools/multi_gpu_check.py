@@ -26,6 +26,8 @@ else:
     uid = [api.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     ctx.comm_init(rank, world, uid[0])
+tuning = int(os.environ.get("ESIKF_TUNING", "0"))  # e.g. 8 = TUNE_PEER_REPLICATED (replicated-solve kernels pulling the peer sum)
+ctx.set_tuning(tuning)
 ctx.set_extrinsics(fr["ext"]); ctx.map_upload(fr["map"], fr["lio_cfg"].voxel_size)
 g = ctx.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"])
 # every rank holds the same posterior (redundant solve on identical all-reduced information)
@@ -56,6 +58,6 @@ if rank == 0:
     ov = vio.update(frv["img"], frv["vis_pos"], w["warp_patch"], w["search_levels"], frv["inv_ref_expo"], frv["state_prior"], frv["state_prior"])
     assert gv["total_iters"] == ov["total_iters"]
     assert_state_close(gv["state"], ov["state"], rot_tol=1e-8, pos_tol=1e-8, cov_tol=1e-6, rest_tol=1e-8)
-    print(f"MULTI_GPU_OK mode={mode} world={world} lio_iters={g['iters']} M={g['M'].tolist()} vio_iters={gv['total_iters']}")
+    print(f"MULTI_GPU_OK mode={mode} tuning={tuning} world={world} lio_iters={g['iters']} M={g['M'].tolist()} vio_iters={gv['total_iters']}")
 ctx.close()
 dist.barrier(); dist.destroy_process_group()
