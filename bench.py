@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--cpu-baseline-frames", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"], help="N>1: in-kernel NVLink peer-memory all-reduce (default) or NCCL per iteration")
+    ap.add_argument("--tuning", type=int, default=0, help="esikf_set_tuning flags (opt-in kernel variants: 1 dealt points, 2 deferred diagnostics, "
+                                                          "4 VIO fast path, 8 replicated solve with peers); 0 = the default kernels")
     return ap.parse_args()
 
 
@@ -228,6 +230,8 @@ def b200_arm(args, rank, world, local_rank):
             uid = [api.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(uid, src=0)
             ctx.comm_init(rank, world, uid[0])
+    if args.tuning:
+        ctx.set_tuning(args.tuning)
     ctx.set_extrinsics(fr["ext"])
     ctx.map_upload(fr["map"], fr["lio_cfg"].voxel_size)
     ctx.vio_set_camera(fr["cam_cfg"], fr["vio_cfg"])
@@ -367,7 +371,7 @@ def b200_arm(args, rank, world, local_rank):
                        "lio_iters": int(rl["iters"]), "vio_iters": int(rv["total_iters"]), "l2": "flushed between steps (256 MiB write, untimed)",
                        "parallelism": (f"points/patches sharded over {world} ranks, 72-double information buffer all-reduced per iteration " +
                                        ("inside the persistent kernel over NVLink peer memory" if args.comm == "p2p" else "with ncclAllReduce")) if world > 1 else "single GPU",
-                       "map_planes": int(len(fr["map"]["planes"])), "matched_points": int(rl["M"][-1]),
+                       "map_planes": int(len(fr["map"]["planes"])), "matched_points": int(rl["M"][-1]), "tuning_flags": int(args.tuning),
                        "loop": ("residual + all-reduce + solve launches per iteration (loop_mode 0)" if (world > 1 and args.comm == "nccl") else
                                 "one persistent cooperative kernel per update" + (", gain solve replicated in every CTA (loop_mode 2)" if world == 1 else ", solve on CTA 0 (loop_mode 1)"))},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
