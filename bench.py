@@ -349,6 +349,35 @@ def b200_arm(args, rank, world, local_rank):
             base = (L - 1 - lvl) * fr["vio_cfg"].max_iterations
             patch_ms += list(tm["vio_patch_ms"][base: base + rv["iters_per_level"][lvl]])
     ctx.set_kernel_timing(False)
+    # in-kernel phase stamps (%globaltimer, CTA 0) of the persistent kernels, separate untimed pass: how long the residual /
+    # Jacobian build of one iteration takes until EVERY CTA has finished it (constants in place -> grid barrier passed)
+    phase = None
+    try:
+        ctx.set_phase_stamps(True)
+        for _ in range(3):
+            with torch.cuda.stream(ext_stream):
+                flush.zero_()
+            ctx.lio_run(prior_h, prior_h, fr["lio_cfg"])
+            ctx.vio_run(post_h, post_h)
+        ctx.synchronize()
+        st_ns = ctx.get_phase_stamps().astype(np.int64)
+        lio_rows = [k for k in range(8) if st_ns[k, 0] > 0 and st_ns[k, 3] > st_ns[k, 1]]
+        vio_rows = [k for k in range(8, 72) if st_ns[k, 0] > 0 and st_ns[k, 3] > st_ns[k, 1]]
+        if lio_rows:
+            build_us = float(np.mean([(st_ns[k, 3] - st_ns[k, 1]) / 1e3 for k in lio_rows]))
+            iter_us = float(np.mean([(st_ns[k, 6] - st_ns[k, 0]) / 1e3 for k in lio_rows]))
+            phase = {"lio_build_us_per_iteration": build_us, "lio_iteration_us": iter_us,
+                     "vio_build_us_per_iteration": float(np.mean([(st_ns[k, 3] - st_ns[k, 1]) / 1e3 for k in vio_rows])) if vio_rows else None,
+                     "vio_iteration_us": float(np.mean([(st_ns[k, 6] - st_ns[k, 0]) / 1e3 for k in vio_rows])) if vio_rows else None,
+                     "note": "CTA 0's %globaltimer stamps, measured in a separate pass with stamping on; build = constants in place until the grid "
+                             "barrier is passed, i.e. until the slowest CTA has finished its slice"}
+    except Exception as e:  # measurement extra: never lose the bench line over it
+        phase = {"error": repr(e)}
+    finally:
+        try:
+            ctx.set_phase_stamps(False)
+        except Exception:
+            pass
     k1_iso_ms = ctx.profile_kernel(0, reps=20, flush_l2=True)
     k1_iso_warm_ms = ctx.profile_kernel(0, reps=20, flush_l2=False)
     k1_ms = float(np.mean(res_ms)) if res_ms else k1_iso_ms
@@ -385,6 +414,9 @@ def b200_arm(args, rank, world, local_rank):
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_point": LIO_BYTES_PER_POINT, "points_per_launch": shard_pts,
                          "iterations_per_launch": int(rl["iters"]), "avg_launch_ms_in_timed_region": lio_ms, "vio_update_ms_in_timed_region": vio_ms,
+                         "residual_build_phase": (dict(phase, achieved=LIO_BYTES_PER_POINT * shard_pts / (phase["lio_build_us_per_iteration"] * 1e-6) / 1e9,
+                                                       frac=LIO_BYTES_PER_POINT * shard_pts / (phase["lio_build_us_per_iteration"] * 1e-6) / 1e9 / peak)
+                                                  if phase and "lio_build_us_per_iteration" in phase else phase),
                          "per_iteration_kernel": {"kernel": "lio_residual_kernel", "achieved": achieved_iter_kernel, "frac": achieved_iter_kernel / peak,
                                                   "algorithmic_bytes_per_launch": alg_bytes_iter},
                          "avg_launch_ms_in_loop": k1_ms,
