@@ -171,3 +171,20 @@ def test_flat_candidate_list_equals_recursive_walk():
     assert np.array_equal(ra["plane"], rb["plane"])
     assert np.array_equal(ra["dis"], rb["dis"])
     np.testing.assert_allclose(ra["R_inv"], rb["R_inv"], rtol=1e-12)
+
+
+def test_solution_vanishes_at_the_low_noise_optimum():
+    """Invariant: started AT the true pose with nearly noise-free measurements the first solution is ~0
+    (here 1e-4 rad / 3e-4 m against 9e-3 rad / 8e-2 m from the usual perturbed prior) and the filter stops early."""
+    cfg = S.LioCfg(dept_err=0.0005, beam_err=0.002)
+    at_truth = S.make_frame(seed=5, n_pts=3000, n_map=120_000, scene_scale=0.4, lio=cfg, prior_sigma=(0.0, 0.0))
+    perturbed = S.make_frame(seed=5, n_pts=3000, n_map=120_000, scene_scale=0.4, lio=cfg)
+    sol = []
+    for fr in (at_truth, perturbed):
+        lio = O.OracleLIO(fr["lio_cfg"], fr["ext"])
+        lio.set_map(fr["map"])
+        r = lio.state_estimation(fr["pts"], fr["state_prior"], fr["state_prior"])
+        sol.append((np.abs(r["solution"][0][:3]).max(), np.abs(r["solution"][0][3:6]).max(), r["iters"]))
+    assert sol[0][0] < 5e-4 and sol[0][1] < 1e-3
+    assert sol[0][0] < 0.05 * sol[1][0] and sol[0][1] < 0.05 * sol[1][1]
+    assert sol[0][2] <= sol[1][2]
