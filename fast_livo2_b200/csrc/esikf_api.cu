@@ -260,8 +260,8 @@ int esikf_create(esikf_ctx **out, int device) {
   cudaFuncSetAttribute(lio_update_repl_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
   cudaFuncSetAttribute(lio_update_repl_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
   cudaFuncSetAttribute(lio_update_repl_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
-  cudaFuncSetAttribute(lio_update_repl_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
-  cudaFuncSetAttribute(vio_update_repl_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(VioSmem) + sizeof(FusedSolveSmem)));
+  cudaFuncSetAttribute(lio_update_repl_peer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
+  cudaFuncSetAttribute(vio_update_repl_peer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(VioSmem) + sizeof(FusedSolveSmem)));
   cudaFuncSetAttribute(vio_update_repl_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(VioSmem) + sizeof(FusedSolveSmem)));
   cudaFuncSetAttribute(vio_update_repl_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(VioSmem) + sizeof(FusedSolveSmem)));
   cudaFuncSetAttribute(vio_update_repl_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VIO_FAST_SMEM);
@@ -284,8 +284,8 @@ int esikf_create(esikf_ctx **out, int device) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, vio_update_repl_kernel<false, true>, VIO_THREADS, VIO_FAST_SMEM);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, vio_update_repl_kernel<true, true>, VIO_THREADS, VIO_FAST_SMEM);
     int occ_g = 0, occ_h = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, lio_update_repl_kernel<false, false, true>, LIO_THREADS, sizeof(LioSmem));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_h, vio_update_repl_kernel<false, false, true>, VIO_THREADS, sizeof(VioSmem) + sizeof(FusedSolveSmem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, lio_update_repl_peer_kernel, LIO_THREADS, sizeof(LioSmem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_h, vio_update_repl_peer_kernel, VIO_THREADS, sizeof(VioSmem) + sizeof(FusedSolveSmem));
     ctx->coop_tuned = occ_a > 0 && occ_b > 0 && occ_c > 0 && occ_d > 0 && occ_e > 0 && occ_f > 0 && occ_g > 0 && occ_h > 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_vr, vio_update_repl_kernel<false, false>, VIO_THREADS, sizeof(VioSmem) + sizeof(FusedSolveSmem));
     ctx->coop_repl = occ_lr > 0 && occ_vr > 0;
@@ -530,12 +530,13 @@ int esikf_lio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
     const bool peer_repl = ctx->p2p && ctx->nranks > 1 && ctx->coop_tuned && (ctx->tuning & ESIKF_TUNE_PEER_REPLICATED);
     if (ctx->loop_mode == 2 && ctx->coop_repl && (ctx->nranks == 1 || peer_repl)) {
       size_t parity_stride = (size_t)ctx->partial_blocks * INFO_N;
-      PeerArgs peer = peer_args(ctx);
-      void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride, (void *)&peer};
+      void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride};
       const uint32_t tune = ctx->coop_tuned ? ctx->tuning : 0u;
       const bool defer = (tune & ESIKF_TUNE_DEFER_DIAGNOSTICS) != 0;
       if (peer_repl) {
-        CK(cudaLaunchCooperativeKernel((const void *)lio_update_repl_kernel<false, false, true>, dim3(grid), dim3(LIO_THREADS), kargs, sizeof(LioSmem), st));
+        PeerArgs peer = peer_args(ctx);
+        void *pargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride, (void *)&peer};
+        CK(cudaLaunchCooperativeKernel((const void *)lio_update_repl_peer_kernel, dim3(grid), dim3(LIO_THREADS), pargs, sizeof(LioSmem), st));
       } else if (tune & ESIKF_TUNE_DEAL_POINTS) {
         int chunks = (ka.count + 31) / 32;  // dealt schedule: every SM takes part as soon as there is a chunk for it
         int gd = chunks < ctx->partial_blocks ? chunks : ctx->partial_blocks;
@@ -748,14 +749,18 @@ int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
     const bool peer_repl = ctx->p2p && ctx->nranks > 1 && ctx->coop_tuned && (ctx->tuning & ESIKF_TUNE_PEER_REPLICATED);
     if (ctx->loop_mode == 2 && ctx->coop_repl && (ctx->nranks == 1 || peer_repl)) {
       size_t parity_stride = (size_t)ctx->partial_blocks * INFO_N;
-      PeerArgs peer = peer_args(ctx);
-      void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride, (void *)&peer};
+      void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride};
       const bool defer = ctx->coop_tuned && (ctx->tuning & ESIKF_TUNE_DEFER_DIAGNOSTICS);
       const bool fast = ctx->coop_tuned && (ctx->tuning & ESIKF_TUNE_VIO_FAST_PATH);
-      const void *fn = peer_repl ? (const void *)vio_update_repl_kernel<false, false, true>
-                       : fast    ? (defer ? (const void *)vio_update_repl_kernel<true, true> : (const void *)vio_update_repl_kernel<false, true>)
-                                 : (defer ? (const void *)vio_update_repl_kernel<true, false> : (const void *)vio_update_repl_kernel<false, false>);
-      CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(VIO_THREADS), kargs, (fast && !peer_repl) ? VIO_FAST_SMEM : sizeof(VioSmem) + sizeof(FusedSolveSmem), st));
+      if (peer_repl) {
+        PeerArgs peer = peer_args(ctx);
+        void *pargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride, (void *)&peer};
+        CK(cudaLaunchCooperativeKernel((const void *)vio_update_repl_peer_kernel, dim3(grid), dim3(VIO_THREADS), pargs, sizeof(VioSmem) + sizeof(FusedSolveSmem), st));
+      } else {
+        const void *fn = fast ? (defer ? (const void *)vio_update_repl_kernel<true, true> : (const void *)vio_update_repl_kernel<false, true>)
+                              : (defer ? (const void *)vio_update_repl_kernel<true, false> : (const void *)vio_update_repl_kernel<false, false>);
+        CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(VIO_THREADS), kargs, fast ? VIO_FAST_SMEM : sizeof(VioSmem) + sizeof(FusedSolveSmem), st));
+      }
     } else {
       PeerArgs peer = peer_args(ctx);
       void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&peer};

@@ -413,9 +413,9 @@ __device__ __forceinline__ void lio_consts_from_resident(LioSmem &sm, const Fuse
 // (warp 1, while thread 0 polls) instead of right after the solve, where it delays CTA 0's next slice — and with it the
 // whole grid — by the ~1 us the "publish" phase takes in profiles/loop_modes_r01_mode2.txt.
 // PEER: every CTA pulls the peer-reduced information buffer from the local NVLink mailbox (CTA 0 pushed it), see peer_push.
-template <bool DEAL, bool DEFER, bool PEER = false>
-__global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_repl_kernel(const LioKernelArgs a, const SolveArgs sa_in, unsigned int *barrier, unsigned int *barrier_next,
-                                                                          unsigned long long *stamps, size_t partial_parity_stride, const PeerArgs peer) {
+template <bool DEAL, bool DEFER, bool PEER>
+__device__ __forceinline__ void lio_update_repl_body(const LioKernelArgs &a, const SolveArgs &sa_in, unsigned int *barrier, unsigned int *barrier_next,
+                                                     unsigned long long *stamps, size_t partial_parity_stride, const PeerArgs &peer) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   LioSmem &sm = *reinterpret_cast<LioSmem *>(smem_raw);
   FusedSolveSmem &fs = *reinterpret_cast<FusedSolveSmem *>(sm.fs_raw);
@@ -503,6 +503,19 @@ __global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_repl_kernel(const L
   }
 }
 
+template <bool DEAL, bool DEFER>
+__global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_repl_kernel(const LioKernelArgs a, const SolveArgs sa_in, unsigned int *barrier, unsigned int *barrier_next,
+                                                                          unsigned long long *stamps, size_t partial_parity_stride) {
+  PeerArgs none;
+  none.mbox = nullptr, none.rank = 0, none.nranks = 1, none.seq_base = 0;
+  lio_update_repl_body<DEAL, DEFER, false>(a, sa_in, barrier, barrier_next, stamps, partial_parity_stride, none);
+}
+// the same loop with peer GPUs attached (ESIKF_TUNE_PEER_REPLICATED)
+__global__ void __launch_bounds__(LIO_THREADS, 1) lio_update_repl_peer_kernel(const LioKernelArgs a, const SolveArgs sa_in, unsigned int *barrier, unsigned int *barrier_next,
+                                                                               unsigned long long *stamps, size_t partial_parity_stride, const PeerArgs peer) {
+  lio_update_repl_body<false, false, true>(a, sa_in, barrier, barrier_next, stamps, partial_parity_stride, peer);
+}
+
 __device__ __forceinline__ void vio_consts_from_resident(VioSmem &sm, const VioKernelArgs &a, const FusedSolveSmem &fs) {
   const int tid = threadIdx.x;
   if (tid < 9) {
@@ -525,9 +538,9 @@ __device__ __forceinline__ void vio_consts_from_resident(VioSmem &sm, const VioK
 
 // FAST: per-patch inputs cached across iterations + exact-reciprocal tap-stride arithmetic (vio_process_range<true>) and
 // the boxminus overlapped with the gain elimination (vio_solve_block<true>); bit-identical results.
-template <bool DEFER, bool FAST, bool PEER = false>
-__global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_repl_kernel(const VioKernelArgs a, SolveArgs sa, unsigned int *barrier, unsigned int *barrier_next,
-                                                                          unsigned long long *stamps, size_t partial_parity_stride, const PeerArgs peer) {
+template <bool DEFER, bool FAST, bool PEER>
+__device__ __forceinline__ void vio_update_repl_body(const VioKernelArgs &a, SolveArgs sa, unsigned int *barrier, unsigned int *barrier_next,
+                                                     unsigned long long *stamps, size_t partial_parity_stride, const PeerArgs &peer) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   VioSmem &sm = *reinterpret_cast<VioSmem *>(smem_raw);
   FusedSolveSmem &fs = *reinterpret_cast<FusedSolveSmem *>(smem_raw + sizeof(VioSmem));
@@ -618,6 +631,18 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_repl_kernel(const V
     vio_solve_block(sa, fs.sm, fs.io, fs.ctrl, false, true);
     if (threadIdx.x == 0) *a.ctrl = fs.ctrl;
   }
+}
+
+template <bool DEFER, bool FAST>
+__global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_repl_kernel(const VioKernelArgs a, SolveArgs sa, unsigned int *barrier, unsigned int *barrier_next,
+                                                                          unsigned long long *stamps, size_t partial_parity_stride) {
+  PeerArgs none;
+  none.mbox = nullptr, none.rank = 0, none.nranks = 1, none.seq_base = 0;
+  vio_update_repl_body<DEFER, FAST, false>(a, sa, barrier, barrier_next, stamps, partial_parity_stride, none);
+}
+__global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_repl_peer_kernel(const VioKernelArgs a, SolveArgs sa, unsigned int *barrier, unsigned int *barrier_next,
+                                                                               unsigned long long *stamps, size_t partial_parity_stride, const PeerArgs peer) {
+  vio_update_repl_body<false, false, true>(a, sa, barrier, barrier_next, stamps, partial_parity_stride, peer);
 }
 
 }  // namespace esikf
