@@ -148,3 +148,37 @@ def test_shim_incremental_map_sync_equals_fresh_upload(small_frame):
                                   C.byref(n2))
     assert rc == 0 and n2.value == 0  # nothing changed between the two syncs
     assert np.array_equal(out_inc, out_fresh)
+
+
+def test_lio_association_on_voxel_boundaries_and_negative_keys(gpu_ctx, small_frame):
+    """Bit-exact voxel indexing where it is fragile (same scan as the CPU cross-check in test_oracle_numpy_crosscheck.py): world
+    points exactly on voxel boundaries with both signs (trunc(q - 1) vs floor), half a float ulp to either side, z == 0."""
+    from fast_livo2_b200 import synthetic as S
+    from parity_util import assert_state_close
+
+    fr = dict(small_frame)
+    fr["ext"] = S.Extrinsics(np.eye(3), np.zeros(3), small_frame["ext"].Rcl, small_frame["ext"].Pcl)
+    st = S.unpack_state(small_frame["state_prior"])
+    state = S.pack_state(np.eye(3), np.zeros(3), 1.0, st["v"], g=st["g"], cov=st["cov"])
+    vs = fr["lio_cfg"].voxel_size
+    keys = fr["map"]["keys"]
+    rng = np.random.default_rng(4)
+    pick = keys[rng.choice(len(keys), 60, replace=False)].astype(np.float64)
+    on_corner = (pick * vs).astype(np.float32)
+    on_face = on_corner.copy()
+    on_face[:, 1] += np.float32(0.37 * vs)
+    inside = ((pick + rng.uniform(0.05, 0.95, pick.shape)) * vs).astype(np.float32)
+    zero_z = inside.copy()
+    zero_z[:, 2] = 0.0
+    pts = np.ascontiguousarray(np.concatenate([on_corner, on_face, np.nextafter(on_corner, np.float32(-np.inf)), np.nextafter(on_corner, np.float32(np.inf)),
+                                               inside, zero_z]))
+    gpu_ctx.set_extrinsics(fr["ext"])
+    gpu_ctx.map_upload(fr["map"], vs)
+    g = gpu_ctx.lio_update(pts, state, state, fr["lio_cfg"])
+    lio = O.OracleLIO(fr["lio_cfg"], fr["ext"])
+    lio.set_map(fr["map"])
+    o = lio.state_estimation(pts, state, state)
+    assert g["iters"] == o["iters"] and np.array_equal(g["M"], o["M"]) and o["M"][0] > 20
+    assert np.array_equal(g["match_plane"], o["match_plane"]) and np.array_equal(g["normal_plane"], o["normal_plane"])
+    assert np.array_equal(g["dis_to_plane"], o["dis_to_plane"])
+    assert_state_close(g["state"], o["state"])

@@ -55,18 +55,17 @@ def _eval(pl, pw, var, sigma_num):
     return 1.0 / np.sqrt(sig) * np.exp(-0.5 * float(dtp) * float(dtp) / sig), f32(sd)
 
 
-def test_numpy_restatement_agrees_with_cpp_oracle(small_frame):
-    fr = small_frame
+def _check_one_lio_iteration(fr, pts, state):
+    """One LIO pass of the C++ oracle against the numpy restatement, point by point; returns (matched, via neighbour, multi-plane)."""
     cfg, ext, vm = fr["lio_cfg"], fr["ext"], fr["map"]
-    st = S.unpack_state(fr["state_prior"])
+    st = S.unpack_state(state)
     R, t, P = st["R"], st["p"], st["cov"]
     roots = {tuple(k): (f, c) for k, f, c in zip(vm["keys"].tolist(), vm["first"], vm["count"])}
     vsf = float(f32(cfg.voxel_size))
     ql = float(f32(f32(cfg.voxel_size) / f32(4)))
-    pts = fr["pts"][:700]
     lio = O.OracleLIO(cfg, ext)
     lio.set_map(vm)
-    sp = lio.single_pass(pts, fr["state_prior"], fr["state_prior"])
+    sp = lio.single_pass(pts, state, state)
     HTH, HTz, n_match, n_neigh, n_multi = np.zeros((6, 6)), np.zeros(6), 0, 0, 0
     for i, pb in enumerate(pts.astype(np.float64)):
         pz = pb.copy()
@@ -123,12 +122,46 @@ def test_numpy_restatement_agrees_with_cpp_oracle(small_frame):
         np.testing.assert_allclose(sp["R_inv"][i], rinv, rtol=1e-11)
         HTH += rinv * np.outer(H, H)
         HTz += rinv * H * (-float(best[2]))
-    assert n_match > 500 and n_multi > 0
     # the full oracle's first-iteration information matrix over the same points
-    r = lio.state_estimation(pts, fr["state_prior"], fr["state_prior"])
+    r = lio.state_estimation(pts, state, state)
     assert r["M"][0] == n_match
-    np.testing.assert_allclose(r["HTH"][0], HTH, rtol=1e-11)
-    np.testing.assert_allclose(r["HTz"][0], HTz, rtol=1e-9, atol=1e-9)
+    if n_match:
+        np.testing.assert_allclose(r["HTH"][0], HTH, rtol=1e-11)
+        np.testing.assert_allclose(r["HTz"][0], HTz, rtol=1e-9, atol=1e-9)
+    return n_match, n_neigh, n_multi
+
+
+def test_numpy_restatement_agrees_with_cpp_oracle(small_frame):
+    fr = small_frame
+    n_match, _, n_multi = _check_one_lio_iteration(fr, fr["pts"][:700], fr["state_prior"])
+    assert n_match > 500 and n_multi > 0
+
+
+def test_numpy_restatement_agrees_on_voxel_boundaries_and_negative_keys(small_frame):
+    """The float voxel key (voxel_map.cpp:665-671: double quotient narrowed to float, "-1 if negative", truncation) and the
+    unit-mixing neighbour rule (:680-691) where they are fragile: world points EXACTLY on voxel boundaries (identity pose and
+    extrinsics, coordinates that are exact multiples of the voxel size, both signs — trunc(q - 1) differs from floor there),
+    z == 0 (the 0.001 substitution of :352) and points half a float ulp away from a boundary."""
+    fr = dict(small_frame)
+    fr["ext"] = S.Extrinsics(np.eye(3), np.zeros(3), small_frame["ext"].Rcl, small_frame["ext"].Pcl)
+    st = S.unpack_state(small_frame["state_prior"])
+    state = S.pack_state(np.eye(3), np.zeros(3), 1.0, st["v"], g=st["g"], cov=st["cov"])
+    vs = fr["lio_cfg"].voxel_size
+    keys = fr["map"]["keys"]
+    rng = np.random.default_rng(4)
+    pick = keys[rng.choice(len(keys), 60, replace=False)].astype(np.float64)
+    on_corner = (pick * vs).astype(np.float32)                      # the low corner of existing voxels: exact multiples
+    on_face = on_corner.copy()
+    on_face[:, 1] += np.float32(0.37 * vs)                          # exact in x and z only
+    just_below = np.nextafter(on_corner, np.float32(-np.inf))
+    just_above = np.nextafter(on_corner, np.float32(np.inf))
+    inside = ((pick + rng.uniform(0.05, 0.95, pick.shape)) * vs).astype(np.float32)
+    zero_z = inside.copy()
+    zero_z[:, 2] = 0.0
+    pts = np.ascontiguousarray(np.concatenate([on_corner, on_face, just_below, just_above, inside, zero_z]))
+    assert (pts < 0).any() and (pts > 0).any()
+    n_match, n_neigh, _ = _check_one_lio_iteration(fr, pts, state)
+    assert n_match > 20
 
 
 def test_numpy_restatement_of_one_vio_iteration(small_vio_frame):
