@@ -5,7 +5,7 @@
 #    inverse-compositional VIO variant against the oracle);
 # 2. resident LIO + VIO step time of the default and of every flag combination on BASELINE config 2, with phase stamps.
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_loop_modes.py tests/test_gpu_vio_inverse.py tests/test_gpu_z_new_entry_points.py -q -m gpu > gpurun_out/tuning_tests.log 2>&1
+ESIKF_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_loop_modes.py tests/test_gpu_vio_inverse.py tests/test_gpu_z_new_entry_points.py -q -m gpu > gpurun_out/tuning_tests.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/tuning_tests.log
 TUNING=1,2,4,6,7 STAMPS=1 MODES=2 STEPS=30 timeout 240 python tools/loop_mode_check.py > gpurun_out/tuning_timing.log 2>&1
 echo "check rc=$?" >> gpurun_out/tuning_timing.log
