@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libesikf_b200.so")
+LIB_PATH = os.environ.get("ESIKF_LIB") or os.path.join(_HERE, "libesikf_b200.so")  # ESIKF_LIB: A/B builds of the same sources (measurement)
 STATE_DOUBLES = 386
 
 
@@ -110,11 +110,11 @@ def load_library():
     return lib
 
 
-TUNE_DEAL_POINTS, TUNE_DEFER_DIAGNOSTICS, TUNE_VIO_FAST_PATH, TUNE_PEER_REPLICATED = 1, 2, 4, 8  # esikf_set_tuning flags
-DEFAULT_LOOP_MODE = 2  # esikf_set_loop_mode: 2 replicated-solve persistent kernel, 1 CTA-0 solve, 0 per-iteration launches
+TUNE_STAGE_LDG = 1  # esikf_set_tuning flag: stage LIO plane records with __ldg copies instead of cp.async.bulk (measurement variant)
+DEFAULT_LOOP_MODE = 2  # esikf_set_loop_mode: 2 (alias 1) persistent kernel per update, 0 per-iteration launches
 
 EXPORTED_SYMBOLS = [
-    "esikf_create", "esikf_destroy", "esikf_last_error", "esikf_stream", "esikf_synchronize", "esikf_launch_count", "esikf_set_solve_mode", "esikf_set_loop_mode", "esikf_set_tuning",
+    "esikf_create", "esikf_destroy", "esikf_last_error", "esikf_stream", "esikf_synchronize", "esikf_host_alloc", "esikf_host_free", "esikf_launch_count", "esikf_set_solve_mode", "esikf_set_loop_mode", "esikf_set_tuning",
     "esikf_set_extrinsics", "esikf_map_upload", "esikf_map_patch", "esikf_lio_set_scan", "esikf_lio_run", "esikf_lio_fetch",
     "esikf_lio_update", "esikf_lio_fetch_point_cov", "esikf_vio_set_camera", "esikf_vio_set_image", "esikf_vio_set_patches",
     "esikf_vio_run", "esikf_vio_fetch", "esikf_vio_update", "esikf_vio_get_image_patch", "esikf_vio_set_ref_images",
@@ -185,7 +185,7 @@ class Context:
         self._ck(self.lib.esikf_set_loop_mode(self.h, mode))
 
     def set_tuning(self, flags):
-        """OR of TUNE_DEAL_POINTS / TUNE_DEFER_DIAGNOSTICS / TUNE_VIO_FAST_PATH (opt-in variants of the default kernels); 0 = none."""
+        """OR of the TUNE_* measurement variants; 0 = none."""
         self._ck(self.lib.esikf_set_tuning(self.h, flags))
 
     def set_extrinsics(self, ext):

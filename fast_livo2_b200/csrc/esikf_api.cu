@@ -75,7 +75,7 @@ template <typename T> struct DevBuf {
   }
 };
 
-#define VIO_FAST_SMEM (sizeof(VioSmem) + sizeof(FusedSolveSmem) + VIO_WARPS * sizeof(VioPatchSlot))
+#define VIO_PERSIST_SMEM (sizeof(VioSmem) + sizeof(FusedSolveSmem))
 
 struct esikf_ctx {
   int device = 0;
@@ -84,24 +84,25 @@ struct esikf_ctx {
   std::string err;
   int64_t launches = 0;
   int solve_mode = 0;
-  int loop_mode = 2;      // 2: persistent cooperative kernel per update, solve replicated in every CTA (one grid barrier per
-                          //    iteration; with peers attached it runs as mode 1), 1: persistent kernel with the solve on CTA 0
-                          //    (two barriers; carries the NVLink peer all-reduce), 0: one residual + one solve launch per iteration
+  int loop_mode = 2;      // >= 1: one persistent cooperative kernel per update (gain solve replicated in every CTA, one grid
+                          //    barrier per iteration; carries the NVLink peer exchange when peers are attached),
+                          // 0: one residual + one solve launch per iteration (NCCL communicator, kernel timing)
   int coop_ok = 0;
   int coop_lio = 0, coop_vio = 0;  // co-resident CTAs per SM of the persistent kernels
-  bool coop_repl = false;          // the replicated-solve variants fit as well
-  bool coop_tuned = false;         // ... and so do their opt-in variants
-  uint32_t tuning = 0;             // ESIKF_TUNE_* flags (opt-in variants of the loop_mode 2 kernels)
+  uint32_t tuning = 0;             // ESIKF_TUNE_* flags (measurement variants)
   DevBuf<unsigned int> barrier;       // two grid barriers {counter @ +0, release word @ +128 B}, 256 B apart; launches alternate
   DevBuf<unsigned long long> stamps;  // 8 per slot: 8 LIO slots then 64 VIO slots
   bool want_stamps = false;
   esikf_extrinsics ext{};
-  bool have_ext = false;
+  bool have_ext = false, have_ext_dev = false;
+  double ext_host[12] = {};
 
   // map
   DevBuf<HashSlot> slots;
   uint32_t hash_mask = 0;
-  DevBuf<esikf_plane> planes;
+  DevBuf<esikf_plane> planes;   // the map as uploaded (256-byte records)
+  DevBuf<PlaneRec> recs;        // what the residual kernel reads (144-byte records derived on the device)
+  DevBuf<int32_t> patch_ids;
   int n_planes = 0, n_roots = 0;
   double voxel_size = 0.5;
   bool have_map = false;
@@ -124,6 +125,7 @@ struct esikf_ctx {
   // pinned staging ring for the two packed states of an update (slot reuse guarded by an event)
   enum { STAGE_SLOTS = 16 };
   double *stage = nullptr;
+  unsigned char *stage_ctrl = nullptr;   // pinned copy of the loop-control block read by the fetch calls
   cudaEvent_t stage_ev[STAGE_SLOTS] = {};
   unsigned stage_idx = 0;
   unsigned launch_parity = 0;            // the persistent kernels alternate between two grid-barrier counters
@@ -161,11 +163,11 @@ struct esikf_ctx {
   int rank = 0, nranks = 1;
   ncclComm_t comm = nullptr;
   // NVLink peer-memory all-reduce inside the persistent kernels
-  unsigned long long *mailbox = nullptr;             // own mailbox [2][PEER_MAX_RANKS][PEER_SLOT_WORDS]
+  unsigned long long *mailbox = nullptr;             // own mailbox [2][PEER_MAX_RANKS][PEER_SLOT_WORDS], followed by the exchange counter
   std::vector<unsigned long long *> peer_ptrs;       // mailbox of every rank as mapped into this process
   DevBuf<unsigned long long *> peer_ptrs_dev;
   bool p2p = false;
-  unsigned int peer_seq = 0;
+  unsigned int *peer_seq_dev = nullptr;              // device word: peer exchanges executed so far
 
   // measurement
   bool timing = false;
@@ -226,13 +228,14 @@ int esikf_create(esikf_ctx **out, int device) {
     delete ctx;
     return ESIKF_ERR_CUDA;
   }
-  bool ok = ctx->state_prop.reserve(2 * S_N) == cudaSuccess && ctx->info.reserve(INFO_N) == cudaSuccess &&
+  bool ok = ctx->state_prop.reserve(2 * S_N) == cudaSuccess && ctx->info.reserve(NE_MAX) == cudaSuccess &&
             cudaMallocHost(&ctx->stage, (size_t)esikf_ctx::STAGE_SLOTS * 2 * S_N * sizeof(double)) == cudaSuccess &&
+            cudaMallocHost(&ctx->stage_ctrl, 256) == cudaSuccess &&
             ctx->old_state.reserve(32) == cudaSuccess && ctx->G.reserve(19 * 7) == cudaSuccess &&
             ctx->ctl_block.reserve(sizeof(esikf_lio_stats) + sizeof(Ctrl) + 64 + sizeof(esikf_vio_stats)) == cudaSuccess && ctx->ext_dev.reserve(12) == cudaSuccess &&
             ctx->scratch_state.reserve(S_N) == cudaSuccess;
   ctx->partial_blocks = ctx->sm_count < 160 ? ctx->sm_count : 160;  // persistent residual kernels: one CTA per SM
-  ok = ok && ctx->partials.reserve((size_t)2 * ctx->partial_blocks * INFO_N) == cudaSuccess && ctx->stamps.reserve(8 * 72 + 64 + 160) == cudaSuccess &&
+  ok = ok && ctx->partials.reserve((size_t)2 * ctx->partial_blocks * NE_MAX) == cudaSuccess && ctx->stamps.reserve(8 * 72 + 64 + 160) == cudaSuccess &&
        ctx->barrier.reserve(128) == cudaSuccess;
   if (ok) cudaMemsetAsync(ctx->barrier.p, 0, 128 * sizeof(unsigned int), ctx->stream);
   if (ok) {
@@ -254,53 +257,28 @@ int esikf_create(esikf_ctx **out, int device) {
   cudaFuncSetAttribute(lio_residual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
   cudaFuncSetAttribute(vio_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VioSmem));
   cudaFuncSetAttribute(vio_inverse_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VioSmem));
-  cudaError_t ea = cudaFuncSetAttribute(lio_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
-  cudaError_t eb = cudaFuncSetAttribute(vio_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(VioSmem) + sizeof(FusedSolveSmem)));
-  cudaFuncSetAttribute(lio_update_repl_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
-  cudaFuncSetAttribute(lio_update_repl_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
-  cudaFuncSetAttribute(lio_update_repl_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
-  cudaFuncSetAttribute(lio_update_repl_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
-  cudaFuncSetAttribute(lio_update_repl_peer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
-  cudaFuncSetAttribute(vio_update_repl_peer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(VioSmem) + sizeof(FusedSolveSmem)));
-  cudaFuncSetAttribute(vio_update_repl_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(VioSmem) + sizeof(FusedSolveSmem)));
-  cudaFuncSetAttribute(vio_update_repl_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(VioSmem) + sizeof(FusedSolveSmem)));
-  cudaFuncSetAttribute(vio_update_repl_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VIO_FAST_SMEM);
-  cudaFuncSetAttribute(vio_update_repl_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VIO_FAST_SMEM);
+  cudaError_t ea = cudaFuncSetAttribute(lio_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
+  cudaFuncSetAttribute(lio_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
+  cudaError_t eb = cudaFuncSetAttribute(vio_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VIO_PERSIST_SMEM);
+  cudaFuncSetAttribute(vio_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VIO_PERSIST_SMEM);
   // the persistent kernels need every CTA co-resident: check what the device can hold
-  int occ_l = 0, occ_v = 0, occ_r = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, lio_update_kernel, LIO_THREADS, sizeof(LioSmem));
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_v, vio_update_kernel, VIO_THREADS, sizeof(VioSmem) + sizeof(FusedSolveSmem));
+  int occ_l = 0, occ_v = 0, occ_lp = 0, occ_vp = 0, occ_r = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, lio_update_kernel<false>, LIO_THREADS, sizeof(LioSmem));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lp, lio_update_kernel<true>, LIO_THREADS, sizeof(LioSmem));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_v, vio_update_kernel<false>, VIO_THREADS, VIO_PERSIST_SMEM);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_vp, vio_update_kernel<true>, VIO_THREADS, VIO_PERSIST_SMEM);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, lio_residual_kernel, LIO_THREADS, sizeof(LioSmem));
-  ctx->coop_lio = occ_l, ctx->coop_vio = occ_v;
-  {
-    int occ_lr = 0, occ_vr = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lr, lio_update_repl_kernel<false, false>, LIO_THREADS, sizeof(LioSmem));
-    int occ_a = 0, occ_b = 0, occ_c = 0, occ_d = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, lio_update_repl_kernel<true, false>, LIO_THREADS, sizeof(LioSmem));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, lio_update_repl_kernel<false, true>, LIO_THREADS, sizeof(LioSmem));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, lio_update_repl_kernel<true, true>, LIO_THREADS, sizeof(LioSmem));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_d, vio_update_repl_kernel<true, false>, VIO_THREADS, sizeof(VioSmem) + sizeof(FusedSolveSmem));
-    int occ_e = 0, occ_f = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, vio_update_repl_kernel<false, true>, VIO_THREADS, VIO_FAST_SMEM);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, vio_update_repl_kernel<true, true>, VIO_THREADS, VIO_FAST_SMEM);
-    int occ_g = 0, occ_h = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, lio_update_repl_peer_kernel, LIO_THREADS, sizeof(LioSmem));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_h, vio_update_repl_peer_kernel, VIO_THREADS, sizeof(VioSmem) + sizeof(FusedSolveSmem));
-    ctx->coop_tuned = occ_a > 0 && occ_b > 0 && occ_c > 0 && occ_d > 0 && occ_e > 0 && occ_f > 0 && occ_g > 0 && occ_h > 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_vr, vio_update_repl_kernel<false, false>, VIO_THREADS, sizeof(VioSmem) + sizeof(FusedSolveSmem));
-    ctx->coop_repl = occ_lr > 0 && occ_vr > 0;
-  }
-  if (getenv("ESIKF_DEBUG"))
-    fprintf(stderr, "[esikf] SMs=%d smem LIO=%zu VIO=%zu attr=%d/%d occupancy: lio_update=%d vio_update=%d lio_residual=%d coop=%d\n", ctx->sm_count, sizeof(LioSmem),
-            sizeof(VioSmem), (int)ea, (int)eb, occ_l, occ_v, occ_r, ctx->coop_ok);
+  ctx->coop_lio = occ_l < occ_lp ? occ_l : occ_lp, ctx->coop_vio = occ_v < occ_vp ? occ_v : occ_vp;
   if (getenv("ESIKF_DEBUG")) {
+    fprintf(stderr, "[esikf] SMs=%d smem LIO=%zu VIO=%zu attr=%d/%d occupancy: lio_update=%d vio_update=%d lio_residual=%d coop=%d\n", ctx->sm_count, sizeof(LioSmem),
+            VIO_PERSIST_SMEM, (int)ea, (int)eb, occ_l, occ_v, occ_r, ctx->coop_ok);
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, lio_residual_kernel);
-    fprintf(stderr, "[esikf] lio_residual: regs=%d maxThreads=%d static=%zu maxDyn=%d local=%zu\n", fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.localSizeBytes);
-    cudaFuncGetAttributes(&fa, lio_update_kernel);
-    fprintf(stderr, "[esikf] lio_update: regs=%d maxThreads=%d static=%zu maxDyn=%d local=%zu\n", fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.localSizeBytes);
-    cudaFuncGetAttributes(&fa, vio_update_kernel);
-    fprintf(stderr, "[esikf] vio_update: regs=%d maxThreads=%d static=%zu maxDyn=%d local=%zu\n", fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.localSizeBytes);
+    fprintf(stderr, "[esikf] lio_residual: regs=%d local=%zu\n", fa.numRegs, fa.localSizeBytes);
+    cudaFuncGetAttributes(&fa, lio_update_kernel<false>);
+    fprintf(stderr, "[esikf] lio_update: regs=%d local=%zu\n", fa.numRegs, fa.localSizeBytes);
+    cudaFuncGetAttributes(&fa, vio_update_kernel<false>);
+    fprintf(stderr, "[esikf] vio_update: regs=%d local=%zu\n", fa.numRegs, fa.localSizeBytes);
   }
   cudaGetLastError();
   *out = ctx;
@@ -316,9 +294,10 @@ void esikf_destroy(esikf_ctx *ctx) {
     if ((int)r != ctx->rank && ctx->peer_ptrs[r]) cudaIpcCloseMemHandle(ctx->peer_ptrs[r]);
   if (ctx->mailbox) cudaFree(ctx->mailbox);
   ctx->peer_ptrs_dev.release();
-  ctx->slots.release(), ctx->planes.release(), ctx->pts.release(), ctx->pre.release(), ctx->match_plane.release();
+  ctx->slots.release(), ctx->planes.release(), ctx->recs.release(), ctx->patch_ids.release(), ctx->pts.release(), ctx->pre.release(), ctx->match_plane.release();
   ctx->normal_plane.release(), ctx->dis.release(), ctx->ext_dev.release(), ctx->state_prop.release();
   if (ctx->stage) cudaFreeHost(ctx->stage);
+  if (ctx->stage_ctrl) cudaFreeHost(ctx->stage_ctrl);
   for (int i = 0; i < esikf_ctx::STAGE_SLOTS; i++)
     if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
   ctx->info.release(), ctx->partials.release(), ctx->old_state.release(), ctx->G.release(), ctx->ctl_block.release();
@@ -338,6 +317,18 @@ const char *esikf_last_error(const esikf_ctx *ctx) { return ctx ? ctx->err.c_str
 void *esikf_stream(esikf_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 int64_t esikf_launch_count(const esikf_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+void *esikf_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (bytes == 0 || cudaMallocHost(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void esikf_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
 int esikf_synchronize(esikf_ctx *ctx) {
   if (!ctx) return ESIKF_ERR_ARG;
   CK(cudaStreamSynchronize(ctx->stream));
@@ -349,12 +340,12 @@ int esikf_set_solve_mode(esikf_ctx *ctx, int mode) {
   return ESIKF_OK;
 }
 int esikf_set_loop_mode(esikf_ctx *ctx, int mode) {
-  if (!ctx || mode < 0 || mode > 2) return ESIKF_ERR_ARG;
+  if (!ctx || mode < 0 || mode > 2) return ESIKF_ERR_ARG;  // 1 and 2 both select the persistent kernels
   ctx->loop_mode = mode;
   return ESIKF_OK;
 }
 int esikf_set_tuning(esikf_ctx *ctx, uint32_t flags) {
-  if (!ctx || (flags & ~(uint32_t)(ESIKF_TUNE_DEAL_POINTS | ESIKF_TUNE_DEFER_DIAGNOSTICS | ESIKF_TUNE_VIO_FAST_PATH | ESIKF_TUNE_PEER_REPLICATED))) return ESIKF_ERR_ARG;
+  if (!ctx || (flags & ~(uint32_t)(ESIKF_TUNE_STAGE_LDG))) return ESIKF_ERR_ARG;
   ctx->tuning = flags;
   return ESIKF_OK;
 }
@@ -366,8 +357,11 @@ int esikf_set_extrinsics(esikf_ctx *ctx, const esikf_extrinsics *ext) {
   double h[12];
   memcpy(h, ext->extR, 9 * sizeof(double));
   memcpy(h + 9, ext->extT, 3 * sizeof(double));
+  if (ctx->have_ext_dev && memcmp(h, ctx->ext_host, sizeof(h)) == 0) return ESIKF_OK;  // unchanged (the shim sets it every tick): nothing to do
   CK(cudaMemcpyAsync(ctx->ext_dev.p, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));  // `h` is a stack buffer
+  memcpy(ctx->ext_host, h, sizeof(h));
+  ctx->have_ext_dev = true;
   return ESIKF_OK;
 }
 
@@ -395,8 +389,13 @@ int esikf_map_upload(esikf_ctx *ctx, const int64_t *keys, const int32_t *first, 
   }
   CK(ctx->slots.reserve(cap));
   CK(ctx->planes.reserve((size_t)n_planes + 1));
+  CK(ctx->recs.reserve((size_t)n_planes + 1));
   CK(cudaMemcpyAsync(ctx->slots.p, table.data(), cap * sizeof(HashSlot), cudaMemcpyHostToDevice, ctx->stream));
-  if (n_planes) CK(cudaMemcpyAsync(ctx->planes.p, planes, (size_t)n_planes * sizeof(esikf_plane), cudaMemcpyHostToDevice, ctx->stream));
+  if (n_planes) {
+    CK(cudaMemcpyAsync(ctx->planes.p, planes, (size_t)n_planes * sizeof(esikf_plane), cudaMemcpyHostToDevice, ctx->stream));
+    plane_compact_kernel<<<(n_planes + 127) / 128, 128, 0, ctx->stream>>>(ctx->planes.p, nullptr, n_planes, ctx->recs.p);
+    ctx->launches++;
+  }
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->hash_mask = cap - 1;
   ctx->n_planes = n_planes, ctx->n_roots = n_roots;
@@ -416,6 +415,12 @@ int esikf_map_patch(esikf_ctx *ctx, const int32_t *plane_ids, const esikf_plane 
     while (j < n && plane_ids[j] == plane_ids[j - 1] + 1) j++;  // a run of consecutive ids travels as one copy
     CK(cudaMemcpyAsync(ctx->planes.p + plane_ids[i], planes + i, (size_t)(j - i) * sizeof(esikf_plane), cudaMemcpyHostToDevice, ctx->stream));
     i = j;
+  }
+  if (n > 0) {
+    CK(ctx->patch_ids.reserve(n));
+    CK(cudaMemcpyAsync(ctx->patch_ids.p, plane_ids, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    plane_compact_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->planes.p, ctx->patch_ids.p, n, ctx->recs.p);
+    ctx->launches++;
   }
   CK(cudaStreamSynchronize(ctx->stream));
   return ESIKF_OK;
@@ -444,7 +449,8 @@ static int lio_fill_args(esikf_ctx *ctx, LioKernelArgs &ka, double *state_ptr) {
   ka.partial_stride = ctx->partial_blocks;
   shard_of(ctx->n_pts, ctx->rank, ctx->nranks, ka.begin, ka.count);
   ka.state = state_ptr, ka.prop = ctx->prop.p;
-  ka.slots = ctx->slots.p, ka.hash_mask = ctx->hash_mask, ka.planes = ctx->planes.p;
+  ka.slots = ctx->slots.p, ka.hash_mask = ctx->hash_mask, ka.recs = ctx->recs.p;
+  ka.stage_mode = (ctx->tuning & ESIKF_TUNE_STAGE_LDG) ? 1 : 0;
   memcpy(ka.extR, ctx->ext.extR, sizeof(ka.extR));
   memcpy(ka.extT, ctx->ext.extT, sizeof(ka.extT));
   ka.voxel_size = ctx->lio_cfg.voxel_size;
@@ -460,8 +466,8 @@ static int lio_fill_args(esikf_ctx *ctx, LioKernelArgs &ka, double *state_ptr) {
   return 0;
 }
 static int lio_grid(const esikf_ctx *ctx, int count) {
-  int tiles = (count + LIO_THREADS - 1) / LIO_THREADS;
-  int g = tiles < ctx->partial_blocks ? tiles : ctx->partial_blocks;  // persistent: <= 2 CTAs per SM, equal slices
+  int chunks = (count + 31) / 32;  // whole warps are dealt to the CTAs: every SM takes part as soon as there is a warp for it
+  int g = chunks < ctx->partial_blocks ? chunks : ctx->partial_blocks;
   return g < 1 ? 1 : g;
 }
 // Stage the two packed states of an update in pinned memory and upload them with ONE copy ([state | prop] is contiguous).
@@ -478,15 +484,14 @@ static int upload_states(esikf_ctx *ctx, const double *state_in, const double *s
 static PeerArgs peer_args(esikf_ctx *ctx) {
   PeerArgs p;
   p.mbox = ctx->p2p ? ctx->peer_ptrs_dev.p : nullptr;
+  p.seq = ctx->peer_seq_dev;
   p.rank = ctx->rank, p.nranks = ctx->p2p ? ctx->nranks : 1;
-  p.seq_base = ctx->peer_seq;
-  if (ctx->p2p) ctx->peer_seq += 128;  // > levels * max_iterations: flags stay monotonic across launches (same on every rank)
   return p;
 }
 static int allreduce_info(esikf_ctx *ctx) {
   if (ctx->nranks <= 1) return ESIKF_OK;
   if (!ctx->comm) return fail(ctx, ESIKF_ERR_STATE, "per-iteration launches with %d ranks need esikf_comm_init (NCCL)", ctx->nranks);
-  int r = g_nccl.AllReduce(ctx->info.p, ctx->info.p, INFO_N, NCCL_FLOAT64, NCCL_SUM, ctx->comm, ctx->stream);
+  int r = g_nccl.AllReduce(ctx->info.p, ctx->info.p, NE_MAX, NCCL_FLOAT64, NCCL_SUM, ctx->comm, ctx->stream);
   if (r != 0) return fail(ctx, ESIKF_ERR_COMM, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   return ESIKF_OK;
 }
@@ -522,36 +527,17 @@ int esikf_lio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   sa.max_iterations = cfg->max_iterations, sa.solve_mode = ctx->solve_mode, sa.lio_stats = ctx->lio_stats.p;
   const int grid = lio_grid(ctx, ka.count);
   if (fused_lio) {
-    const unsigned par = ctx->launch_parity++ & 1;
+    const unsigned par = ctx->launch_parity & 1;
     unsigned int *bar = ctx->barrier.p + 64 * par, *bar_next = ctx->barrier.p + 64 * (par ^ 1);  // this launch's barrier / the next launch's (zeroed by the kernel)
     unsigned long long *stamps = ctx->want_stamps ? ctx->stamps.p : nullptr;
     if (stamps) CK(cudaMemsetAsync(stamps, 0, 64 * sizeof(unsigned long long), st));
-    ka.dbg = sa.dbg = ctx->want_stamps ? ctx->stamps.p + 576 : nullptr;
-    const bool peer_repl = ctx->p2p && ctx->nranks > 1 && ctx->coop_tuned && (ctx->tuning & ESIKF_TUNE_PEER_REPLICATED);
-    if (ctx->loop_mode == 2 && ctx->coop_repl && (ctx->nranks == 1 || peer_repl)) {
-      size_t parity_stride = (size_t)ctx->partial_blocks * INFO_N;
-      void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride};
-      const uint32_t tune = ctx->coop_tuned ? ctx->tuning : 0u;
-      const bool defer = (tune & ESIKF_TUNE_DEFER_DIAGNOSTICS) != 0;
-      if (peer_repl) {
-        PeerArgs peer = peer_args(ctx);
-        void *pargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride, (void *)&peer};
-        CK(cudaLaunchCooperativeKernel((const void *)lio_update_repl_peer_kernel, dim3(grid), dim3(LIO_THREADS), pargs, sizeof(LioSmem), st));
-      } else if (tune & ESIKF_TUNE_DEAL_POINTS) {
-        int chunks = (ka.count + 31) / 32;  // dealt schedule: every SM takes part as soon as there is a chunk for it
-        int gd = chunks < ctx->partial_blocks ? chunks : ctx->partial_blocks;
-        if (gd < 1) gd = 1;
-        const void *fn = defer ? (const void *)lio_update_repl_kernel<true, true> : (const void *)lio_update_repl_kernel<true, false>;
-        CK(cudaLaunchCooperativeKernel(fn, dim3(gd), dim3(LIO_THREADS), kargs, sizeof(LioSmem), st));
-      } else {
-        const void *fn = defer ? (const void *)lio_update_repl_kernel<false, true> : (const void *)lio_update_repl_kernel<false, false>;
-        CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(LIO_THREADS), kargs, sizeof(LioSmem), st));
-      }
-    } else {
-      PeerArgs peer = peer_args(ctx);
-      void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&peer};
-      CK(cudaLaunchCooperativeKernel((const void *)lio_update_kernel, dim3(grid), dim3(LIO_THREADS), kargs, sizeof(LioSmem), st));
-    }
+    size_t parity_stride = (size_t)ctx->partial_blocks * NE_MAX;
+    PeerArgs peer = peer_args(ctx);
+    void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride, (void *)&peer};
+    const void *fn = (ctx->p2p && ctx->nranks > 1) ? (const void *)lio_update_kernel<true> : (const void *)lio_update_kernel<false>;
+    cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(LIO_THREADS), kargs, sizeof(LioSmem), st);
+    if (le != cudaSuccess) return fail(ctx, ESIKF_ERR_CUDA, "cooperative launch of lio_update_kernel failed: %s", cudaGetErrorString(le));
+    ctx->launch_parity++;  // only a launch that happened consumes its barrier counter (the kernel zeroes the other one)
     ctx->launches += 1;
     ctx->lio_timed = false;
     return ESIKF_OK;
@@ -574,6 +560,19 @@ int esikf_lio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   return ESIKF_OK;
 }
 
+// Common tail of the fetch calls: bring the loop-control block along, synchronise, and turn an expired in-kernel wait
+// (Ctrl::comm_error, sticky on the device) into ESIKF_ERR_COMM once.
+static int finish_fetch(esikf_ctx *ctx) {
+  Ctrl *h = reinterpret_cast<Ctrl *>(ctx->stage_ctrl);
+  CK(cudaMemcpyAsync(h, ctx->ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (h->comm_error) {
+    cudaMemsetAsync(&ctx->ctrl.p->comm_error, 0, sizeof(int), ctx->stream);
+    return fail(ctx, ESIKF_ERR_COMM, "a bounded in-kernel wait expired (grid barrier or peer mailbox): a rank did not take part in the update");
+  }
+  return ESIKF_OK;
+}
+
 int esikf_lio_fetch(esikf_ctx *ctx, double *state_out, esikf_lio_stats *stats, int32_t *match_plane, int32_t *normal_plane, float *dis_to_plane) {
   if (!ctx) return ESIKF_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
@@ -584,8 +583,7 @@ int esikf_lio_fetch(esikf_ctx *ctx, double *state_out, esikf_lio_stats *stats, i
   if (match_plane && n) CK(cudaMemcpyAsync(match_plane, ctx->match_plane.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (normal_plane && n) CK(cudaMemcpyAsync(normal_plane, ctx->normal_plane.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (dis_to_plane && n) CK(cudaMemcpyAsync(dis_to_plane, ctx->dis.p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return ESIKF_OK;
+  return finish_fetch(ctx);
 }
 
 int esikf_lio_update(esikf_ctx *ctx, const float *pts_xyz, int32_t n, const double *state_in, const double *state_prop, const esikf_lio_cfg *cfg,
@@ -742,30 +740,17 @@ int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   sa.old_state = ctx->old_state.p, sa.G = ctx->G.p, sa.img_point_cov = ctx->vio_cfg.img_point_cov;
   const int grid = vio_grid(ctx, ka.count);
   if (fused_vio) {
-    const unsigned par = ctx->launch_parity++ & 1;
+    const unsigned par = ctx->launch_parity & 1;
     unsigned int *bar = ctx->barrier.p + 64 * par, *bar_next = ctx->barrier.p + 64 * (par ^ 1);
     unsigned long long *stamps = ctx->want_stamps ? ctx->stamps.p + 64 : nullptr;
     if (stamps) CK(cudaMemsetAsync(stamps, 0, 512 * sizeof(unsigned long long), st));
-    const bool peer_repl = ctx->p2p && ctx->nranks > 1 && ctx->coop_tuned && (ctx->tuning & ESIKF_TUNE_PEER_REPLICATED);
-    if (ctx->loop_mode == 2 && ctx->coop_repl && (ctx->nranks == 1 || peer_repl)) {
-      size_t parity_stride = (size_t)ctx->partial_blocks * INFO_N;
-      void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride};
-      const bool defer = ctx->coop_tuned && (ctx->tuning & ESIKF_TUNE_DEFER_DIAGNOSTICS);
-      const bool fast = ctx->coop_tuned && (ctx->tuning & ESIKF_TUNE_VIO_FAST_PATH);
-      if (peer_repl) {
-        PeerArgs peer = peer_args(ctx);
-        void *pargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride, (void *)&peer};
-        CK(cudaLaunchCooperativeKernel((const void *)vio_update_repl_peer_kernel, dim3(grid), dim3(VIO_THREADS), pargs, sizeof(VioSmem) + sizeof(FusedSolveSmem), st));
-      } else {
-        const void *fn = fast ? (defer ? (const void *)vio_update_repl_kernel<true, true> : (const void *)vio_update_repl_kernel<false, true>)
-                              : (defer ? (const void *)vio_update_repl_kernel<true, false> : (const void *)vio_update_repl_kernel<false, false>);
-        CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(VIO_THREADS), kargs, fast ? VIO_FAST_SMEM : sizeof(VioSmem) + sizeof(FusedSolveSmem), st));
-      }
-    } else {
-      PeerArgs peer = peer_args(ctx);
-      void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&peer};
-      CK(cudaLaunchCooperativeKernel((const void *)vio_update_kernel, dim3(grid), dim3(VIO_THREADS), kargs, sizeof(VioSmem) + sizeof(FusedSolveSmem), st));
-    }
+    size_t parity_stride = (size_t)ctx->partial_blocks * NE_MAX;
+    PeerArgs peer = peer_args(ctx);
+    void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride, (void *)&peer};
+    const void *fn = (ctx->p2p && ctx->nranks > 1) ? (const void *)vio_update_kernel<true> : (const void *)vio_update_kernel<false>;
+    cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(VIO_THREADS), kargs, VIO_PERSIST_SMEM, st);
+    if (le != cudaSuccess) return fail(ctx, ESIKF_ERR_CUDA, "cooperative launch of vio_update_kernel failed: %s", cudaGetErrorString(le));
+    ctx->launch_parity++;
     ctx->launches += 1;
     ctx->vio_timed = false;
     return ESIKF_OK;
@@ -814,8 +799,7 @@ int esikf_vio_fetch(esikf_ctx *ctx, double *state_out, esikf_vio_stats *stats, f
   if (state_out) CK(cudaMemcpyAsync(state_out, ctx->state.p, S_N * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (stats) CK(cudaMemcpyAsync(stats, ctx->vio_stats.p, sizeof(esikf_vio_stats), cudaMemcpyDeviceToHost, st));
   if (errors && ctx->n_patches) CK(cudaMemcpyAsync(errors, ctx->errors.p, (size_t)ctx->n_patches * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return ESIKF_OK;
+  return finish_fetch(ctx);
 }
 
 int esikf_vio_update(esikf_ctx *ctx, const uint8_t *img, int32_t width, int32_t height, const double *pos, const float *warp_patch,
@@ -1007,8 +991,10 @@ int esikf_peer_export(esikf_ctx *ctx, char out[64]) {
   if (!ctx || !out) return ESIKF_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   if (!ctx->mailbox) {
-    CK(cudaMalloc(&ctx->mailbox, 2 * PEER_MAX_RANKS * PEER_SLOT_WORDS * sizeof(unsigned long long)));
-    CK(cudaMemset(ctx->mailbox, 0, 2 * PEER_MAX_RANKS * PEER_SLOT_WORDS * sizeof(unsigned long long)));  // tag 0 is never sent
+    const size_t words = (size_t)2 * PEER_MAX_RANKS * PEER_SLOT_WORDS + 2;  // + the exchange counter
+    CK(cudaMalloc(&ctx->mailbox, words * sizeof(unsigned long long)));
+    CK(cudaMemset(ctx->mailbox, 0, words * sizeof(unsigned long long)));  // tag 0 is never sent
+    ctx->peer_seq_dev = reinterpret_cast<unsigned int *>(ctx->mailbox + (size_t)2 * PEER_MAX_RANKS * PEER_SLOT_WORDS);
   }
   cudaIpcMemHandle_t h;
   CK(cudaIpcGetMemHandle(&h, ctx->mailbox));
@@ -1035,7 +1021,8 @@ int esikf_peer_attach(esikf_ctx *ctx, int32_t rank, int32_t nranks, const char *
   }
   CK(ctx->peer_ptrs_dev.reserve(nranks));
   CK(cudaMemcpy(ctx->peer_ptrs_dev.p, ctx->peer_ptrs.data(), nranks * sizeof(unsigned long long *), cudaMemcpyHostToDevice));
-  ctx->rank = rank, ctx->nranks = nranks, ctx->p2p = true, ctx->peer_seq = 0;
+  // mailbox and exchange counter were zeroed at export time (before the host-side all-gather): a peer may already be writing
+  ctx->rank = rank, ctx->nranks = nranks, ctx->p2p = true;
   return ESIKF_OK;
 }
 int esikf_shard_range(int32_t n, int32_t rank, int32_t nranks, int32_t *begin, int32_t *count) {

@@ -1,15 +1,21 @@
 // Solve routines of the B200 ESIKF update: the Kalman gain, the boxplus state update, loop control and the final
-// covariance update. One block: all threads stage P / info / poses in a single global round trip, one warp runs the
-// m x m gain solve, all threads write back. The whole iteration loop runs on the device with no host round trip.
+// covariance update. The whole iteration loop runs on the device with no host round trip.
 //
-//   lio_solve_kernel : src/voxel_map.cpp:462-499  (K_1, G, solution, state_ += solution, convergence / rematch / (I-G)P)
-//   vio_solve_kernel : src/vio.cpp:1636-1685 + :800 (error-gated accept / rollback, K_1, G, solution, final cov -= G cov)
+//   lio_solve_block / lio_solve_kernel : src/voxel_map.cpp:462-499  (K_1, G, solution, state_ += solution, convergence /
+//                                        rematch / (I-G)P)
+//   vio_solve_block / vio_solve_kernel : src/vio.cpp:1636-1685 + :800 (error-gated accept / rollback, K_1, G, solution, final
+//                                        cov -= G cov)
 //
 // Gain: the reference computes K_1 = (H^T H + P^-1)^-1 with two 19x19 partial-pivot inversions and then only uses the
 // first m (6 or 7) columns of K_1. Because H^T H is zero outside its leading m x m block A, the push-through identity gives
 //     K_1[:, :m] = P[:, :m] (I_m + A P_mm)^-1
 // exactly — an m x m solve with 19 right-hand sides, one per lane. solve_mode 1 keeps the literal double inversion (Gauss-
 // Jordan with partial pivoting in shared memory) for parity checks.
+//
+// Critical path inside the persistent kernels: [all CTAs arrived] -> sum of the partial columns -> gain elimination ->
+// boxplus -> next slice. Everything that does not need the new information vector is hoisted out of it:
+// state_propagat (-) state is evaluated by warp 1 while the CTA waits at the grid barrier, and P never changes inside the
+// loop. The elimination itself is one warp, one column per lane.
 #include <float.h>
 #include "esikf_dev.cuh"
 
@@ -18,7 +24,7 @@ namespace esikf {
 struct SolveArgs {
   double *state;        // current iterate (device, packed) — updated in place
   const double *prop;   // state_propagat
-  const double *info;   // reduced information buffer
+  const double *info;   // reduced information vector (compact, NE_MAX doubles)
   Ctrl *ctrl;
   int max_iterations;
   int solve_mode;
@@ -30,18 +36,21 @@ struct SolveArgs {
   double *G;            // 19 x 7 last accepted gain block
   double img_point_cov;
   int level, slot_iter, last_slot;
-  int no_publish;       // replicated-solve kernels: every CTA solves, only CTA 0 writes the results to global memory
-  unsigned long long *dbg;  // measurement only
+  int no_publish;       // persistent kernels: every CTA solves, only one CTA writes the results to global memory
+  unsigned long long *dbg;  // measurement only: [0] gain rows done, [1] boxplus done (thread 0)
 };
 
 struct SolveSmem {
   double P[19 * 19];
-  double A[49];     // m x m information block
+  double A[49];     // m x m information block (full, mirrored from the upper triangle)
   double HTz[8];
   double vec[19];
   double sol[19];
   double *W;        // literal mode (solve_mode 1) workspace, 19 x 38 doubles
   double *K;        // literal mode, 19 x 19 doubles
+  // loop invariants of the gain (P does not change inside an update), gain_setup:
+  double Sinv[49];  // (P_mm pscale)^-1, m x m
+  double B[19][8];  // P[:, :m] P_mm^-1, 19 x m
 };
 struct SolveLiteralScratch {
   double W[19 * 38];
@@ -74,7 +83,12 @@ __device__ inline void so3_log(const double R[9], double out[3]) {
   for (int i = 0; i < 3; i++) out[i] = f * K[i];
 }
 
-// vec = state_propagat (-) state  (common_lib.h:194-206), by lane 0 for the rotation part
+// packed offsets of the additive blocks in error-state order: p(3:6) expo(6) v(7:10) bg(10:13) ba(13:16) g(16:19)
+__device__ __forceinline__ int err_to_packed(int k) {
+  return (k < 6) ? S_P + (k - 3) : (k == 6) ? S_EXPO : (k < 10) ? S_V + (k - 7) : (k < 13) ? S_BG + (k - 10) : (k < 16) ? S_BA + (k - 13) : S_G + (k - 16);
+}
+
+// vec = state_propagat (-) state  (common_lib.h:194-206), by one warp (lane 0 does the rotation part)
 __device__ inline void boxminus_warp(const double *prop, const double *st, double *vec, int lane) {
   if (lane == 0) {
     double Rd[9];
@@ -86,27 +100,24 @@ __device__ inline void boxminus_warp(const double *prop, const double *st, doubl
     vec[0] = l[0], vec[1] = l[1], vec[2] = l[2];
   }
   if (lane >= 3 && lane < 19) {
-    // packed offsets of the additive blocks in error-state order: p(3:6) expo(6) v(7:10) bg(10:13) ba(13:16) g(16:19)
-    int off = (lane < 6) ? S_P + (lane - 3) : (lane == 6) ? S_EXPO : (lane < 10) ? S_V + (lane - 7) : (lane < 13) ? S_BG + (lane - 10)
-              : (lane < 16) ? S_BA + (lane - 13) : S_G + (lane - 16);
+    const int off = err_to_packed(lane);
     vec[lane] = prop[off] - st[off];
   }
 }
 
-// state (+)= sol  (common_lib.h:182-192)
+// state (+)= sol  (common_lib.h:182-192) by one warp: every lane evaluates Exp (same instructions, no divergence cost),
+// lanes 0..8 each form one entry of R * Exp(sol[0:3]), lanes 3..18 add the vector blocks.
 __device__ inline void boxplus_warp(double *st, const double *sol, int lane) {
-  if (lane == 0) {
-    double E[9], Rn[9];
-    so3_exp(sol, E);
-    for (int i = 0; i < 3; i++)
-      for (int j = 0; j < 3; j++) Rn[i * 3 + j] = st[S_R + i * 3] * E[j] + st[S_R + i * 3 + 1] * E[3 + j] + st[S_R + i * 3 + 2] * E[6 + j];
-    for (int i = 0; i < 9; i++) st[S_R + i] = Rn[i];
+  double E[9];
+  so3_exp(sol, E);
+  double rn = 0.0;
+  if (lane < 9) {
+    const int i = lane / 3, j = lane - 3 * i;
+    rn = st[S_R + i * 3] * E[j] + st[S_R + i * 3 + 1] * E[3 + j] + st[S_R + i * 3 + 2] * E[6 + j];
   }
-  if (lane >= 3 && lane < 19) {
-    int off = (lane < 6) ? S_P + (lane - 3) : (lane == 6) ? S_EXPO : (lane < 10) ? S_V + (lane - 7) : (lane < 13) ? S_BG + (lane - 10)
-              : (lane < 16) ? S_BA + (lane - 13) : S_G + (lane - 16);
-    st[off] += sol[lane];
-  }
+  __syncwarp();
+  if (lane < 9) st[S_R + lane] = rn;
+  if (lane >= 3 && lane < 19) st[err_to_packed(lane)] += sol[lane];
 }
 
 // In-place inverse of a 19x19 in shared memory by one warp (Gauss-Jordan, partial pivoting) — literal mode only.
@@ -147,7 +158,53 @@ __device__ inline void inverse19_warp(const double *Ain, double *W /*19x38*/, do
   __syncwarp();
 }
 
-// Gain block x = K_1[lane, 0:m] for every lane < 19. PS = P * pscale (pscale = 1 for LIO, 1/img_point_cov for VIO).
+// Gain. With S = P_mm pscale (pscale = 1 for LIO, 1/img_point_cov for VIO) and A = H^T R^-1 H:
+//     K_1[:, :m] = P[:, :m] pscale (I + A S)^-1 = (P[:, :m] P_mm^-1) (S^-1 + A)^-1 = B C^-1,
+// where B (19 x m) and S^-1 only depend on P — loop invariants, formed once per update by gain_setup — and C = S^-1 + A is
+// symmetric positive definite, so the per-iteration elimination needs no pivot search and no row exchanges: m steps of
+// {broadcast the pivot column, reciprocal, rank-1 update}, one column per lane. That is what sits on the critical path of
+// every iteration (all CTAs wait for it), and it is a third of the instructions of the pivoted elimination on I + A S.
+//
+// One elimination sweep of the augmented system [C | RHS columns], one column per lane (col[i] = entry in row i), without
+// pivoting: afterwards a right-hand-side lane holds its solution vector.
+template <int m> __device__ __forceinline__ void spd_sweep(double col[m]) {
+#pragma unroll
+  for (int k = 0; k < m; k++) {
+    const double pv = __shfl_sync(0xffffffffu, col[k], k);
+    double f[m];
+#pragma unroll
+    for (int i = 0; i < m; i++) f[i] = __shfl_sync(0xffffffffu, col[i], k);
+    const double vk = col[k] * __drcp_rn(pv);  // correctly rounded reciprocal: the value of 1.0 / pv without the division subroutine
+    col[k] = vk;
+#pragma unroll
+    for (int i = 0; i < m; i++)
+      if (i != k) col[i] -= f[i] * vk;
+  }
+}
+
+// Once per update, by one warp: S^-1 and B = P[:, :m] P_mm^-1 into shared memory. Lanes 0..m-1 own the columns of S (SPD),
+// lanes m..18 the right-hand sides P[r, :m] pscale (rows r >= m of B; rows r < m are unit vectors), lanes 19..19+m-1 the
+// unit vectors (rows of S^-1): 19 + m <= 26 columns.
+template <int m> __device__ inline void gain_setup(SolveSmem &sm, double pscale, int lane) {
+  double col[m];
+#pragma unroll
+  for (int i = 0; i < m; i++) {
+    double v = 0.0;
+    if (lane < 19) v = sm.P[lane * 19 + i] * pscale;  // column `lane` of S for lane < m (S symmetric), row `lane` of P[:, :m] otherwise
+    else if (lane < 19 + m) v = (i == lane - 19) ? 1.0 : 0.0;
+    col[i] = v;
+  }
+  spd_sweep<m>(col);
+#pragma unroll
+  for (int i = 0; i < m; i++) {
+    if (lane < m) sm.B[lane][i] = (i == lane) ? 1.0 : 0.0;
+    else if (lane < 19) sm.B[lane][i] = col[i];
+    else if (lane < 19 + m) sm.Sinv[(lane - 19) * m + i] = col[i];
+  }
+  __syncwarp();
+}
+
+// Gain block x = K_1[lane, 0:m] for every lane < 19 (needs gain_setup<m> on this sm for solve_mode 0).
 template <int m>
 __device__ inline void gain_rows(SolveSmem &sm, double pscale, int solve_mode, int lane, double x[m]) {
   if (solve_mode == 1) {
@@ -162,51 +219,17 @@ __device__ inline void gain_rows(SolveSmem &sm, double pscale, int solve_mode, i
       for (int j = 0; j < m; j++) x[j] = sm.K[lane * 19 + j];
     return;
   }
-  // Warp-cooperative Gauss-Jordan with partial pivoting on the augmented system  M^T [X^T] = [P[:, :m]^T] :
-  // lane c < m owns column c of M^T (= row c of M = I + A P_mm), lane m + r owns the right-hand side of state row r
-  // (P[r, 0:m] * pscale). After the sweep lane m + r holds K_1[r, 0:m]. m + 19 <= 32 columns, m pivots.
+  // lane c < m: column c of C = S^-1 + A (symmetric); lane m + r: right-hand side B[r, :] of state row r
   double col[m];
   if (lane < m) {
 #pragma unroll
-    for (int i = 0; i < m; i++) {
-      double s = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-      for (int k = 0; k < m; k++) s += sm.A[lane * m + k] * (sm.P[k * 19 + i] * pscale);
-      col[i] = s;
-    }
+    for (int i = 0; i < m; i++) col[i] = sm.Sinv[i * m + lane] + sm.A[i * m + lane];
   } else {
     const int r = (lane - m) < 19 ? (lane - m) : 0;
 #pragma unroll
-    for (int i = 0; i < m; i++) col[i] = sm.P[r * 19 + i] * pscale;
+    for (int i = 0; i < m; i++) col[i] = sm.B[r][i];
   }
-#pragma unroll
-  for (int k = 0; k < m; k++) {
-    // pivot row: largest |entry| of column k among rows k..m-1, found by the lane that owns column k
-    int p = k;
-    double best = fabs(col[k]);
-#pragma unroll
-    for (int i = k + 1; i < m; i++) {
-      const double v = fabs(col[i]);
-      if (v > best) best = v, p = i;
-    }
-    p = __shfl_sync(0xffffffffu, p, k);
-#pragma unroll
-    for (int i = k + 1; i < m; i++) {
-      const bool sw = (p == i);
-      const double u = col[k], v = col[i];
-      col[k] = sw ? v : u;
-      col[i] = sw ? u : v;
-    }
-    const double pv = __shfl_sync(0xffffffffu, col[k], k);
-    double f[m];
-#pragma unroll
-    for (int i = 0; i < m; i++) f[i] = __shfl_sync(0xffffffffu, col[i], k);
-    const double vk = col[k] * (1.0 / pv);
-    col[k] = vk;
-#pragma unroll
-    for (int i = 0; i < m; i++)
-      if (i != k) col[i] -= f[i] * vk;
-  }
+  spd_sweep<m>(col);
 #pragma unroll
   for (int i = 0; i < m; i++) x[i] = __shfl_sync(0xffffffffu, col[i], (lane + m) & 31);
 }
@@ -217,7 +240,7 @@ __device__ inline double warp_norm3(const double *v) { return sqrt(v[0] * v[0] +
 
 // Staging shared by both solve routines: one global round trip brings P, info, the pose parts of state / prior / old_state.
 struct SolveIO {
-  double info[INFO_N];
+  double info[NE_MAX];
   double st[32];   // first 25 doubles of the packed state (R p expo v bg ba g)
   double pr[32];   // same of state_propagat
   double old[32];  // VIO old_state
@@ -226,18 +249,18 @@ struct SolveIO {
 };
 
 // Needs >= 192 threads. Every global load is issued before the first shared-memory store, so the staging costs one
-// L2 round trip. __ldcg: the data was written by other SMs of this same grid when called from the persistent kernels.
+// L2 round trip.
 __device__ __forceinline__ void solve_load(SolveSmem &sm, SolveIO &io, const SolveArgs &a, bool want_old) {
   const int t = threadIdx.x, nt = blockDim.x;
   const double p0 = (t < 361) ? __ldcg(a.state + S_COV + t) : 0.0;
   const double p1 = (t + nt < 361) ? __ldcg(a.state + S_COV + t + nt) : 0.0;
-  const double i0 = (t < INFO_N) ? __ldcg(a.info + t) : 0.0;
+  const double i0 = (t < NE_MAX) ? __ldcg(a.info + t) : 0.0;
   const double s0 = (t < 25) ? __ldcg(a.state + t) : 0.0;
   const double r0 = (t < 25) ? a.prop[t] : 0.0;
   const double o0 = (want_old && t < 25) ? __ldcg(a.old_state + t) : 0.0;
   if (t < 361) sm.P[t] = p0;
   if (t + nt < 361) sm.P[t + nt] = p1;
-  if (t < INFO_N) io.info[t] = i0;
+  if (t < NE_MAX) io.info[t] = i0;
   if (t < 25) {
     io.st[t] = s0;
     io.pr[t] = r0;
@@ -245,8 +268,21 @@ __device__ __forceinline__ void solve_load(SolveSmem &sm, SolveIO &io, const Sol
   }
 }
 
-// Diagnostics of the iteration just solved (what the reference prints at voxel_map.cpp:404-405). Not needed by the other
-// CTAs, so the persistent kernel writes them after publishing the state.
+// m x m information block and H^T z out of the compact vector (mirrored), by one warp.
+template <int M> __device__ __forceinline__ void unpack_info(SolveSmem &sm, const SolveIO &io, int lane) {
+  constexpr int T = M * (M + 1) / 2;
+  for (int idx = lane; idx < M * M; idx += 32) {
+    const int i = idx / M, j = idx - M * i;
+    sm.A[idx] = io.info[(i <= j) ? tri_of(M, i, j) : tri_of(M, j, i)];
+  }
+  if (lane < M) sm.HTz[lane] = io.info[T + lane];
+  __syncwarp();
+}
+#define INFO_EXTRA(M) ((M) * ((M) + 1) / 2 + (M))      // sum |d| / sum res^2
+#define INFO_COUNTM(M) ((M) * ((M) + 1) / 2 + (M) + 1) // matched points / n_meas
+
+// Diagnostics of the iteration just solved (what the reference prints at voxel_map.cpp:404-405): plain global stores by a
+// few threads, nobody inside the kernel reads them.
 __device__ __forceinline__ void lio_write_stats(const SolveArgs &a, SolveSmem &sm, SolveIO &io) {
   const int tid = threadIdx.x, iterCount = io.flags[3];
   if (a.lio_stats && iterCount < 8) {
@@ -256,37 +292,35 @@ __device__ __forceinline__ void lio_write_stats(const SolveArgs &a, SolveSmem &s
     for (int t = tid; t < 19; t += blockDim.x) S.solution[iterCount][t] = sm.sol[t];
     if (tid == 0) {
       S.iters = iterCount + 1;
-      S.effct_feat_num[iterCount] = (int)io.info[INFO_COUNT];
-      S.total_residual[iterCount] = io.info[INFO_ABS];
+      S.effct_feat_num[iterCount] = (int)io.info[INFO_COUNTM(6)];
+      S.total_residual[iterCount] = io.info[INFO_EXTRA(6)];
       S.converged[iterCount] = io.flags[0];
     }
   }
 }
 
 // One LIO gain solve + state update (src/voxel_map.cpp:462-499) by the calling block. Returns EKF_stop_flg.
-// `ctrl` is the loop-control block the routine reads and updates (global memory for the per-iteration kernels, CTA 0's
-// shared-memory copy inside the persistent kernel). `resident`: P / poses / info are already staged in sm / io.
-__device__ __noinline__ bool lio_solve_block(const SolveArgs &a, SolveSmem &sm, SolveIO &io, Ctrl &ctrl, bool defer_stats, bool resident) {
+// `ctrl` is the loop-control block the routine reads and updates (global memory for the per-iteration kernels, the CTA's
+// shared-memory copy inside the persistent kernel). resident: P / poses / info are already staged in sm / io.
+// vec_ready: state_propagat (-) state_ is already in sm.vec (the persistent kernel evaluates it inside the barrier wait).
+__device__ __noinline__ bool lio_solve_block(const SolveArgs &a, SolveSmem &sm, SolveIO &io, Ctrl &ctrl, bool resident, bool vec_ready) {
   const int tid = threadIdx.x, lane = tid & 31;
   const int iterCount = ctrl.iter;
   const int rematch0 = ctrl.rematch_num;
-  dbg_stamp(a.dbg, 16);
-  if (!resident) solve_load(sm, io, a, false);
-  __syncthreads();
-  dbg_stamp(a.dbg, 17);
-  double x[6], g[6];
-  if (tid < 32) {
-    for (int idx = lane; idx < 36; idx += 32) sm.A[idx] = io.info[(idx / 6) * 8 + (idx % 6)];  // H^T R^-1 H
-    if (lane < 6) sm.HTz[lane] = io.info[lane * 8 + 6];                                          // H^T R^-1 z
-    __syncwarp();
-    dbg_stamp(a.dbg, 18);
-    gain_rows<6>(sm, 1.0, a.solve_mode, lane, x);
-    dbg_stamp(a.dbg, 19);
-  } else if (tid < 64) {
-    boxminus_warp(io.pr, io.st, sm.vec, lane);  // vec = state_propagat (-) state_, concurrently on warp 1 (:470)
+  if (!resident) {
+    solve_load(sm, io, a, false);
+    __syncthreads();
   }
-  __syncthreads();
+  if (!vec_ready) {
+    if (tid >= 32 && tid < 64) boxminus_warp(io.pr, io.st, sm.vec, lane);  // vec = state_propagat (-) state_ (:470)
+    if (!resident && tid >= 64 && tid < 96 && a.solve_mode == 0) gain_setup<6>(sm, 1.0, lane);  // per-iteration launches: nothing is kept
+    __syncthreads();
+  }
   if (tid < 32) {
+    unpack_info<6>(sm, io, lane);  // H^T R^-1 H, H^T R^-1 z
+    double x[6], g[6];
+    gain_rows<6>(sm, 1.0, a.solve_mode, lane, x);
+    if (a.dbg && tid == 0) a.dbg[0] = globaltimer_ns();
     // G[lane, 0:6] = K_1[lane, 0:6] * HTH   (voxel_map.cpp:469)
 #pragma unroll
     for (int j = 0; j < 6; j++) {
@@ -305,40 +339,35 @@ __device__ __noinline__ bool lio_solve_block(const SolveArgs &a, SolveSmem &sm, 
       for (int j = 0; j < 6; j++) io.g[lane][j] = g[j];
     }
     __syncwarp();
-    dbg_stamp(a.dbg, 20);
     boxplus_warp(io.st, sm.sol, lane);  // state_ += solution (:474)
-    dbg_stamp(a.dbg, 21);
+    if (a.dbg && tid == 0) a.dbg[1] = globaltimer_ns();
     if (lane == 0) {
       const bool converged = (warp_norm3(sm.sol) * 57.3 < 0.01) && (warp_norm3(sm.sol + 3) * 100 < 0.015);  // :477
       int rematch = rematch0;
       if (converged || ((rematch == 0) && (iterCount == (a.max_iterations - 2)))) rematch++;  // :482
       const bool stop = (rematch >= 2) || (iterCount == a.max_iterations - 1);                // :485
-      io.flags[0] = converged, io.flags[1] = rematch, io.flags[2] = stop;
+      io.flags[0] = converged, io.flags[1] = rematch, io.flags[2] = stop, io.flags[3] = iterCount;
+      ctrl.iter = iterCount + 1;
+      ctrl.rematch_num = rematch;
+      ctrl.stop = stop ? 1 : 0;
     }
   }
   __syncthreads();
   const bool stop = io.flags[2] != 0;
-  if (!a.no_publish)
+  if (!a.no_publish) {
     for (int t = tid; t < 25; t += blockDim.x) a.state[t] = io.st[t];
-  if (stop && !a.no_publish) {
-    // cov = (I - G) cov   (:489-490); G only has its first 6 columns
-    for (int t = tid; t < 361; t += blockDim.x) {
-      const int r = t / 19, c = t - 19 * r;
-      double s = sm.P[t];
+    if (stop) {
+      // cov = (I - G) cov   (:489-490); G only has its first 6 columns
+      for (int t = tid; t < 361; t += blockDim.x) {
+        const int r = t / 19, c = t - 19 * r;
+        double s = sm.P[t];
 #pragma unroll
-      for (int j = 0; j < 6; j++) s -= io.g[r][j] * sm.P[j * 19 + c];
-      a.state[S_COV + t] = s;
+        for (int j = 0; j < 6; j++) s -= io.g[r][j] * sm.P[j * 19 + c];
+        a.state[S_COV + t] = s;
+      }
     }
+    lio_write_stats(a, sm, io);
   }
-  io.flags[3] = iterCount;
-  __syncthreads();
-  dbg_stamp(a.dbg, 22);
-  if (tid == 0) {
-    ctrl.iter = iterCount + 1;
-    ctrl.rematch_num = io.flags[1];
-    ctrl.stop = stop ? 1 : 0;
-  }
-  if (!defer_stats) lio_write_stats(a, sm, io);
   return stop;
 }
 
@@ -347,12 +376,15 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lio_solve_kernel(const Solve
   __shared__ SolveSmem sm;
   __shared__ SolveIO io;
   __shared__ SolveLiteralScratch lit;
-  if (threadIdx.x == 0) sm.W = lit.W, sm.K = lit.K;
+  __shared__ Ctrl ctrl;
+  if (threadIdx.x == 0) sm.W = lit.W, sm.K = lit.K, ctrl = *a.ctrl;
   __syncthreads();
-  lio_solve_block(a, sm, io, *a.ctrl, false, false);
+  lio_solve_block(a, sm, io, ctrl, false, false);
+  __syncthreads();
+  if (threadIdx.x == 0) a.ctrl->iter = ctrl.iter, a.ctrl->rematch_num = ctrl.rematch_num, a.ctrl->stop = ctrl.stop;
 }
 
-__device__ __forceinline__ void vio_write_stats(const SolveArgs &a, SolveSmem &sm, SolveIO &io, const Ctrl &ctrl) {
+__device__ __forceinline__ void vio_write_stats(const SolveArgs &a, SolveSmem &sm, SolveIO &io) {
   const int tid = threadIdx.x, level = a.level, iteration = a.slot_iter;
   const bool accepted = io.flags[0] != 0, ran = io.flags[2] != 0;
   if (ran && a.vio_stats && level < 8) {
@@ -372,46 +404,40 @@ __device__ __forceinline__ void vio_write_stats(const SolveArgs &a, SolveSmem &s
 }
 
 // One VIO accept/rollback + gain solve (src/vio.cpp:1636-1685) by the calling block; on the last slot also the final
-// covariance update (:800). Returns EKF_end of the level.
-// OVERLAP (opt-in, same arithmetic): warp 1's boxminus runs concurrently with warp 0's accept test and gain elimination;
-// the two warps meet at a named barrier right before the solution needs `vec`, instead of a CTA barrier after the boxminus.
-template <bool OVERLAP = false>
-__device__ __forceinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &sm, SolveIO &io, Ctrl &ctrl, bool defer_stats, bool resident) {
+// covariance update (:800). Returns EKF_end of the level. vec_ready as for lio_solve_block.
+__device__ __noinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &sm, SolveIO &io, Ctrl &ctrl, bool resident, bool vec_ready) {
   const int tid = threadIdx.x, lane = tid & 31;
   const bool level_done_in = (a.slot_iter == 0) ? false : (ctrl.level_done != 0);   // entering a level: EKF_end = false (vio.cpp:1527)
   const float last_error_in = (a.slot_iter == 0) ? FLT_MAX : ctrl.last_error;       // :1528
   const int has_G_in = ctrl.has_G;
   if (level_done_in && !a.last_slot) return true;
-  if (!resident) solve_load(sm, io, a, a.slot_iter != 0);
-  __syncthreads();
-  if (a.slot_iter == 0)
-    for (int t = tid; t < 25; t += blockDim.x) io.old[t] = io.st[t];  // old_state = *state at level entry (:1523)
-  __syncthreads();
-  const int level = a.level, iteration = a.slot_iter;
-  // vec = state_propagat (-) state on warp 1 while warp 0 decides accept / rollback and runs the gain solve (:1664)
-  if (tid >= 32 && tid < 64 && !level_done_in) {
-    boxminus_warp(io.pr, io.st, sm.vec, lane);
-    if (OVERLAP) asm volatile("bar.sync 1, 64;" ::: "memory");  // meets warp 0 below
+  if (!resident) {
+    solve_load(sm, io, a, a.slot_iter != 0);
+    __syncthreads();
   }
-  if (!OVERLAP) __syncthreads();
+  if (!vec_ready && !level_done_in) {
+    // vec = state_propagat (-) state (:1664) on warp 1
+    if (tid >= 32 && tid < 64) boxminus_warp(io.pr, io.st, sm.vec, lane);
+    if (!resident && tid >= 64 && tid < 96 && a.solve_mode == 0) gain_setup<7>(sm, 1.0 / a.img_point_cov, lane);  // per-iteration launches: nothing is kept
+    __syncthreads();
+  }
   if (tid < 32) {
     bool accepted = false, ekf_end = level_done_in;
     float error = 0.f, last_error = last_error_in;
     if (!level_done_in) {
+      if (a.slot_iter == 0 && lane < 25) io.old[lane] = io.st[lane];  // old_state = *state at level entry (:1523)
       // error = sum(res^2) / n_meas as float (vio.cpp:1636)
-      const double sum_sq = io.info[7 * 8 + 7];
-      const int n_meas = (int)io.info[INFO_COUNT];
+      const double sum_sq = io.info[INFO_EXTRA(7)];
+      const int n_meas = (int)io.info[INFO_COUNTM(7)];
       error = __fdiv_rn((float)sum_sq, (float)n_meas);
       if (error <= last_error) {  // :1648
         accepted = true;
         if (lane < 25) io.old[lane] = io.st[lane];  // old_state = *state
         last_error = error;
-        for (int idx = lane; idx < 49; idx += 32) sm.A[idx] = io.info[(idx / 7) * 8 + (idx % 7)];  // H^T H 7x7
-        if (lane < 7) sm.HTz[lane] = io.info[lane * 8 + 7];
-        __syncwarp();
+        unpack_info<7>(sm, io, lane);  // H^T H 7x7, H^T z
         double x[7];
         gain_rows<7>(sm, 1.0 / a.img_point_cov, a.solve_mode, lane, x);
-        if (OVERLAP) asm volatile("bar.sync 1, 64;" ::: "memory");  // vec = state_propagat (-) state is complete
+        if (a.dbg && tid == 0) a.dbg[0] = globaltimer_ns();
         double g[7];
 #pragma unroll
         for (int j = 0; j < 7; j++) {
@@ -430,10 +456,11 @@ __device__ __forceinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &s
         }
         __syncwarp();
         boxplus_warp(io.st, sm.sol, lane);
+        if (a.dbg && tid == 0) a.dbg[1] = globaltimer_ns();
         // :1675 (float constants 57.3f / 100.0f / 0.001f promote to double against the double norm)
         ekf_end = (warp_norm3(sm.sol) * (double)57.3f < (double)0.001f) && (warp_norm3(sm.sol + 3) * (double)100.0f < (double)0.001f);
       } else {
-        if (OVERLAP) asm volatile("bar.sync 1, 64;" ::: "memory");  // warp 1 still reads io.st for the (unused) boxminus
+        __syncwarp();
         if (lane < 25) io.st[lane] = io.old[lane];  // *state = old_state  (:1679)
         ekf_end = true;
       }
@@ -442,6 +469,14 @@ __device__ __forceinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &s
       io.flags[0] = accepted, io.flags[1] = ekf_end, io.flags[2] = !level_done_in;
       reinterpret_cast<float *>(io.flags)[3] = last_error;
       reinterpret_cast<float *>(io.flags)[4] = error;
+      if (!level_done_in) {
+        ctrl.iter += 1;
+        ctrl.last_error = last_error;
+        if (a.slot_iter == 0) ctrl.accepted_in_level = 0;
+        if (accepted) ctrl.has_G = 1, ctrl.accepted_in_level += 1;
+      }
+      ctrl.level_done = ekf_end;
+      if (a.last_slot) ctrl.stop = 1;
     }
   }
   __syncthreads();
@@ -453,9 +488,9 @@ __device__ __forceinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &s
     }
     if (accepted)
       for (int t = tid; t < 133; t += blockDim.x) a.G[t] = io.g[t / 7][t % 7];
-    if (!defer_stats) vio_write_stats(a, sm, io, ctrl);
+    vio_write_stats(a, sm, io);
   }
-  if (a.last_slot) {
+  if (a.last_slot && !a.no_publish) {
     // state->cov -= G * state->cov   (vio.cpp:800) with the last accepted G (this slot's if accepted, else the stored one)
     const bool haveG = accepted || has_G_in;
     if (haveG)
@@ -466,18 +501,6 @@ __device__ __forceinline__ bool vio_solve_block(const SolveArgs &a, SolveSmem &s
         a.state[S_COV + t] = sm.P[t] - s;
       }
   }
-  __syncthreads();
-  if (tid == 0) {
-    if (ran) {
-      ctrl.iter += 1;
-      ctrl.last_error = reinterpret_cast<float *>(io.flags)[3];
-      if (a.slot_iter == 0) ctrl.accepted_in_level = 0;
-      if (accepted) ctrl.has_G = 1, ctrl.accepted_in_level += 1;
-    }
-    ctrl.level_done = io.flags[1];
-    if (a.last_slot) ctrl.stop = 1;
-  }
-  __syncthreads();
   return io.flags[1] != 0;
 }
 
@@ -485,9 +508,16 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) vio_solve_kernel(const Solve
   __shared__ SolveSmem sm;
   __shared__ SolveIO io;
   __shared__ SolveLiteralScratch lit;
-  if (threadIdx.x == 0) sm.W = lit.W, sm.K = lit.K;
+  __shared__ Ctrl ctrl;
+  if (threadIdx.x == 0) sm.W = lit.W, sm.K = lit.K, ctrl = *a.ctrl;
   __syncthreads();
-  vio_solve_block(a, sm, io, *a.ctrl, false, false);
+  vio_solve_block(a, sm, io, ctrl, false, false);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned bc = a.ctrl->block_counter;
+    *a.ctrl = ctrl;
+    a.ctrl->block_counter = bc;
+  }
 }
 
 }  // namespace esikf

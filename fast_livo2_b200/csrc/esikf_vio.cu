@@ -109,9 +109,22 @@ __device__ __forceinline__ float bil(float wtl, float wtr, float wbl, float wbr,
   return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wtl, a), __fmul_rn(wtr, b)), __fmul_rn(wbl, c)), __fmul_rn(wbr, d));
 }
 
+// What a warp keeps about one of ITS patches across the iterations of a persistent update: the iteration-invariant inputs,
+// the 11 x 11 strided tap footprint of the level-0 image (re-staged only when the integer tap base or the stride moves —
+// sub-pixel motion between iterations leaves it in place) and the 64 reference-patch values of the current pyramid level.
+// With it a steady-state iteration of a patch touches no global memory at all.
+#define VIO_KMAX 2  // cached patches per warp (2 x 16 warps x 148 SMs = 4.7 k patches resident)
+struct VioPatchCache {
+  double X, Y, Z, inv_ref_expo;
+  long long tile_base0;  // linear index of tile (0,0) in the image the taps were staged from
+  int search_level, tile_scale, pv_level, have;
+  float taps[128];       // 11 x 11 strided image taps of the patch footprint (level-0 image, stride 2^pyramid_level)
+  float pv[64];          // warp_patch of the level being processed
+};
+
 struct __align__(128) VioSmem {
   double rows[VIO_WARPS][64][8];  // first: double4 stores need 32-byte alignment
-  float taps[VIO_WARPS][128];     // 11 x 11 strided image taps of the patch footprint (level-0 image, stride 2^pyramid_level)
+  VioPatchCache cache[VIO_WARPS][VIO_KMAX];
   float grid[VIO_WARPS][104];     // 10 x 10 bilinear values: patch pixels plus a one-pixel ring for the central differences
   double Rcw[9], Pcw[3];
   double inv_expo;
@@ -139,58 +152,46 @@ __device__ __forceinline__ void vio_load_consts(VioSmem &sm, const VioKernelArgs
   __syncthreads();
 }
 
-// What a warp keeps about ITS patch across the iterations of a persistent update (FAST variant, one patch per warp): the
-// iteration-invariant inputs in shared memory (one slot per warp) and the lane's two reference-patch values of the current
-// pyramid level in registers — an L2 round trip per iteration that the default path spends at the top of the loop.
-struct VioPatchSlot {
-  double X, Y, Z, inv_ref_expo;
-  int search_level, pad;
-};
-struct VioLaneCache {
-  float2 Pv;
-  int level;   // pyramid level Pv belongs to (-1: none)
-  bool have;   // the warp's slot is filled
-};
+__device__ __forceinline__ void vio_cache_reset(VioSmem &sm) {
+  for (int t = threadIdx.x; t < VIO_WARPS * VIO_KMAX; t += blockDim.x) {
+    VioPatchCache &c = sm.cache[t / VIO_KMAX][t % VIO_KMAX];
+    c.have = 0, c.pv_level = -1, c.tile_scale = 0, c.tile_base0 = 0;
+  }
+}
 
 // Photometric residual / Jacobian build of the patches [lo, hi) of this rank's shard at pyramid level `level`.
-// FAST (opt-in, bit-identical results): per-patch inputs cached across iterations (slots / lc), and the divisions by the
-// power-of-two tap stride replaced by multiplications with its exact reciprocal (same quotient bit for bit).
-template <bool FAST = false>
+// Patch lo + warp + 16 k belongs to (warp, k). cached: the CTA's patches fit the per-warp cache (k < VIO_KMAX) and the
+// caller keeps `sm.cache` alive between calls (persistent kernel); otherwise slot 0 is plain scratch, refilled every time.
+// Divisions by the power-of-two tap stride are multiplications with its exact reciprocal (same quotient bit for bit).
 __device__ __forceinline__ void vio_process_range(const VioKernelArgs &a, VioSmem &sm, int level, int lo, int hi, double &D0, double &D1,
-                                                  double &n_meas, VioPatchSlot *slots = nullptr, VioLaneCache *lc = nullptr) {
+                                                  double &n_meas, bool cached) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long npix = (long)a.cam.width * a.cam.height;
   const int width = a.cam.width;
   const double inv_expo = sm.inv_expo;
-  float *const sT = sm.taps[warp];
   float *const sG = sm.grid[warp];
-  const bool single = FAST && (hi - lo <= VIO_WARPS);  // one patch per warp: it is the same patch in every iteration
-  for (int lp = lo + warp; lp < hi; lp += VIO_WARPS) {
+  int k = 0;
+  for (int lp = lo + warp; lp < hi; lp += VIO_WARPS, k++) {
     const int i = a.begin + lp;
-    int search_level;
-    double X, Y, Z, inv_ref_expo_c = 0.0;
-    if (FAST && single && lc->have) {
-      const VioPatchSlot &ps = slots[warp];
-      search_level = ps.search_level, X = ps.X, Y = ps.Y, Z = ps.Z, inv_ref_expo_c = ps.inv_ref_expo;
-    } else {
-      search_level = a.search_levels[i];
-      X = a.pos[3 * (size_t)i], Y = a.pos[3 * (size_t)i + 1], Z = a.pos[3 * (size_t)i + 2];
-      if (FAST) {
-        inv_ref_expo_c = a.inv_expo_list[i];
-        if (single) {
-          if (lane == 0) {
-            VioPatchSlot &ps = slots[warp];
-            ps.search_level = search_level, ps.X = X, ps.Y = Y, ps.Z = Z, ps.inv_ref_expo = inv_ref_expo_c;
-          }
-          lc->have = true;
-        }
+    VioPatchCache &c = sm.cache[warp][cached ? k : 0];
+    const bool fill = !cached || !c.have;  // decisions on the shared slot are read first, acted on after a warp barrier
+    __syncwarp();
+    if (fill) {
+      if (lane == 0) {
+        c.search_level = a.search_levels[i];
+        c.X = a.pos[3 * (size_t)i], c.Y = a.pos[3 * (size_t)i + 1], c.Z = a.pos[3 * (size_t)i + 2];
+        c.inv_ref_expo = a.inv_expo_list[i];
+        c.have = 1, c.pv_level = -1, c.tile_scale = 0;
       }
+      __syncwarp();
     }
+    const int search_level = c.search_level;
+    const double X = c.X, Y = c.Y, Z = c.Z, inv_ref_expo = c.inv_ref_expo;
     const int pyramid_level = level + search_level;
     const int scale = 1 << pyramid_level;
-    // 2^-pyramid_level assembled from its exponent bits (FAST) — the value 1.0f / (float)scale has
-    const float inv_scale = FAST ? __int_as_float((127 - pyramid_level) << 23) : 1.0f / (float)scale;
-    const double inv_scale_d = FAST ? __longlong_as_double((long long)(1023 - pyramid_level) << 52) : 0.0;
+    // 2^-pyramid_level assembled from its exponent bits — the value 1.0f / (float)scale has; x / 2^k == x * 2^-k exactly
+    const float inv_scale = __int_as_float((127 - pyramid_level) << 23);
+    const double inv_scale_d = __longlong_as_double((long long)(1023 - pyramid_level) << 52);
     const double pf0 = sm.Rcw[0] * X + sm.Rcw[1] * Y + sm.Rcw[2] * Z + sm.Pcw[0];
     const double pf1 = sm.Rcw[3] * X + sm.Rcw[4] * Y + sm.Rcw[5] * Z + sm.Pcw[1];
     const double pf2 = sm.Rcw[6] * X + sm.Rcw[7] * Y + sm.Rcw[8] * Z + sm.Pcw[2];
@@ -198,28 +199,37 @@ __device__ __forceinline__ void vio_process_range(const VioKernelArgs &a, VioSme
     world2cam(a.cam, pf0, pf1, pf2, pcu, pcv);
     // bilinear weights (:1580-1589) — float, via double (1.0 - subpix)
     const float u_ref = (float)pcu, v_ref = (float)pcv;
-    // x / 2^k == x * 2^-k exactly (no rounding in either), so the FAST forms give the same floats
-    const int u_ref_i = (int)(floorf(FAST ? (float)(pcu * inv_scale_d) : (float)(pcu / scale)) * scale);
-    const int v_ref_i = (int)(floorf(FAST ? (float)(pcv * inv_scale_d) : (float)(pcv / scale)) * scale);
-    const float subpix_u = FAST ? __fmul_rn(u_ref - (float)u_ref_i, inv_scale) : (u_ref - (float)u_ref_i) / (float)scale;
-    const float subpix_v = FAST ? __fmul_rn(v_ref - (float)v_ref_i, inv_scale) : (v_ref - (float)v_ref_i) / (float)scale;
+    const int u_ref_i = (int)(floorf((float)(pcu * inv_scale_d)) * scale);
+    const int v_ref_i = (int)(floorf((float)(pcv * inv_scale_d)) * scale);
+    const float subpix_u = __fmul_rn(u_ref - (float)u_ref_i, inv_scale);
+    const float subpix_v = __fmul_rn(v_ref - (float)v_ref_i, inv_scale);
     const float w_tl = (float)((1.0 - subpix_u) * (1.0 - subpix_v));
     const float w_tr = (float)(subpix_u * (1.0 - subpix_v));
     const float w_bl = (float)((1.0 - subpix_u) * subpix_v);
     const float w_br = subpix_u * subpix_v;
 
-    // stage the 11 x 11 tap footprint: tile (r, c) <-> image linear index base0 + r*scale*width + c*scale, where tile
-    // (1,1) is the top-left tap of patch pixel (0,0) (:1597)
+    // the 11 x 11 tap footprint: tile (r, c) <-> image linear index base0 + r*scale*width + c*scale, where tile (1,1) is the
+    // top-left tap of patch pixel (0,0) (:1597). Staged only when the footprint moved.
     {
-      const long base0 = (long)(v_ref_i - 5 * scale) * width + (u_ref_i - 5 * scale);
-      const long sw = (long)scale * width;
+      const long long base0 = (long long)(v_ref_i - 5 * scale) * width + (u_ref_i - 5 * scale);
+      const bool restage = (c.tile_scale != scale || c.tile_base0 != base0), repv = (c.pv_level != level);
+      __syncwarp();
+      if (restage) {
+        const long sw = (long)scale * width;
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int t = lane + 32 * k;
-        if (t < 121) {
-          const int r = t / 11, c = t - 11 * r;
-          sT[t] = tap(a.img, base0 + r * sw + (long)c * scale, npix);
+        for (int q = 0; q < 4; q++) {
+          const int t = lane + 32 * q;
+          if (t < 121) {
+            const int r = t / 11, cc = t - 11 * r;
+            c.taps[t] = tap(a.img, (long)base0 + r * sw + (long)cc * scale, npix);
+          }
         }
+        if (lane == 0) c.tile_scale = scale, c.tile_base0 = base0;
+      }
+      if (repv) {
+        const float2 v = *reinterpret_cast<const float2 *>(a.warp_patch + (size_t)i * 64 * a.levels + 64 * level + 2 * lane);
+        *reinterpret_cast<float2 *>(&c.pv[2 * lane]) = v;
+        if (lane == 0) c.pv_level = level;
       }
     }
     // computeProjectionJacobian (:189-201) and the per-patch 2x3 maps so that per pixel JdR = [du dv] WR, Jdt = [du dv] WT (:1611-1617):
@@ -231,25 +241,18 @@ __device__ __forceinline__ void vio_process_range(const VioKernelArgs &a, VioSme
     const double Q10 = J11 * pf2 + J12 * (-pf1), Q11 = J12 * pf0, Q12 = J11 * (-pf0);
     double WR[2][3], WT[2][3];
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-      WR[0][c] = sc * ((Q00 * a.Rci[c] + Q01 * a.Rci[3 + c] + Q02 * a.Rci[6 + c]) - (J00 * a.Jdp_dR[c] + J02 * a.Jdp_dR[6 + c]));
-      WR[1][c] = sc * ((Q10 * a.Rci[c] + Q11 * a.Rci[3 + c] + Q12 * a.Rci[6 + c]) - (J11 * a.Jdp_dR[3 + c] + J12 * a.Jdp_dR[6 + c]));
-      WT[0][c] = -sc * (J00 * sm.Rcw[c] + J02 * sm.Rcw[6 + c]);
-      WT[1][c] = -sc * (J11 * sm.Rcw[3 + c] + J12 * sm.Rcw[6 + c]);
-    }
-    const double inv_ref_expo = FAST ? inv_ref_expo_c : a.inv_expo_list[i];
-    float2 Pv;
-    if (FAST && single && lc->level == level) {
-      Pv = lc->Pv;
-    } else {
-      Pv = *reinterpret_cast<const float2 *>(a.warp_patch + (size_t)i * 64 * a.levels + 64 * level + 2 * lane);
-      if (FAST && single) lc->Pv = Pv, lc->level = level;
+    for (int cc = 0; cc < 3; cc++) {
+      WR[0][cc] = sc * ((Q00 * a.Rci[cc] + Q01 * a.Rci[3 + cc] + Q02 * a.Rci[6 + cc]) - (J00 * a.Jdp_dR[cc] + J02 * a.Jdp_dR[6 + cc]));
+      WR[1][cc] = sc * ((Q10 * a.Rci[cc] + Q11 * a.Rci[3 + cc] + Q12 * a.Rci[6 + cc]) - (J11 * a.Jdp_dR[3 + cc] + J12 * a.Jdp_dR[6 + cc]));
+      WT[0][cc] = -sc * (J00 * sm.Rcw[cc] + J02 * sm.Rcw[6 + cc]);
+      WT[1][cc] = -sc * (J11 * sm.Rcw[3 + cc] + J12 * sm.Rcw[6 + cc]);
     }
     __syncwarp();
+    const float *const sT = c.taps;
     // bilinear value grid: G(a,b) = cur_value of patch pixel (a-1, b-1), a,b in 0..9 (same float op order as :1619-1620)
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int g = lane + 32 * k;
+    for (int q = 0; q < 4; q++) {
+      const int g = lane + 32 * q;
       if (g < 100) {
         const int ga = g / 10, gb = g - 10 * ga;
         const float *t0 = sT + ga * 11 + gb;
@@ -257,37 +260,42 @@ __device__ __forceinline__ void vio_process_range(const VioKernelArgs &a, VioSme
       }
     }
     __syncwarp();
-    double sq = 0.0;
+    const float2 Pv = *reinterpret_cast<const float2 *>(&c.pv[2 * lane]);
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
-      const int pix = 2 * lane + k;  // = x*8 + y
+    for (int q = 0; q < 2; q++) {
+      const int pix = 2 * lane + q;  // = x*8 + y
       const int x = pix >> 3, y = pix & 7;
       const float *gc = sG + (x + 1) * 10 + (y + 1);
       // du = 0.5f * (cur(x, y+1) - cur(x, y-1)), dv = 0.5f * (cur(x+1, y) - cur(x-1, y))   (:1600-1609)
       const float du = __fmul_rn(0.5f, __fsub_rn(gc[1], gc[-1]));
       const float dv = __fmul_rn(0.5f, __fsub_rn(gc[10], gc[-10]));
       const double cur_value = (double)gc[0];
-      const double res = inv_expo * cur_value - inv_ref_expo * (double)(k == 0 ? Pv.x : Pv.y);
+      const double res = inv_expo * cur_value - inv_ref_expo * (double)(q == 0 ? Pv.x : Pv.y);
       const double ddu = (double)du, ddv = (double)dv;
       double4 *dst = reinterpret_cast<double4 *>(&sm.rows[warp][pix][0]);
       dst[0] = make_double4(ddu * WR[0][0] + ddv * WR[1][0], ddu * WR[0][1] + ddv * WR[1][1], ddu * WR[0][2] + ddv * WR[1][2],
                             ddu * WT[0][0] + ddv * WT[1][0]);
       dst[1] = make_double4(ddu * WT[0][1] + ddv * WT[1][1], ddu * WT[0][2] + ddv * WT[1][2], a.exposure_en ? cur_value : 0.0, res);
-      sq += res * res;
     }
-    // patch error (visual_submap->errors[i], :1632): fp64 tree sum narrowed to float
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    if (lane == 0) a.errors[i] = (float)sq;
     n_meas += 64.0;
     __syncwarp();
     {
+      // four independent accumulator pairs: the 16 contraction steps form 4 dependency chains of 4 instead of one of 16
       const int g = lane >> 2, t = lane & 3;
+      double A0 = 0.0, A1 = 0.0, B0 = 0.0, B1 = 0.0, C0 = 0.0, C1 = 0.0, E0 = 0.0, E1 = 0.0;
 #pragma unroll
-      for (int s = 0; s < 16; s++) {
-        const double v = sm.rows[warp][4 * s + t][g];
-        dmma_m8n8k4(D0, D1, v, v);
+      for (int s = 0; s < 16; s += 4) {
+        const double v0 = sm.rows[warp][4 * s + t][g], v1 = sm.rows[warp][4 * s + 4 + t][g], v2 = sm.rows[warp][4 * s + 8 + t][g], v3 = sm.rows[warp][4 * s + 12 + t][g];
+        dmma_m8n8k4(A0, A1, v0, v0);
+        dmma_m8n8k4(B0, B1, v1, v1);
+        dmma_m8n8k4(C0, C1, v2, v2);
+        dmma_m8n8k4(E0, E1, v3, v3);
       }
+      const double p0 = (A0 + B0) + (C0 + E0), p1 = (A1 + B1) + (C1 + E1);  // this patch's 8 x 8 block
+      D0 += p0, D1 += p1;
+      // patch error (visual_submap->errors[i], :1632) = sum of the 64 squared residuals = element (7, 7) of the patch's block
+      // (lane 31 holds it): fp64 sum narrowed to float, no separate reduction
+      if (lane == 31) a.errors[i] = (float)p1;
     }
     __syncwarp();
   }
@@ -308,8 +316,8 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_patch_kernel(const VioKern
   double D0 = 0.0, D1 = 0.0, n_meas = 0.0;
   int lo, hi;
   vio_block_range(a.count, lo, hi);
-  vio_process_range(a, sm, a.level, lo, hi, D0, D1, n_meas);
-  reduce_info<VIO_WARPS>(sm.red, D0, D1, n_meas, false, a.partials, a.partial_stride, a.info, a.ctrl);
+  vio_process_range(a, sm, a.level, lo, hi, D0, D1, n_meas, false);
+  reduce_info<VIO_WARPS, 7>(sm.red, D0, D1, n_meas, a.partials, a.partial_stride, a.info, a.ctrl);
 }
 
 
@@ -585,7 +593,7 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_inverse_patch_kernel(const
     }
     __syncwarp();
   }
-  reduce_info<VIO_WARPS>(sm.red, D0, D1, n_meas, false, a.partials, a.partial_stride, a.info, a.ctrl);
+  reduce_info<VIO_WARPS, 7>(sm.red, D0, D1, n_meas, a.partials, a.partial_stride, a.info, a.ctrl);
 }
 
 }  // namespace esikf

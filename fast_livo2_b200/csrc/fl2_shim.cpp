@@ -151,14 +151,21 @@ void VoxelMapManager::StateEstimation(StatesGroup &state_propagat) {
   cfg.voxel_size = config_setting_.max_voxel_size_, cfg.sigma_num = config_setting_.sigma_num_;
   cfg.dept_err = config_setting_.dept_err_, cfg.beam_err = config_setting_.beam_err_;
   cfg.max_layer = config_setting_.max_layer_, cfg.max_iterations = config_setting_.max_iterations_;
-  double sin[ESIKF_STATE_DOUBLES], sprop[ESIKF_STATE_DOUBLES], sout[ESIKF_STATE_DOUBLES];
+  // every buffer that crosses PCIe is staged in page-locked memory owned by the manager (grow-only, no allocation per tick)
+  double *sbuf = st_state_.get(3 * ESIKF_STATE_DOUBLES);
+  float *pts = st_pts_.get((size_t)n * 3 + 4), *dis = st_dis_.get((size_t)n + 1);
+  int32_t *match = st_match_.get((size_t)n + 1), *normal = st_normal_.get((size_t)n + 1);
+  if (!sbuf || !pts || !dis || !match || !normal) {
+    last_status_ = ESIKF_ERR_CUDA, last_error_ = "pinned staging allocation failed";
+    return;
+  }
+  double *sin = sbuf, *sprop = sbuf + ESIKF_STATE_DOUBLES, *sout = sbuf + 2 * ESIKF_STATE_DOUBLES;
   state_.pack(sin);
   state_propagat.pack(sprop);
-  std::vector<int32_t> match(n), normal(n);
-  std::vector<float> dis(n);
   esikf_lio_stats stats;
   static_assert(sizeof(PointXYZ) == 12, "xyz float32");
-  last_status_ = esikf_lio_update(ctx_, n ? &feats_down_body_[0].x : nullptr, n, sin, sprop, &cfg, sout, &stats, match.data(), normal.data(), dis.data());
+  if (n) memcpy(pts, &feats_down_body_[0].x, (size_t)n * 12);
+  last_status_ = esikf_lio_update(ctx_, n ? pts : nullptr, n, sin, sprop, &cfg, sout, &stats, match, normal, dis);
   if (last_status_) {
     last_error_ = esikf_last_error(ctx_);
     return;
@@ -166,15 +173,20 @@ void VoxelMapManager::StateEstimation(StatesGroup &state_propagat) {
   state_.unpack(sout);                 // _state = voxelmap_manager->state_  (LIVMapper.cpp:371)
   position_last_ = state_.pos_end;     // src/voxel_map.cpp:492
   effct_feat_num_ = stats.iters > 0 ? stats.effct_feat_num[stats.iters - 1] : 0;
+  last_iters_ = stats.iters;
   if (!fill_point_lists_) return;
   // body_cov_list_ / cross_mat_list_ (LIVMapper.cpp:418-419), pv_list_ (:372) and ptpl_list_ (:446)
-  std::vector<double> bc((size_t)n * 9), cm((size_t)n * 9);
-  if ((last_status_ = esikf_lio_fetch_point_cov(ctx_, bc.data(), cm.data())) != 0) {
+  double *cov = st_cov_.get((size_t)n * 18 + 2);
+  if (!cov) {
+    last_status_ = ESIKF_ERR_CUDA, last_error_ = "pinned staging allocation failed";
+    return;
+  }
+  const double *bc = cov, *cm = cov + (size_t)n * 9;
+  if ((last_status_ = esikf_lio_fetch_point_cov(ctx_, cov, cov + (size_t)n * 9)) != 0) {
     last_error_ = esikf_last_error(ctx_);
     return;
   }
-  body_cov_list_.assign(n, M3D()), cross_mat_list_.assign(n, M3D());
-  std::vector<pointWithVar>().swap(pv_list_);
+  body_cov_list_.resize(n), cross_mat_list_.resize(n);
   pv_list_.resize(n);
   ptpl_list_.clear();
   const double *R = state_.rot_end.m;
@@ -182,6 +194,7 @@ void VoxelMapManager::StateEstimation(StatesGroup &state_propagat) {
     memcpy(body_cov_list_[i].m, &bc[(size_t)i * 9], 72);
     memcpy(cross_mat_list_[i].m, &cm[(size_t)i * 9], 72);
     pointWithVar &pv = pv_list_[i];
+    pv = pointWithVar();  // the reference rebuilds pv_list_ from default-constructed elements every call (voxel_map.cpp:362-363)
     pv.point_b[0] = feats_down_body_[i].x, pv.point_b[1] = feats_down_body_[i].y, pv.point_b[2] = feats_down_body_[i].z;
     pv.body_var = body_cov_list_[i];
     // point_w / var are recomputed by the caller with the posterior state right after the call (LIVMapper.cpp:413-423);
@@ -225,26 +238,33 @@ void VIOManager::computeJacobianAndUpdateEKF(const GrayImage &img) {
   if (!ctx_ || !state || !state_propagat || !visual_submap) return;
   if (total_points == 0) return;  // src/vio.cpp:786
   const int n = total_points, L = patch_pyrimid_level;
-  std::vector<double> pos((size_t)n * 3);
-  std::vector<float> wp((size_t)n * 64 * L);
-  std::vector<int32_t> sl(n);
+  double *pos = st_pos_.get((size_t)n * 3), *ie = st_ie_.get(n), *sbuf = st_state_.get(3 * ESIKF_STATE_DOUBLES);
+  float *wp = st_wp_.get((size_t)n * 64 * L), *err = st_err_.get(n);
+  int32_t *sl = st_sl_.get(n);
+  uint8_t *im = st_img_.get((size_t)img.cols * img.rows);
+  if (!pos || !ie || !sbuf || !wp || !err || !sl || !im) {
+    last_status_ = ESIKF_ERR_CUDA, last_error_ = "pinned staging allocation failed";
+    return;
+  }
   for (int i = 0; i < n; i++) {
     for (int k = 0; k < 3; k++) pos[(size_t)3 * i + k] = visual_submap->voxel_points_pos[i][k];
     memcpy(&wp[(size_t)i * 64 * L], visual_submap->warp_patch[i].data(), sizeof(float) * 64 * L);
     sl[i] = visual_submap->search_levels[i];
+    ie[i] = visual_submap->inv_expo_list[i];
   }
-  double sin[ESIKF_STATE_DOUBLES], sprop[ESIKF_STATE_DOUBLES], sout[ESIKF_STATE_DOUBLES];
+  memcpy(im, img.data, (size_t)img.cols * img.rows);
+  double *sin = sbuf, *sprop = sbuf + ESIKF_STATE_DOUBLES, *sout = sbuf + 2 * ESIKF_STATE_DOUBLES;
   state->pack(sin);
   state_propagat->pack(sprop);
-  visual_submap->errors.resize(n);
   esikf_vio_stats stats;
-  last_status_ = esikf_vio_update(ctx_, img.data, img.cols, img.rows, pos.data(), wp.data(), sl.data(), visual_submap->inv_expo_list.data(), n, sin, sprop,
-                                  sout, &stats, visual_submap->errors.data());
+  last_status_ = esikf_vio_update(ctx_, im, img.cols, img.rows, pos, wp, sl, ie, n, sin, sprop, sout, &stats, err);
   if (last_status_) {
     last_error_ = esikf_last_error(ctx_);
     return;
   }
+  visual_submap->errors.assign(err, err + n);
   state->unpack(sout);
+  last_total_iters_ = stats.total_iters;
 }
 
 // include/vio.h:151 / src/vio.cpp:203-225: writes patch_tmp[patch_size_total * level + row * patch_size + col]
@@ -527,5 +547,105 @@ int fl2_shim_patch_helpers(const esikf_camera *cam, const esikf_vio_cfg *vcfg, c
   esikf_destroy(ctx);
   return rc;
 }
+
+// ---- persistent session for the end-to-end measurement through the drop-in classes (bench.py e2e_shim): the managers,
+// the host octree and the visual sub-map live across ticks like they do inside LIVMapper.
+struct ShimSession {
+  VoxelMapConfig cfg;
+  VoxelMap map;
+  VoxelMapManager *mgr = nullptr;
+  VIOManager *vio = nullptr;
+  SubSparseMap sub;
+  StatesGroup st, stp;
+  bool has_vio = false;
+  esikf_camera cam{};
+  esikf_vio_cfg vcfg{};
+  ~ShimSession() {
+    delete vio;
+    delete mgr;
+    for (auto &kv : map) delete kv.second;
+  }
+};
+
+void *fl2_shim_session_create(const int64_t *keys, const int32_t *first, const int32_t *count, int n_roots, const esikf_plane *planes, int n_planes,
+                              const esikf_lio_cfg *lcfg, const esikf_extrinsics *ext, const esikf_camera *cam, const esikf_vio_cfg *vcfg, int device) {
+  (void)n_planes;
+  ShimSession *s = new ShimSession;
+  s->cfg.max_voxel_size_ = lcfg->voxel_size, s->cfg.max_layer_ = lcfg->max_layer, s->cfg.max_iterations_ = lcfg->max_iterations;
+  s->cfg.beam_err_ = lcfg->beam_err, s->cfg.dept_err_ = lcfg->dept_err, s->cfg.sigma_num_ = lcfg->sigma_num;
+  build_tree(s->map, s->cfg, keys, first, count, n_roots, planes);
+  s->mgr = new VoxelMapManager(s->cfg, s->map, device);
+  if (s->mgr->last_status_) {
+    delete s;
+    return nullptr;
+  }
+  memcpy(s->mgr->extR_.m, ext->extR, 72);
+  memcpy(s->mgr->extT_.v, ext->extT, 24);
+  s->mgr->SyncDeviceMap();
+  if (s->mgr->last_status_) {
+    delete s;
+    return nullptr;
+  }
+  if (cam && vcfg) {
+    s->has_vio = true, s->cam = *cam, s->vcfg = *vcfg;
+    s->vio = new VIOManager(s->mgr->context());
+    VIOManager &vio = *s->vio;
+    vio.state = &s->st, vio.state_propagat = &s->stp, vio.visual_submap = &s->sub;
+    vio.patch_pyrimid_level = vcfg->patch_pyrimid_level, vio.max_iterations = vcfg->max_iterations, vio.img_point_cov = vcfg->img_point_cov;
+    vio.exposure_estimate_en = vcfg->exposure_estimate_en != 0;
+    vio.cam = *cam;
+    memcpy(vio.Rcl.m, ext->Rcl, 72), memcpy(vio.Pcl.v, ext->Pcl, 24), memcpy(vio.extR.m, ext->extR, 72), memcpy(vio.extT.v, ext->extT, 24);
+    vio.initializeVIO();
+    if (vio.last_status_) {
+      delete s;
+      return nullptr;
+    }
+  }
+  return s;
+}
+
+// One LIVMapper tick pair: LIO (LIVMapper.cpp:356-372) then VIO on the LIO posterior (:305, vio.cpp:1810). iters_out[0] = LIO
+// iterations, [1] = VIO iterations.
+int fl2_shim_session_step(void *h, const float *pts, int n, const double *state_in, const double *state_prop, const uint8_t *img, int n_patches, const double *pos,
+                          const float *warp_patch, const int32_t *search_levels, const double *inv_expo, double *lio_state_out, double *vio_state_out, int32_t *iters_out) {
+  ShimSession *s = static_cast<ShimSession *>(h);
+  if (!s) return ESIKF_ERR_ARG;
+  VoxelMapManager &mgr = *s->mgr;
+  mgr.feats_down_body_.resize(n);
+  if (n) memcpy(mgr.feats_down_body_.data(), pts, (size_t)n * 12);
+  mgr.feats_down_size_ = n;
+  mgr.state_.unpack(state_in);  // voxelmap_manager->state_ = _state  (LIVMapper.cpp:257)
+  StatesGroup prop;
+  prop.unpack(state_prop);
+  mgr.StateEstimation(prop);    // LIVMapper.cpp:370
+  if (mgr.last_status_) return mgr.last_status_;
+  mgr.state_.pack(lio_state_out);
+  iters_out[0] = mgr.last_iters_, iters_out[1] = 0;
+  if (s->has_vio && n_patches > 0) {
+    VIOManager &vio = *s->vio;
+    s->st = mgr.state_, s->stp = mgr.state_;
+    SubSparseMap &sub = s->sub;
+    const int L = s->vcfg.patch_pyrimid_level;
+    if ((int)sub.voxel_points_pos.size() != n_patches) {  // the visual sub-map of the tick (retrieveFromVisualSparseMap's output)
+      sub.voxel_points_pos.resize(n_patches), sub.warp_patch.resize(n_patches), sub.search_levels.resize(n_patches), sub.inv_expo_list.resize(n_patches);
+    }
+    for (int i = 0; i < n_patches; i++) {
+      for (int k = 0; k < 3; k++) sub.voxel_points_pos[i][k] = pos[3 * i + k];
+      sub.warp_patch[i].assign(warp_patch + (size_t)i * 64 * L, warp_patch + (size_t)(i + 1) * 64 * L);
+      sub.search_levels[i] = search_levels[i];
+      sub.inv_expo_list[i] = inv_expo[i];
+    }
+    vio.total_points = n_patches;
+    GrayImage im;
+    im.data = img, im.cols = s->cam.width, im.rows = s->cam.height;
+    vio.computeJacobianAndUpdateEKF(im);
+    if (vio.last_status_) return vio.last_status_;
+    s->st.pack(vio_state_out);
+    iters_out[1] = vio.last_total_iters_;
+  }
+  return 0;
+}
+
+void fl2_shim_session_destroy(void *h) { delete static_cast<ShimSession *>(h); }
 
 }  // extern "C"

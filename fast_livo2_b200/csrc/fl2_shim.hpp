@@ -116,6 +116,30 @@ bool FlattenVoxelMap(const VoxelMap &map, const VoxelMapConfig &cfg, FlatVoxelMa
 // (refitted planes: what esikf_map_patch takes). is_update_ is not used: the reference sets it on every fit and never clears it.
 bool DiffFlatVoxelMaps(const FlatVoxelMap &synced, const FlatVoxelMap &now, std::vector<int32_t> &changed_ids);
 
+// Grow-only page-locked host buffer (esikf_host_alloc): the staging areas the shim hands to the C ABI, so that every
+// per-tick copy is a DMA from / into pinned memory instead of a driver-staged pageable copy.
+template <typename T> class PinnedBuf {
+ public:
+  PinnedBuf() = default;
+  PinnedBuf(const PinnedBuf &) = delete;
+  PinnedBuf &operator=(const PinnedBuf &) = delete;
+  ~PinnedBuf() { esikf_host_free(p_); }
+  T *get(size_t n) {
+    if (n > cap_) {
+      esikf_host_free(p_);
+      cap_ = n + n / 4 + 16;
+      p_ = static_cast<T *>(esikf_host_alloc(cap_ * sizeof(T)));
+      if (!p_) cap_ = 0;
+    }
+    return p_;
+  }
+  T *data() { return p_; }
+
+ private:
+  T *p_ = nullptr;
+  size_t cap_ = 0;
+};
+
 class VoxelMapManager {
  public:
   VoxelMapConfig config_setting_;
@@ -132,6 +156,7 @@ class VoxelMapManager {
   std::vector<PointToPlane> ptpl_list_;
   bool fill_point_lists_ = true;   // pv_list_ / ptpl_list_ / cross_mat_list_ / body_cov_list_ (off: state_ only)
   int last_status_ = 0;            // esikf_status of the last call (the reference's calls return void)
+  int last_iters_ = 0;             // iterations executed by the last StateEstimation
   std::string last_error_;
 
   VoxelMapManager(VoxelMapConfig &config_setting, VoxelMap &voxel_map, int device = 0);
@@ -148,6 +173,9 @@ class VoxelMapManager {
   esikf_ctx *ctx_ = nullptr;
   FlatVoxelMap flat_;
   bool map_synced_ = false, device_has_map_ = false;
+  PinnedBuf<float> st_pts_, st_dis_;
+  PinnedBuf<int32_t> st_match_, st_normal_;
+  PinnedBuf<double> st_state_, st_cov_;
 };
 
 // include/vio.h:26-57 restated over flat storage
@@ -175,6 +203,7 @@ class VIOManager {
   M3D extR;  // setImuToLidarExtrinsic / setLidarToCameraExtrinsic (src/vio.cpp:29-39)
   V3D extT;
   int last_status_ = 0;
+  int last_total_iters_ = 0;  // iterations executed by the last computeJacobianAndUpdateEKF
   std::string last_error_;
 
   explicit VIOManager(esikf_ctx *shared_ctx);  // shares the device context (and stream) of the VoxelMapManager
@@ -188,6 +217,10 @@ class VIOManager {
 
  private:
   esikf_ctx *ctx_ = nullptr;
+  PinnedBuf<double> st_pos_, st_ie_, st_state_;
+  PinnedBuf<float> st_wp_, st_err_;
+  PinnedBuf<int32_t> st_sl_;
+  PinnedBuf<uint8_t> st_img_;
 };
 
 }  // namespace fl2b200

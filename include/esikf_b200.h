@@ -16,6 +16,7 @@
 #ifndef ESIKF_B200_H_
 #define ESIKF_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -30,7 +31,8 @@ enum esikf_status {
   ESIKF_ERR_CUDA = -2,        /* a CUDA runtime call failed; see esikf_last_error */
   ESIKF_ERR_ARG = -3,         /* bad argument (null pointer, negative size, key out of range ...) */
   ESIKF_ERR_STATE = -4,       /* call order (e.g. lio_run before map_upload / set_scan) */
-  ESIKF_ERR_COMM = -5         /* NCCL / peer-memory set-up failed */
+  ESIKF_ERR_COMM = -5         /* NCCL / peer-memory set-up failed, or a bounded in-kernel wait (grid barrier, peer mailbox)
+                                 expired: the update that reported it is invalid (returned by the fetch calls) */
 };
 
 /* StatesGroup (include/common_lib.h:126-223) as a packed POD, 386 doubles:
@@ -120,36 +122,25 @@ const char *esikf_last_error(const esikf_ctx *ctx);
 /* The CUDA stream (cudaStream_t) every kernel of this context is launched on. */
 void *esikf_stream(esikf_ctx *ctx);
 int esikf_synchronize(esikf_ctx *ctx);
+/* Page-locked host memory for callers that stage the per-tick buffers themselves (the C++ shim does): copies from / into
+ * it are DMA transfers instead of driver-staged pageable copies. NULL on failure; free(NULL) is a no-op. */
+void *esikf_host_alloc(size_t bytes);
+void esikf_host_free(void *p);
 /* Number of kernels launched by this context since creation (bench.py "gpu_launches"). */
 int64_t esikf_launch_count(const esikf_ctx *ctx);
 /* solve_mode: 0 = Woodbury 6x6/7x7 form of (H^T H + P^-1)^-1 (default), 1 = literal two 19x19
  * partial-pivot inversions as at src/voxel_map.cpp:468 / src/vio.cpp:1661. */
 int esikf_set_solve_mode(esikf_ctx *ctx, int mode);
 /* loop_mode: how the iteration loop of an update is driven. Results of all modes are bit-identical.
- *   2 (default) = one persistent cooperative kernel per update; every CTA sums the per-CTA partial blocks and runs the
- *       gain solve itself, so an iteration costs one grid barrier and the state never goes through global memory.
- *       With peer GPUs attached (esikf_peer_attach) the update runs as mode 1.
- *   1 = one persistent cooperative kernel per update, gain solve on CTA 0 (two grid barriers per iteration); carries
- *       the in-kernel NVLink all-reduce of the information buffer.
+ *   2 (default; 1 is accepted as an alias) = one persistent cooperative kernel per update: every CTA keeps the state on
+ *       chip, sums the per-CTA partial vectors after ONE grid barrier per iteration and runs the gain solve itself. With
+ *       peer GPUs attached (esikf_peer_attach) the same kernel also carries the NVLink exchange of the information vector.
  *   0 = one residual + one solve launch per iteration (also used with an NCCL communicator or kernel timing on). */
 int esikf_set_loop_mode(esikf_ctx *ctx, int mode);
-/* Opt-in variants of the default (loop_mode 2, one GPU) kernels, OR-ed flags; 0 = none (default). They change when / in
- * which order work is done, not the algorithm: every combination is deterministic and keeps the association bit-identical.
- *   ESIKF_TUNE_DEAL_POINTS       : LIO points assigned to CTAs as 32-point chunks dealt round-robin over all SMs instead of
- *                                  one contiguous block per CTA (evens out sub-divided / unmatched regions of the scan;
- *                                  the fixed summation order of H^T R^-1 H — its last bits — follows the assignment).
- *   ESIKF_TUNE_DEFER_DIAGNOSTICS : CTA 0 writes the per-iteration diagnostics while it waits at the next grid barrier
- *                                  instead of right after the solve (same values, off the critical path).
- *   ESIKF_TUNE_VIO_FAST_PATH     : VIO keeps the iteration-invariant inputs of a warp's patch on chip across iterations,
- *                                  replaces divisions by the power-of-two tap stride with exact multiplications and
- *                                  overlaps the boxminus with the gain elimination (bit-identical results).
- *   ESIKF_TUNE_PEER_REPLICATED   : with peer GPUs attached, keep the replicated-solve kernels: CTA 0 pushes the rank's
- *                                  information buffer into every rank's mailbox and EVERY CTA pulls the rank-ordered sum
- *                                  from the local one (same sum as loop_mode 1's exchange, one grid barrier per iteration). */
-#define ESIKF_TUNE_DEAL_POINTS 1u
-#define ESIKF_TUNE_DEFER_DIAGNOSTICS 2u
-#define ESIKF_TUNE_VIO_FAST_PATH 4u
-#define ESIKF_TUNE_PEER_REPLICATED 8u
+/* Measurement variants, OR-ed flags; 0 = none (default). Same results bit for bit.
+ *   ESIKF_TUNE_STAGE_LDG : LIO plane records are brought into shared memory by coalesced half-warp __ldg copies instead of
+ *                          one cp.async.bulk (TMA engine) per lane — the round-1 staging, kept to measure against. */
+#define ESIKF_TUNE_STAGE_LDG 1u
 int esikf_set_tuning(esikf_ctx *ctx, uint32_t flags);
 int esikf_set_extrinsics(esikf_ctx *ctx, const esikf_extrinsics *ext);
 

@@ -1,0 +1,18 @@
+// Stand-in for the ROS 1 types voxel_map.cpp names (parameter loading, marker publishing) — never exercised by the oracle
+// checks, present so the reference's translation unit compiles unmodified.
+#pragma once
+#include <string>
+#include <vector>
+namespace ros {
+class NodeHandle {
+ public:
+  template <class T> void param(const std::string &, T &v, const T &d) const { v = d; }
+};
+class Publisher {
+ public:
+  template <class M> void publish(const M &) const {}
+};
+struct Time { Time() {} static Time now() { return Time(); } };
+struct Duration { Duration() {} explicit Duration(double) {} };
+struct Rate { explicit Rate(double) {} void sleep() {} };
+}  // namespace ros

@@ -24,6 +24,8 @@ def load(kind="parity"):
     if kind in _libs:
         return _libs[kind]
     path = os.path.join(ORACLE_DIR, f"liborc_{kind}.so")
+    if kind == "baseline" and os.environ.get("ORC_BASELINE_SO") and os.path.exists(os.environ["ORC_BASELINE_SO"]):
+        path = os.environ["ORC_BASELINE_SO"]  # built on the host the timing runs on (bench.py native_baseline_build)
     if not os.path.exists(path):
         build_oracle()
     lib = C.CDLL(path)

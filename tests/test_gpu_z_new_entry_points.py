@@ -150,7 +150,6 @@ def test_shim_incremental_map_sync_equals_fresh_upload(small_frame):
     assert np.array_equal(out_inc, out_fresh)
 
 
-@pytest.mark.skipif(os.environ.get("ESIKF_EXPERIMENTAL") != "1", reason="written after the round's last GPU call; tools/validate_tuning.sh runs it")
 def test_lio_association_on_voxel_boundaries_and_negative_keys(gpu_ctx, small_frame):
     """Bit-exact voxel indexing where it is fragile (same scan as the CPU cross-check in test_oracle_numpy_crosscheck.py): world
     points exactly on voxel boundaries with both signs (trunc(q - 1) vs floor), half a float ulp to either side, z == 0."""

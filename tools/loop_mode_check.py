@@ -12,7 +12,7 @@ import torch  # noqa: E402
 
 from fast_livo2_b200 import api, synthetic as S  # noqa: E402
 
-MODES = [int(m) for m in os.environ.get("MODES", "2,1,0").split(",")]
+MODES = [int(m) for m in os.environ.get("MODES", "2,0").split(",")]
 STEPS = int(os.environ.get("STEPS", 30))
 
 
@@ -112,13 +112,19 @@ def check(fr, label, time_it):
                 ctx.vio_run(post_h, post_h)
             ctx.synchronize()
             s = ctx.get_phase_stamps().astype(np.int64)
-            names = ["consts", "slice", "barrier", "reduce", "solve", "publish"]
-            for slot in range(72):
-                if s[slot, 0] == 0:
-                    continue
-                d = np.diff(s[slot, :7])
-                print(("LIO" if slot < 8 else "VIO"), slot if slot < 8 else slot - 8, " ".join(f"{n}={x / 1000:.2f}us" for n, x in zip(names, d)),
-                      f"total={(s[slot, 6] - s[slot, 0]) / 1000:.2f}us", flush=True)
+            names = ["consts", "slice", "barrier", "reduce", "solve"]
+            rows = [k for k in range(72) if s[k, 0] != 0]
+            for j, slot in enumerate(rows):
+                d = np.diff(s[slot, :6])
+                nxt = s[rows[j + 1], 0] if j + 1 < len(rows) and (rows[j + 1] < 8) == (slot < 8) else s[slot, 5]
+                fine = f" [gain={(s[slot, 6] - s[slot, 4]) / 1000:.2f} boxplus={(s[slot, 7] - s[slot, 6]) / 1000:.2f} rest={(s[slot, 5] - s[slot, 7]) / 1000:.2f}]" if s[slot, 6] else ""
+                print(("LIO" if slot < 8 else "VIO"), slot if slot < 8 else slot - 8, " ".join(f"{n}={x / 1000:.2f}us" for n, x in zip(names, d)) + fine,
+                      f"to-next={(nxt - s[slot, 5]) / 1000:.2f}us total={(nxt - s[slot, 0]) / 1000:.2f}us", flush=True)
+            c = ctx.cta_stamps.astype(np.int64)
+            c = c[c > 0]
+            if len(c) and s[3, 0]:
+                print(f"per-CTA slice end of LIO iteration 3 relative to CTA 0's iteration start (us): n={len(c)} min={(c.min() - s[3, 0]) / 1e3:.2f} "
+                      f"p50={(np.median(c) - s[3, 0]) / 1e3:.2f} p90={(np.percentile(c, 90) - s[3, 0]) / 1e3:.2f} max={(c.max() - s[3, 0]) / 1e3:.2f}", flush=True)
         ctx.set_tuning(0)
     ctx.close()
     return ok

@@ -32,7 +32,11 @@ if world > 1:
 cfg_name = os.environ.get("PARITY_CFG", "cfg2")
 modes = os.environ.get("PARITY_MODES", "p2p").split(",")
 steps = int(os.environ.get("PARITY_STEPS", "30"))
-fr = W.frame(cfg_name)
+if world > 1 and rank != 0:
+    dist.barrier()
+fr = W.frame(cfg_name)  # one rank builds (or finds) the seeded frame, the others read the same pickle
+if world > 1 and rank == 0:
+    dist.barrier()
 n, npatch = len(fr["pts"]), len(fr["vis_pos"])
 failures = []
 

@@ -21,21 +21,3 @@ for _ in range(steps):
     r = ctx.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"])
     v = ctx.vio_update(fr["img"], fr["vis_pos"], w["warp_patch"], w["search_levels"], fr["inv_ref_expo"], r["state"], r["state"])
 print("iters", r["iters"], v["total_iters"], "M", r["M"])
-if os.environ.get("STAMPS"):
-    ctx.set_phase_stamps(True)
-    r = ctx.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"])
-    ctx.get_phase_stamps(); d = ctx.debug_stamps.astype(np.int64)
-    print('LIO tile phases (us): probe,stage,assoc,extra,neigh,jac,dmma =', np.round(np.diff(d[0:8])/1000,2))
-    c = ctx.cta_stamps.astype(np.int64); c = c[c > 0]; s3 = ctx.get_phase_stamps().astype(np.int64)[3]
-    print('per-CTA slice end of LIO iteration 3 relative to CTA0 iteration start (us): n=%d min=%.2f p50=%.2f p90=%.2f max=%.2f ; barrier released at %.2f' % (len(c), (c.min()-s3[0])/1e3, (np.median(c)-s3[0])/1e3, (np.percentile(c,90)-s3[0])/1e3, (c.max()-s3[0])/1e3, (s3[3]-s3[0])/1e3))
-    print('sorted tail (us):', np.round((np.sort(c)[-12:]-s3[0])/1e3,2), ' which CTAs:', np.argsort(ctx.cta_stamps.astype(np.int64)[:len(c)])[-12:])
-    print('reduce (us)', (d[13]-d[12])/1000, ' solve phases load,boxminus,gain,sol,boxplus,write =', np.round(np.diff(d[16:23])/1000,2))
-    for rep in range(2):
-        r = ctx.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"])
-        v = ctx.vio_update(fr["img"], fr["vis_pos"], w["warp_patch"], w["search_levels"], fr["inv_ref_expo"], r["state"], r["state"])
-    s = ctx.get_phase_stamps().astype(np.int64)
-    names = ["consts", "slice", "barrierA", "reduce", "solve", "barrierB"]
-    for slot in range(72):
-        if s[slot, 0] == 0: continue
-        d = np.diff(s[slot, :7])
-        print(("LIO" if slot < 8 else "VIO"), slot if slot < 8 else slot - 8, " ".join(f"{n}={x/1000:.2f}us" for n, x in zip(names, d)), f"total={(s[slot,6]-s[slot,0])/1000:.2f}us")
