@@ -1,6 +1,9 @@
 // Stand-in for the ROS 1 types voxel_map.cpp names (parameter loading, marker publishing) — never exercised by the oracle
 // checks, present so the reference's translation unit compiles unmodified.
 #pragma once
+#include <deque>
+#include <iostream>
+#include <map>
 #include <string>
 #include <vector>
 namespace ros {

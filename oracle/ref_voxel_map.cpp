@@ -1,0 +1,160 @@
+// oracle/_ref — the reference's OWN LIO update, compiled from where it lies (/root/reference/src/voxel_map.cpp with
+// include/voxel_map.h, common_lib.h, utils/*.h, unmodified) against the stand-in headers of oracle/ref_shim/ (Eigen, PCL,
+// ROS message types: none of them is in this image). TEST INFRASTRUCTURE ONLY: used to pin the oracle restatement
+// (oracle/orc_lio.cpp) against the reference's code — tests/test_oracle_ref_pin.py — and, optionally, as a CPU timing of the
+// reference source. No reference source is copied into this repository; this file only #includes it and adds a C entry
+// point that builds the octree the reference walks from the flat map arrays and runs VoxelMapManager::StateEstimation.
+#define ROOT_DIR ""
+#include <cstring>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "/root/reference/src/voxel_map.cpp"
+
+namespace {
+// the 256-byte plane record of include/esikf_b200.h (restated here: the oracle side must not include product headers)
+struct FlatPlane {
+  double center[3];
+  double normal[3];
+  double plane_var[21];
+  float d;
+  float radius;
+  int32_t layer;
+  int32_t path;
+  int32_t pad[6];
+};
+static_assert(sizeof(FlatPlane) == 256, "flat plane record");
+
+void unpack_state(const double *s, StatesGroup &st) {
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) st.rot_end(i, j) = s[3 * i + j];
+  for (int i = 0; i < 3; i++) st.pos_end(i) = s[9 + i], st.vel_end(i) = s[13 + i], st.bias_g(i) = s[16 + i], st.bias_a(i) = s[19 + i], st.gravity(i) = s[22 + i];
+  st.inv_expo_time = s[12];
+  for (int i = 0; i < 19; i++)
+    for (int j = 0; j < 19; j++) st.cov(i, j) = s[25 + 19 * i + j];
+}
+void pack_state(const StatesGroup &st, double *s) {
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) s[3 * i + j] = st.rot_end(i, j);
+  for (int i = 0; i < 3; i++) s[9 + i] = st.pos_end(i), s[13 + i] = st.vel_end(i), s[16 + i] = st.bias_g(i), s[19 + i] = st.bias_a(i), s[22 + i] = st.gravity(i);
+  s[12] = st.inv_expo_time;
+  for (int i = 0; i < 19; i++)
+    for (int j = 0; j < 19; j++) s[25 + 19 * i + j] = st.cov(i, j);
+}
+}  // namespace
+
+extern "C" {
+
+// cfg: voxel_size, max_layer, max_iterations, sigma_num, dept_err, beam_err.
+// Outputs: state_out (386), M_out[8] (effective feature num per iteration, parsed from the reference's own console line,
+// voxel_map.cpp:404-405), iters_out, normals_out (n x 3: pv_list_[i].normal), and the final ptpl_list_ as
+// ptpl_center (k x 3), ptpl_dis (k), ptpl_point_b (k x 3) with k = *n_ptpl (capacity n). Returns 0.
+int ref_lio_state_estimation(const int64_t *keys, const int32_t *first, const int32_t *count, int n_roots, const void *planes_v, int n_planes, const double *cfg,
+                             const double *extR, const double *extT, const float *pts, int n, const double *state_in, const double *state_prop, double *state_out,
+                             int32_t *M_out, int32_t *iters_out, double *normals_out, int32_t *n_ptpl, double *ptpl_center, float *ptpl_dis, float *ptpl_point_b,
+                             double *seconds_out) {
+  (void)n_planes;
+  const FlatPlane *planes = static_cast<const FlatPlane *>(planes_v);
+  VoxelMapConfig config;
+  config.max_voxel_size_ = cfg[0], config.max_layer_ = (int)cfg[1], config.max_iterations_ = (int)cfg[2], config.sigma_num_ = cfg[3];
+  config.dept_err_ = cfg[4], config.beam_err_ = cfg[5];
+  config.layer_init_num_ = std::vector<int>{5, 5, 5, 5, 5};
+  config.max_points_num_ = 50, config.planner_threshold_ = 0.01, config.is_pub_plane_map_ = false;
+  config.sliding_thresh = 8, config.map_sliding_en = false, config.half_map_size = 100;
+  std::unordered_map<VOXEL_LOCATION, VoxelOctoTree *> voxel_map;
+  // the octree build_single_residual walks: roots positioned like BuildVoxelMap does (voxel_map.cpp:575-581), plane nodes at
+  // (layer, path) carrying the fitted plane
+  const float voxel_size = config.max_voxel_size_;
+  for (int r = 0; r < n_roots; r++) {
+    VOXEL_LOCATION position(keys[3 * r], keys[3 * r + 1], keys[3 * r + 2]);
+    VoxelOctoTree *root = new VoxelOctoTree(config.max_layer_, 0, 5, config.max_points_num_, (float)config.planner_threshold_);
+    root->quater_length_ = voxel_size / 4;
+    root->voxel_center_[0] = (0.5 + position.x) * voxel_size;
+    root->voxel_center_[1] = (0.5 + position.y) * voxel_size;
+    root->voxel_center_[2] = (0.5 + position.z) * voxel_size;
+    root->init_octo_ = true;
+    voxel_map[position] = root;
+    for (int c = 0; c < count[r]; c++) {
+      const FlatPlane &f = planes[first[r] + c];
+      VoxelOctoTree *node = root;
+      for (int l = 0; l < f.layer; l++) {
+        const int leaf = (f.path >> (3 * l)) & 7;
+        if (node->leaves_[leaf] == nullptr) {
+          VoxelOctoTree *ch = new VoxelOctoTree(config.max_layer_, l + 1, 5, config.max_points_num_, (float)config.planner_threshold_);
+          const int xyz[3] = {(leaf >> 2) & 1, (leaf >> 1) & 1, leaf & 1};
+          for (int k = 0; k < 3; k++) ch->voxel_center_[k] = node->voxel_center_[k] + (2 * xyz[k] - 1) * node->quater_length_;
+          ch->quater_length_ = node->quater_length_ / 2;
+          ch->init_octo_ = true;
+          node->leaves_[leaf] = ch;
+        }
+        node = node->leaves_[leaf];
+      }
+      VoxelPlane &p = *node->plane_ptr_;
+      for (int k = 0; k < 3; k++) p.center_(k) = f.center[k], p.normal_(k) = f.normal[k];
+      int t = 0;
+      for (int i = 0; i < 6; i++)
+        for (int j = i; j < 6; j++) p.plane_var_(i, j) = p.plane_var_(j, i) = f.plane_var[t++];
+      p.d_ = f.d, p.radius_ = f.radius, p.is_plane_ = true, p.is_init_ = true;
+    }
+  }
+  int rc = 0;
+  {
+    VoxelMapManager mgr(config, voxel_map);
+    for (int i = 0; i < 3; i++) {
+      for (int j = 0; j < 3; j++) mgr.extR_(i, j) = extR[3 * i + j];
+      mgr.extT_(i) = extT[i];
+    }
+    mgr.feats_down_body_->points.resize(n);
+    for (int i = 0; i < n; i++) {
+      PointType &p = mgr.feats_down_body_->points[i];
+      p.x = pts[3 * i], p.y = pts[3 * i + 1], p.z = pts[3 * i + 2];
+    }
+    mgr.feats_down_size_ = n;
+    unpack_state(state_in, mgr.state_);  // voxelmap_manager->state_ = _state (LIVMapper.cpp:257)
+    StatesGroup prop;
+    unpack_state(state_prop, prop);
+    // the reference reports the per-iteration effective feature number on std::cout only: capture it
+    std::ostringstream captured;
+    std::streambuf *old = std::cout.rdbuf(captured.rdbuf());
+    const double t0 = omp_get_wtime();
+    mgr.StateEstimation(prop);  // LIVMapper.cpp:370
+    const double t1 = omp_get_wtime();
+    std::cout.rdbuf(old);
+    if (seconds_out) *seconds_out = t1 - t0;
+    int iters = 0;
+    {
+      const std::string txt = captured.str(), key = "effective feature num: ";
+      size_t pos = 0;
+      while ((pos = txt.find(key, pos)) != std::string::npos && iters < 8) {
+        pos += key.size();
+        M_out[iters++] = atoi(txt.c_str() + pos);
+      }
+    }
+    *iters_out = iters;
+    pack_state(mgr.state_, state_out);
+    for (int i = 0; i < n; i++)
+      for (int k = 0; k < 3; k++) normals_out[3 * i + k] = mgr.pv_list_[i].normal(k);
+    const int k = (int)mgr.ptpl_list_.size();
+    *n_ptpl = k;
+    for (int i = 0; i < k && i < n; i++) {
+      const PointToPlane &q = mgr.ptpl_list_[i];
+      for (int c = 0; c < 3; c++) ptpl_center[3 * i + c] = q.center_(c), ptpl_point_b[3 * i + c] = (float)q.point_b_(c);
+      ptpl_dis[i] = q.dis_to_plane_;
+    }
+  }
+  for (auto &kv : voxel_map) delete kv.second;
+  return rc;
+}
+
+// calcBodyCov of the reference (voxel_map.cpp:15-34) for one point.
+void ref_calc_body_cov(const double *pb, float range_inc, float degree_inc, double *cov9) {
+  Eigen::Vector3d p(pb[0], pb[1], pb[2]);
+  Eigen::Matrix3d cov;
+  calcBodyCov(p, range_inc, degree_inc, cov);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) cov9[3 * i + j] = cov(i, j);
+}
+
+}  // extern "C"

@@ -268,3 +268,41 @@ def inverse_refs_from_frame(fr):
     f = pc / np.linalg.norm(pc, axis=1, keepdims=True)
     return dict(ref_imgs=[fr["img_ref"]], ref_img_index=np.zeros(n, np.int32), ref_px=np.ascontiguousarray(fr["px_ref"], dtype=np.float64),
                 ref_f=np.ascontiguousarray(f), ref_R=np.tile(R.reshape(1, 9), (n, 1)), ref_pos=np.tile(-R.T @ t, (n, 1)))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# oracle/_ref: the reference's own src/voxel_map.cpp compiled against stand-in headers (oracle/ref_voxel_map.cpp). Present
+# only where it was built (the build container has /root/reference; the .so travels with the snapshot).
+REF_LIO_SO = os.path.join(ORACLE_DIR, "_ref", "libfl2_ref_lio.so")
+
+
+def ref_lio_available():
+    return os.path.exists(REF_LIO_SO)
+
+
+def ref_lio_state_estimation(fr, state_in=None, state_prop=None, cfg=None, pts=None):
+    """VoxelMapManager::StateEstimation of the REFERENCE SOURCE on a synthetic frame's flat map / scan."""
+    lib = C.CDLL(REF_LIO_SO)
+    cfg = cfg or fr["lio_cfg"]
+    m = fr["map"]
+    k, f, c, p = (np.ascontiguousarray(m["keys"], dtype=np.int64), np.ascontiguousarray(m["first"], dtype=np.int32), np.ascontiguousarray(m["count"], dtype=np.int32),
+                  np.ascontiguousarray(m["planes"]))
+    pts = np.ascontiguousarray(fr["pts"] if pts is None else pts, dtype=np.float32)
+    n = len(pts)
+    si = c64(fr["state_prior"] if state_in is None else state_in)
+    sp = c64(fr["state_prior"] if state_prop is None else state_prop)
+    cf = np.array([cfg.voxel_size, cfg.max_layer, cfg.max_iterations, cfg.sigma_num, cfg.dept_err, cfg.beam_err], dtype=np.float64)
+    out = np.zeros(STATE_PACK)
+    M = np.zeros(8, np.int32)
+    iters, nptpl = C.c_int32(0), C.c_int32(0)
+    normals = np.zeros((n, 3))
+    centers = np.zeros((n, 3))
+    dis = np.zeros(n, np.float32)
+    pb = np.zeros((n, 3), np.float32)
+    secs = C.c_double(0)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.ref_lio_state_estimation(vp(k), vp(f), vp(c), len(f), vp(p), len(p), vp(cf), vp(c64(fr["ext"].extR)), vp(c64(fr["ext"].extT)), vp(pts), n, vp(si), vp(sp),
+                                      vp(out), vp(M), C.byref(iters), vp(normals), C.byref(nptpl), vp(centers), vp(dis), vp(pb), C.byref(secs))
+    assert rc == 0
+    kk = nptpl.value
+    return dict(state=out, iters=iters.value, M=M[:iters.value].copy(), normals=normals, ptpl_center=centers[:kk], ptpl_dis=dis[:kk], ptpl_point_b=pb[:kk], secs=secs.value)

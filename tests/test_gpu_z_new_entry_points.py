@@ -150,32 +150,25 @@ def test_shim_incremental_map_sync_equals_fresh_upload(small_frame):
     assert np.array_equal(out_inc, out_fresh)
 
 
-def test_lio_association_on_voxel_boundaries_and_negative_keys(gpu_ctx, small_frame):
-    """Bit-exact voxel indexing where it is fragile (same scan as the CPU cross-check in test_oracle_numpy_crosscheck.py): world
-    points exactly on voxel boundaries with both signs (trunc(q - 1) vs floor), half a float ulp to either side, z == 0."""
+@pytest.mark.parametrize("kind", ["voxel_0.5", "voxel_0.4", "voxel_2.0"])
+def test_lio_association_on_voxel_boundaries_and_negative_keys(gpu_ctx, kind):
+    """Bit-exact voxel indexing and neighbour rule where they are fragile (parity_util.edge_scan: points exactly on voxel
+    corners / faces with both signs, one float ulp to either side, z == 0, and off-plane points that send the lookup to
+    the one neighbour voxel the unit-mixing rule picks), for the three voxel sizes of the shipped configs: 0.5 (exact
+    reciprocal: multiply), 0.4 (true fp64 division) and 2.0. The same scans go through the reference source on the CPU in
+    tests/test_oracle_ref_pin.py::test_edge_scan_oracle_reproduces_the_reference_source."""
+    from conftest import get_frame
     from fast_livo2_b200 import synthetic as S
-    from parity_util import assert_state_close
+    from parity_util import assert_state_close, edge_scan
+    from test_oracle_ref_pin import EDGE_FRAMES
 
-    fr = dict(small_frame)
-    fr["ext"] = S.Extrinsics(np.eye(3), np.zeros(3), small_frame["ext"].Rcl, small_frame["ext"].Pcl)
-    st = S.unpack_state(small_frame["state_prior"])
-    state = S.pack_state(np.eye(3), np.zeros(3), 1.0, st["v"], g=st["g"], cov=st["cov"])
+    fr = get_frame(**EDGE_FRAMES[kind])
+    pts, ext, state = edge_scan(fr)
     vs = fr["lio_cfg"].voxel_size
-    keys = fr["map"]["keys"]
-    rng = np.random.default_rng(4)
-    pick = keys[rng.choice(len(keys), 60, replace=False)].astype(np.float64)
-    on_corner = (pick * vs).astype(np.float32)
-    on_face = on_corner.copy()
-    on_face[:, 1] += np.float32(0.37 * vs)
-    inside = ((pick + rng.uniform(0.05, 0.95, pick.shape)) * vs).astype(np.float32)
-    zero_z = inside.copy()
-    zero_z[:, 2] = 0.0
-    pts = np.ascontiguousarray(np.concatenate([on_corner, on_face, np.nextafter(on_corner, np.float32(-np.inf)), np.nextafter(on_corner, np.float32(np.inf)),
-                                               inside, zero_z]))
-    gpu_ctx.set_extrinsics(fr["ext"])
+    gpu_ctx.set_extrinsics(ext)
     gpu_ctx.map_upload(fr["map"], vs)
     g = gpu_ctx.lio_update(pts, state, state, fr["lio_cfg"])
-    lio = O.OracleLIO(fr["lio_cfg"], fr["ext"])
+    lio = O.OracleLIO(fr["lio_cfg"], ext)
     lio.set_map(fr["map"])
     o = lio.state_estimation(pts, state, state)
     assert g["iters"] == o["iters"] and np.array_equal(g["M"], o["M"]) and o["M"][0] > 20
