@@ -394,12 +394,17 @@ def b200_arm(args, rank, world, local_rank):
     # ---------------- parity of THIS run against the CPU oracle — at every N, and it fails the run
     parity = parity_block(fr, r0, v0, world) if rank == 0 else None
     if dist is not None:
+        torch.cuda.synchronize()
         dist.barrier()  # the oracle runs for seconds on rank 0: nobody launches an update that would wait for it inside a kernel
 
     ext_stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
+        # Drain the update stream BEFORE the collective: a persistent update kernel occupies every SM (co-resident cooperative
+        # grid) and spins on its peers, and an NCCL kernel of the barrier that slips in between two queued updates on one rank
+        # keeps that rank's next cooperative launch from becoming resident while the peers wait for it inside their kernels.
+        torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
@@ -493,7 +498,8 @@ def b200_arm(args, rank, world, local_rank):
             e2e_shim = {"value": its / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / K, "iters_per_step": its / K,
                         "path": "fl2b200::VoxelMapManager::StateEstimation + VIOManager::computeJacobianAndUpdateEKF (libfl2_shim.so), pageable std::vector "
                                 "buffers, fill_point_lists_ = true (pv_list_ / ptpl_list_ rebuilt on the host every tick)",
-                        "state_equal_to_c_abi": bool(np.array_equal(s_lio, r0["state"]) and (not has_vio or np.array_equal(s_vio, v0["state"])))}
+                        "state_equal_to_c_abi": bool(np.array_equal(s_lio, r0["state"]) and (not has_vio or np.array_equal(s_vio, v0["state"]))),
+                        "max_abs_state_diff_to_c_abi": [float(np.abs(s_lio - r0["state"]).max()), float(np.abs(s_vio - v0["state"]).max()) if has_vio else 0.0]}
             close()
         except Exception as e:  # measurement extra: never lose the bench line over it
             e2e_shim = {"error": repr(e)}

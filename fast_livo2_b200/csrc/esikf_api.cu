@@ -365,6 +365,18 @@ int esikf_set_extrinsics(esikf_ctx *ctx, const esikf_extrinsics *ext) {
   return ESIKF_OK;
 }
 
+int esikf_set_lidar_extrinsics(esikf_ctx *ctx, const double extR[9], const double extT[3]) {
+  if (!ctx || !extR || !extT) return ESIKF_ERR_ARG;
+  esikf_extrinsics e = ctx->ext;
+  if (!ctx->have_ext) {
+    memset(&e, 0, sizeof(e));
+    e.Rcl[0] = e.Rcl[4] = e.Rcl[8] = 1.0;
+  }
+  memcpy(e.extR, extR, sizeof(e.extR));
+  memcpy(e.extT, extT, sizeof(e.extT));
+  return esikf_set_extrinsics(ctx, &e);
+}
+
 // ---------------------------------------------------------------------------------------------------------------- map
 int esikf_map_upload(esikf_ctx *ctx, const int64_t *keys, const int32_t *first, const int32_t *count, int32_t n_roots,
                      const esikf_plane *planes, int32_t n_planes, double voxel_size) {

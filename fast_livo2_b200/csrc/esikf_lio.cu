@@ -28,6 +28,9 @@ namespace esikf {
 #ifndef LIO_COLD
 #define LIO_COLD __forceinline__
 #endif
+#ifndef LIO_FULL_REC
+#define LIO_FULL_REC 0  // cold candidates: head first, covariance part after the range gate (0, default) or the whole record in one round trip (1). Measured on config 2: 123.3 us against 132.0 us per LIO update — the 18 extra live registers of the one-trip form cost more in spills than the saved L2 round trip (profiles/loop_modes_r02_ab_cold_paths.txt)
+#endif
 #define LIO_THREADS 704  // 22 warps, one CTA per SM: 148 x 704 = 104k points in a single round
 #define LIO_WARPS (LIO_THREADS / 32)
 
@@ -312,12 +315,37 @@ __device__ __forceinline__ EvalOut eval_cold(const double *__restrict__ q, const
                                              const LioSmem &sm, double sigma_num) {
   EvalOut o;
   o.pass = false, o.sigma_l = 0.0, o.dis = 0.f, o.dis_to_plane = 0.f;
-  const RecHead h = load_head(q);
+#if !LIO_FULL_REC
+  {
+    const RecHead h = load_head(q);
+    const Gate1 g = gate_range(h, pw);
+    if (g.pass) {
+      double m0, m1, m2;
+      rot_t_n(sm.R, h, m0, m1, m2);
+      const double sigma_l = sigma_plane(q, g.e0, g.e1, g.e2) + quad_bc(bc, m0, m1, m2) + spp_of(h, cx, cy, cz, sm.Ptt, sm.Ppp);
+      if ((double)g.dis_to_plane < sigma_num * sqrt(sigma_l)) o.pass = true, o.sigma_l = sigma_l, o.dis = (float)g.sd, o.dis_to_plane = g.dis_to_plane;
+    }
+    return o;
+  }
+#endif
+  // the whole 144-byte record in ONE round trip (these records come from global memory: a second, dependent trip for the
+  // covariance part after the range gate would double the latency of the pass)
+  const double2 *__restrict__ q2 = reinterpret_cast<const double2 *>(q);
+  const double2 r0 = __ldg(q2), r1 = __ldg(q2 + 1), r2 = __ldg(q2 + 2), r3 = __ldg(q2 + 3), r4 = __ldg(q2 + 4), r5 = __ldg(q2 + 5), r6 = __ldg(q2 + 6), r7 = __ldg(q2 + 7),
+                r8 = __ldg(q2 + 8);
+  RecHead h;
+  h.c0 = r0.x, h.c1 = r0.y, h.c2 = r1.x, h.n0 = r1.y, h.n1 = r2.x, h.n2 = r2.y;
+  h.d = __int_as_float((int)(__double_as_longlong(r8.x) & 0xffffffffll)), h.radius = __int_as_float((int)(__double_as_longlong(r8.x) >> 32));
   const Gate1 g = gate_range(h, pw);
   if (g.pass) {
     double m0, m1, m2;
     rot_t_n(sm.R, h, m0, m1, m2);
-    const double sigma_l = sigma_plane(q, g.e0, g.e1, g.e2) + quad_bc(bc, m0, m1, m2) + spp_of(h, cx, cy, cz, sm.Ptt, sm.Ppp);
+    // sigma_plane on the registers: paa = r3 r4 r5 (xx xy | xz yy | yz zz), b = r6.x r6.y r7.x, cnn = r7.y
+    const double t0 = g.e0 * r3.x + g.e1 * r3.y + g.e2 * r4.x;
+    const double t1 = g.e0 * r3.y + g.e1 * r4.y + g.e2 * r5.x;
+    const double t2 = g.e0 * r4.x + g.e1 * r5.x + g.e2 * r5.y;
+    const double sp = (t0 * g.e0 + t1 * g.e1 + t2 * g.e2) + 2.0 * (g.e0 * r6.x + g.e1 * r6.y + g.e2 * r7.x) + r7.y;
+    const double sigma_l = sp + quad_bc(bc, m0, m1, m2) + spp_of(h, cx, cy, cz, sm.Ptt, sm.Ppp);
     if ((double)g.dis_to_plane < sigma_num * sqrt(sigma_l)) o.pass = true, o.sigma_l = sigma_l, o.dis = (float)g.sd, o.dis_to_plane = g.dis_to_plane;
   }
   return o;
@@ -701,18 +729,17 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
     // ---- phase 3: association. Resident record first (hot path), then the extras of sub-divided voxels / neighbour voxel.
     int best_idx = -1;
     float best_dis = 0.f;
-    double m0 = 0, m1 = 0, m2 = 0;  // R^T n of the resident record (reused by the Jacobian row)
     const bool have0 = valid && found && count > 0;
-    RecHead h0;
-    h0.c0 = h0.c1 = h0.c2 = h0.n0 = h0.n1 = h0.n2 = 0.0, h0.d = h0.radius = 0.f;
     bool pass0 = false;
     double sigma0 = 0.0;
     float dis0 = 0.f, dtp0 = 0.f;
     if (have0) {
-      h0 = load_head(slot);
+      // nothing of this block stays live past it but the verdict: the Jacobian phase re-reads the slot (registers)
+      const RecHead h0 = load_head(slot);
       const Gate1 g = gate_range(h0, pw);
-      rot_t_n(sm.R, h0, m0, m1, m2);
       if (g.pass) {
+        double m0, m1, m2;
+        rot_t_n(sm.R, h0, m0, m1, m2);
         const double2 sw = *reinterpret_cast<const double2 *>(slot + SL_SPP);  // {spp, wgt}
         sigma0 = sigma_plane(slot, g.e0, g.e1, g.e2) + quad_bc(slot + SL_BC, m0, m1, m2) + sw.x;
         if ((double)g.dis_to_plane < a.sigma_num * sqrt(sigma0)) pass0 = true, dis0 = (float)g.sd, dtp0 = g.dis_to_plane;
@@ -721,7 +748,7 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
     }
     const bool pend1 = have0 && count > 1;
     const bool need_nb = valid && found && !pend1 && best_idx < 0;  // for pend1 lanes: decided after their extras
-    if (__any_sync(0xffffffffu, pend1 || need_nb)) {  // cold: out of line, narrow arguments
+    if (__any_sync(0xffffffffu, pend1 || need_nb)) {  // cold: narrow arguments, everything else comes from shared memory
       const AssocOut ao = lio_cold_assoc(sm, warp, lane, (pend1 ? 1u : 0u) | ((valid && found) ? 2u : 0u) | (pass0 ? 4u : 0u), (float)pw[0], (float)pw[1], (float)pw[2],
                                          first, count, sigma0, dis0, dtp0);
       best_idx = ao.idx, best_dis = ao.dis;
@@ -734,15 +761,19 @@ __device__ __forceinline__ void lio_process_range(const LioKernelArgs &a, LioSme
     if (matched) {
       const bool hot = have0 && best_idx == (int)first;
       const double *__restrict__ q = hot ? slot : reinterpret_cast<const double *>(a.recs + best_idx);
-      const RecHead h = hot ? h0 : load_head(q);
-      rn0 = h.n0, rn1 = h.n1, rn2 = h.n2;
+      double m0, m1, m2;
+      {
+        const double2 *__restrict__ q2 = reinterpret_cast<const double2 *>(q);
+        const double2 a1 = q2[1], a2 = q2[2];  // c2 n0 | n1 n2
+        rn0 = a1.y, rn1 = a2.x, rn2 = a2.y;
+        m0 = sm.R[0] * rn0 + sm.R[3] * rn1 + sm.R[6] * rn2, m1 = sm.R[1] * rn0 + sm.R[4] * rn1 + sm.R[7] * rn2, m2 = sm.R[2] * rn0 + sm.R[5] * rn1 + sm.R[8] * rn2;
+      }
       const double2 sw = *reinterpret_cast<const double2 *>(slot + SL_SPP);  // {spp, wgt}
       wgt = (reinterpret_cast<const int *>(slot + SL_META)[1] == best_idx) ? sw.y : lio_cold_wgt(sm, warp, lane, q, best_idx);
       float px, py, pz;
       slot_point(slot, px, py, pz);
       double pi0, pi1, pi2;
       p_imu(a.extR, a.extT, px, py, pz, pi0, pi1, pi2);
-      if (!hot) rot_t_n(sm.R, h, m0, m1, m2);
       // A = [p_imu]x R^T n with the CURRENT rotation (:453)
       row0 = -pi2 * m1 + pi1 * m2;
       row1 = pi2 * m0 - pi0 * m2;

@@ -137,12 +137,8 @@ void VoxelMapManager::StateEstimation(StatesGroup &state_propagat) {
   if (!ctx_) return;
   if (!map_synced_) SyncDeviceMap();
   if (!map_synced_) return;
-  esikf_extrinsics ext;
-  memset(&ext, 0, sizeof(ext));
-  memcpy(ext.extR, extR_.m, sizeof(ext.extR));
-  memcpy(ext.extT, extT_.v, sizeof(ext.extT));
-  ext.Rcl[0] = ext.Rcl[4] = ext.Rcl[8] = 1.0;
-  if ((last_status_ = esikf_set_extrinsics(ctx_, &ext)) != 0) {
+  // lidar -> imu extrinsics only: the camera part belongs to the VIOManager sharing this context (it must survive the LIO tick)
+  if ((last_status_ = esikf_set_lidar_extrinsics(ctx_, extR_.m, extT_.v)) != 0) {
     last_error_ = esikf_last_error(ctx_);
     return;
   }

@@ -143,6 +143,9 @@ int esikf_set_loop_mode(esikf_ctx *ctx, int mode);
 #define ESIKF_TUNE_STAGE_LDG 1u
 int esikf_set_tuning(esikf_ctx *ctx, uint32_t flags);
 int esikf_set_extrinsics(esikf_ctx *ctx, const esikf_extrinsics *ext);
+/* Only the lidar -> imu part (extR_, extT_ of VoxelMapManager, LIVMapper.cpp:125-126); the camera part set before is kept.
+ * Cheap when nothing changed (no copy, no synchronisation): the LIO shim calls it every tick. */
+int esikf_set_lidar_extrinsics(esikf_ctx *ctx, const double extR[9], const double extT[3]);
 
 /* ---------------------------------------------------------------- voxel map mirror
  * Device mirror of `std::unordered_map<VOXEL_LOCATION, VoxelOctoTree*> voxel_map_`
