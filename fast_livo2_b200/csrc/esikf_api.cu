@@ -259,14 +259,16 @@ int esikf_create(esikf_ctx **out, int device) {
   cudaFuncSetAttribute(vio_inverse_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VioSmem));
   cudaError_t ea = cudaFuncSetAttribute(lio_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
   cudaFuncSetAttribute(lio_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LioSmem));
-  cudaError_t eb = cudaFuncSetAttribute(vio_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VIO_PERSIST_SMEM);
-  cudaFuncSetAttribute(vio_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VIO_PERSIST_SMEM);
+  cudaError_t eb = cudaFuncSetAttribute(vio_update_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VIO_PERSIST_SMEM);
+  cudaFuncSetAttribute(vio_update_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VIO_PERSIST_SMEM);
+  cudaFuncSetAttribute(vio_update_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VIO_PERSIST_SMEM);
+  cudaFuncSetAttribute(vio_update_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VIO_PERSIST_SMEM);
   // the persistent kernels need every CTA co-resident: check what the device can hold
   int occ_l = 0, occ_v = 0, occ_lp = 0, occ_vp = 0, occ_r = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, lio_update_kernel<false>, LIO_THREADS, sizeof(LioSmem));
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lp, lio_update_kernel<true>, LIO_THREADS, sizeof(LioSmem));
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_v, vio_update_kernel<false>, VIO_THREADS, VIO_PERSIST_SMEM);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_vp, vio_update_kernel<true>, VIO_THREADS, VIO_PERSIST_SMEM);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_v, vio_update_kernel<false, false>, VIO_THREADS, VIO_PERSIST_SMEM);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_vp, vio_update_kernel<true, true>, VIO_THREADS, VIO_PERSIST_SMEM);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, lio_residual_kernel, LIO_THREADS, sizeof(LioSmem));
   ctx->coop_lio = occ_l < occ_lp ? occ_l : occ_lp, ctx->coop_vio = occ_v < occ_vp ? occ_v : occ_vp;
   if (getenv("ESIKF_DEBUG")) {
@@ -277,7 +279,7 @@ int esikf_create(esikf_ctx **out, int device) {
     fprintf(stderr, "[esikf] lio_residual: regs=%d local=%zu\n", fa.numRegs, fa.localSizeBytes);
     cudaFuncGetAttributes(&fa, lio_update_kernel<false>);
     fprintf(stderr, "[esikf] lio_update: regs=%d local=%zu\n", fa.numRegs, fa.localSizeBytes);
-    cudaFuncGetAttributes(&fa, vio_update_kernel<false>);
+    cudaFuncGetAttributes(&fa, vio_update_kernel<false, false>);
     fprintf(stderr, "[esikf] vio_update: regs=%d local=%zu\n", fa.numRegs, fa.localSizeBytes);
   }
   cudaGetLastError();
@@ -737,7 +739,7 @@ int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
     if (ctx->n_inv_refs != ctx->n_patches) return fail(ctx, ESIKF_ERR_STATE, "vio_run: inverse_composition_en needs esikf_vio_set_inverse_refs for the %d patches (have %d)", ctx->n_patches, ctx->n_inv_refs);
     if (ctx->ref_w != ctx->cam.width || ctx->ref_h != ctx->cam.height) return fail(ctx, ESIKF_ERR_STATE, "vio_run: reference images must have the camera's size");
   }
-  const bool fused_vio = !inverse && ctx->n_patches > 0 && ctx->loop_mode >= 1 && (ctx->nranks == 1 || ctx->p2p) && ctx->coop_ok && ctx->coop_vio > 0 && !ctx->timing;
+  const bool fused_vio = ctx->n_patches > 0 && ctx->loop_mode >= 1 && (ctx->nranks == 1 || ctx->p2p) && ctx->coop_ok && ctx->coop_vio > 0 && !ctx->timing;
   if (!fused_vio) {
     CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), st));
     CK(cudaMemsetAsync(ctx->vio_stats.p, 0, sizeof(esikf_vio_stats), st));
@@ -751,6 +753,14 @@ int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   sa.max_iterations = ctx->vio_cfg.max_iterations, sa.solve_mode = ctx->solve_mode, sa.vio_stats = ctx->vio_stats.p;
   sa.old_state = ctx->old_state.p, sa.G = ctx->G.p, sa.img_point_cov = ctx->vio_cfg.img_point_cov;
   const int grid = vio_grid(ctx, ka.count);
+  VioInvArgs iv;
+  memset(&iv, 0, sizeof(iv));
+  if (inverse) {
+    CK(ctx->H_sub_inv.reserve((size_t)ka.count * 64 * 6 + 8));
+    iv.ref_imgs = ctx->ref_img_ptrs.p, iv.ref_idx = ctx->inv_ref_idx.p, iv.ref_px = ctx->inv_ref_px.p, iv.ref_f = ctx->inv_ref_f.p;
+    iv.ref_R = ctx->inv_ref_R.p, iv.ref_pos = ctx->inv_ref_pos.p, iv.H_sub_inv = ctx->H_sub_inv.p;
+    iv.ref_w = ctx->ref_w, iv.ref_h = ctx->ref_h, iv.fx = ctx->cam.fx, iv.fy = ctx->cam.fy;
+  }
   if (fused_vio) {
     const unsigned par = ctx->launch_parity & 1;
     unsigned int *bar = ctx->barrier.p + 64 * par, *bar_next = ctx->barrier.p + 64 * (par ^ 1);
@@ -758,8 +768,10 @@ int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
     if (stamps) CK(cudaMemsetAsync(stamps, 0, 512 * sizeof(unsigned long long), st));
     size_t parity_stride = (size_t)ctx->partial_blocks * NE_MAX;
     PeerArgs peer = peer_args(ctx);
-    void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride, (void *)&peer};
-    const void *fn = (ctx->p2p && ctx->nranks > 1) ? (const void *)vio_update_kernel<true> : (const void *)vio_update_kernel<false>;
+    void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride, (void *)&peer, (void *)&iv};
+    const bool peers = ctx->p2p && ctx->nranks > 1;
+    const void *fn = inverse ? (peers ? (const void *)vio_update_kernel<true, true> : (const void *)vio_update_kernel<false, true>)
+                             : (peers ? (const void *)vio_update_kernel<true, false> : (const void *)vio_update_kernel<false, false>);
     cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(VIO_THREADS), kargs, VIO_PERSIST_SMEM, st);
     if (le != cudaSuccess) return fail(ctx, ESIKF_ERR_CUDA, "cooperative launch of vio_update_kernel failed: %s", cudaGetErrorString(le));
     ctx->launch_parity++;
@@ -769,14 +781,6 @@ int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   }
   ctx->vio_timed = ctx->timing;
   ctx->vio_slots = ctx->vio_cfg.patch_pyrimid_level * ctx->vio_cfg.max_iterations;
-  VioInvArgs iv;
-  memset(&iv, 0, sizeof(iv));
-  if (inverse) {
-    CK(ctx->H_sub_inv.reserve((size_t)ka.count * 64 * 6 + 8));
-    iv.ref_imgs = ctx->ref_img_ptrs.p, iv.ref_idx = ctx->inv_ref_idx.p, iv.ref_px = ctx->inv_ref_px.p, iv.ref_f = ctx->inv_ref_f.p;
-    iv.ref_R = ctx->inv_ref_R.p, iv.ref_pos = ctx->inv_ref_pos.p, iv.H_sub_inv = ctx->H_sub_inv.p;
-    iv.ref_w = ctx->ref_w, iv.ref_h = ctx->ref_h, iv.fx = ctx->cam.fx, iv.fy = ctx->cam.fy;
-  }
   int slot = 0;
   for (int level = ctx->vio_cfg.patch_pyrimid_level - 1; level >= 0; level--) {
     if (inverse) {  // has_ref_patch_cache = false at every level (vio.cpp:794): H_sub_inv of this level's tap stride

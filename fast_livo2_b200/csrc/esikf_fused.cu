@@ -261,9 +261,12 @@ __device__ __forceinline__ void vio_consts_from_resident(VioSmem &sm, const VioK
   __syncthreads();
 }
 
-template <bool PEER>
+// INVERSE: the inverse-compositional variant (vio/inverse_composition_en, src/vio.cpp:792-795, 1327-1518) in the same loop:
+// every warp precomputes H_sub_inv of ITS patches when a level starts (precomputeReferencePatches; written and later read by
+// the same lanes, so no barrier is involved) and the per-iteration build is vio_inverse_process_range.
+template <bool PEER, bool INVERSE>
 __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKernelArgs a, SolveArgs sa, unsigned int *barrier, unsigned int *barrier_next, unsigned long long *stamps,
-                                                                     size_t partial_parity_stride, const PeerArgs peer) {
+                                                                     size_t partial_parity_stride, const PeerArgs peer, const VioInvArgs inv) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   VioSmem &sm = *reinterpret_cast<VioSmem *>(smem_raw);
   FusedSolveSmem &fs = *reinterpret_cast<FusedSolveSmem *>(smem_raw + sizeof(VioSmem));
@@ -299,7 +302,13 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKer
       vio_consts_from_resident(sm, a, fs);
       stamp(stamps, sk);
       double D0 = 0.0, D1 = 0.0, n_meas = 0.0;
-      vio_process_range(a, sm, level, lo, hi, D0, D1, n_meas, cached);
+      if (INVERSE) {
+        if (it == 0)
+          for (int lp = lo + (int)(threadIdx.x >> 5); lp < hi; lp += VIO_WARPS) vio_inverse_precompute_patch(a, inv, level, lp, threadIdx.x & 31);
+        vio_inverse_process_range(a, inv, sm, level, lo, hi, fs.io.st + S_R, fs.io.st + S_P, D0, D1, n_meas);
+      } else {
+        vio_process_range(a, sm, level, lo, hi, D0, D1, n_meas, cached);
+      }
       stamp(stamps, sk);
       double *const part = a.partials + (size_t)(cur & 1) * partial_parity_stride;
       store_partials<VIO_WARPS, 7>(sm.red, D0, D1, n_meas, part, a.partial_stride);

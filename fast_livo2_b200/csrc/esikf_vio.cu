@@ -455,11 +455,8 @@ struct VioInvArgs {
   double fx, fy;
 };
 
-// precomputeReferencePatches (:1327-1396) for one level: one warp per point, two pixels per lane.
-__global__ void vio_inverse_precompute_kernel(const VioKernelArgs a, const VioInvArgs v, int level) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int lp = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (lp >= a.count) return;
+// precomputeReferencePatches (:1327-1396) for one point at one level by one warp, two pixels per lane.
+__device__ __forceinline__ void vio_inverse_precompute_patch(const VioKernelArgs &a, const VioInvArgs &v, int level, int lp, int lane) {
   const int i = a.begin + lp;
   const int scale = 1 << level;
   const uint8_t *__restrict__ img = v.ref_imgs[v.ref_idx[i]];
@@ -516,26 +513,24 @@ __global__ void vio_inverse_precompute_kernel(const VioKernelArgs a, const VioIn
     }
   }
 }
+__global__ void vio_inverse_precompute_kernel(const VioKernelArgs a, const VioInvArgs v, int level) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lp = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (lp >= a.count) return;
+  vio_inverse_precompute_patch(a, v, level, lp, lane);
+}
 
 // One iteration of updateStateInverse's measurement build (:1420-1480) at pyramid level a.level: residual / rows of this
 // rank's patches contracted on the tensor-core path into the same 8 x 8 block layout as the forward kernel
 // (H^T H in [0..5][0..5], row / column 6 zero, H^T z in column 7, sum res^2 in [7][7]).
-__global__ void __launch_bounds__(VIO_THREADS, 1) vio_inverse_patch_kernel(const VioKernelArgs a, const VioInvArgs v) {
-  if (a.slot_iter > 0 && a.ctrl->level_done) return;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  VioSmem &sm = *reinterpret_cast<VioSmem *>(smem_raw);
-  __shared__ double Rwi[9], Pwi[3];
-  vio_load_consts(sm, a);
-  if (threadIdx.x < 9) Rwi[threadIdx.x] = __ldcg(a.state + S_R + threadIdx.x);
-  if (threadIdx.x < 3) Pwi[threadIdx.x] = __ldcg(a.state + S_P + threadIdx.x);
-  __syncthreads();
+// Measurement build of updateStateInverse (:1420-1480) over the patches [lo, hi) of this rank's shard at pyramid level
+// `level`; Rwi / Pwi: the current pose. Shared by the per-iteration kernel and the persistent kernel (bit-identical).
+__device__ __forceinline__ void vio_inverse_process_range(const VioKernelArgs &a, const VioInvArgs &v, VioSmem &sm, int level, int lo, int hi, const double *Rwi,
+                                                          const double *Pwi, double &D0, double &D1, double &n_meas) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int level = a.level, scale = 1 << level;
+  const int scale = 1 << level;
   const long npix = (long)a.cam.width * a.cam.height;
   const int width = a.cam.width;
-  double D0 = 0.0, D1 = 0.0, n_meas = 0.0;
-  int lo, hi;
-  vio_block_range(a.count, lo, hi);
   for (int lp = lo + warp; lp < hi; lp += VIO_WARPS) {
     const int i = a.begin + lp;
     const double X = a.pos[3 * (size_t)i], Y = a.pos[3 * (size_t)i + 1], Z = a.pos[3 * (size_t)i + 2];
@@ -593,6 +588,24 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_inverse_patch_kernel(const
     }
     __syncwarp();
   }
+}
+
+// One iteration of updateStateInverse's measurement build at pyramid level a.level: residual / rows of this rank's patches
+// contracted on the tensor-core path into the same 8 x 8 block layout as the forward kernel (H^T H in [0..5][0..5], row /
+// column 6 zero, H^T z in column 7, sum res^2 in [7][7]).
+__global__ void __launch_bounds__(VIO_THREADS, 1) vio_inverse_patch_kernel(const VioKernelArgs a, const VioInvArgs v) {
+  if (a.slot_iter > 0 && a.ctrl->level_done) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  VioSmem &sm = *reinterpret_cast<VioSmem *>(smem_raw);
+  __shared__ double Rwi[9], Pwi[3];
+  vio_load_consts(sm, a);
+  if (threadIdx.x < 9) Rwi[threadIdx.x] = __ldcg(a.state + S_R + threadIdx.x);
+  if (threadIdx.x < 3) Pwi[threadIdx.x] = __ldcg(a.state + S_P + threadIdx.x);
+  __syncthreads();
+  double D0 = 0.0, D1 = 0.0, n_meas = 0.0;
+  int lo, hi;
+  vio_block_range(a.count, lo, hi);
+  vio_inverse_process_range(a, v, sm, a.level, lo, hi, Rwi, Pwi, D0, D1, n_meas);
   reduce_info<VIO_WARPS, 7>(sm.red, D0, D1, n_meas, a.partials, a.partial_stride, a.info, a.ctrl);
 }
 

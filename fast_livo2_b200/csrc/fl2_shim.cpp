@@ -170,8 +170,17 @@ void VoxelMapManager::StateEstimation(StatesGroup &state_propagat) {
   position_last_ = state_.pos_end;     // src/voxel_map.cpp:492
   effct_feat_num_ = stats.iters > 0 ? stats.effct_feat_num[stats.iters - 1] : 0;
   last_iters_ = stats.iters;
-  if (!fill_point_lists_) return;
-  // body_cov_list_ / cross_mat_list_ (LIVMapper.cpp:418-419), pv_list_ (:372) and ptpl_list_ (:446)
+  lists_pending_ = fill_point_lists_;
+  if (fill_point_lists_ && !lazy_point_lists_) MaterializePointLists();
+}
+
+// body_cov_list_ / cross_mat_list_ (LIVMapper.cpp:418-419), pv_list_ (:372) and ptpl_list_ (:446) of the last StateEstimation
+void VoxelMapManager::MaterializePointLists() {
+  if (!ctx_ || !lists_pending_) return;
+  lists_pending_ = false;
+  const int n = feats_down_size_;
+  const int32_t *match = st_match_.data(), *normal = st_normal_.data();
+  const float *dis = st_dis_.data();
   double *cov = st_cov_.get((size_t)n * 18 + 2);
   if (!cov) {
     last_status_ = ESIKF_ERR_CUDA, last_error_ = "pinned staging allocation failed";
@@ -640,6 +649,24 @@ int fl2_shim_session_step(void *h, const float *pts, int n, const double *state_
     iters_out[1] = vio.last_total_iters_;
   }
   return 0;
+}
+
+// mode 0: pv_list_ / ptpl_list_ / body_cov_list_ / cross_mat_list_ filled inside every StateEstimation (the reference's member
+// contract); 1: filled lazily (MaterializePointLists — never, in the timed loop of a caller that does not read them); 2: off.
+void fl2_shim_session_point_lists(void *h, int mode) {
+  ShimSession *s = static_cast<ShimSession *>(h);
+  if (!s) return;
+  s->mgr->fill_point_lists_ = (mode != 2);
+  s->mgr->lazy_point_lists_ = (mode == 1);
+}
+// number of entries the lists hold after materialising them (checks the lazy path in the tests)
+int fl2_shim_session_materialize(void *h, int32_t *n_pv, int32_t *n_ptpl) {
+  ShimSession *s = static_cast<ShimSession *>(h);
+  if (!s) return ESIKF_ERR_ARG;
+  s->mgr->MaterializePointLists();
+  if (n_pv) *n_pv = (int32_t)s->mgr->pv_list_.size();
+  if (n_ptpl) *n_ptpl = (int32_t)s->mgr->ptpl_list_.size();
+  return s->mgr->last_status_;
 }
 
 void fl2_shim_session_destroy(void *h) { delete static_cast<ShimSession *>(h); }

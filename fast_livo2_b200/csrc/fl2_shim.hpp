@@ -154,7 +154,10 @@ class VoxelMapManager {
   std::vector<M3D> cross_mat_list_, body_cov_list_;
   std::vector<pointWithVar> pv_list_;
   std::vector<PointToPlane> ptpl_list_;
-  bool fill_point_lists_ = true;   // pv_list_ / ptpl_list_ / cross_mat_list_ / body_cov_list_ (off: state_ only)
+  bool fill_point_lists_ = true;   // pv_list_ / ptpl_list_ / cross_mat_list_ / body_cov_list_ filled by StateEstimation (off: state_ only)
+  bool lazy_point_lists_ = false;  // with fill_point_lists_: fill them on MaterializePointLists() instead of inside StateEstimation —
+                                   // the 14 MB device->host copy of the per-point covariances and the host loops over the scan
+                                   // only happen for callers that read the lists (LIVMapper's host-side UpdateVoxelMap does)
   int last_status_ = 0;            // esikf_status of the last call (the reference's calls return void)
   int last_iters_ = 0;             // iterations executed by the last StateEstimation
   std::string last_error_;
@@ -167,6 +170,7 @@ class VoxelMapManager {
   void MarkMapDirty() { map_synced_ = false; }
   int last_sync_patched_ = -1;     // planes patched by the last SyncDeviceMap, -1 = it was a full upload
   void StateEstimation(StatesGroup &state_propagat);  // include/voxel_map.h:229
+  void MaterializePointLists();                       // fills the four lists from the last StateEstimation (idempotent per call of it)
   esikf_ctx *context() { return ctx_; }
 
  private:
@@ -176,6 +180,7 @@ class VoxelMapManager {
   PinnedBuf<float> st_pts_, st_dis_;
   PinnedBuf<int32_t> st_match_, st_normal_;
   PinnedBuf<double> st_state_, st_cov_;
+  bool lists_pending_ = false;
 };
 
 // include/vio.h:26-57 restated over flat storage

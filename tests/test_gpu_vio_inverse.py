@@ -77,3 +77,35 @@ def test_inverse_variant_matches_golden_vectors(gpu_ctx):
     assert np.array_equal(v["accepted_per_level"], gi["vio_accepted_per_level"])
     assert_state_close(v["state"], gi["vio_state"], rot_tol=1e-8, pos_tol=1e-8, cov_tol=1e-6, rest_tol=1e-8)
     np.testing.assert_allclose(v["errors"], gi["vio_errors"], rtol=2e-6, atol=1e-3)
+
+
+def test_inverse_variant_persistent_kernel_is_bit_identical_to_per_iteration_launches(gpu_ctx, small_vio_frame):
+    """loop_mode 2 runs the inverse-compositional loop inside the same persistent kernel as the forward variant
+    (vio_update_kernel<.., INVERSE>: H_sub_inv of a level precomputed by the warp that later reads it); it must reproduce
+    the per-iteration launches (loop_mode 0: precompute kernel + patch kernel + solve kernel) bit for bit."""
+    from fast_livo2_b200 import api
+    from test_gpu_loop_modes import VIO_KEYS, _bits_equal
+
+    fr = small_vio_frame
+    inv_cfg = dataclasses.replace(fr["vio_cfg"], inverse_composition_en=True)
+    refs = O.inverse_refs_from_frame(fr)
+    prior = _vio_prior(fr)
+    out = {}
+    try:
+        _setup(gpu_ctx, fr)
+        w = _gpu_warp(gpu_ctx, fr, prior)
+        gpu_ctx.vio_set_camera(fr["cam_cfg"], inv_cfg)
+        gpu_ctx.vio_set_inverse_refs(refs["ref_img_index"], refs["ref_px"], refs["ref_f"], refs["ref_R"], refs["ref_pos"])
+        n = len(fr["vis_pos"])
+        args = (fr["img"], fr["vis_pos"], w["warp_patch"], w["search_levels"], np.ones(n), prior, prior)
+        for mode in (0, 2, 2, 0):
+            gpu_ctx.set_loop_mode(mode)
+            out.setdefault(mode, []).append(gpu_ctx.vio_update(*args))
+    finally:
+        gpu_ctx.set_loop_mode(api.DEFAULT_LOOP_MODE)
+        gpu_ctx.vio_set_camera(fr["cam_cfg"], fr["vio_cfg"])
+    ref = out[0][0]
+    assert ref["total_iters"] >= 3
+    for r in out[2] + out[0][1:]:
+        assert r["total_iters"] == ref["total_iters"]
+        _bits_equal(ref, r, VIO_KEYS)

@@ -102,6 +102,37 @@ def check(fr, label, time_it):
             lio = np.mean([a.elapsed_time(b) for a, b, _ in evs]) * 1e3
             vio = np.mean([b.elapsed_time(c) for _, b, c in evs]) * 1e3
             print(f"[{label}] mode {mode} tuning {sched}: LIO {lio:.1f} us  VIO {vio:.1f} us  step {lio + vio:.1f} us  -> {iters / ((lio + vio) * 1e-6):.0f} it/s resident", flush=True)
+        if os.environ.get("INVERSE"):  # the inverse-compositional variant (f4): persistent kernel vs per-iteration launches
+            import dataclasses
+            R, t = fr["T_ref"]
+            pc = fr["vis_pos"] @ R.T + t
+            f = pc / np.linalg.norm(pc, axis=1, keepdims=True)
+            ctx.vio_set_camera(fr["cam_cfg"], dataclasses.replace(fr["vio_cfg"], inverse_composition_en=True))
+            ctx.vio_set_inverse_refs(np.zeros(n, np.int32), np.ascontiguousarray(fr["px_ref"], dtype=np.float64), np.ascontiguousarray(f), np.tile(R.reshape(1, 9), (n, 1)),
+                                     np.tile(-R.T @ t, (n, 1)))
+            res = {}
+            for mode in (2, 0):
+                ctx.set_loop_mode(mode)
+                ctx.set_tuning(0)
+                evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(STEPS)]
+                for k in range(-3, STEPS):
+                    with torch.cuda.stream(ext_stream):
+                        flush.zero_()
+                        if k >= 0:
+                            evs[k][0].record(ext_stream)
+                    ctx.vio_run(post_h, post_h)
+                    if k >= 0:
+                        with torch.cuda.stream(ext_stream):
+                            evs[k][1].record(ext_stream)
+                torch.cuda.synchronize()
+                res[mode] = ctx.vio_fetch()
+                vio = np.mean([a.elapsed_time(b) for a, b in evs]) * 1e3
+                print(f"[{label}] inverse-compositional VIO, mode {mode}: {vio:.1f} us for {res[mode]['total_iters']} iterations (per level {res[mode]['iters_per_level'][:fr['vio_cfg'].levels].tolist()})"
+                      f" -> {vio / max(1, res[mode]['total_iters']):.2f} us / iteration", flush=True)
+            bv = same({k: res[2][k] for k in ("state", "errors", "iters_per_level", "HTH", "HTz", "solution")}, {k: res[0][k] for k in ("state", "errors", "iters_per_level", "HTH", "HTz", "solution")})
+            ok = ok and not bv
+            print(f"[{label}] inverse-compositional VIO, mode 0 vs mode 2: differing keys {bv}", flush=True)
+            ctx.vio_set_camera(fr["cam_cfg"], fr["vio_cfg"])
         if os.environ.get("STAMPS"):
             ctx.set_loop_mode(runs[-1][0])
             ctx.set_tuning(runs[-1][1])
