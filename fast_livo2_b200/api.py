@@ -110,7 +110,8 @@ def load_library():
     return lib
 
 
-TUNE_STAGE_LDG = 1  # esikf_set_tuning flag: stage LIO plane records with __ldg copies instead of cp.async.bulk (measurement variant)
+TUNE_STAGE_LDG = 1
+TUNE_VIO_TMA = 2  # esikf_set_tuning flag: stage LIO plane records with __ldg copies instead of cp.async.bulk (measurement variant)
 DEFAULT_LOOP_MODE = 2  # esikf_set_loop_mode: 2 (alias 1) persistent kernel per update, 0 per-iteration launches
 
 EXPORTED_SYMBOLS = [

@@ -1,6 +1,7 @@
 // Host side of the C ABI declared in include/esikf_b200.h: context, device mirror of the voxel map, staging of the
 // per-tick inputs, and the launch sequences of the LIO / VIO update loops. No CPU fallback: every entry point fails
 // with a status code when the device or an input is missing.
+#include <cuda.h>
 #include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
@@ -142,6 +143,9 @@ struct esikf_ctx {
   bool have_cam = false;
   DevBuf<uint8_t> img;
   int img_w = 0, img_h = 0;
+  VioTma tma;                      // tensor maps of `img` (ESIKF_TUNE_VIO_TMA), encoded for tma_img / tma_w x tma_h
+  const uint8_t *tma_img = nullptr;
+  int tma_w = 0, tma_h = 0;
   DevBuf<double> vis_pos, inv_expo;
   DevBuf<float> warp_patch, errors;
   DevBuf<int32_t> search_levels;
@@ -347,7 +351,7 @@ int esikf_set_loop_mode(esikf_ctx *ctx, int mode) {
   return ESIKF_OK;
 }
 int esikf_set_tuning(esikf_ctx *ctx, uint32_t flags) {
-  if (!ctx || (flags & ~(uint32_t)(ESIKF_TUNE_STAGE_LDG))) return ESIKF_ERR_ARG;
+  if (!ctx || (flags & ~(uint32_t)(ESIKF_TUNE_STAGE_LDG | ESIKF_TUNE_VIO_TMA))) return ESIKF_ERR_ARG;
   ctx->tuning = flags;
   return ESIKF_OK;
 }
@@ -724,6 +728,34 @@ static int vio_grid(const esikf_ctx *ctx, int count) {
   return g < 1 ? 1 : g;
 }
 
+// Tiled tensor maps of the level-0 u8 image, one per tap stride 1 << l (see VioTma). Encoded through the driver entry
+// point (no link-time dependency on libcuda). Images whose row pitch is not a multiple of 16 bytes cannot be described:
+// the variant then stays on the per-lane loads (enabled = 0).
+static int vio_encode_tma(esikf_ctx *ctx) {
+  if (ctx->tma_img == ctx->img.p && ctx->tma_w == ctx->img_w && ctx->tma_h == ctx->img_h) return ESIKF_OK;
+  memset(&ctx->tma, 0, sizeof(ctx->tma));
+  ctx->tma_img = ctx->img.p, ctx->tma_w = ctx->img_w, ctx->tma_h = ctx->img_h;
+  if (ctx->img_w % 16 != 0 || ((uintptr_t)ctx->img.p & 15)) return ESIKF_OK;
+  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fn)
+    return fail(ctx, ESIKF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  static_assert(sizeof(CUtensorMap) == 128, "descriptor size");
+  for (int l = 0; l <= VIO_TMA_MAXLVL; l++) {
+    const cuuint64_t dims[2] = {(cuuint64_t)ctx->img_w, (cuuint64_t)ctx->img_h};
+    const cuuint64_t strides[1] = {(cuuint64_t)ctx->img_w};  // bytes between rows
+    const cuuint32_t box[2] = {16u << l, 11u << l};
+    const cuuint32_t estr[2] = {1u, 1u << l};
+    CUresult r = ((encode_fn)fn)(reinterpret_cast<CUtensorMap *>(ctx->tma.map[l]), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)ctx->img.p, dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, ESIKF_ERR_CUDA, "cuTensorMapEncodeTiled (tap stride %d) failed: %d", 1 << l, (int)r);
+  }
+  ctx->tma.enabled = 1;
+  return ESIKF_OK;
+}
+
 int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_prop) {
   if (!ctx || !state_in || !state_prop) return fail(ctx, ESIKF_ERR_ARG, "vio_run: null argument");
   if (!ctx->have_cam || !ctx->have_ext) return fail(ctx, ESIKF_ERR_STATE, "vio_run before vio_set_camera / set_extrinsics");
@@ -768,7 +800,15 @@ int esikf_vio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
     if (stamps) CK(cudaMemsetAsync(stamps, 0, 512 * sizeof(unsigned long long), st));
     size_t parity_stride = (size_t)ctx->partial_blocks * NE_MAX;
     PeerArgs peer = peer_args(ctx);
-    void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride, (void *)&peer, (void *)&iv};
+    VioTma tma_off;
+    tma_off.enabled = 0;
+    VioTma *tma = &tma_off;
+    if (ctx->tuning & ESIKF_TUNE_VIO_TMA) {
+      int rc = vio_encode_tma(ctx);
+      if (rc) return rc;
+      tma = &ctx->tma;
+    }
+    void *kargs[] = {(void *)&ka, (void *)&sa, (void *)&bar, (void *)&bar_next, (void *)&stamps, (void *)&parity_stride, (void *)&peer, (void *)&iv, (void *)tma};
     const bool peers = ctx->p2p && ctx->nranks > 1;
     const void *fn = inverse ? (peers ? (const void *)vio_update_kernel<true, true> : (const void *)vio_update_kernel<false, true>)
                              : (peers ? (const void *)vio_update_kernel<true, false> : (const void *)vio_update_kernel<false, false>);

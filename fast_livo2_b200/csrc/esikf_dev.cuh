@@ -207,6 +207,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                "r"(smem_u32(bar))
                : "memory");
 }
+// 2-D tiled TMA load (cp.async.bulk.tensor, SASS UTMALDG): box of the tensor map at element coordinates (x, y) -> shared
+// memory, completion on the mbarrier. Out-of-bounds elements arrive as zeros and still count towards the byte total.
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const void *tmap, int x, int y, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(x),
+               "r"(y), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
 

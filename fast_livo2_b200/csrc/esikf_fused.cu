@@ -266,7 +266,8 @@ __device__ __forceinline__ void vio_consts_from_resident(VioSmem &sm, const VioK
 // the same lanes, so no barrier is involved) and the per-iteration build is vio_inverse_process_range.
 template <bool PEER, bool INVERSE>
 __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKernelArgs a, SolveArgs sa, unsigned int *barrier, unsigned int *barrier_next, unsigned long long *stamps,
-                                                                     size_t partial_parity_stride, const PeerArgs peer, const VioInvArgs inv) {
+                                                                     size_t partial_parity_stride, const PeerArgs peer, const VioInvArgs inv,
+                                                                     const __grid_constant__ VioTma tma) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   VioSmem &sm = *reinterpret_cast<VioSmem *>(smem_raw);
   FusedSolveSmem &fs = *reinterpret_cast<FusedSolveSmem *>(smem_raw + sizeof(VioSmem));
@@ -291,6 +292,9 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKer
   solve_load(fs.sm, fs.io, sa, false);
   vio_cache_reset(sm);
   unsigned int seq = PEER ? __ldcg(peer.seq) : 0u;
+  unsigned tma_phase = 0;  // parity of this warp's TMA barrier
+  if (threadIdx.x < VIO_WARPS) mbar_init(&sm.tma_bar[threadIdx.x], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   if ((threadIdx.x >> 5) == VIO_WARPS - 1 && sa.solve_mode == 0) gain_setup<7>(fs.sm, 1.0 / sa.img_point_cov, threadIdx.x & 31);  // loop invariants of the gain
   int slot = 0;
@@ -307,7 +311,7 @@ __global__ void __launch_bounds__(VIO_THREADS, 1) vio_update_kernel(const VioKer
           for (int lp = lo + (int)(threadIdx.x >> 5); lp < hi; lp += VIO_WARPS) vio_inverse_precompute_patch(a, inv, level, lp, threadIdx.x & 31);
         vio_inverse_process_range(a, inv, sm, level, lo, hi, fs.io.st + S_R, fs.io.st + S_P, D0, D1, n_meas);
       } else {
-        vio_process_range(a, sm, level, lo, hi, D0, D1, n_meas, cached);
+        vio_process_range(a, sm, level, lo, hi, D0, D1, n_meas, cached, tma.enabled ? &tma : nullptr, &tma_phase);
       }
       stamp(stamps, sk);
       double *const part = a.partials + (size_t)(cur & 1) * partial_parity_stride;

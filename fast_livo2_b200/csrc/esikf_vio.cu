@@ -122,8 +122,23 @@ struct VioPatchCache {
   float pv[64];          // warp_patch of the level being processed
 };
 
+// Tap footprints through the TMA unit (tuning flag ESIKF_TUNE_VIO_TMA): one tiled tensor map of the u8 image per tap
+// stride s = 1, 2, 4, 8 — box {16 s bytes, 11 s rows} traversed with elementStrides {1, s} (TMA cannot stride the
+// innermost dimension), i.e. 11 image rows of 16 s contiguous bytes land in shared memory with ONE instruction issued by
+// one lane, at an arbitrary (unaligned) start pixel; the 11 x 11 taps are then picked out at stride s. Footprints that
+// leave the image (the reference's raw linear-index reads wrap to the neighbouring row there, TMA would zero-fill) and
+// strides 16 / 32 (elementStrides <= 8) keep the per-lane loads.
+#define VIO_TMA_MAXLVL 3
+#define VIO_TMA_TILE_BYTES (11 * (16 << VIO_TMA_MAXLVL))
+struct VioTma {
+  alignas(64) unsigned char map[VIO_TMA_MAXLVL + 1][128];  // CUtensorMap per level (opaque 128-byte descriptors)
+  int enabled;
+};
+
 struct __align__(128) VioSmem {
   double rows[VIO_WARPS][64][8];  // first: double4 stores need 32-byte alignment
+  alignas(128) unsigned char tile[VIO_WARPS][VIO_TMA_TILE_BYTES];  // TMA landing area of a warp's footprint (u8 rows)
+  unsigned long long tma_bar[VIO_WARPS];
   VioPatchCache cache[VIO_WARPS][VIO_KMAX];
   float grid[VIO_WARPS][104];     // 10 x 10 bilinear values: patch pixels plus a one-pixel ring for the central differences
   double Rcw[9], Pcw[3];
@@ -164,7 +179,7 @@ __device__ __forceinline__ void vio_cache_reset(VioSmem &sm) {
 // caller keeps `sm.cache` alive between calls (persistent kernel); otherwise slot 0 is plain scratch, refilled every time.
 // Divisions by the power-of-two tap stride are multiplications with its exact reciprocal (same quotient bit for bit).
 __device__ __forceinline__ void vio_process_range(const VioKernelArgs &a, VioSmem &sm, int level, int lo, int hi, double &D0, double &D1,
-                                                  double &n_meas, bool cached) {
+                                                  double &n_meas, bool cached, const VioTma *tma = nullptr, unsigned *tma_phase = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long npix = (long)a.cam.width * a.cam.height;
   const int width = a.cam.width;
@@ -210,18 +225,32 @@ __device__ __forceinline__ void vio_process_range(const VioKernelArgs &a, VioSme
 
     // the 11 x 11 tap footprint: tile (r, c) <-> image linear index base0 + r*scale*width + c*scale, where tile (1,1) is the
     // top-left tap of patch pixel (0,0) (:1597). Staged only when the footprint moved.
+    // The loads are issued here and consumed after the Jacobian constants below (their latency hides behind that math).
+    float tv[4] = {0.f, 0.f, 0.f, 0.f};
+    bool restage, by_tma = false;
     {
       const long long base0 = (long long)(v_ref_i - 5 * scale) * width + (u_ref_i - 5 * scale);
-      const bool restage = (c.tile_scale != scale || c.tile_base0 != base0), repv = (c.pv_level != level);
+      const bool repv = (c.pv_level != level);
+      restage = (c.tile_scale != scale || c.tile_base0 != base0);
       __syncwarp();
       if (restage) {
-        const long sw = (long)scale * width;
+        const int x0 = u_ref_i - 5 * scale, y0 = v_ref_i - 5 * scale;
+        by_tma = tma && pyramid_level <= VIO_TMA_MAXLVL && x0 >= 0 && y0 >= 0 && x0 + 10 * scale < width && y0 + 10 * scale < a.cam.height;
+        if (by_tma) {
+          if (lane == 0) {
+            fence_proxy_async_smem();  // the landing area was last read through the generic proxy
+            mbar_arrive_expect_tx(&sm.tma_bar[warp], 11u * (16u << pyramid_level));
+            tma_load_2d(sm.tile[warp], tma->map[pyramid_level], x0, y0, &sm.tma_bar[warp]);
+          }
+        } else {
+          const long sw = (long)scale * width;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int t = lane + 32 * q;
-          if (t < 121) {
-            const int r = t / 11, cc = t - 11 * r;
-            c.taps[t] = tap(a.img, (long)base0 + r * sw + (long)cc * scale, npix);
+          for (int q = 0; q < 4; q++) {
+            const int t = lane + 32 * q;
+            if (t < 121) {
+              const int r = t / 11, cc = t - 11 * r;
+              tv[q] = tap(a.img, (long)base0 + r * sw + (long)cc * scale, npix);
+            }
           }
         }
         if (lane == 0) c.tile_scale = scale, c.tile_base0 = base0;
@@ -246,6 +275,26 @@ __device__ __forceinline__ void vio_process_range(const VioKernelArgs &a, VioSme
       WR[1][cc] = sc * ((Q10 * a.Rci[cc] + Q11 * a.Rci[3 + cc] + Q12 * a.Rci[6 + cc]) - (J11 * a.Jdp_dR[3 + cc] + J12 * a.Jdp_dR[6 + cc]));
       WT[0][cc] = -sc * (J00 * sm.Rcw[cc] + J02 * sm.Rcw[6 + cc]);
       WT[1][cc] = -sc * (J11 * sm.Rcw[3 + cc] + J12 * sm.Rcw[6 + cc]);
+    }
+    if (restage) {
+      if (by_tma) {
+        mbar_wait(&sm.tma_bar[warp], *tma_phase & 1u);
+        *tma_phase ^= 1u;
+        const unsigned char *raw = sm.tile[warp];
+        const unsigned inner = 16u << pyramid_level;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int t = lane + 32 * q;
+          if (t < 121) {
+            const int r = t / 11, cc = t - 11 * r;
+            c.taps[t] = (float)raw[r * inner + (unsigned)cc * scale];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (lane + 32 * q < 121) c.taps[lane + 32 * q] = tv[q];
+      }
     }
     __syncwarp();
     const float *const sT = c.taps;

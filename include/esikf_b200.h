@@ -139,8 +139,13 @@ int esikf_set_solve_mode(esikf_ctx *ctx, int mode);
 int esikf_set_loop_mode(esikf_ctx *ctx, int mode);
 /* Measurement variants, OR-ed flags; 0 = none (default). Same results bit for bit.
  *   ESIKF_TUNE_STAGE_LDG : LIO plane records are brought into shared memory by coalesced half-warp __ldg copies instead of
- *                          one cp.async.bulk (TMA engine) per lane — the round-1 staging, kept to measure against. */
+ *                          one cp.async.bulk (TMA engine) per lane — the round-1 staging, kept to measure against.
+ *   ESIKF_TUNE_VIO_TMA   : VIO tap footprints (the 11 x 11 strided taps of a patch, vio.cpp:1595-1631) are brought in by ONE
+ *                          tiled TMA load per patch (cp.async.bulk.tensor.2d of 11 image rows, elementStrides {1, s}) instead
+ *                          of four byte loads per lane. Needs an image row pitch that is a multiple of 16 bytes; otherwise,
+ *                          for tap strides 16 / 32 and for footprints leaving the image the per-lane loads are used. */
 #define ESIKF_TUNE_STAGE_LDG 1u
+#define ESIKF_TUNE_VIO_TMA 2u
 int esikf_set_tuning(esikf_ctx *ctx, uint32_t flags);
 int esikf_set_extrinsics(esikf_ctx *ctx, const esikf_extrinsics *ext);
 /* Only the lidar -> imu part (extR_, extT_ of VoxelMapManager, LIVMapper.cpp:125-126); the camera part set before is kept.

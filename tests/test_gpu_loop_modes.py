@@ -118,3 +118,30 @@ def test_vio_patch_cache_with_two_and_more_patches_per_warp_and_search_levels(gp
     assert a["total_iters"] == b["total_iters"] == b2["total_iters"]
     _bits_equal(a, b, VIO_KEYS)
     _bits_equal(a, b2, VIO_KEYS)
+
+
+def test_vio_tap_footprints_through_tma_are_bit_identical(gpu_ctx):
+    """ESIKF_TUNE_VIO_TMA: the 11 x 11 tap footprint arrives by one tiled TMA load (cp.async.bulk.tensor.2d, elementStrides
+    {1, s}) instead of per-lane byte loads. BASELINE config-2 image (640 x 512, pitch a multiple of 16) with search levels
+    0 / 1 / 2 so that every tap stride up to 8 goes through the tensor maps and strides 16 / 32 fall back."""
+    fr = get_frame(seed=0, n_pts=100_000, n_map=1_000_000, n_patches=2000)
+    _setup(gpu_ctx, fr)
+    prior = _vio_prior(fr)
+    w = _gpu_warp(gpu_ctx, fr, prior)
+    n = len(fr["vis_pos"])
+    out = []
+    try:
+        for sl in (w["search_levels"], (np.arange(n) % 3).astype(np.int32)):
+            args = (fr["img"], fr["vis_pos"], w["warp_patch"], sl, fr["inv_ref_expo"], prior, prior)
+            gpu_ctx.set_tuning(0)
+            a = gpu_ctx.vio_update(*args)
+            gpu_ctx.set_tuning(api.TUNE_VIO_TMA)
+            b = gpu_ctx.vio_update(*args)
+            b2 = gpu_ctx.vio_update(*args)
+            out.append((a, b, b2))
+    finally:
+        gpu_ctx.set_tuning(0)
+    for a, b, b2 in out:
+        assert a["total_iters"] == b["total_iters"] == b2["total_iters"] and a["total_iters"] >= 4
+        _bits_equal(a, b, VIO_KEYS)
+        _bits_equal(a, b2, VIO_KEYS)
