@@ -79,6 +79,13 @@ def load_library():
     lib.esikf_set_extrinsics.argtypes = [vp, C.POINTER(ExtrinsicsC)]
     lib.esikf_map_upload.argtypes = [vp, i64p, ip, ip, C.c_int32, vp, C.c_int32, C.c_double]
     lib.esikf_map_patch.argtypes = [vp, ip, vp, C.c_int32]
+    lib.esikf_map_device_init.argtypes = [vp, vp]
+    lib.esikf_map_device_build.argtypes = [vp, vp]
+    lib.esikf_map_device_update.argtypes = [vp, vp]
+    lib.esikf_map_device_update_points.argtypes = [vp, vp, vp, C.c_int32]
+    lib.esikf_map_device_stats.argtypes = [vp, vp]
+    lib.esikf_map_device_download.argtypes = [vp, vp, vp, vp, C.c_int32, vp, C.c_int32, vp, vp]
+    lib.esikf_lio_fetch_normals.argtypes = [vp, vp]
     lib.esikf_lio_set_scan.argtypes = [vp, vp, C.c_int32]
     lib.esikf_lio_run.argtypes = [vp, vp, vp, C.POINTER(LioCfgC)]
     lib.esikf_lio_fetch.argtypes = [vp, vp, C.POINTER(LioStatsC), vp, vp, vp]
@@ -114,9 +121,20 @@ TUNE_STAGE_LDG = 1
 TUNE_VIO_TMA = 2  # esikf_set_tuning flag: stage LIO plane records with __ldg copies instead of cp.async.bulk (measurement variant)
 DEFAULT_LOOP_MODE = 2  # esikf_set_loop_mode: 2 (alias 1) persistent kernel per update, 0 per-iteration launches
 
+class MapCfgC(C.Structure):
+    _fields_ = [("voxel_size", C.c_double), ("min_eigen_value", C.c_double), ("dept_err", C.c_double), ("beam_err", C.c_double), ("max_layer", C.c_int32),
+                ("max_points_num", C.c_int32), ("layer_init_num", C.c_int32 * 8), ("pad", C.c_int32), ("root_capacity", C.c_int64), ("node_capacity", C.c_int64),
+                ("record_capacity", C.c_int64), ("point_capacity", C.c_int64)]
+
+
+class MapStatsC(C.Structure):
+    _fields_ = [("roots", C.c_int32), ("nodes", C.c_int32), ("records", C.c_int32), ("touched_roots", C.c_int32), ("errors", C.c_int32), ("pad", C.c_int32),
+                ("pool_points", C.c_int64)]
+
+
 EXPORTED_SYMBOLS = [
     "esikf_create", "esikf_destroy", "esikf_last_error", "esikf_stream", "esikf_synchronize", "esikf_host_alloc", "esikf_host_free", "esikf_launch_count", "esikf_set_solve_mode", "esikf_set_loop_mode", "esikf_set_tuning",
-    "esikf_set_extrinsics", "esikf_set_lidar_extrinsics", "esikf_map_upload", "esikf_map_patch", "esikf_lio_set_scan", "esikf_lio_run", "esikf_lio_fetch",
+    "esikf_set_extrinsics", "esikf_set_lidar_extrinsics", "esikf_map_upload", "esikf_map_patch", "esikf_map_device_init", "esikf_map_device_build", "esikf_map_device_update", "esikf_map_device_update_points", "esikf_map_device_stats", "esikf_map_device_download", "esikf_lio_fetch_normals", "esikf_lio_set_scan", "esikf_lio_run", "esikf_lio_fetch",
     "esikf_lio_update", "esikf_lio_fetch_point_cov", "esikf_vio_set_camera", "esikf_vio_set_image", "esikf_vio_set_patches",
     "esikf_vio_run", "esikf_vio_fetch", "esikf_vio_update", "esikf_vio_get_image_patch", "esikf_vio_set_ref_images",
     "esikf_vio_warp_patches", "esikf_vio_warp_affine", "esikf_vio_set_inverse_refs", "esikf_comm_unique_id", "esikf_comm_init", "esikf_comm_rank", "esikf_shard_range", "esikf_peer_export", "esikf_peer_attach", "esikf_profile_kernel", "esikf_set_kernel_timing", "esikf_get_kernel_timing", "esikf_set_phase_stamps", "esikf_get_phase_stamps",
@@ -208,6 +226,48 @@ class Context:
         ids = _c(ids, np.int32)
         planes = np.ascontiguousarray(planes)
         self._ck(self.lib.esikf_map_patch(self.h, ids.ctypes.data_as(C.POINTER(C.c_int32)), planes.ctypes.data, len(ids)))
+
+    # ------------------------------------------------------------------ device-resident map
+    def map_device_init(self, cfg, root_capacity=0, node_capacity=0, record_capacity=0, point_capacity=0):
+        """cfg: synthetic.LioCfg (voxel_size, min_eigen_value, dept_err, beam_err, max_layer, max_points_num, layer_init_num)."""
+        m = MapCfgC()
+        m.voxel_size, m.min_eigen_value, m.dept_err, m.beam_err = cfg.voxel_size, cfg.min_eigen_value, cfg.dept_err, cfg.beam_err
+        m.max_layer, m.max_points_num = cfg.max_layer, cfg.max_points_num
+        for k in range(8):
+            m.layer_init_num[k] = cfg.layer_init_num[min(k, len(cfg.layer_init_num) - 1)]
+        m.root_capacity, m.node_capacity, m.record_capacity, m.point_capacity = root_capacity, node_capacity, record_capacity, point_capacity
+        self._ck(self.lib.esikf_map_device_init(self.h, C.byref(m)))
+
+    def map_device_build(self, state):
+        self._ck(self.lib.esikf_map_device_build(self.h, _c(state, np.float64).ctypes.data))
+
+    def map_device_update(self, state=None):
+        self._ck(self.lib.esikf_map_device_update(self.h, None if state is None else _c(state, np.float64).ctypes.data))
+
+    def map_device_update_points(self, point_w, var):
+        pw, v = _c(point_w, np.float64).reshape(-1, 3), _c(var, np.float64).reshape(-1, 9)
+        self._ck(self.lib.esikf_map_device_update_points(self.h, pw.ctypes.data, v.ctypes.data, len(pw)))
+
+    def map_device_stats(self):
+        st = MapStatsC()
+        self._ck(self.lib.esikf_map_device_stats(self.h, C.byref(st)))
+        return {f: getattr(st, f) for f, _ in MapStatsC._fields_ if f != "pad"}
+
+    def map_device_download(self):
+        from .synthetic import PLANE_DTYPE
+
+        nr, npl = C.c_int32(0), C.c_int32(0)
+        self._ck(self.lib.esikf_map_device_download(self.h, None, None, None, 0, None, 0, C.byref(nr), C.byref(npl)))
+        keys, first, count = np.zeros((max(nr.value, 1), 3), np.int64), np.zeros(max(nr.value, 1), np.int32), np.zeros(max(nr.value, 1), np.int32)
+        planes = np.zeros(max(npl.value, 1), PLANE_DTYPE)
+        self._ck(self.lib.esikf_map_device_download(self.h, keys.ctypes.data, first.ctypes.data, count.ctypes.data, len(first), planes.ctypes.data, len(planes),
+                                                    C.byref(nr), C.byref(npl)))
+        return dict(keys=keys[:nr.value], first=first[:nr.value], count=count[:nr.value], planes=planes[:npl.value])
+
+    def lio_fetch_normals(self):
+        out = np.zeros((self.n_pts, 3), np.float64)
+        self._ck(self.lib.esikf_lio_fetch_normals(self.h, out.ctypes.data))
+        return out
 
     # ------------------------------------------------------------------ LIO
     def lio_set_scan(self, pts):

@@ -18,6 +18,7 @@
 #include "esikf_solve.cu"
 #include "esikf_vio.cu"
 #include "esikf_fused.cu"
+#include "esikf_map.cu"
 
 using namespace esikf;
 
@@ -107,6 +108,22 @@ struct esikf_ctx {
   int n_planes = 0, n_roots = 0;
   double voxel_size = 0.5;
   bool have_map = false;
+
+  // device-resident map (esikf_map_device_*): octree nodes, point lists and refits stay on the GPU
+  bool dev_map = false;
+  esikf_map_cfg map_cfg{};
+  MapArena arena{};
+  DevBuf<int> map_slot_root, map_slot_cap, map_rec_node, map_counters, map_work;
+  DevBuf<unsigned long long> map_counters64;
+  DevBuf<MapNode> map_nodes;
+  DevBuf<double> map_pool, map_pt, map_pt_normal;
+  DevBuf<unsigned int> map_key_in, map_key_out, map_idx_in, map_idx_out;
+  DevBuf<MapTouched> map_touched;
+  DevBuf<unsigned char> map_sort_tmp;
+  int map_pt_n = 0;            // points the normal snapshot / last map step covers
+  bool map_normals_valid = false;
+  int map_hash_bits = 0;
+  esikf_map_stats map_last{};
 
   // LIO
   DevBuf<float> pts;
@@ -302,6 +319,9 @@ void esikf_destroy(esikf_ctx *ctx) {
   ctx->peer_ptrs_dev.release();
   ctx->slots.release(), ctx->planes.release(), ctx->recs.release(), ctx->patch_ids.release(), ctx->pts.release(), ctx->pre.release(), ctx->match_plane.release();
   ctx->normal_plane.release(), ctx->dis.release(), ctx->ext_dev.release(), ctx->state_prop.release();
+  ctx->map_slot_root.release(), ctx->map_slot_cap.release(), ctx->map_rec_node.release(), ctx->map_counters.release(), ctx->map_work.release(), ctx->map_counters64.release();
+  ctx->map_nodes.release(), ctx->map_pool.release(), ctx->map_pt.release(), ctx->map_pt_normal.release(), ctx->map_key_in.release(), ctx->map_key_out.release();
+  ctx->map_idx_in.release(), ctx->map_idx_out.release(), ctx->map_touched.release(), ctx->map_sort_tmp.release();
   if (ctx->stage) cudaFreeHost(ctx->stage);
   if (ctx->stage_ctrl) cudaFreeHost(ctx->stage_ctrl);
   for (int i = 0; i < esikf_ctx::STAGE_SLOTS; i++)
@@ -419,12 +439,14 @@ int esikf_map_upload(esikf_ctx *ctx, const int64_t *keys, const int32_t *first, 
   ctx->n_planes = n_planes, ctx->n_roots = n_roots;
   ctx->voxel_size = voxel_size;
   ctx->have_map = true;
+  ctx->dev_map = false;  // a host-flattened map replaces a device-resident one
   return ESIKF_OK;
 }
 
 int esikf_map_patch(esikf_ctx *ctx, const int32_t *plane_ids, const esikf_plane *planes, int32_t n) {
   if (!ctx || n < 0 || (n > 0 && (!plane_ids || !planes))) return fail(ctx, ESIKF_ERR_ARG, "map_patch: bad argument");
   if (!ctx->have_map) return fail(ctx, ESIKF_ERR_STATE, "map_patch before map_upload");
+  if (ctx->dev_map) return fail(ctx, ESIKF_ERR_STATE, "map_patch: the map is device-resident (esikf_map_device_init); it refits itself");
   CK(cudaSetDevice(ctx->device));
   for (int i = 0; i < n; i++)
     if (plane_ids[i] < 0 || plane_ids[i] >= ctx->n_planes) return fail(ctx, ESIKF_ERR_ARG, "map_patch: plane id %d", plane_ids[i]);
@@ -440,6 +462,230 @@ int esikf_map_patch(esikf_ctx *ctx, const int32_t *plane_ids, const esikf_plane 
     plane_compact_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->planes.p, ctx->patch_ids.p, n, ctx->recs.p);
     ctx->launches++;
   }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return ESIKF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ device-resident map (f1)
+static int map_check_errors(esikf_ctx *ctx, const char *what) {
+  int c[4];
+  unsigned long long pool_used = 0;
+  CK(cudaMemcpyAsync(c, ctx->map_counters.p, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&pool_used, ctx->map_counters64.p, sizeof(pool_used), cudaMemcpyDeviceToHost, ctx->stream));
+  int work[2];
+  CK(cudaMemcpyAsync(work, ctx->map_work.p, sizeof(work), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->map_last.nodes = c[0], ctx->map_last.records = c[1], ctx->map_last.errors = c[2], ctx->map_last.roots = c[3];
+  ctx->map_last.pool_points = (int64_t)pool_used, ctx->map_last.touched_roots = work[0];
+  ctx->n_planes = c[1] < (int)ctx->arena.rec_cap ? c[1] : (int)ctx->arena.rec_cap;
+  ctx->n_roots = c[3];
+  if (c[2]) {
+    ctx->have_map = false;  // the map is not trustworthy any more: the next lio_run must not use it
+    return fail(ctx, ESIKF_ERR_STATE, "%s: device map capacity exceeded (flags 0x%x:%s%s%s%s%s%s) — raise the esikf_map_cfg capacities and rebuild", what, c[2],
+                (c[2] & MAP_ERR_NODES) ? " nodes" : "", (c[2] & MAP_ERR_POOL) ? " point-pool" : "", (c[2] & MAP_ERR_RECS) ? " records" : "",
+                (c[2] & MAP_ERR_HASH) ? " hash" : "", (c[2] & MAP_ERR_KEY) ? " key-range" : "", (c[2] & MAP_ERR_STACK) ? " octree-depth" : "");
+  }
+  return ESIKF_OK;
+}
+
+int esikf_map_device_init(esikf_ctx *ctx, const esikf_map_cfg *cfg) {
+  if (!ctx || !cfg || !(cfg->voxel_size > 0) || cfg->max_layer < 0 || cfg->max_layer >= MAP_MAX_LAYERS || cfg->max_points_num < 1)
+    return fail(ctx, ESIKF_ERR_ARG, "map_device_init: bad argument");
+  for (int k = 0; k <= cfg->max_layer; k++)
+    if (cfg->layer_init_num[k] < 1) return fail(ctx, ESIKF_ERR_ARG, "map_device_init: layer_init_num[%d] = %d", k, cfg->layer_init_num[k]);
+  CK(cudaSetDevice(ctx->device));
+  const int64_t roots = cfg->root_capacity > 0 ? cfg->root_capacity : (1 << 20);
+  uint32_t cap = 1024;
+  int bits = 10;
+  while ((int64_t)cap < 2 * roots) cap <<= 1, bits++;
+  const int64_t node_cap = cfg->node_capacity > 0 ? cfg->node_capacity : 4 * roots;
+  const int64_t rec_cap = cfg->record_capacity > 0 ? cfg->record_capacity : 4 * roots;
+  const int64_t pool_cap = cfg->point_capacity > 0 ? cfg->point_capacity : 64 * roots;
+  if (node_cap > 0x7fffffff || rec_cap > 0x7fffffff || pool_cap > 0x7fffffff) return fail(ctx, ESIKF_ERR_ARG, "map_device_init: capacity above 2^31");
+  CK(ctx->slots.reserve(cap));
+  CK(ctx->map_slot_root.reserve(cap));
+  CK(ctx->map_slot_cap.reserve(cap));
+  CK(ctx->map_nodes.reserve((size_t)node_cap));
+  CK(ctx->map_pool.reserve((size_t)pool_cap * MAP_PT_D));
+  CK(ctx->recs.reserve((size_t)rec_cap));
+  CK(ctx->planes.reserve((size_t)rec_cap));
+  CK(ctx->map_rec_node.reserve((size_t)rec_cap));
+  CK(ctx->map_counters.reserve(8));
+  CK(ctx->map_counters64.reserve(2));
+  CK(ctx->map_work.reserve(4));
+  MapArena &A = ctx->arena;
+  A.slots = ctx->slots.p, A.hash_mask = cap - 1, A.slot_root = ctx->map_slot_root.p, A.slot_cap = ctx->map_slot_cap.p;
+  A.nodes = ctx->map_nodes.p, A.node_cap = (int)node_cap, A.pool = ctx->map_pool.p, A.pool_cap = pool_cap;
+  A.recs = ctx->recs.p, A.planes = ctx->planes.p, A.rec_node = ctx->map_rec_node.p, A.rec_cap = (int)rec_cap;
+  A.counters = ctx->map_counters.p, A.counters64 = ctx->map_counters64.p;
+  A.cfg.voxel_size = (float)cfg->voxel_size, A.cfg.planer_threshold = (float)cfg->min_eigen_value;
+  A.cfg.max_layer = cfg->max_layer, A.cfg.max_points_num = cfg->max_points_num;
+  for (int k = 0; k < MAP_MAX_LAYERS; k++) A.cfg.layer_init_num[k] = cfg->layer_init_num[k <= cfg->max_layer ? k : cfg->max_layer];
+  map_reset_kernel<<<(cap + 255) / 256, 256, 0, ctx->stream>>>(A);
+  CK(cudaMemsetAsync(ctx->map_work.p, 0, 4 * sizeof(int), ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->launches++;
+  ctx->map_cfg = *cfg;
+  ctx->map_hash_bits = bits;
+  ctx->hash_mask = cap - 1;
+  ctx->voxel_size = cfg->voxel_size;
+  ctx->n_planes = 0, ctx->n_roots = 0;
+  ctx->dev_map = true, ctx->have_map = true;  // an empty map is a valid map (nothing matches)
+  ctx->map_normals_valid = false;
+  memset(&ctx->map_last, 0, sizeof(ctx->map_last));
+  return ESIKF_OK;
+}
+
+// sort by slot, list the touched roots, replay them
+static int map_apply_points(esikf_ctx *ctx, int n, bool build) {
+  cudaStream_t st = ctx->stream;
+  const unsigned int invalid = ctx->arena.hash_mask + 1u;
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->map_key_in.p, ctx->map_key_out.p, ctx->map_idx_in.p, ctx->map_idx_out.p, n, 0, ctx->map_hash_bits + 1, st);
+  CK(ctx->map_sort_tmp.reserve(tmp_bytes + 16));
+  CK(cub::DeviceRadixSort::SortPairs(ctx->map_sort_tmp.p, tmp_bytes, ctx->map_key_in.p, ctx->map_key_out.p, ctx->map_idx_in.p, ctx->map_idx_out.p, n, 0,
+                                     ctx->map_hash_bits + 1, st));
+  CK(cudaMemsetAsync(ctx->map_work.p, 0, 2 * sizeof(int), st));
+  map_heads_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->map_key_out.p, n, invalid, ctx->map_touched.p, ctx->map_work.p);
+  map_replay_kernel<<<ctx->sm_count * 4, 128, 0, st>>>(ctx->arena, ctx->map_touched.p, ctx->map_work.p, ctx->map_idx_out.p, ctx->map_pt.p, build ? 1 : 0);
+  ctx->launches += 4;
+  CK(cudaGetLastError());
+  return map_check_errors(ctx, build ? "map_device_build" : "map_device_update");
+}
+
+static int map_reserve_tick(esikf_ctx *ctx, int n) {
+  CK(ctx->map_pt.reserve((size_t)n * MAP_PT_D + 16));
+  CK(ctx->map_pt_normal.reserve((size_t)n * 3 + 4));
+  CK(ctx->map_key_in.reserve(n + 1));
+  CK(ctx->map_key_out.reserve(n + 1));
+  CK(ctx->map_idx_in.reserve(n + 1));
+  CK(ctx->map_idx_out.reserve(n + 1));
+  CK(ctx->map_touched.reserve(n + 1));
+  return ESIKF_OK;
+}
+
+static int map_from_scan(esikf_ctx *ctx, const double *state, bool build) {
+  if (!ctx) return ESIKF_ERR_ARG;
+  if (!ctx->dev_map) return fail(ctx, ESIKF_ERR_STATE, "map_device_%s before esikf_map_device_init", build ? "build" : "update");
+  if (!ctx->have_ext) return fail(ctx, ESIKF_ERR_STATE, "map_device_%s before set_extrinsics", build ? "build" : "update");
+  if (!build && ctx->scan_fresh) return fail(ctx, ESIKF_ERR_STATE, "map_device_update: the resident scan has not been through esikf_lio_run yet");
+  if (build && ctx->map_last.roots > 0) return fail(ctx, ESIKF_ERR_STATE, "map_device_build needs an empty map (esikf_map_device_init resets it)");
+  CK(cudaSetDevice(ctx->device));
+  const int n = ctx->n_pts;
+  if (n == 0) return ESIKF_OK;
+  int rc = map_reserve_tick(ctx, n);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  const double *dev_state = ctx->state.p;  // the posterior the last update left on the device
+  if (state) {
+    CK(ctx->scratch_state.reserve(S_N));
+    CK(cudaMemcpyAsync(ctx->scratch_state.p, state, S_N * sizeof(double), cudaMemcpyHostToDevice, st));
+    dev_state = ctx->scratch_state.p;
+  }
+  MapPointArgs a;
+  memset(&a, 0, sizeof(a));
+  a.pts = ctx->pts.p, a.pre = ctx->pre.p, a.pre_stride = ctx->pre_stride, a.n = n, a.state = dev_state;
+  memcpy(a.extR, ctx->ext.extR, 72), memcpy(a.extT, ctx->ext.extT, 24);
+  a.build = build ? 1 : 0, a.dept_err = (float)ctx->map_cfg.dept_err, a.beam_err = (float)ctx->map_cfg.beam_err;
+  a.match_plane = build ? nullptr : ctx->normal_plane.p, a.recs = ctx->recs.p, a.pt_normal = ctx->map_pt_normal.p;
+  a.pt = ctx->map_pt.p, a.pt_slot = ctx->map_key_in.p, a.pt_idx = ctx->map_idx_in.p, a.invalid_slot = ctx->arena.hash_mask + 1u;
+  map_points_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->arena, a);
+  ctx->map_pt_n = n, ctx->map_normals_valid = !build;
+  return map_apply_points(ctx, n, build);
+}
+
+int esikf_map_device_build(esikf_ctx *ctx, const double *state) {
+  if (ctx && !state) return fail(ctx, ESIKF_ERR_ARG, "map_device_build: the pose the scan is mapped with is required");
+  return map_from_scan(ctx, state, true);
+}
+int esikf_map_device_update(esikf_ctx *ctx, const double *state) { return map_from_scan(ctx, state, false); }
+
+int esikf_map_device_update_points(esikf_ctx *ctx, const double *point_w, const double *var, int32_t n) {
+  if (!ctx || n < 0 || (n > 0 && (!point_w || !var))) return fail(ctx, ESIKF_ERR_ARG, "map_device_update_points: bad argument");
+  if (!ctx->dev_map) return fail(ctx, ESIKF_ERR_STATE, "map_device_update_points before esikf_map_device_init");
+  if (n == 0) return ESIKF_OK;
+  CK(cudaSetDevice(ctx->device));
+  int rc = map_reserve_tick(ctx, n);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  // [n][12] = point_w | var: two strided copies
+  CK(cudaMemcpy2DAsync(ctx->map_pt.p, MAP_PT_D * sizeof(double), point_w, 3 * sizeof(double), 3 * sizeof(double), n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpy2DAsync(ctx->map_pt.p + 3, MAP_PT_D * sizeof(double), var, 9 * sizeof(double), 9 * sizeof(double), n, cudaMemcpyHostToDevice, st));
+  map_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->arena, ctx->map_pt.p, n, ctx->map_key_in.p, ctx->map_idx_in.p, ctx->arena.hash_mask + 1u);
+  ctx->launches++;
+  ctx->map_normals_valid = false;
+  return map_apply_points(ctx, n, false);
+}
+
+int esikf_map_device_stats(esikf_ctx *ctx, esikf_map_stats *out) {
+  if (!ctx || !out) return fail(ctx, ESIKF_ERR_ARG, "map_device_stats: bad argument");
+  if (!ctx->dev_map) return fail(ctx, ESIKF_ERR_STATE, "map_device_stats before esikf_map_device_init");
+  *out = ctx->map_last;
+  return ESIKF_OK;
+}
+
+int esikf_map_device_download(esikf_ctx *ctx, int64_t *keys, int32_t *first, int32_t *count, int32_t roots_cap, esikf_plane *planes, int32_t planes_cap, int32_t *n_roots,
+                              int32_t *n_planes) {
+  if (!ctx || !n_roots || !n_planes) return fail(ctx, ESIKF_ERR_ARG, "map_device_download: bad argument");
+  if (!ctx->dev_map) return fail(ctx, ESIKF_ERR_STATE, "map_device_download before esikf_map_device_init");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const bool fill = keys && first && count && planes && roots_cap > 0;
+  DevBuf<long long> d_keys;
+  DevBuf<int32_t> d_first, d_count;
+  DevBuf<esikf_plane> d_planes;
+  DevBuf<int> d_out;
+  CK(d_out.reserve(2));
+  CK(cudaMemsetAsync(d_out.p, 0, 2 * sizeof(int), st));
+  if (fill) {
+    CK(d_keys.reserve((size_t)roots_cap * 3));
+    CK(d_first.reserve(roots_cap));
+    CK(d_count.reserve(roots_cap));
+    CK(d_planes.reserve(planes_cap > 0 ? planes_cap : 1));
+  }
+  const unsigned cap = ctx->arena.hash_mask + 1u;
+  map_download_kernel<<<(cap + 255) / 256, 256, 0, st>>>(ctx->arena, fill ? d_keys.p : nullptr, d_first.p, d_count.p, d_planes.p, fill ? roots_cap : 0, fill ? planes_cap : 0, d_out.p);
+  ctx->launches++;
+  int out[2];
+  CK(cudaMemcpyAsync(out, d_out.p, sizeof(out), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *n_roots = out[0], *n_planes = out[1];
+  int rc = ESIKF_OK;
+  if (fill) {
+    if (out[0] > roots_cap || out[1] > planes_cap)
+      rc = fail(ctx, ESIKF_ERR_ARG, "map_device_download: %d roots / %d planes do not fit the buffers (%d / %d)", out[0], out[1], roots_cap, planes_cap);
+    else {
+      CK(cudaMemcpy(keys, d_keys.p, (size_t)out[0] * 3 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(first, d_first.p, (size_t)out[0] * sizeof(int32_t), cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(count, d_count.p, (size_t)out[0] * sizeof(int32_t), cudaMemcpyDeviceToHost));
+      if (out[1]) CK(cudaMemcpy(planes, d_planes.p, (size_t)out[1] * sizeof(esikf_plane), cudaMemcpyDeviceToHost));
+    }
+  }
+  d_keys.release(), d_first.release(), d_count.release(), d_planes.release(), d_out.release();
+  return rc;
+}
+
+// pv.normal of every point of the last update (voxel_map.cpp:744: the plane that last became the point's best candidate in any
+// iteration — normal_plane, not the final match; zero when there never was one): snapshotted by esikf_map_device_update
+// before the records may move, otherwise gathered from the records now
+__global__ void gather_normals_kernel(const int32_t *__restrict__ match_plane, const PlaneRec *__restrict__ recs, int n, double *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int m = match_plane[i];
+  for (int k = 0; k < 3; k++) out[3 * (size_t)i + k] = m >= 0 ? recs[m].n[k] : 0.0;
+}
+int esikf_lio_fetch_normals(esikf_ctx *ctx, double *normals) {
+  if (!ctx || !normals) return fail(ctx, ESIKF_ERR_ARG, "lio_fetch_normals: bad argument");
+  if (!ctx->have_map || ctx->scan_fresh) return fail(ctx, ESIKF_ERR_STATE, "lio_fetch_normals before lio_run");
+  CK(cudaSetDevice(ctx->device));
+  const int n = ctx->n_pts;
+  if (n == 0) return ESIKF_OK;
+  if (!(ctx->dev_map && ctx->map_normals_valid && ctx->map_pt_n == n)) {
+    CK(ctx->map_pt_normal.reserve((size_t)n * 3 + 4));
+    gather_normals_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->normal_plane.p, ctx->recs.p, n, ctx->map_pt_normal.p);
+    ctx->launches++;
+  }
+  CK(cudaMemcpyAsync(normals, ctx->map_pt_normal.p, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return ESIKF_OK;
 }

@@ -599,6 +599,23 @@ def make_frame(seed=0, n_pts=5000, n_map=200_000, n_patches=0, lio: LioCfg | Non
     return frame
 
 
+def scan_at(rects, ext: Extrinsics, R_wi, p_wi, n_pts, lio: LioCfg, rng, fov="sphere"):
+    """One noisy body-frame scan (float32, n_pts x 3) of the scene from the IMU pose (R_wi, p_wi): the per-tick input of a
+    multi-tick run (tests of the device-resident map)."""
+    R_wl = R_wi @ ext.extR
+    p_wl = R_wi @ ext.extT + p_wi
+    hits = np.zeros((0, 3))
+    while len(hits) < n_pts:
+        d = rng.normal(size=(int(n_pts * 1.3) + 64, 3))
+        if fov != "sphere":
+            d = d * 0.45 + np.array([1.0, 0, 0])
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        t, idx, hit = raycast(rects, p_wl, d @ R_wl.T)
+        hits = np.concatenate([hits, hit[(idx >= 0) & (t > 0.8)]])
+    sc_l = (hits[:n_pts] - p_wl) @ R_wl
+    return np.ascontiguousarray(add_sensor_noise(sc_l, lio.dept_err, lio.beam_err, rng).astype(np.float32))
+
+
 # ----------------------------------------------------------------------------- on-disk cache (frames take tens of seconds to build)
 def cached_frame(cache_dir=None, **kw):
     """make_frame(**kw) with a pickle cache keyed by the arguments (defaults to <repo>/.frame_cache)."""

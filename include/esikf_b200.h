@@ -162,6 +162,48 @@ int esikf_map_upload(esikf_ctx *ctx, const int64_t *keys, const int32_t *first, 
 /* Overwrite planes whose VoxelPlane::is_update_ flag was set by UpdateVoxelMap (voxel_map.h:86). */
 int esikf_map_patch(esikf_ctx *ctx, const int32_t *plane_ids, const esikf_plane *planes, int32_t n);
 
+/* ---------------------------------------------------------------- device-resident voxel map
+ * VoxelMapManager::BuildVoxelMap / UpdateVoxelMap (src/voxel_map.cpp:532-591, 609-641) with the octrees, the nodes' point
+ * lists (temp_points_) and the plane refits (init_plane, :55-135) kept on the GPU: after a LIO update the map absorbs the
+ * scan without any plane, point list or key crossing PCIe, and the next esikf_lio_run reads the refitted records in place.
+ * Replaces the per-tick host refit + flatten + esikf_map_patch of a host-owned map (esikf_map_upload stays available; the
+ * two forms are exclusive: whichever was set up last owns the context's map). */
+typedef struct esikf_map_cfg {
+  double voxel_size;          /* lio/voxel_size       max_voxel_size_ */
+  double min_eigen_value;     /* lio/min_eigen_value  planner_threshold_ */
+  double dept_err, beam_err;  /* lio/dept_err, lio/beam_err (BuildVoxelMap's own calcBodyCov, :546) */
+  int32_t max_layer;          /* lio/max_layer (<= 7) */
+  int32_t max_points_num;     /* lio/max_points_num */
+  int32_t layer_init_num[8];  /* lio/layer_init_num, entries 0..max_layer are used */
+  int32_t pad;
+  /* capacities, fixed at init (nothing is allocated per tick); 0 = default derived from root_capacity (default 2^20):
+   * nodes 4 x, plane records 4 x, stored points 64 x the roots. Exceeding one is reported by the update call
+   * (ESIKF_ERR_STATE, flags in esikf_map_stats.errors) and invalidates the map. */
+  int64_t root_capacity, node_capacity, record_capacity, point_capacity;
+} esikf_map_cfg;
+typedef struct esikf_map_stats {
+  int32_t roots, nodes, records; /* root voxels, octree nodes, record slots handed out (incl. dead blocks of relocated lists) */
+  int32_t touched_roots;         /* roots the last build / update replayed */
+  int32_t errors;                /* 1 nodes | 2 point pool | 4 records | 8 hash | 16 key outside +-2^20 | 32 octree depth */
+  int32_t pad;
+  int64_t pool_points;           /* point slots handed out */
+} esikf_map_stats;
+/* Empty device map with the given configuration (drops any map the context held). */
+int esikf_map_device_init(esikf_ctx *ctx, const esikf_map_cfg *cfg);
+/* BuildVoxelMap on the resident scan (esikf_lio_set_scan) at pose `state` (packed, host): LIVMapper.cpp:356-366. Needs an
+ * empty map. */
+int esikf_map_device_build(esikf_ctx *ctx, const double *state);
+/* LIVMapper.cpp:413-424: world points / covariances of the resident scan with the posterior of the update that just ran
+ * (state == NULL: the one resident on the device; else a packed host state), then UpdateVoxelMap(pv_list_). Call after
+ * esikf_lio_run / esikf_lio_update of this scan and before the VIO update overwrites the resident state. */
+int esikf_map_device_update(esikf_ctx *ctx, const double *state);
+/* UpdateVoxelMap(input_points) with the caller's own lists: point_w [n][3], var [n][9] row-major (host). */
+int esikf_map_device_update_points(esikf_ctx *ctx, const double *point_w, const double *var, int32_t n);
+int esikf_map_device_stats(esikf_ctx *ctx, esikf_map_stats *out);
+/* The map in esikf_map_upload's flat form (roots in no particular order). keys == NULL: sizes only. */
+int esikf_map_device_download(esikf_ctx *ctx, int64_t *keys, int32_t *first, int32_t *count, int32_t roots_cap, esikf_plane *planes, int32_t planes_cap,
+                              int32_t *n_roots, int32_t *n_planes);
+
 /* ---------------------------------------------------------------- LIO update (StateEstimation)
  * Staged form (device-resident between calls):
  *   set_scan : feats_down_body_ (xyz float32, n points) -> device + per-frame calcBodyCov/crossmat
@@ -179,6 +221,9 @@ int esikf_lio_update(esikf_ctx *ctx, const float *pts_xyz, int32_t n, const doub
                      const esikf_lio_cfg *cfg, double *state_out, esikf_lio_stats *stats, int32_t *match_plane,
                      int32_t *normal_plane, float *dis_to_plane);
 /* body_cov_list_ / cross_mat_list_ (include/voxel_map.h:215-216) of the current scan: n x 9 doubles each. */
+/* pv_list_[i].normal of the last update (src/voxel_map.cpp:744; zero for an unmatched point): [n][3] doubles. Valid after the
+ * map absorbed the scan too (esikf_map_device_update snapshots the normals before plane records may move). */
+int esikf_lio_fetch_normals(esikf_ctx *ctx, double *normals);
 int esikf_lio_fetch_point_cov(esikf_ctx *ctx, double *body_cov9 /* nullable */, double *cross_mat9 /* nullable */);
 
 /* ---------------------------------------------------------------- VIO update (computeJacobianAndUpdateEKF)

@@ -104,6 +104,39 @@ void orc_lio_update_map(void *h, const double *pts_world, const double *var9, in
   }
   m->UpdateVoxelMap(pts);
 }
+// First LiDAR frame (LIVMapper.cpp:356-366): feats_down_world_ = transformLidar(state, feats_down_body_), BuildVoxelMap().
+void orc_lio_tick_build_map(void *h, const float *pts_body, int n, const double *state) {
+  VoxelMapManager *m = (VoxelMapManager *)h;
+  m->feats_down_body_.assign(pts_body, pts_body + 3 * (size_t)n);
+  m->feats_down_size_ = n;
+  unpack_state(state, m->state_);
+  m->TransformLidar(m->state_.rot_end, m->state_.pos_end, m->feats_down_body_, m->feats_down_world_);  // same expression as LIVMapper::transformLidar (:645)
+  m->BuildVoxelMap();
+}
+// After StateEstimation (LIVMapper.cpp:413-424): world points with the posterior pose, var from body_cov_list_ / cross_mat_list_
+// and the posterior covariance, then UpdateVoxelMap(pv_list_). Optionally returns the lists (n x 3, n x 9).
+void orc_lio_tick_update_map(void *h, double *pts_world_out, double *var_out) {
+  VoxelMapManager *m = (VoxelMapManager *)h;
+  const StatesGroup &st = m->state_;
+  std::vector<float> world;
+  m->TransformLidar(st.rot_end, st.pos_end, m->feats_down_body_, world);
+  const M3 RE = st.rot_end * m->extR_;
+  M3 Prr, Ppp;
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) Prr(r, c) = st.cov(r, c), Ppp(r, c) = st.cov(3 + r, 3 + c);
+  for (size_t i = 0; i < m->pv_list_.size(); i++) {
+    m->pv_list_[i].point_w = v3(world[3 * i], world[3 * i + 1], world[3 * i + 2]);
+    const M3 point_crossmat = m->cross_mat_list_[i];
+    M3 var = m->body_cov_list_[i];
+    var = RE * var * T(RE) + (point_crossmat * -1.0) * Prr * T(point_crossmat * -1.0) + Ppp;
+    m->pv_list_[i].var = var;
+    if (pts_world_out)
+      for (int k = 0; k < 3; k++) pts_world_out[3 * i + k] = m->pv_list_[i].point_w[k];
+    if (var_out)
+      for (int k = 0; k < 9; k++) var_out[9 * i + k] = var.a[k];
+  }
+  m->UpdateVoxelMap(m->pv_list_);
+}
 // Two-call flatten: sizes first (planes == NULL), then fill.
 void orc_lio_flatten(void *h, int *n_roots, int *n_planes, int64_t *keys, int32_t *first, int32_t *count, void *planes) {
   VoxelMapManager *m = (VoxelMapManager *)h;

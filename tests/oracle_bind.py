@@ -36,6 +36,8 @@ def load(kind="parity"):
     lib.orc_lio_set_map_flat.argtypes = [vp, i64p, ip, ip, C.c_int, vp, C.c_int]
     lib.orc_lio_build_map.argtypes = [vp, fp, fp, C.c_int, dp]
     lib.orc_lio_update_map.argtypes = [vp, dp, dp, C.c_int]
+    lib.orc_lio_tick_build_map.argtypes = [vp, fp, C.c_int, dp]
+    lib.orc_lio_tick_update_map.argtypes = [vp, dp, dp]
     lib.orc_lio_flatten.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), i64p, ip, ip, vp]
     lib.orc_lio_state_estimation.restype = C.c_double
     lib.orc_lio_state_estimation.argtypes = [vp, fp, C.c_int, dp, dp, dp, ip, ip, fp, dp, dp, dp]
@@ -110,6 +112,21 @@ class OracleLIO:
         pb = np.ascontiguousarray(pts_body_f32, dtype=np.float32)
         self.lib.orc_lio_build_map(self.h, fptr(pw), fptr(pb), len(pw), dptr(c64(state)))
 
+    def tick_build_map(self, pts_body_f32, state):
+        """First LiDAR frame, LIVMapper.cpp:356-366."""
+        pb = np.ascontiguousarray(pts_body_f32, dtype=np.float32)
+        self.lib.orc_lio_tick_build_map(self.h, fptr(pb), len(pb), dptr(c64(state)))
+
+    def tick_update_map(self, want_lists=False):
+        """LIVMapper.cpp:413-424 after state_estimation(): UpdateVoxelMap with the posterior; optionally the lists it used."""
+        if not want_lists:
+            self.lib.orc_lio_tick_update_map(self.h, None, None)
+            return None
+        n = self._last_n
+        pw, var = np.zeros((n, 3)), np.zeros((n, 9))
+        self.lib.orc_lio_tick_update_map(self.h, dptr(pw), dptr(var))
+        return pw, var
+
     def flatten(self):
         from fast_livo2_b200.synthetic import PLANE_DTYPE
 
@@ -125,6 +142,7 @@ class OracleLIO:
     def state_estimation(self, pts, state_in, state_prop):
         pts = np.ascontiguousarray(pts, dtype=np.float32)
         n = len(pts)
+        self._last_n = n
         out = np.zeros(STATE_PACK)
         match = np.zeros(n, np.int32)
         normal = np.zeros(n, np.int32)
