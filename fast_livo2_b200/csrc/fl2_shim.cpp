@@ -2,6 +2,8 @@
 // the packed buffers of the C ABI (libesikf_b200.so, resolved at load time through the dynamic linker).
 #include "fl2_shim.hpp"
 
+#include <chrono>
+
 #include <cmath>
 #include <cstring>
 
@@ -104,6 +106,10 @@ VoxelMapManager::~VoxelMapManager() { esikf_destroy(ctx_); }
 
 void VoxelMapManager::SyncDeviceMap() {
   if (!ctx_) return;
+  if (device_map_) {  // the device owns the map: nothing to mirror
+    map_synced_ = true;
+    return;
+  }
   std::string err;
   FlatVoxelMap now;
   if (!FlattenVoxelMap(voxel_map_, config_setting_, now, &err)) {
@@ -130,6 +136,74 @@ void VoxelMapManager::SyncDeviceMap() {
     device_has_map_ = true;
   }
   map_synced_ = (last_status_ == 0);
+}
+
+void VoxelMapManager::EnableDeviceMap() {
+  if (!ctx_) return;
+  esikf_map_cfg m;
+  memset(&m, 0, sizeof(m));
+  m.voxel_size = config_setting_.max_voxel_size_, m.min_eigen_value = config_setting_.planner_threshold_;
+  m.dept_err = config_setting_.dept_err_, m.beam_err = config_setting_.beam_err_;
+  m.max_layer = config_setting_.max_layer_, m.max_points_num = config_setting_.max_points_num_;
+  const std::vector<int> &lin = config_setting_.layer_init_num_;
+  for (int k = 0; k < 8; k++) m.layer_init_num[k] = lin.empty() ? 5 : lin[k < (int)lin.size() ? k : (int)lin.size() - 1];
+  m.root_capacity = config_setting_.device_root_capacity_;
+  if ((last_status_ = esikf_map_device_init(ctx_, &m)) != 0) {
+    last_error_ = esikf_last_error(ctx_);
+    return;
+  }
+  device_map_ = true, map_synced_ = true, device_has_map_ = true;
+}
+
+// include/voxel_map.h:231 / src/voxel_map.cpp:532-591 with feats_down_world_ = transformLidar(state_) (LIVMapper.cpp:360)
+void VoxelMapManager::BuildVoxelMap() {
+  if (!ctx_ || !device_map_) {
+    last_status_ = ESIKF_ERR_STATE, last_error_ = "BuildVoxelMap: EnableDeviceMap first (a host-owned voxel_map_ is built by the reference's own code)";
+    return;
+  }
+  const int n = feats_down_size_;
+  float *pts = st_pts_.get((size_t)n * 3 + 4);
+  double *sbuf = st_state_.get(3 * ESIKF_STATE_DOUBLES);
+  if (!pts || !sbuf) {
+    last_status_ = ESIKF_ERR_CUDA, last_error_ = "pinned staging allocation failed";
+    return;
+  }
+  if (n) memcpy(pts, &feats_down_body_[0].x, (size_t)n * 12);
+  state_.pack(sbuf);
+  if ((last_status_ = esikf_set_lidar_extrinsics(ctx_, extR_.m, extT_.v)) == 0 && (last_status_ = esikf_lio_set_scan(ctx_, pts, n)) == 0)
+    last_status_ = esikf_map_device_build(ctx_, sbuf);
+  if (last_status_) last_error_ = esikf_last_error(ctx_);
+}
+
+// LIVMapper.cpp:413-424: pv_list_[i].point_w / .var with the posterior, then UpdateVoxelMap(pv_list_) — on the device
+void VoxelMapManager::UpdateVoxelMap() {
+  if (!ctx_ || !device_map_) {
+    last_status_ = ESIKF_ERR_STATE, last_error_ = "UpdateVoxelMap(): EnableDeviceMap first";
+    return;
+  }
+  double *sbuf = st_state_.get(3 * ESIKF_STATE_DOUBLES);
+  state_.pack(sbuf);  // _state == voxelmap_manager->state_ at this point of the tick (LIVMapper.cpp:371); 3 kB
+  if ((last_status_ = esikf_map_device_update(ctx_, sbuf)) != 0) last_error_ = esikf_last_error(ctx_);
+}
+
+// include/voxel_map.h:232 / src/voxel_map.cpp:609-641
+void VoxelMapManager::UpdateVoxelMap(const std::vector<pointWithVar> &input_points) {
+  if (!ctx_ || !device_map_) {
+    last_status_ = ESIKF_ERR_STATE, last_error_ = "UpdateVoxelMap: EnableDeviceMap first";
+    return;
+  }
+  const size_t n = input_points.size();
+  double *buf = st_cov_.get(n * 12 + 2);
+  if (!buf) {
+    last_status_ = ESIKF_ERR_CUDA, last_error_ = "pinned staging allocation failed";
+    return;
+  }
+  double *pw = buf, *var = buf + n * 3;
+  for (size_t i = 0; i < n; i++) {
+    for (int k = 0; k < 3; k++) pw[3 * i + k] = input_points[i].point_w[k];
+    memcpy(var + 9 * i, input_points[i].var.m, 72);
+  }
+  if ((last_status_ = esikf_map_device_update_points(ctx_, pw, var, (int32_t)n)) != 0) last_error_ = esikf_last_error(ctx_);
 }
 
 // include/voxel_map.h:229 / src/voxel_map.cpp:338-511
@@ -194,6 +268,16 @@ void VoxelMapManager::MaterializePointLists() {
   body_cov_list_.resize(n), cross_mat_list_.resize(n);
   pv_list_.resize(n);
   ptpl_list_.clear();
+  const double *dev_normals = nullptr;
+  if (device_map_) {  // no host VoxelPlane exists: pv.normal comes from the device records
+    double *nb = st_normals_.get((size_t)n * 3 + 2);
+    if (!nb || (last_status_ = esikf_lio_fetch_normals(ctx_, nb)) != 0) {
+      last_error_ = nb ? esikf_last_error(ctx_) : "pinned staging allocation failed";
+      if (!nb) last_status_ = ESIKF_ERR_CUDA;
+      return;
+    }
+    dev_normals = nb;
+  }
   const double *R = state_.rot_end.m;
   for (int i = 0; i < n; i++) {
     memcpy(body_cov_list_[i].m, &bc[(size_t)i * 9], 72);
@@ -208,6 +292,17 @@ void VoxelMapManager::MaterializePointLists() {
     for (int r = 0; r < 3; r++) pi[r] = extR_.m[3 * r] * pv.point_b[0] + extR_.m[3 * r + 1] * pv.point_b[1] + extR_.m[3 * r + 2] * pv.point_b[2] + extT_[r];
     for (int r = 0; r < 3; r++) pw[r] = R[3 * r] * pi[0] + R[3 * r + 1] * pi[1] + R[3 * r + 2] * pi[2] + state_.pos_end[r];
     for (int r = 0; r < 3; r++) pv.point_w[r] = (double)(float)pw[r];
+    if (dev_normals) {
+      for (int k = 0; k < 3; k++) pv.normal[k] = dev_normals[3 * (size_t)i + k];
+      if (match[i] >= 0) {  // the plane's own fields stay on the device (esikf_map_device_download); what the tick produced is filled
+        PointToPlane q;
+        memset(q.plane_var_, 0, sizeof(q.plane_var_));
+        q.point_b_ = pv.point_b, q.point_w_ = pv.point_w, q.normal_ = pv.normal, q.body_cov_ = pv.body_var;
+        q.is_valid_ = true, q.dis_to_plane_ = dis[i];
+        ptpl_list_.push_back(q);
+      }
+      continue;
+    }
     if (normal[i] >= 0) pv.normal = flat_.plane_src[normal[i]]->normal_;  // pv.normal (voxel_map.cpp:744), zero if never matched
     if (match[i] >= 0) {
       const VoxelPlane &pl = *flat_.plane_src[match[i]];
@@ -565,6 +660,7 @@ struct ShimSession {
   bool has_vio = false;
   esikf_camera cam{};
   esikf_vio_cfg vcfg{};
+  long long manager_ns = 0;
   ~ShimSession() {
     delete vio;
     delete mgr;
@@ -622,7 +718,9 @@ int fl2_shim_session_step(void *h, const float *pts, int n, const double *state_
   mgr.state_.unpack(state_in);  // voxelmap_manager->state_ = _state  (LIVMapper.cpp:257)
   StatesGroup prop;
   prop.unpack(state_prop);
+  const auto t_lio0 = std::chrono::steady_clock::now();
   mgr.StateEstimation(prop);    // LIVMapper.cpp:370
+  s->manager_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_lio0).count();
   if (mgr.last_status_) return mgr.last_status_;
   mgr.state_.pack(lio_state_out);
   iters_out[0] = mgr.last_iters_, iters_out[1] = 0;
@@ -643,7 +741,9 @@ int fl2_shim_session_step(void *h, const float *pts, int n, const double *state_
     vio.total_points = n_patches;
     GrayImage im;
     im.data = img, im.cols = s->cam.width, im.rows = s->cam.height;
+    const auto t_vio0 = std::chrono::steady_clock::now();
     vio.computeJacobianAndUpdateEKF(im);
+    s->manager_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_vio0).count();
     if (vio.last_status_) return vio.last_status_;
     s->st.pack(vio_state_out);
     iters_out[1] = vio.last_total_iters_;
@@ -667,6 +767,38 @@ int fl2_shim_session_materialize(void *h, int32_t *n_pv, int32_t *n_ptpl) {
   if (n_pv) *n_pv = (int32_t)s->mgr->pv_list_.size();
   if (n_ptpl) *n_ptpl = (int32_t)s->mgr->ptpl_list_.size();
   return s->mgr->last_status_;
+}
+
+// Device-resident map for the session: the map the session was created with is dropped, an empty device map takes its place and
+// absorbs `pts` at `state` through BuildVoxelMap (first LiDAR frame, LIVMapper.cpp:356-366).
+int fl2_shim_session_device_map(void *h, const float *pts, int n, const double *state, double min_eigen_value, int max_points_num, long long root_capacity) {
+  ShimSession *s = static_cast<ShimSession *>(h);
+  if (!s) return ESIKF_ERR_ARG;
+  VoxelMapManager &mgr = *s->mgr;
+  mgr.config_setting_.planner_threshold_ = min_eigen_value, mgr.config_setting_.max_points_num_ = max_points_num;
+  mgr.config_setting_.device_root_capacity_ = root_capacity;
+  mgr.EnableDeviceMap();
+  if (mgr.last_status_) return mgr.last_status_;
+  mgr.feats_down_body_.resize(n);
+  if (n) memcpy(mgr.feats_down_body_.data(), pts, (size_t)n * 12);
+  mgr.feats_down_size_ = n;
+  mgr.state_.unpack(state);
+  mgr.BuildVoxelMap();
+  return mgr.last_status_;
+}
+// LIVMapper.cpp:413-424 after the LIO half of a tick: the device map absorbs the scan with the LIO posterior.
+int fl2_shim_session_update_map(void *h) {
+  ShimSession *s = static_cast<ShimSession *>(h);
+  if (!s) return ESIKF_ERR_ARG;
+  s->mgr->UpdateVoxelMap();
+  return s->mgr->last_status_;
+}
+
+// nanoseconds the last step spent inside StateEstimation + computeJacobianAndUpdateEKF (the two calls LIVMapper makes; filling
+// the managers' members from the harness' flat buffers — which LIVMapper already holds in that shape — is outside)
+long long fl2_shim_session_manager_ns(void *h) {
+  ShimSession *s = static_cast<ShimSession *>(h);
+  return s ? s->manager_ns : 0;
 }
 
 void fl2_shim_session_destroy(void *h) { delete static_cast<ShimSession *>(h); }

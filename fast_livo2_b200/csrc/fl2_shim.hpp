@@ -97,6 +97,11 @@ struct VoxelMapConfig {
   int max_layer_ = 2;
   int max_iterations_ = 5;
   double beam_err_ = 0.05, dept_err_ = 0.02, sigma_num_ = 3.0;
+  // map-building part (read by the device-resident map only; a host-owned map is built by the reference's own code)
+  double planner_threshold_ = 0.0025;  // lio/min_eigen_value
+  int max_points_num_ = 50;            // lio/max_points_num
+  std::vector<int> layer_init_num_{5, 5, 5, 5, 5};
+  long long device_root_capacity_ = 0;  // 0: esikf_map_device_init's default (2^20 root voxels)
 };
 
 struct PointXYZ { float x, y, z; };  // pcl::PointXYZINormal's xyz as consumed at src/voxel_map.cpp:351,520-521
@@ -170,6 +175,17 @@ class VoxelMapManager {
   void MarkMapDirty() { map_synced_ = false; }
   int last_sync_patched_ = -1;     // planes patched by the last SyncDeviceMap, -1 = it was a full upload
   void StateEstimation(StatesGroup &state_propagat);  // include/voxel_map.h:229
+  // ---- device-resident map: the octrees, point lists and refits live on the GPU (esikf_map_device_*); voxel_map_ is not used
+  // and SyncDeviceMap is never needed. EnableDeviceMap once after construction, then the reference's own call sequence:
+  //   BuildVoxelMap()              first LiDAR frame, from feats_down_body_ and state_      (include/voxel_map.h:231, LIVMapper.cpp:356-366)
+  //   UpdateVoxelMap()             LIVMapper.cpp:413-424 in ONE call: world points + covariances with the posterior and the
+  //                                update, all on the device (nothing but a status crosses PCIe)
+  //   UpdateVoxelMap(input_points) the reference's signature (include/voxel_map.h:232) with host lists
+  void EnableDeviceMap();
+  bool device_map_ = false;
+  void BuildVoxelMap();
+  void UpdateVoxelMap();
+  void UpdateVoxelMap(const std::vector<pointWithVar> &input_points);
   void MaterializePointLists();                       // fills the four lists from the last StateEstimation (idempotent per call of it)
   esikf_ctx *context() { return ctx_; }
 
@@ -179,7 +195,7 @@ class VoxelMapManager {
   bool map_synced_ = false, device_has_map_ = false;
   PinnedBuf<float> st_pts_, st_dis_;
   PinnedBuf<int32_t> st_match_, st_normal_;
-  PinnedBuf<double> st_state_, st_cov_;
+  PinnedBuf<double> st_state_, st_cov_, st_normals_;
   bool lists_pending_ = false;
 };
 
