@@ -84,6 +84,7 @@ def load_library():
     lib.esikf_map_device_update.argtypes = [vp, vp]
     lib.esikf_map_device_update_points.argtypes = [vp, vp, vp, C.c_int32]
     lib.esikf_map_device_stats.argtypes = [vp, vp]
+    lib.esikf_map_device_slide.argtypes = [vp, vp, vp]
     lib.esikf_map_device_download.argtypes = [vp, vp, vp, vp, C.c_int32, vp, C.c_int32, vp, vp]
     lib.esikf_lio_fetch_normals.argtypes = [vp, vp]
     lib.esikf_lio_set_scan.argtypes = [vp, vp, C.c_int32]
@@ -134,7 +135,7 @@ class MapStatsC(C.Structure):
 
 EXPORTED_SYMBOLS = [
     "esikf_create", "esikf_destroy", "esikf_last_error", "esikf_stream", "esikf_synchronize", "esikf_host_alloc", "esikf_host_free", "esikf_launch_count", "esikf_set_solve_mode", "esikf_set_loop_mode", "esikf_set_tuning",
-    "esikf_set_extrinsics", "esikf_set_lidar_extrinsics", "esikf_map_upload", "esikf_map_patch", "esikf_map_device_init", "esikf_map_device_build", "esikf_map_device_update", "esikf_map_device_update_points", "esikf_map_device_stats", "esikf_map_device_download", "esikf_lio_fetch_normals", "esikf_lio_set_scan", "esikf_lio_run", "esikf_lio_fetch",
+    "esikf_set_extrinsics", "esikf_set_lidar_extrinsics", "esikf_map_upload", "esikf_map_patch", "esikf_map_device_init", "esikf_map_device_build", "esikf_map_device_update", "esikf_map_device_update_points", "esikf_map_device_slide", "esikf_map_device_stats", "esikf_map_device_download", "esikf_lio_fetch_normals", "esikf_lio_set_scan", "esikf_lio_run", "esikf_lio_fetch",
     "esikf_lio_update", "esikf_lio_fetch_point_cov", "esikf_vio_set_camera", "esikf_vio_set_image", "esikf_vio_set_patches",
     "esikf_vio_run", "esikf_vio_fetch", "esikf_vio_update", "esikf_vio_get_image_patch", "esikf_vio_set_ref_images",
     "esikf_vio_warp_patches", "esikf_vio_warp_affine", "esikf_vio_set_inverse_refs", "esikf_comm_unique_id", "esikf_comm_init", "esikf_comm_rank", "esikf_shard_range", "esikf_peer_export", "esikf_peer_attach", "esikf_profile_kernel", "esikf_set_kernel_timing", "esikf_get_kernel_timing", "esikf_set_phase_stamps", "esikf_get_phase_stamps",
@@ -247,6 +248,11 @@ class Context:
     def map_device_update_points(self, point_w, var):
         pw, v = _c(point_w, np.float64).reshape(-1, 3), _c(var, np.float64).reshape(-1, 9)
         self._ck(self.lib.esikf_map_device_update_points(self.h, pw.ctypes.data, v.ctypes.data, len(pw)))
+
+    def map_device_slide(self, key_min=None, key_max=None):
+        lo = None if key_min is None else _c(key_min, np.int64)
+        hi = None if key_max is None else _c(key_max, np.int64)
+        self._ck(self.lib.esikf_map_device_slide(self.h, None if lo is None else lo.ctypes.data, None if hi is None else hi.ctypes.data))
 
     def map_device_stats(self):
         st = MapStatsC()

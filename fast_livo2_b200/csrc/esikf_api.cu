@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "esikf_dev.cuh"
@@ -120,6 +121,14 @@ struct esikf_ctx {
   DevBuf<unsigned int> map_key_in, map_key_out, map_idx_in, map_idx_out;
   DevBuf<MapTouched> map_touched;
   DevBuf<unsigned char> map_sort_tmp;
+  // second arena: esikf_map_device_slide copies the surviving roots into it, then the two change roles
+  DevBuf<HashSlot> slots2;
+  DevBuf<esikf_plane> planes2;
+  DevBuf<PlaneRec> recs2;
+  DevBuf<int> map_slot_root2, map_slot_cap2, map_rec_node2, map_counters2, map_survivors;
+  DevBuf<unsigned long long> map_counters64_2;
+  DevBuf<MapNode> map_nodes2;
+  DevBuf<double> map_pool2;
   int map_pt_n = 0;            // points the normal snapshot / last map step covers
   bool map_normals_valid = false;
   int map_hash_bits = 0;
@@ -322,6 +331,8 @@ void esikf_destroy(esikf_ctx *ctx) {
   ctx->map_slot_root.release(), ctx->map_slot_cap.release(), ctx->map_rec_node.release(), ctx->map_counters.release(), ctx->map_work.release(), ctx->map_counters64.release();
   ctx->map_nodes.release(), ctx->map_pool.release(), ctx->map_pt.release(), ctx->map_pt_normal.release(), ctx->map_key_in.release(), ctx->map_key_out.release();
   ctx->map_idx_in.release(), ctx->map_idx_out.release(), ctx->map_touched.release(), ctx->map_sort_tmp.release();
+  ctx->slots2.release(), ctx->planes2.release(), ctx->recs2.release(), ctx->map_slot_root2.release(), ctx->map_slot_cap2.release(), ctx->map_rec_node2.release();
+  ctx->map_counters2.release(), ctx->map_survivors.release(), ctx->map_counters64_2.release(), ctx->map_nodes2.release(), ctx->map_pool2.release();
   if (ctx->stage) cudaFreeHost(ctx->stage);
   if (ctx->stage_ctrl) cudaFreeHost(ctx->stage_ctrl);
   for (int i = 0; i < esikf_ctx::STAGE_SLOTS; i++)
@@ -615,6 +626,46 @@ int esikf_map_device_update_points(esikf_ctx *ctx, const double *point_w, const 
   ctx->launches++;
   ctx->map_normals_valid = false;
   return map_apply_points(ctx, n, false);
+}
+
+// mapSliding / clearMemOutOfMap (src/voxel_map.cpp:924-971)
+int esikf_map_device_slide(esikf_ctx *ctx, const int64_t key_min[3], const int64_t key_max[3]) {
+  if (!ctx) return ESIKF_ERR_ARG;
+  if (!ctx->dev_map) return fail(ctx, ESIKF_ERR_STATE, "map_device_slide before esikf_map_device_init");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const MapArena S = ctx->arena;
+  const unsigned cap = S.hash_mask + 1u;
+  CK(ctx->slots2.reserve(cap));
+  CK(ctx->map_slot_root2.reserve(cap));
+  CK(ctx->map_slot_cap2.reserve(cap));
+  CK(ctx->map_nodes2.reserve((size_t)S.node_cap));
+  CK(ctx->map_pool2.reserve((size_t)S.pool_cap * MAP_PT_D));
+  CK(ctx->recs2.reserve((size_t)S.rec_cap));
+  CK(ctx->planes2.reserve((size_t)S.rec_cap));
+  CK(ctx->map_rec_node2.reserve((size_t)S.rec_cap));
+  CK(ctx->map_counters2.reserve(8));
+  CK(ctx->map_counters64_2.reserve(2));
+  CK(ctx->map_survivors.reserve((size_t)(ctx->map_last.roots > 0 ? ctx->map_last.roots : 1) + 1));
+  MapArena D = S;
+  D.slots = ctx->slots2.p, D.slot_root = ctx->map_slot_root2.p, D.slot_cap = ctx->map_slot_cap2.p, D.nodes = ctx->map_nodes2.p, D.pool = ctx->map_pool2.p;
+  D.recs = ctx->recs2.p, D.planes = ctx->planes2.p, D.rec_node = ctx->map_rec_node2.p, D.counters = ctx->map_counters2.p, D.counters64 = ctx->map_counters64_2.p;
+  const long long big = 1ll << 40;
+  const long long lo[3] = {key_min ? key_min[0] : -big, key_min ? key_min[1] : -big, key_min ? key_min[2] : -big};
+  const long long hi[3] = {key_max ? key_max[0] : big, key_max ? key_max[1] : big, key_max ? key_max[2] : big};
+  map_reset_kernel<<<(cap + 255) / 256, 256, 0, st>>>(D);
+  CK(cudaMemsetAsync(ctx->map_work.p, 0, 2 * sizeof(int), st));
+  map_survivors_kernel<<<(cap + 255) / 256, 256, 0, st>>>(S, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], ctx->map_survivors.p, ctx->map_work.p);
+  map_copy_kernel<<<ctx->sm_count * 4, 128, 0, st>>>(S, D, ctx->map_survivors.p, ctx->map_work.p);
+  ctx->launches += 3;
+  CK(cudaGetLastError());
+  // the fresh arena becomes the map (also when the copy reports an error: the status says so and the map is invalidated)
+  std::swap(ctx->slots, ctx->slots2), std::swap(ctx->map_slot_root, ctx->map_slot_root2), std::swap(ctx->map_slot_cap, ctx->map_slot_cap2);
+  std::swap(ctx->map_nodes, ctx->map_nodes2), std::swap(ctx->map_pool, ctx->map_pool2), std::swap(ctx->recs, ctx->recs2), std::swap(ctx->planes, ctx->planes2);
+  std::swap(ctx->map_rec_node, ctx->map_rec_node2), std::swap(ctx->map_counters, ctx->map_counters2), std::swap(ctx->map_counters64, ctx->map_counters64_2);
+  ctx->arena = D;
+  ctx->map_normals_valid = false;  // record positions of the last update are gone
+  return map_check_errors(ctx, "map_device_slide");
 }
 
 int esikf_map_device_stats(esikf_ctx *ctx, esikf_map_stats *out) {

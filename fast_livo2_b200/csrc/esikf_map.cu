@@ -196,6 +196,28 @@ __global__ void __launch_bounds__(256) map_download_kernel(const MapArena A, lon
   for (int j = 0; j < c; j++) planes[off + j] = A.planes[A.slots[s].first + j];
 }
 
+// mapSliding: list the occupied slots inside the box, then one warp per surviving root copies it into the fresh arena
+__global__ void __launch_bounds__(256) map_survivors_kernel(const MapArena S, long long lx, long long ly, long long lz, long long hx, long long hy, long long hz, int *survivors, int *work) {
+  const unsigned int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > S.hash_mask) return;
+  const unsigned long long k = S.slots[s].key;
+  if (k == ESIKF_KEY_EMPTY || S.slot_root[s] < 0) return;
+  const long long lo[3] = {lx, ly, lz}, hi[3] = {hx, hy, hz};
+  if (!map_key_in_box(k, lo, hi)) return;
+  survivors[atomicAdd(&work[0], 1)] = (int)s;
+}
+__global__ void __launch_bounds__(128) map_copy_kernel(const MapArena S, const MapArena D, const int *__restrict__ survivors, int *work) {
+  const WarpCoop co;
+  const int n = *reinterpret_cast<volatile int *>(&work[0]);
+  for (;;) {
+    int t = 0;
+    if (co.lane() == 0) t = atomicAdd(&work[1], 1);
+    t = co.bcast(t);
+    if (t >= n) break;
+    map_copy_root(S, D, co, survivors[t]);
+  }
+}
+
 __global__ void map_reset_kernel(const MapArena A) {
   const unsigned int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s <= A.hash_mask) {

@@ -599,4 +599,78 @@ MAP_HD void map_replay_root(const MapArena &A, const C &co, int slot, const unsi
   map_emit_root(A, co, slot);
 }
 
+// ---- mapSliding / clearMemOutOfMap (:924-971) as a copy into a fresh arena: the roots inside the box are re-inserted with their
+// whole sub-trees, point lists sized to their content and a tight record block — which also reclaims the dead record
+// blocks and the list space earlier growth left behind. S is read-only.
+template <class C>
+MAP_HD bool map_copy_root(const MapArena &S, const MapArena &D, const C &co, int src_slot) {
+  const unsigned long long k = S.slots[src_slot].key;
+  const int dslot = map_slot_of(D, k);
+  if (dslot < 0) {
+    map_raise(D, MAP_ERR_HASH);
+    return false;
+  }
+  int src_stack[MAP_STACK], dst_stack[MAP_STACK];
+  int sp = 0;
+  const MapNode &sr = S.nodes[S.slot_root[src_slot]];
+  const int droot = map_new_node(D, co, 0, sr.center, sr.quarter);
+  if (droot < 0) return false;
+  src_stack[sp] = S.slot_root[src_slot], dst_stack[sp] = droot, sp++;
+  while (sp > 0) {
+    --sp;
+    const int si = src_stack[sp], di = dst_stack[sp];
+    const MapNode &sn = S.nodes[si];
+    MapNode &dn = D.nodes[di];
+    if (co.lane() == 0) {
+      dn.new_points = sn.new_points, dn.init_octo = sn.init_octo, dn.update_enable = sn.update_enable, dn.octo_state = sn.octo_state;
+      dn.is_plane = sn.is_plane, dn.points_size = sn.points_size, dn.d = sn.d, dn.radius = sn.radius;
+      for (int q = 0; q < 3; q++) dn.pc[q] = sn.pc[q], dn.pn[q] = sn.pn[q];
+      for (int q = 0; q < 21; q++) dn.plane_var[q] = sn.plane_var[q];
+    }
+    co.sync();
+    if (sn.list_size > 0) {
+      const int want = sn.list_size < 8 ? 8 : sn.list_size;
+      unsigned long long off = 0;
+      if (co.lane() == 0) off = map_atomic_add64(&D.counters64[0], (unsigned long long)want);
+      const int lo = co.bcast((int)(off & 0xffffffffull)), hi = co.bcast((int)(off >> 32));
+      off = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo;
+      if ((long long)(off + want) > D.pool_cap) {
+        map_raise(D, MAP_ERR_POOL);
+        return false;
+      }
+      const double *src = S.pool + (size_t)sn.list_off * MAP_PT_D;
+      double *dst = D.pool + off * MAP_PT_D;
+      for (int w = co.lane(); w < sn.list_size * MAP_PT_D; w += C::N) dst[w] = src[w];
+      if (co.lane() == 0) dn.list_off = (int)off, dn.list_size = sn.list_size, dn.list_cap = want;
+      co.sync();
+    }
+    for (int l = 0; l < 8; l++) {
+      const int sc = sn.children[l];
+      if (sc < 0) continue;
+      const int dc = map_new_node(D, co, S.nodes[sc].layer, S.nodes[sc].center, S.nodes[sc].quarter);
+      if (dc < 0) return false;
+      if (co.lane() == 0) dn.children[l] = dc;
+      co.sync();
+      if (sp >= MAP_STACK) {
+        map_raise(D, MAP_ERR_STACK);
+        return false;
+      }
+      src_stack[sp] = sc, dst_stack[sp] = dc, sp++;
+    }
+  }
+  if (co.lane() == 0) {
+    D.slot_root[dslot] = droot, D.slot_cap[dslot] = 0;
+    D.slots[dslot].first = 0, D.slots[dslot].count = 0;
+    map_atomic_add(&D.counters[3], 1);
+  }
+  co.sync();
+  map_emit_root(D, co, dslot);
+  return true;
+}
+// should_remove of clearMemOutOfMap (:958) negated
+MAP_HD bool map_key_in_box(unsigned long long k, const long long *lo, const long long *hi) {
+  const long long x = (long long)(k >> 42) - ESIKF_KEY_BIAS, y = (long long)((k >> 21) & (ESIKF_KEY_RANGE - 1)) - ESIKF_KEY_BIAS, z = (long long)(k & (ESIKF_KEY_RANGE - 1)) - ESIKF_KEY_BIAS;
+  return !(x > hi[0] || x < lo[0] || y > hi[1] || y < lo[1] || z > hi[2] || z < lo[2]);
+}
+
 }  // namespace esikf

@@ -186,6 +186,25 @@ void VoxelMapManager::UpdateVoxelMap() {
   if ((last_status_ = esikf_map_device_update(ctx_, sbuf)) != 0) last_error_ = esikf_last_error(ctx_);
 }
 
+// src/voxel_map.cpp:924-948: nothing until the sensor moved sliding_thresh, then roots further than half_map_size voxels go
+void VoxelMapManager::mapSliding() {
+  if (!ctx_ || !device_map_) {
+    last_status_ = ESIKF_ERR_STATE, last_error_ = "mapSliding: EnableDeviceMap first (a host-owned voxel_map_ slides in the reference's own code)";
+    return;
+  }
+  double d2 = 0;
+  for (int k = 0; k < 3; k++) d2 += (position_last_[k] - last_slide_position[k]) * (position_last_[k] - last_slide_position[k]);
+  if (sqrt(d2) < config_setting_.sliding_thresh) return;
+  last_slide_position = position_last_;
+  int64_t lo[3], hi[3];
+  for (int j = 0; j < 3; j++) {
+    float loc = (float)(position_last_[j] / config_setting_.max_voxel_size_);  // :938 (double quotient narrowed to float)
+    if (loc < 0) loc -= 1.0;
+    lo[j] = (int64_t)loc - config_setting_.half_map_size, hi[j] = (int64_t)loc + config_setting_.half_map_size;
+  }
+  if ((last_status_ = esikf_map_device_slide(ctx_, lo, hi)) != 0) last_error_ = esikf_last_error(ctx_);
+}
+
 // include/voxel_map.h:232 / src/voxel_map.cpp:609-641
 void VoxelMapManager::UpdateVoxelMap(const std::vector<pointWithVar> &input_points) {
   if (!ctx_ || !device_map_) {

@@ -102,6 +102,9 @@ struct VoxelMapConfig {
   int max_points_num_ = 50;            // lio/max_points_num
   std::vector<int> layer_init_num_{5, 5, 5, 5, 5};
   long long device_root_capacity_ = 0;  // 0: esikf_map_device_init's default (2^20 root voxels)
+  bool map_sliding_en = false;          // local_map/map_sliding_en
+  int half_map_size = 100;              // local_map/half_map_size
+  double sliding_thresh = 8.0;          // local_map/sliding_thresh
 };
 
 struct PointXYZ { float x, y, z; };  // pcl::PointXYZINormal's xyz as consumed at src/voxel_map.cpp:351,520-521
@@ -186,6 +189,8 @@ class VoxelMapManager {
   void BuildVoxelMap();
   void UpdateVoxelMap();
   void UpdateVoxelMap(const std::vector<pointWithVar> &input_points);
+  void mapSliding();  // include/voxel_map.h:247 / src/voxel_map.cpp:924-948 (device-resident map); uses position_last_, sliding_thresh, half_map_size
+  V3D last_slide_position;
   void MaterializePointLists();                       // fills the four lists from the last StateEstimation (idempotent per call of it)
   esikf_ctx *context() { return ctx_; }
 

@@ -199,6 +199,11 @@ int esikf_map_device_build(esikf_ctx *ctx, const double *state);
 int esikf_map_device_update(esikf_ctx *ctx, const double *state);
 /* UpdateVoxelMap(input_points) with the caller's own lists: point_w [n][3], var [n][9] row-major (host). */
 int esikf_map_device_update_points(esikf_ctx *ctx, const double *point_w, const double *var, int32_t n);
+/* mapSliding / clearMemOutOfMap (src/voxel_map.cpp:924-971): root voxels whose key lies outside [key_min, key_max]
+ * (component-wise, inclusive) are dropped; the survivors are copied into a second arena of the same capacities, which also
+ * reclaims dead record blocks and point-list slack (NULL bounds: compaction only). The per-point plane ids of the last
+ * update are void afterwards (esikf_lio_fetch normals / ids refer to the old records): call it between ticks. */
+int esikf_map_device_slide(esikf_ctx *ctx, const int64_t key_min[3], const int64_t key_max[3]);
 int esikf_map_device_stats(esikf_ctx *ctx, esikf_map_stats *out);
 /* The map in esikf_map_upload's flat form (roots in no particular order). keys == NULL: sizes only. */
 int esikf_map_device_download(esikf_ctx *ctx, int64_t *keys, int32_t *first, int32_t *count, int32_t roots_cap, esikf_plane *planes, int32_t planes_cap,

@@ -86,6 +86,15 @@ void orc_lio_set_map_flat(void *h, const int64_t *keys, const int32_t *first, co
   ((VoxelMapManager *)h)->FromFlat(keys, first, count, n_roots, (const FlatPlane *)planes, n_planes);
 }
 
+// Oracle bookkeeping: a match needs the chosen plane's flat id (orc_lio.cpp: "require a chosen plane"), which Flatten assigns. Maps
+// that grow natively (BuildVoxelMap / UpdateVoxelMap) get their ids refreshed after every change.
+static void refresh_flat_ids(VoxelMapManager *m) {
+  std::vector<int64_t> k;
+  std::vector<int32_t> f, c;
+  std::vector<FlatPlane> p;
+  m->Flatten(k, f, c, p);
+}
+
 // BuildVoxelMap (src/voxel_map.cpp:532-591) from world/body points at `state`.
 void orc_lio_build_map(void *h, const float *pts_world, const float *pts_body, int n, const double *state) {
   VoxelMapManager *m = (VoxelMapManager *)h;
@@ -93,6 +102,7 @@ void orc_lio_build_map(void *h, const float *pts_world, const float *pts_body, i
   m->feats_down_body_.assign(pts_body, pts_body + 3 * (size_t)n);
   unpack_state(state, m->state_);
   m->BuildVoxelMap();
+  refresh_flat_ids(m);
 }
 // UpdateVoxelMap (src/voxel_map.cpp:609-641) with caller-supplied world points + 3x3 vars.
 void orc_lio_update_map(void *h, const double *pts_world, const double *var9, int n) {
@@ -103,6 +113,7 @@ void orc_lio_update_map(void *h, const double *pts_world, const double *var9, in
     for (int k = 0; k < 9; k++) pts[i].var.a[k] = var9[9 * (size_t)i + k];
   }
   m->UpdateVoxelMap(pts);
+  refresh_flat_ids(m);
 }
 // First LiDAR frame (LIVMapper.cpp:356-366): feats_down_world_ = transformLidar(state, feats_down_body_), BuildVoxelMap().
 void orc_lio_tick_build_map(void *h, const float *pts_body, int n, const double *state) {
@@ -112,6 +123,7 @@ void orc_lio_tick_build_map(void *h, const float *pts_body, int n, const double 
   unpack_state(state, m->state_);
   m->TransformLidar(m->state_.rot_end, m->state_.pos_end, m->feats_down_body_, m->feats_down_world_);  // same expression as LIVMapper::transformLidar (:645)
   m->BuildVoxelMap();
+  refresh_flat_ids(m);
 }
 // After StateEstimation (LIVMapper.cpp:413-424): world points with the posterior pose, var from body_cov_list_ / cross_mat_list_
 // and the posterior covariance, then UpdateVoxelMap(pv_list_). Optionally returns the lists (n x 3, n x 9).
@@ -136,6 +148,24 @@ void orc_lio_tick_update_map(void *h, double *pts_world_out, double *var_out) {
       for (int k = 0; k < 9; k++) var_out[9 * i + k] = var.a[k];
   }
   m->UpdateVoxelMap(m->pv_list_);
+  refresh_flat_ids(m);
+}
+// clearMemOutOfMap (src/voxel_map.cpp:950-971): root voxels outside the box are deleted. Returns how many.
+int orc_lio_clear_out_of_map(void *h, int x_max, int x_min, int y_max, int y_min, int z_max, int z_min) {
+  VoxelMapManager *m = (VoxelMapManager *)h;
+  int deleted = 0;
+  for (auto it = m->voxel_map_.begin(); it != m->voxel_map_.end();) {
+    const VOXEL_LOCATION &loc = it->first;
+    const bool should_remove = loc.x > x_max || loc.x < x_min || loc.y > y_max || loc.y < y_min || loc.z > z_max || loc.z < z_min;
+    if (should_remove) {
+      delete it->second;
+      it = m->voxel_map_.erase(it);
+      deleted++;
+    } else {
+      ++it;
+    }
+  }
+  return deleted;
 }
 // Two-call flatten: sizes first (planes == NULL), then fill.
 void orc_lio_flatten(void *h, int *n_roots, int *n_planes, int64_t *keys, int32_t *first, int32_t *count, void *planes) {

@@ -31,6 +31,7 @@ class HostMap:
         self.lib.maph_flatten.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         self.lib.maph_usage.argtypes = [C.c_void_p, C.c_void_p]
         self.lib.maph_destroy.argtypes = [C.c_void_p]
+        self.lib.maph_slide.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lin = np.zeros(8, np.int32)
         lin[:len(cfg.layer_init_num)] = cfg.layer_init_num
         lin[len(cfg.layer_init_num):] = cfg.layer_init_num[-1]
@@ -53,6 +54,11 @@ class HostMap:
         planes = np.zeros(npl.value, PLANE_DTYPE)
         self.lib.maph_flatten(self.h, C.byref(nr), C.byref(npl), keys.ctypes.data, first.ctypes.data, count.ctypes.data, planes.ctypes.data)
         return dict(keys=keys, first=first, count=count, planes=planes)
+
+    def slide(self, lo, hi):
+        """mapSliding: keep the roots whose key lies in [lo, hi] (component-wise); everything is rebuilt into a fresh arena."""
+        lo, hi = np.ascontiguousarray(lo, np.int64), np.ascontiguousarray(hi, np.int64)
+        return self.lib.maph_slide(self.h, lo.ctypes.data, hi.ctypes.data)
 
     def usage(self):
         u = np.zeros(4, np.int64)

@@ -90,6 +90,26 @@ void maph_flatten(void *h, int *n_roots, int *n_planes, long long *keys, int *fi
   }
   *n_roots = nr, *n_planes = np;
 }
+// mapSliding: keep the roots with lo <= key <= hi (component-wise), rebuilt into a fresh arena of the same capacities
+int maph_slide(void *h, const long long *lo, const long long *hi) {
+  HostMap *m = (HostMap *)h;
+  const MapArena &S = m->A;
+  HostMap *d = (HostMap *)maph_create(S.cfg.voxel_size, S.cfg.planer_threshold, S.cfg.max_layer, S.cfg.max_points_num, S.cfg.layer_init_num, (int)S.hash_mask + 1, S.node_cap,
+                                     S.pool_cap, S.rec_cap);
+  SerialCoop co;
+  for (size_t s = 0; s < m->slots.size(); s++)
+    if (m->slots[s].key != ESIKF_KEY_EMPTY && m->slot_root[s] >= 0 && map_key_in_box(m->slots[s].key, lo, hi)) map_copy_root(S, d->A, co, (int)s);
+  const int err = d->counters[2];
+  // the handle keeps its identity: move the new storage in
+  m->slots.swap(d->slots), m->slot_root.swap(d->slot_root), m->slot_cap.swap(d->slot_cap), m->rec_node.swap(d->rec_node), m->nodes.swap(d->nodes);
+  m->pool.swap(d->pool), m->recs.swap(d->recs), m->planes.swap(d->planes);
+  memcpy(m->counters, d->counters, sizeof(m->counters)), m->counters64[0] = d->counters64[0];
+  MapArena &A = m->A;
+  A.slots = m->slots.data(), A.slot_root = m->slot_root.data(), A.slot_cap = m->slot_cap.data(), A.nodes = m->nodes.data(), A.pool = m->pool.data();
+  A.recs = m->recs.data(), A.planes = m->planes.data(), A.rec_node = m->rec_node.data();
+  delete d;
+  return err;
+}
 void maph_usage(void *h, long long *out4) {
   HostMap *m = (HostMap *)h;
   out4[0] = m->counters[0], out4[1] = m->counters[1], out4[2] = (long long)m->counters64[0], out4[3] = m->counters[3];

@@ -95,6 +95,36 @@ def test_lio_tick_loop_with_device_side_map_refresh_tracks_the_oracle(gpu_ctx):
     assert n > 1000 and st["errors"] == 0
 
 
+def test_device_map_sliding_matches_clear_mem_out_of_map_and_keeps_tracking(gpu_ctx):
+    """esikf_map_device_slide (mapSliding / clearMemOutOfMap, src/voxel_map.cpp:924-971) against the oracle's deletion, then more
+    ticks on the compacted map."""
+    cfg = S.LioCfg()
+    rng = np.random.default_rng(17)
+    rects = S.make_scene("room", 0.5)
+    orc = _oracle(cfg)
+    gpu_ctx.map_device_init(cfg, root_capacity=1 << 16)
+    lo_w, hi_w = np.array([-12.0, -9.0, -3.0]), np.array([12.0, 9.0, 5.0])
+    for tick in range(6):
+        pw, var = _tick_points(rng, rects, 6000, lo_w, hi_w)
+        _oracle_update(orc, pw, var)
+        gpu_ctx.map_device_update_points(pw, var)
+    before = gpu_ctx.map_device_stats()
+    c, half = np.array([4, -2, 1]), 12
+    deleted = orc.lib.orc_lio_clear_out_of_map(orc.h, int(c[0] + half), int(c[0] - half), int(c[1] + half), int(c[1] - half), int(c[2] + half), int(c[2] - half))
+    gpu_ctx.map_device_slide(c - half, c + half)
+    after = gpu_ctx.map_device_stats()
+    assert deleted > 0 and after["roots"] == before["roots"] - deleted and after["pool_points"] < before["pool_points"] and after["errors"] == 0
+    MB.compare_flat_maps(gpu_ctx.map_device_download(), orc.flatten())
+    for tick in range(4):
+        pw, var = _tick_points(rng, rects, 6000, lo_w, hi_w)
+        _oracle_update(orc, pw, var)
+        gpu_ctx.map_device_update_points(pw, var)
+        MB.compare_flat_maps(gpu_ctx.map_device_download(), orc.flatten())
+    # compaction only
+    gpu_ctx.map_device_slide()
+    MB.compare_flat_maps(gpu_ctx.map_device_download(), orc.flatten())
+
+
 def test_device_map_capacity_errors_are_statuses(gpu_ctx):
     cfg = S.LioCfg()
     rng = np.random.default_rng(2)

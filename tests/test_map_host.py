@@ -95,6 +95,35 @@ def test_build_voxel_map_form_matches_the_oracle():
         MB.compare_flat_maps(hm3.flatten(), orc3.flatten(), rtol=1e-7)
 
 
+def test_map_sliding_keeps_the_box_and_later_ticks_still_match():
+    """mapSliding / clearMemOutOfMap (src/voxel_map.cpp:924-971): roots outside the box around the sensor are dropped. The device
+    form copies the survivors into a fresh arena (which also reclaims dead record blocks and list slack); the map must equal the
+    oracle's after the deletion AND keep tracking it through the following ticks (node state, point lists and counters survived)."""
+    cfg = S.LioCfg()
+    rng = np.random.default_rng(17)
+    rects = S.make_scene("room", 0.5)
+    orc, hm = _oracle(cfg), MB.HostMap(cfg)
+    lo_w, hi_w = np.array([-12.0, -9.0, -3.0]), np.array([12.0, 9.0, 5.0])
+    for tick in range(6):
+        pw, var = _tick_points(rng, rects, 6000, lo_w, hi_w)
+        _oracle_update(orc, pw, var)
+        assert hm.apply(pw, var) == 0
+    before = hm.usage()
+    # sensor at voxel (4, -2, 1), half_map_size 12 voxels
+    c, half = np.array([4, -2, 1]), 12
+    deleted = orc.lib.orc_lio_clear_out_of_map(orc.h, int(c[0] + half), int(c[0] - half), int(c[1] + half), int(c[1] - half), int(c[2] + half), int(c[2] - half))
+    assert hm.slide(c - half, c + half) == 0
+    after = hm.usage()
+    assert deleted > 0 and after["roots"] == before["roots"] - deleted
+    assert after["pool_points"] < before["pool_points"] and after["recs"] <= before["recs"]  # compaction
+    MB.compare_flat_maps(hm.flatten(), orc.flatten())
+    for tick in range(4):
+        pw, var = _tick_points(rng, rects, 6000, lo_w, hi_w)
+        _oracle_update(orc, pw, var)
+        assert hm.apply(pw, var) == 0
+        MB.compare_flat_maps(hm.flatten(), orc.flatten())
+
+
 def test_capacity_errors_are_reported_not_ignored():
     cfg = S.LioCfg()
     rng = np.random.default_rng(2)
