@@ -815,6 +815,7 @@ int esikf_lio_run(esikf_ctx *ctx, const double *state_in, const double *state_pr
   if (!ctx || !state_in || !state_prop || !cfg) return fail(ctx, ESIKF_ERR_ARG, "lio_run: null argument");
   if (!ctx->have_map) return fail(ctx, ESIKF_ERR_STATE, "lio_run before map_upload");
   if (!ctx->have_ext) return fail(ctx, ESIKF_ERR_STATE, "lio_run before set_extrinsics");
+  ctx->map_normals_valid = false;  // a snapshot of pv.normal belongs to the update it was taken after
   if (cfg->max_iterations < 1 || cfg->max_iterations > 8) return fail(ctx, ESIKF_ERR_ARG, "lio_run: max_iterations must be in [1,8]");
   CK(cudaSetDevice(ctx->device));
   ctx->lio_cfg = *cfg;
@@ -1043,7 +1044,7 @@ static int vio_encode_tma(esikf_ctx *ctx) {
   for (int l = 0; l <= VIO_TMA_MAXLVL; l++) {
     const cuuint64_t dims[2] = {(cuuint64_t)ctx->img_w, (cuuint64_t)ctx->img_h};
     const cuuint64_t strides[1] = {(cuuint64_t)ctx->img_w};  // bytes between rows
-    const cuuint32_t box[2] = {16u << l, 11u << l};
+    const cuuint32_t box[2] = {VIO_TMA_INNER(l), 11u << l};
     const cuuint32_t estr[2] = {1u, 1u << l};
     CUresult r = ((encode_fn)fn)(reinterpret_cast<CUtensorMap *>(ctx->tma.map[l]), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)ctx->img.p, dims, strides, box, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -123,13 +123,16 @@ struct VioPatchCache {
 };
 
 // Tap footprints through the TMA unit (tuning flag ESIKF_TUNE_VIO_TMA): one tiled tensor map of the u8 image per tap
-// stride s = 1, 2, 4, 8 — box {16 s bytes, 11 s rows} traversed with elementStrides {1, s} (TMA cannot stride the
-// innermost dimension), i.e. 11 image rows of 16 s contiguous bytes land in shared memory with ONE instruction issued by
-// one lane, at an arbitrary (unaligned) start pixel; the 11 x 11 taps are then picked out at stride s. Footprints that
-// leave the image (the reference's raw linear-index reads wrap to the neighbouring row there, TMA would zero-fill) and
-// strides 16 / 32 (elementStrides <= 8) keep the per-lane loads.
+// stride s = 1, 2, 4, 8 — box {W_s bytes, 11 s rows} traversed with elementStrides {1, s} (TMA cannot stride the
+// innermost dimension), i.e. 11 image rows of W_s contiguous bytes land in shared memory with ONE instruction issued by
+// one lane; the 11 x 11 taps are then picked out at stride s. The box must START on a 16-byte boundary of the innermost
+// dimension (measured: tools/tma_probe.cu — an unaligned x coordinate raises an illegal-instruction fault on sm_100,
+// profiles/tma_probe_r02.txt), so the start pixel is rounded down to a multiple of 16 and W_s = 16 ceil((16 + 10 s) / 16)
+// covers the worst offset: 32, 48, 64, 96 bytes. Footprints that leave the image (the reference's raw linear-index reads
+// wrap to the neighbouring row there, TMA would zero-fill) and strides 16 / 32 (elementStrides <= 8) keep the per-lane loads.
 #define VIO_TMA_MAXLVL 3
-#define VIO_TMA_TILE_BYTES (11 * (16 << VIO_TMA_MAXLVL))
+#define VIO_TMA_INNER(l) (16u * ((16u + (10u << (l)) + 15u) / 16u))
+#define VIO_TMA_TILE_BYTES (11 * 96 + 96)
 struct VioTma {
   alignas(64) unsigned char map[VIO_TMA_MAXLVL + 1][128];  // CUtensorMap per level (opaque 128-byte descriptors)
   int enabled;
@@ -239,8 +242,8 @@ __device__ __forceinline__ void vio_process_range(const VioKernelArgs &a, VioSme
         if (by_tma) {
           if (lane == 0) {
             fence_proxy_async_smem();  // the landing area was last read through the generic proxy
-            mbar_arrive_expect_tx(&sm.tma_bar[warp], 11u * (16u << pyramid_level));
-            tma_load_2d(sm.tile[warp], tma->map[pyramid_level], x0, y0, &sm.tma_bar[warp]);
+            mbar_arrive_expect_tx(&sm.tma_bar[warp], 11u * VIO_TMA_INNER(pyramid_level));
+            tma_load_2d(sm.tile[warp], tma->map[pyramid_level], x0 & ~15, y0, &sm.tma_bar[warp]);
           }
         } else {
           const long sw = (long)scale * width;
@@ -280,8 +283,8 @@ __device__ __forceinline__ void vio_process_range(const VioKernelArgs &a, VioSme
       if (by_tma) {
         mbar_wait(&sm.tma_bar[warp], *tma_phase & 1u);
         *tma_phase ^= 1u;
-        const unsigned char *raw = sm.tile[warp];
-        const unsigned inner = 16u << pyramid_level;
+        const unsigned inner = VIO_TMA_INNER(pyramid_level);
+        const unsigned char *raw = sm.tile[warp] + ((u_ref_i - 5 * scale) & 15);  // the box starts at the 16-byte boundary below the first tap
 #pragma unroll
         for (int q = 0; q < 4; q++) {
           const int t = lane + 32 * q;

@@ -68,7 +68,7 @@ def test_shim_session_with_device_resident_map_equals_the_c_abi_tick_loop(small_
     cfg, ext = fr["lio_cfg"], fr["ext"]
     shim = C.CDLL(os.path.join(ROOT, "fast_livo2_b200", "libfl2_shim.so"))
     shim.fl2_shim_session_create.restype = C.c_void_p
-    shim.fl2_shim_session_create.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int]
+    shim.fl2_shim_session_create.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int]
     shim.fl2_shim_session_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7
     shim.fl2_shim_session_device_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_longlong]
     shim.fl2_shim_session_update_map.argtypes = [C.c_void_p]
