@@ -53,6 +53,49 @@ struct PlaneRec {
 };
 static_assert(sizeof(PlaneRec) == 144, "compact plane record is 9 x 16 bytes");
 
+// ---- arithmetic of a plane fit: single-rounded products and sums in the written order, never contracted into FMAs, so that the
+// device reproduces the host evaluation of the same expressions (and with it the oracle's) bit for bit
+__host__ __device__ __forceinline__ double m_mul(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+__host__ __device__ __forceinline__ double m_add(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+__host__ __device__ __forceinline__ double m_sub(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dsub_rn(a, b);
+#else
+  return a - b;
+#endif
+}
+__host__ __device__ __forceinline__ double m_dot3(double a0, double b0, double a1, double b1, double a2, double b2) { return m_add(m_add(m_mul(a0, b0), m_mul(a1, b1)), m_mul(a2, b2)); }
+
+// 256-byte map plane -> the 144-byte record (one definition for the upload / patch kernel and the device-resident map, evaluated
+// without FMA contraction: both paths hand the residual kernel bit-identical records for the same plane)
+__host__ __device__ constexpr int tri6u(int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); }  // i <= j
+__host__ __device__ __forceinline__ void compact_plane(const esikf_plane &p, PlaneRec &r) {
+  const double n0 = p.normal[0], n1 = p.normal[1], n2 = p.normal[2];
+  for (int j = 0; j < 3; j++) r.c[j] = p.center[j], r.n[j] = p.normal[j];
+  r.paa[0] = p.plane_var[tri6u(0, 0)], r.paa[1] = p.plane_var[tri6u(0, 1)], r.paa[2] = p.plane_var[tri6u(0, 2)];
+  r.paa[3] = p.plane_var[tri6u(1, 1)], r.paa[4] = p.plane_var[tri6u(1, 2)], r.paa[5] = p.plane_var[tri6u(2, 2)];
+  for (int i = 0; i < 3; i++) r.b[i] = m_dot3(p.plane_var[tri6u(i, 3)], n0, p.plane_var[tri6u(i, 4)], n1, p.plane_var[tri6u(i, 5)], n2);
+  const double *v = p.plane_var;
+  // n^T Pbb n as (n^T Pbb) n
+  const double t0 = m_dot3(n0, v[tri6u(3, 3)], n1, v[tri6u(3, 4)], n2, v[tri6u(3, 5)]);
+  const double t1 = m_dot3(n0, v[tri6u(3, 4)], n1, v[tri6u(4, 4)], n2, v[tri6u(4, 5)]);
+  const double t2 = m_dot3(n0, v[tri6u(3, 5)], n1, v[tri6u(4, 5)], n2, v[tri6u(5, 5)]);
+  r.cnn = m_dot3(t0, n0, t1, n1, t2, n2);
+  r.d = p.d, r.radius = p.radius, r.pad = 0.0;
+}
+
 // ---- reduced information of one iteration, compact: for an m-column measurement (m = 6 LIO, 7 VIO)
 //   [0, T)          upper triangle of H^T R^-1 H, row-major (i <= j),  T = m (m + 1) / 2
 //   [T, T + m)      H^T R^-1 z

@@ -139,16 +139,8 @@ __global__ void plane_compact_kernel(const esikf_plane *__restrict__ planes, con
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int id = ids ? ids[k] : k;
-  const esikf_plane &p = planes[id];
   PlaneRec r;
-  const double n0 = p.normal[0], n1 = p.normal[1], n2 = p.normal[2];
-  for (int j = 0; j < 3; j++) r.c[j] = p.center[j], r.n[j] = p.normal[j];
-  r.paa[0] = p.plane_var[tri6(0, 0)], r.paa[1] = p.plane_var[tri6(0, 1)], r.paa[2] = p.plane_var[tri6(0, 2)];
-  r.paa[3] = p.plane_var[tri6(1, 1)], r.paa[4] = p.plane_var[tri6(1, 2)], r.paa[5] = p.plane_var[tri6(2, 2)];
-  for (int i = 0; i < 3; i++) r.b[i] = p.plane_var[tri6(i, 3)] * n0 + p.plane_var[tri6(i, 4)] * n1 + p.plane_var[tri6(i, 5)] * n2;
-  const double bb[6] = {p.plane_var[tri6(3, 3)], p.plane_var[tri6(3, 4)], p.plane_var[tri6(3, 5)], p.plane_var[tri6(4, 4)], p.plane_var[tri6(4, 5)], p.plane_var[tri6(5, 5)]};
-  r.cnn = quad3_sym(bb, n0, n1, n2);
-  r.d = p.d, r.radius = p.radius, r.pad = 0.0;
+  compact_plane(planes[id], r);
   recs[id] = r;
 }
 

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) map_points_kernel(const MapArena A, const
     sPr[threadIdx.x] = a.state[S_COV + r * 19 + c];            // cov.block<3,3>(0,0)
     sPp[threadIdx.x] = a.state[S_COV + (3 + r) * 19 + 3 + c];  // cov.block<3,3>(3,3)
     // M = rot_end * extR
-    sM[threadIdx.x] = a.state[S_R + 3 * r] * a.extR[c] + a.state[S_R + 3 * r + 1] * a.extR[3 + c] + a.state[S_R + 3 * r + 2] * a.extR[6 + c];
+    sM[threadIdx.x] = m_dot3(a.state[S_R + 3 * r], a.extR[c], a.state[S_R + 3 * r + 1], a.extR[3 + c], a.state[S_R + 3 * r + 2], a.extR[6 + c]);
   }
   if (threadIdx.x < 3) st[threadIdx.x] = a.state[S_P + threadIdx.x];
   __syncthreads();
@@ -91,17 +91,18 @@ __global__ void __launch_bounds__(256) map_points_kernel(const MapArena A, const
   // (M B) M^T
   double MB[9], var[9];
   for (int r = 0; r < 3; r++)
-    for (int c = 0; c < 3; c++) MB[3 * r + c] = sM[3 * r] * B[c] + sM[3 * r + 1] * B[3 + c] + sM[3 * r + 2] * B[6 + c];
+    for (int c = 0; c < 3; c++) MB[3 * r + c] = m_dot3(sM[3 * r], B[c], sM[3 * r + 1], B[3 + c], sM[3 * r + 2], B[6 + c]);
   // (-C) P_rot (-C)^T with C = [cv]x
   const double nC[9] = {-0.0, cv[2], -cv[1], -cv[2], -0.0, cv[0], cv[1], -cv[0], -0.0};
   double CP[9];
   for (int r = 0; r < 3; r++)
-    for (int c = 0; c < 3; c++) CP[3 * r + c] = nC[3 * r] * sPr[c] + nC[3 * r + 1] * sPr[3 + c] + nC[3 * r + 2] * sPr[6 + c];
+    for (int c = 0; c < 3; c++) CP[3 * r + c] = m_dot3(nC[3 * r], sPr[c], nC[3 * r + 1], sPr[3 + c], nC[3 * r + 2], sPr[6 + c]);
   for (int r = 0; r < 3; r++)
     for (int c = 0; c < 3; c++) {
-      const double t1 = MB[3 * r] * sM[3 * c] + MB[3 * r + 1] * sM[3 * c + 1] + MB[3 * r + 2] * sM[3 * c + 2];
-      const double t2 = CP[3 * r] * nC[3 * c] + CP[3 * r + 1] * nC[3 * c + 1] + CP[3 * r + 2] * nC[3 * c + 2];
-      var[3 * r + c] = t1 + t2 + sPp[3 * r + c];
+      // single-rounded, uncontracted, in the order of the reference's matrix expression (the fits amplify input rounding)
+      const double t1 = m_dot3(MB[3 * r], sM[3 * c], MB[3 * r + 1], sM[3 * c + 1], MB[3 * r + 2], sM[3 * c + 2]);
+      const double t2 = m_dot3(CP[3 * r], nC[3 * c], CP[3 * r + 1], nC[3 * c + 1], CP[3 * r + 2], nC[3 * c + 2]);
+      var[3 * r + c] = m_add(m_add(t1, t2), sPp[3 * r + c]);
     }
   double *o = a.pt + (size_t)i * MAP_PT_D;
   for (int k = 0; k < 3; k++) o[k] = pw[k];

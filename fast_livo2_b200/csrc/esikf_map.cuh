@@ -103,26 +103,32 @@ MAP_HD void map_raise(const MapArena &A, int flag) {
 #endif
 }
 
-// ---- cooperation policies
+// ---- cooperation policies. ordered_add<K>: acc[k] += term[k] of lane 0, then of lane 1, ... — the lanes hold consecutive
+// points, so the sum runs in the serial order of the reference's loop and every lane ends with the bit-identical total.
 struct SerialCoop {
   static constexpr int N = 1;
   MAP_HD int lane() const { return 0; }
-  MAP_HD double sum(double v) const { return v; }
   MAP_HD int bcast(int v) const { return v; }
   MAP_HD void sync() const {}
+  template <int K>
+  MAP_HD void ordered_add(double *acc, const double *term, int valid_lanes) const {
+    if (valid_lanes > 0)
+      for (int k = 0; k < K; k++) acc[k] = m_add(acc[k], term[k]);
+  }
 };
 #ifdef __CUDACC__
 struct WarpCoop {
   static constexpr int N = 32;
   __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
-  // butterfly: every lane ends with the bit-identical total (the control flow that follows must not diverge)
-  __device__ __forceinline__ double sum(double v) const {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-  }
   __device__ __forceinline__ int bcast(int v) const { return __shfl_sync(0xffffffffu, v, 0); }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
+  template <int K>
+  __device__ __forceinline__ void ordered_add(double *acc, const double *term, int valid_lanes) const {
+    for (int j = 0; j < valid_lanes; j++) {  // valid_lanes is warp-uniform
+#pragma unroll
+      for (int k = 0; k < K; k++) acc[k] = __dadd_rn(acc[k], __shfl_sync(0xffffffffu, term[k], j));
+    }
+  }
 };
 #endif
 
@@ -240,29 +246,29 @@ MAP_HD void map_eig_sym3(const double *A9, double evals[3], double V[9]) {
   double a[9];
   for (int k = 0; k < 9; k++) a[k] = A9[k], V[k] = (k % 4 == 0) ? 1.0 : 0.0;
   for (int sweep = 0; sweep < 64; sweep++) {
-    const double off = fabs(a[1]) + fabs(a[2]) + fabs(a[5]);
-    const double diag = fabs(a[0]) + fabs(a[4]) + fabs(a[8]);
-    if (off <= 1e-18 * diag || off == 0.0) break;
+    const double off = m_add(m_add(fabs(a[1]), fabs(a[2])), fabs(a[5]));
+    const double diag = m_add(m_add(fabs(a[0]), fabs(a[4])), fabs(a[8]));
+    if (off <= m_mul(1e-18, diag) || off == 0.0) break;
     for (int p = 0; p < 2; p++)
       for (int q = p + 1; q < 3; q++) {
         if (a[p * 3 + q] == 0.0) continue;
-        const double theta = (a[q * 3 + q] - a[p * 3 + p]) / (2.0 * a[p * 3 + q]);
-        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        const double theta = m_sub(a[q * 3 + q], a[p * 3 + p]) / m_mul(2.0, a[p * 3 + q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / m_add(fabs(theta), sqrt(m_add(m_mul(theta, theta), 1.0)));
+        const double c = 1.0 / sqrt(m_add(m_mul(t, t), 1.0)), s = m_mul(t, c);
         for (int k = 0; k < 3; k++) {
           const double akp = a[k * 3 + p], akq = a[k * 3 + q];
-          a[k * 3 + p] = c * akp - s * akq;
-          a[k * 3 + q] = s * akp + c * akq;
+          a[k * 3 + p] = m_sub(m_mul(c, akp), m_mul(s, akq));
+          a[k * 3 + q] = m_add(m_mul(s, akp), m_mul(c, akq));
         }
         for (int k = 0; k < 3; k++) {
           const double apk = a[p * 3 + k], aqk = a[q * 3 + k];
-          a[p * 3 + k] = c * apk - s * aqk;
-          a[q * 3 + k] = s * apk + c * aqk;
+          a[p * 3 + k] = m_sub(m_mul(c, apk), m_mul(s, aqk));
+          a[q * 3 + k] = m_add(m_mul(s, apk), m_mul(c, aqk));
         }
         for (int k = 0; k < 3; k++) {
           const double vkp = V[k * 3 + p], vkq = V[k * 3 + q];
-          V[k * 3 + p] = c * vkp - s * vkq;
-          V[k * 3 + q] = s * vkp + c * vkq;
+          V[k * 3 + p] = m_sub(m_mul(c, vkp), m_mul(s, vkq));
+          V[k * 3 + q] = m_add(m_mul(s, vkp), m_mul(c, vkq));
         }
       }
   }
@@ -271,7 +277,8 @@ MAP_HD void map_eig_sym3(const double *A9, double evals[3], double V[9]) {
 
 MAP_HD constexpr int map_tri6(int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); }  // i <= j
 
-// init_plane(temp_points_, plane_ptr_)   (:55-135). The per-point sums run lane-strided; every lane ends with the same fit.
+// init_plane(temp_points_, plane_ptr_)   (:55-135). Lane l of a round holds point base + l; the per-point terms are added in
+// point order (ordered_add), every lane ends with the same fit, and it is the fit the serial host evaluation produces.
 template <class C>
 MAP_HD void map_init_plane(const MapArena &A, const C &co, int node) {
   MapNode &n = A.nodes[node];
@@ -279,17 +286,21 @@ MAP_HD void map_init_plane(const MapArena &A, const C &co, int node) {
   const double *pts = A.pool + (size_t)(n.list_off < 0 ? 0 : n.list_off) * MAP_PT_D;
   // covariance_ += p p^T ; center_ += p   (:64-68)
   double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // xx xy xz yy yz zz | x y z
-  for (int i = co.lane(); i < np; i += C::N) {
-    const double *p = pts + (size_t)i * MAP_PT_D;
-    s[0] += p[0] * p[0], s[1] += p[0] * p[1], s[2] += p[0] * p[2], s[3] += p[1] * p[1], s[4] += p[1] * p[2], s[5] += p[2] * p[2];
-    s[6] += p[0], s[7] += p[1], s[8] += p[2];
+  for (int base = 0; base < np; base += C::N) {
+    const int i = base + co.lane();
+    double t[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (i < np) {
+      const double *p = pts + (size_t)i * MAP_PT_D;
+      t[0] = m_mul(p[0], p[0]), t[1] = m_mul(p[0], p[1]), t[2] = m_mul(p[0], p[2]), t[3] = m_mul(p[1], p[1]), t[4] = m_mul(p[1], p[2]), t[5] = m_mul(p[2], p[2]);
+      t[6] = p[0], t[7] = p[1], t[8] = p[2];
+    }
+    co.template ordered_add<9>(s, t, np - base < C::N ? np - base : C::N);
   }
-  for (int k = 0; k < 9; k++) s[k] = co.sum(s[k]);
   const double dn = (double)np;
   const double c[3] = {s[6] / dn, s[7] / dn, s[8] / dn};
   double cov[9];
-  cov[0] = s[0] / dn - c[0] * c[0], cov[1] = s[1] / dn - c[0] * c[1], cov[2] = s[2] / dn - c[0] * c[2];
-  cov[4] = s[3] / dn - c[1] * c[1], cov[5] = s[4] / dn - c[1] * c[2], cov[8] = s[5] / dn - c[2] * c[2];
+  cov[0] = m_sub(s[0] / dn, m_mul(c[0], c[0])), cov[1] = m_sub(s[1] / dn, m_mul(c[0], c[1])), cov[2] = m_sub(s[2] / dn, m_mul(c[0], c[2]));
+  cov[4] = m_sub(s[3] / dn, m_mul(c[1], c[1])), cov[5] = m_sub(s[4] / dn, m_mul(c[1], c[2])), cov[8] = m_sub(s[5] / dn, m_mul(c[2], c[2]));
   cov[3] = cov[1], cov[6] = cov[2], cov[7] = cov[5];
   double ev[3], V[9];
   map_eig_sym3(cov, ev, V);
@@ -304,40 +315,45 @@ MAP_HD void map_init_plane(const MapArena &A, const C &co, int node) {
   if (is_plane) {
     const double vmin[3] = {V[imin], V[3 + imin], V[6 + imin]};
     const double jq = 1.0 / np;  // J_Q = I / points_size_ (:83-84)
-    for (int i = co.lane(); i < np; i += C::N) {
-      const double *p = pts + (size_t)i * MAP_PT_D, *var = p + 3;
-      // F rows (:95-108): F_m = (p - c)^T / (n (l_min - l_m)) * (v_m v_min^T + v_min v_m^T), zero for m = min
-      double F[9];
-      for (int m = 0; m < 3; m++) {
-        if (m == imin) {
-          F[3 * m] = F[3 * m + 1] = F[3 * m + 2] = 0.0;
-          continue;
+    for (int base = 0; base < np; base += C::N) {
+      const int i = base + co.lane();
+      double T[21];
+      for (int k = 0; k < 21; k++) T[k] = 0.0;
+      if (i < np) {
+        const double *p = pts + (size_t)i * MAP_PT_D, *var = p + 3;
+        // F rows (:95-108): F_m = (p - c)^T / (n (l_min - l_m)) * (v_m v_min^T + v_min v_m^T), zero for m = min
+        double F[9];
+        for (int m = 0; m < 3; m++) {
+          if (m == imin) {
+            F[3 * m] = F[3 * m + 1] = F[3 * m + 2] = 0.0;
+            continue;
+          }
+          const double den = m_mul((double)np, m_sub(ev[imin], ev[m]));
+          const double r[3] = {m_sub(p[0], c[0]) / den, m_sub(p[1], c[1]) / den, m_sub(p[2], c[2]) / den};
+          const double vm[3] = {V[m], V[3 + m], V[6 + m]};
+          for (int cc = 0; cc < 3; cc++) {
+            double acc = 0.0;
+            for (int k = 0; k < 3; k++) acc = m_add(acc, m_mul(r[k], m_add(m_mul(vm[k], vmin[cc]), m_mul(vmin[k], vm[cc]))));
+            F[3 * m + cc] = acc;
+          }
         }
-        const double den = (double)np * (ev[imin] - ev[m]);
-        const double r[3] = {(p[0] - c[0]) / den, (p[1] - c[1]) / den, (p[2] - c[2]) / den};
-        const double vm[3] = {V[m], V[3 + m], V[6 + m]};
-        for (int cc = 0; cc < 3; cc++) {
-          double acc = 0.0;
-          for (int k = 0; k < 3; k++) acc += r[k] * (vm[k] * vmin[cc] + vmin[k] * vm[cc]);
-          F[3 * m + cc] = acc;
-        }
+        // J = [evecs F ; J_Q]  (6 x 3), plane_var_ += J var J^T  (:110-112)
+        double J[18];
+        for (int a = 0; a < 3; a++)
+          for (int cc = 0; cc < 3; cc++) {
+            double acc = 0.0;
+            for (int m = 0; m < 3; m++) acc = m_add(acc, m_mul(V[a * 3 + m], F[3 * m + cc]));
+            J[a * 3 + cc] = acc;
+            J[(3 + a) * 3 + cc] = (a == cc) ? jq : 0.0;
+          }
+        double JV[18];
+        for (int a = 0; a < 6; a++)
+          for (int l = 0; l < 3; l++) JV[a * 3 + l] = m_dot3(J[a * 3], var[l], J[a * 3 + 1], var[3 + l], J[a * 3 + 2], var[6 + l]);
+        for (int a = 0; a < 6; a++)
+          for (int b = a; b < 6; b++) T[map_tri6(a, b)] = m_dot3(JV[a * 3], J[b * 3], JV[a * 3 + 1], J[b * 3 + 1], JV[a * 3 + 2], J[b * 3 + 2]);
       }
-      // J = [evecs F ; J_Q]  (6 x 3), plane_var_ += J var J^T  (:110-112)
-      double J[18];
-      for (int a = 0; a < 3; a++)
-        for (int cc = 0; cc < 3; cc++) {
-          double acc = 0.0;
-          for (int m = 0; m < 3; m++) acc += V[a * 3 + m] * F[3 * m + cc];
-          J[a * 3 + cc] = acc;
-          J[(3 + a) * 3 + cc] = (a == cc) ? jq : 0.0;
-        }
-      double JV[18];
-      for (int a = 0; a < 6; a++)
-        for (int l = 0; l < 3; l++) JV[a * 3 + l] = J[a * 3] * var[l] + J[a * 3 + 1] * var[3 + l] + J[a * 3 + 2] * var[6 + l];
-      for (int a = 0; a < 6; a++)
-        for (int b = a; b < 6; b++) P[map_tri6(a, b)] += JV[a * 3] * J[b * 3] + JV[a * 3 + 1] * J[b * 3 + 1] + JV[a * 3 + 2] * J[b * 3 + 2];
+      co.template ordered_add<21>(P, T, np - base < C::N ? np - base : C::N);
     }
-    for (int k = 0; k < 21; k++) P[k] = co.sum(P[k]);
   }
   if (co.lane() == 0) {
     n.points_size = np;
@@ -346,7 +362,7 @@ MAP_HD void map_init_plane(const MapArena &A, const C &co, int node) {
     if (is_plane) {
       for (int k = 0; k < 3; k++) n.pn[k] = V[k * 3 + imin];
       n.radius = (float)sqrt(ev[imax]);
-      n.d = (float)(-(n.pn[0] * c[0] + n.pn[1] * c[1] + n.pn[2] * c[2]));
+      n.d = (float)(-m_dot3(n.pn[0], c[0], n.pn[1], c[1], n.pn[2], c[2]));
       n.is_plane = 1;
     } else {
       for (int k = 0; k < 3; k++) n.pn[k] = 0.0;
@@ -489,18 +505,7 @@ MAP_HD void map_full_record(const MapNode &n, int path, esikf_plane &f) {
   f.d = n.d, f.radius = n.radius, f.layer = n.layer, f.path = path;
   for (int k = 0; k < 6; k++) f.pad[k] = 0;
 }
-MAP_HD void map_compact_record(const esikf_plane &p, PlaneRec &r) {
-  const double n0 = p.normal[0], n1 = p.normal[1], n2 = p.normal[2];
-  for (int j = 0; j < 3; j++) r.c[j] = p.center[j], r.n[j] = p.normal[j];
-  r.paa[0] = p.plane_var[map_tri6(0, 0)], r.paa[1] = p.plane_var[map_tri6(0, 1)], r.paa[2] = p.plane_var[map_tri6(0, 2)];
-  r.paa[3] = p.plane_var[map_tri6(1, 1)], r.paa[4] = p.plane_var[map_tri6(1, 2)], r.paa[5] = p.plane_var[map_tri6(2, 2)];
-  for (int i = 0; i < 3; i++) r.b[i] = p.plane_var[map_tri6(i, 3)] * n0 + p.plane_var[map_tri6(i, 4)] * n1 + p.plane_var[map_tri6(i, 5)] * n2;
-  const double *v = p.plane_var;
-  // n^T Pbb n, same association as quad3_sym in esikf_lio.cu
-  r.cnn = v[map_tri6(3, 3)] * n0 * n0 + v[map_tri6(4, 4)] * n1 * n1 + v[map_tri6(5, 5)] * n2 * n2 +
-          2.0 * (v[map_tri6(3, 4)] * n0 * n1 + v[map_tri6(3, 5)] * n0 * n2 + v[map_tri6(4, 5)] * n1 * n2);
-  r.d = p.d, r.radius = p.radius, r.pad = 0.0;
-}
+MAP_HD void map_compact_record(const esikf_plane &p, PlaneRec &r) { compact_plane(p, r); }
 
 // Candidate planes of a root in the order build_single_residual visits them (:721, :771-784): a node that is a plane is a
 // candidate, otherwise its existing leaves are searched while layer < max_layer. emit == false only counts.

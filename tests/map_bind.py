@@ -66,7 +66,7 @@ class HostMap:
         return dict(nodes=int(u[0]), recs=int(u[1]), pool_points=int(u[2]), roots=int(u[3]))
 
 
-def compare_flat_maps(a, b, rtol=1e-9, what=("a", "b")):
+def compare_flat_maps(a, b, rtol=1e-9, what=("a", "b"), exact=False):
     """Same root keys, same candidate count per root, candidate j of a root = the same plane (centre, +-normal, plane_var, d,
     radius, layer, path) within rtol. Returns the number of planes compared. The eigenvector sign of a fit is free: a flipped
     normal flips d and the normal-position cross block of plane_var."""
@@ -79,6 +79,10 @@ def compare_flat_maps(a, b, rtol=1e-9, what=("a", "b")):
     sel_a = np.concatenate([np.arange(f, f + c) for f, c in zip(a["first"][ia], a["count"][ia])] or [np.zeros(0, np.int64)]).astype(np.int64)
     sel_b = np.concatenate([np.arange(f, f + c) for f, c in zip(b["first"][ib], b["count"][ib])] or [np.zeros(0, np.int64)]).astype(np.int64)
     pa, pb = a["planes"][sel_a], b["planes"][sel_b]
+    if exact:  # every byte of every candidate record (centre, normal incl. its sign, plane_var, d, radius, layer, path)
+        bad = np.nonzero(pa.view(np.uint8).reshape(len(pa), -1) != pb.view(np.uint8).reshape(len(pb), -1))[0]
+        assert len(bad) == 0, f"{len(np.unique(bad))} of {len(pa)} plane records differ between {what[0]} and {what[1]}"
+        return len(pa)
     assert np.array_equal(pa["layer"], pb["layer"]) and np.array_equal(pa["path"], pb["path"]), "candidate order (layer / path) differs"
     np.testing.assert_allclose(pa["center"], pb["center"], rtol=rtol, atol=1e-12)
     sign = np.sign((pa["normal"] * pb["normal"]).sum(1))

@@ -31,7 +31,8 @@ def test_device_update_voxel_map_matches_the_oracle_for_ten_ticks(gpu_ctx, cfg):
         pw, var = _tick_points(rng, rects, 6000, lo, lo + np.array([8.0, 16.0, 6.0]))
         _oracle_update(orc, pw, var)
         gpu_ctx.map_device_update_points(pw, var)
-        n = MB.compare_flat_maps(gpu_ctx.map_device_download(), orc.flatten(), what=("device map", "oracle"))
+        # refits add the per-point terms in point order without FMA contraction: bit-identical to the serial evaluation
+        n = MB.compare_flat_maps(gpu_ctx.map_device_download(), orc.flatten(), what=("device map", "oracle"), exact=True)
         assert n > 0
     st = gpu_ctx.map_device_stats()
     assert st["errors"] == 0 and st["roots"] == len(orc.flatten()["keys"]) and st["touched_roots"] > 0
@@ -79,7 +80,7 @@ def test_lio_tick_loop_with_device_side_map_refresh_tracks_the_oracle(gpu_ctx):
         g = gpu_ctx.lio_update(scan, pr_dev, pr_dev, cfg)
         o = orc.state_estimation(scan, pr_orc, pr_orc)
         assert g["iters"] == o["iters"] and np.array_equal(np.asarray(g["M"])[:g["iters"]], o["M"]), (k, g["M"], o["M"])
-        assert_state_close(g["state"], o["state"], rot_tol=1e-9, pos_tol=1e-9, cov_tol=1e-7, rest_tol=1e-9)
+        assert_state_close(g["state"], o["state"], rot_tol=1e-9, pos_tol=2e-9, cov_tol=1e-7, rest_tol=1e-9)
         matched.append(int(o["M"][-1]))
         # pv.normal of every point (zero when unmatched) before and after the map moved the records
         nb = gpu_ctx.lio_fetch_normals()

@@ -47,7 +47,7 @@ def test_ten_ticks_of_update_voxel_map_match_the_oracle(cfg):
         total += len(pw)
         _oracle_update(orc, pw, var)
         assert hm.apply(pw, var) == 0
-        n = MB.compare_flat_maps(hm.flatten(), orc.flatten(), what=("device state machine", "oracle"))
+        n = MB.compare_flat_maps(hm.flatten(), orc.flatten(), what=("device state machine", "oracle"), exact=True)  # serial policy: bit for bit
         assert n > 0
     u = hm.usage()
     assert u["roots"] == len(orc.flatten()["keys"]) and total > 30000

@@ -21,3 +21,11 @@ for _ in range(steps):
     r = ctx.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"])
     v = ctx.vio_update(fr["img"], fr["vis_pos"], w["warp_patch"], w["search_levels"], fr["inv_ref_expo"], r["state"], r["state"])
 print("iters", r["iters"], v["total_iters"], "M", r["M"])
+if os.environ.get("ESIKF_MAP"):  # device-resident map: build from the scan at the true pose, then LIO update + map update per step
+    ctx.map_device_init(fr["lio_cfg"], root_capacity=1 << 19)
+    ctx.lio_set_scan(fr["pts"])
+    ctx.map_device_build(fr["state_true"])
+    for _ in range(steps):
+        r = ctx.lio_update(fr["pts"], fr["state_prior"], fr["state_prior"], fr["lio_cfg"])
+        ctx.map_device_update()
+    print("device map", ctx.map_device_stats(), "M", r["M"])

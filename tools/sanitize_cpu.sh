@@ -9,7 +9,7 @@ mkdir -p $OUT
 CXX=/usr/bin/g++
 FLAGS="-std=c++17 -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -fPIC -shared"
 (cd $ROOT/oracle && $CXX $FLAGS -ffp-contract=off -fopenmp -o $OUT/liborc_parity.so orc_lio.cpp orc_vio.cpp orc_capi.cpp)
-$CXX $FLAGS -o $OUT/libfl2_shim.so $ROOT/fast_livo2_b200/csrc/fl2_shim.cpp -L$ROOT/fast_livo2_b200 -lesikf_b200 -Wl,-rpath,$ROOT/fast_livo2_b200
+$CXX $FLAGS -fopenmp -o $OUT/libfl2_shim.so $ROOT/fast_livo2_b200/csrc/fl2_shim.cpp -L$ROOT/fast_livo2_b200 -lesikf_b200 -Wl,-rpath,$ROOT/fast_livo2_b200
 cd $ROOT
 LD_PRELOAD="$($CXX -print-file-name=libasan.so) $($CXX -print-file-name=libubsan.so)" ASAN_OPTIONS=detect_leaks=0:halt_on_error=0 python - <<'PY'
 import ctypes as C, sys
