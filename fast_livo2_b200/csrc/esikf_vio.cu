@@ -481,7 +481,8 @@ __global__ void warp_affine_kernel(const uint8_t *const *__restrict__ ref_imgs, 
     const uint8_t *__restrict__ img = ref_imgs[ref_idx[i]];
     const int xi = (int)floorf(px0), yi = (int)floorf(px1);
     const float sx = px0 - (float)xi, sy = px1 - (float)yi;
-    const float w00 = __fmul_rn(1.0f - sx, 1.0f - sy), w01 = __fmul_rn(1.0f - sx, sy), w10 = __fmul_rn(sx, 1.0f - sy), w11 = __fmul_rn(sx, sy);
+    const float w00 = __fmul_rn(1.0f - sx, 1.0f - sy), w01 = __fmul_rn(1.0f - sx, sy), w10 = __fmul_rn(sx, 1.0f - sy);
+    const float w11 = __fsub_rn(__fsub_rn(__fsub_rn(1.0f, w00), w01), w10);  // vikit: the last weight is the remainder 1 - w00 - w01 - w10
     const uint8_t *p = img + (long)yi * cols + xi;
     val = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w00, (float)p[0]), __fmul_rn(w01, (float)p[cols])), __fmul_rn(w10, (float)p[1])),
                     __fmul_rn(w11, (float)p[cols + 1]));

@@ -86,7 +86,7 @@ float interpolateMat_8u(const Image &mat, float u, float v) {
   float w00 = (1.0f - subpix_x) * (1.0f - subpix_y);
   float w01 = (1.0f - subpix_x) * subpix_y;
   float w10 = subpix_x * (1.0f - subpix_y);
-  float w11 = subpix_x * subpix_y;
+  float w11 = 1.0f - w00 - w01 - w10;  // vikit computes the last weight as the remainder, not as a product
   const int stride = mat.cols;
   const uint8_t *ptr = mat.data + y * stride + x;
   return w00 * ptr[0] + w01 * ptr[stride] + w10 * ptr[1] + w11 * ptr[stride + 1];

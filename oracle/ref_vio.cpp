@@ -17,6 +17,7 @@
 #include <unordered_map>
 using namespace std;
 typedef unsigned char uchar;
+#include "/root/reference/src/voxel_map.cpp"  // VoxelOctoTree::find_correspond etc., referenced by the retrieval code of vio.cpp
 #include "/root/reference/src/frame.cpp"
 #include "/root/reference/src/visual_point.cpp"
 #include "/root/reference/src/vio.cpp"
@@ -125,7 +126,7 @@ double ref_vio_update(void *h, const uint8_t *img, int n_pts, const double *pos,
 void ref_vio_set_inverse(void *h, int enable) { ((RefVio *)h)->v.inverse_composition_en = enable != 0; }
 double ref_vio_update_inverse(void *h, const uint8_t *img, int n_pts, const double *pos, const float *warp_patch, const int32_t *search_levels, const double *inv_expo_list,
                               const uint8_t *const *ref_imgs, int n_imgs, const int32_t *ref_img_index, const double *ref_px, const double *ref_f, const double *ref_R,
-                              const double *ref_pos, const double *state_in, const double *state_prop, double *state_out, float *errors_out) {
+                              const double *ref_pos /* translation t of T_f_w_ = (R, t) */, const double *state_in, const double *state_prop, double *state_out, float *errors_out) {
   RefVio *r = (RefVio *)h;
   VIOManager &v = r->v;
   unpack_state(state_in, r->st);
@@ -140,8 +141,7 @@ double ref_vio_update_inverse(void *h, const uint8_t *img, int n_pts, const doub
     M3D R;
     for (int a = 0; a < 3; a++)
       for (int b = 0; b < 3; b++) R(a, b) = ref_R[9 * i + 3 * a + b];
-    const V3D c(ref_pos[3 * i], ref_pos[3 * i + 1], ref_pos[3 * i + 2]);  // camera centre in the world: pos() = -R^T t  =>  t = -R c
-    const V3D t = (R * c) * -1.0;
+    const V3D t(ref_pos[3 * i], ref_pos[3 * i + 1], ref_pos[3 * i + 2]);  // translation of T_f_w_ (Feature::pos() is then -R^T t)
     Feature *f = new Feature(r->owned[i], new float[64], V2D(ref_px[2 * i], ref_px[2 * i + 1]), V3D(ref_f[3 * i], ref_f[3 * i + 1], ref_f[3 * i + 2]), SE3(R, t), 0);
     f->img_ = r->ref_imgs[ref_img_index[i]];
     r->owned[i]->ref_patch = f;
@@ -157,6 +157,16 @@ double ref_vio_update_inverse(void *h, const uint8_t *img, int n_pts, const doub
   if (errors_out)
     for (int i = 0; i < n_pts; i++) errors_out[i] = v.visual_submap->errors[i];
   return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// H_sub_inv of the last precomputeReferencePatches (the last level processed: level 0), row-major [n * 64][6]
+int ref_vio_get_h_sub_inv(void *h, double *out, int max_doubles) {
+  VIOManager &v = ((RefVio *)h)->v;
+  const int rows = (int)v.H_sub_inv.rows();
+  if (rows * 6 > max_doubles) return -1;
+  for (int r = 0; r < rows; r++)
+    for (int c = 0; c < 6; c++) out[6 * r + c] = v.H_sub_inv(r, c);
+  return rows * 6;
 }
 
 // getImagePatch (vio.cpp:203-225): patch_out must hold levels * 64 floats; only [level * 64, level * 64 + 64) is written

@@ -199,7 +199,7 @@ class OracleVIO:
                     HTH=stats[81:3217].reshape(8, 8, 7, 7), HTz=stats[3217:3665].reshape(8, 8, 7), solution=stats[3665:4881].reshape(8, 8, 19),
                     secs=secs)
 
-    def set_inverse_refs(self, ref_imgs, ref_img_index, ref_px, ref_f, ref_R, ref_pos):
+    def set_inverse_refs(self, ref_imgs, ref_img_index, ref_px, ref_f, ref_R, ref_pos, ref_t=None):
         """Reference-feature data of the inverse-compositional variant (Feature::img_, px_, f_, T_f_w_ rotation, pos())."""
         self._ref_imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in ref_imgs]
         arr = (C.c_void_p * len(self._ref_imgs))(*[im.ctypes.data for im in self._ref_imgs])
@@ -285,7 +285,7 @@ def inverse_refs_from_frame(fr):
     pc = fr["vis_pos"] @ R.T + t
     f = pc / np.linalg.norm(pc, axis=1, keepdims=True)
     return dict(ref_imgs=[fr["img_ref"]], ref_img_index=np.zeros(n, np.int32), ref_px=np.ascontiguousarray(fr["px_ref"], dtype=np.float64),
-                ref_f=np.ascontiguousarray(f), ref_R=np.tile(R.reshape(1, 9), (n, 1)), ref_pos=np.tile(-R.T @ t, (n, 1)))
+                ref_f=np.ascontiguousarray(f), ref_R=np.tile(R.reshape(1, 9), (n, 1)), ref_pos=np.tile(-R.T @ t, (n, 1)), ref_t=np.tile(t, (n, 1)))
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -324,3 +324,94 @@ def ref_lio_state_estimation(fr, state_in=None, state_prop=None, cfg=None, pts=N
     assert rc == 0
     kk = nptpl.value
     return dict(state=out, iters=iters.value, M=M[:iters.value].copy(), normals=normals, ptpl_center=centers[:kk], ptpl_dis=dis[:kk], ptpl_point_b=pb[:kk], secs=secs.value)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# oracle/_ref/libfl2_ref_vio.so: the reference's own src/vio.cpp (+ frame.cpp, visual_point.cpp) compiled against stand-in
+# headers (oracle/ref_vio.cpp). vikit's pinhole model and interpolateMat_8u are restatements (un-vendored dependency).
+REF_VIO_SO = os.path.join(ORACLE_DIR, "_ref", "libfl2_ref_vio.so")
+
+
+def ref_vio_available():
+    return os.path.exists(REF_VIO_SO)
+
+
+class RefVIO:
+    """VIOManager of the REFERENCE SOURCE (pinhole camera only)."""
+
+    def __init__(self, cam_cfg, ext, vio_cfg):
+        self.lib = C.CDLL(REF_VIO_SO)
+        L = self.lib
+        L.ref_vio_create.restype = C.c_void_p
+        L.ref_vio_create.argtypes = [C.c_void_p] * 6
+        L.ref_vio_destroy.argtypes = [C.c_void_p]
+        L.ref_vio_update.restype = C.c_double
+        L.ref_vio_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 10
+        L.ref_vio_update_inverse.restype = C.c_double
+        L.ref_vio_update_inverse.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 9
+        L.ref_vio_get_image_patch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_vio_warp_affine.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ref_vio_warp_matrix.restype = C.c_int
+        L.ref_vio_warp_matrix.argtypes = [C.c_void_p] * 9
+        self.cam, self.cfg = cam_cfg, vio_cfg
+        a = lambda x: c64(x).ctypes.data
+        self._keep = [c64(cam_cfg.as_array()), c64(ext.extR), c64(ext.extT), c64(ext.Rcl), c64(ext.Pcl), c64(vio_cfg.as_array())]
+        self.h = L.ref_vio_create(*[k.ctypes.data for k in self._keep])
+        assert self.h, "ref_vio_create failed (only the pinhole model is available in the stand-in vikit)"
+
+    def __del__(self):
+        try:
+            self.lib.ref_vio_destroy(self.h)
+        except Exception:
+            pass
+
+    def update(self, img, pos, warp_patch, search_levels, inv_expo, state_in, state_prop):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        pos, wp = c64(pos), np.ascontiguousarray(warp_patch, dtype=np.float32)
+        sl, ie = np.ascontiguousarray(search_levels, dtype=np.int32), c64(inv_expo)
+        n = len(pos)
+        out, err, G, HTH = np.zeros(STATE_PACK), np.zeros(n, np.float32), np.zeros((19, 19)), np.zeros((19, 19))
+        si, sp = c64(state_in), c64(state_prop)
+        secs = self.lib.ref_vio_update(self.h, img.ctypes.data, n, pos.ctypes.data, wp.ctypes.data, sl.ctypes.data, ie.ctypes.data, si.ctypes.data, sp.ctypes.data,
+                                       out.ctypes.data, err.ctypes.data, G.ctypes.data, HTH.ctypes.data)
+        return dict(state=out, errors=err, G=G, H_T_H=HTH, secs=secs)
+
+    def update_inverse(self, img, pos, warp_patch, search_levels, inv_expo, refs, state_in, state_prop):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        pos, wp = c64(pos), np.ascontiguousarray(warp_patch, dtype=np.float32)
+        sl, ie = np.ascontiguousarray(search_levels, dtype=np.int32), c64(inv_expo)
+        n = len(pos)
+        imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in refs["ref_imgs"]]
+        arr = (C.c_void_p * len(imgs))(*[im.ctypes.data for im in imgs])
+        idx = np.ascontiguousarray(refs["ref_img_index"], dtype=np.int32)
+        # the reference's Feature holds T_f_w_ = (R, t); pos() is derived from it. ref_t, when present, is that t; else t = -R pos
+        R = c64(np.asarray(refs["ref_R"]).reshape(n, 9))
+        t = refs["ref_t"] if "ref_t" in refs else -np.einsum("nij,nj->ni", R.reshape(n, 3, 3), np.asarray(refs["ref_pos"]))
+        px, f, rp = c64(refs["ref_px"]), c64(refs["ref_f"]), c64(t)
+        out, err = np.zeros(STATE_PACK), np.zeros(n, np.float32)
+        si, sp = c64(state_in), c64(state_prop)
+        self.lib.ref_vio_update_inverse(self.h, img.ctypes.data, n, pos.ctypes.data, wp.ctypes.data, sl.ctypes.data, ie.ctypes.data, C.cast(arr, C.c_void_p), len(imgs),
+                                        idx.ctypes.data, px.ctypes.data, f.ctypes.data, R.ctypes.data, rp.ctypes.data, si.ctypes.data, sp.ctypes.data, out.ctypes.data,
+                                        err.ctypes.data)
+        return dict(state=out, errors=err)
+
+    def get_image_patch(self, img, pc, level):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        out = np.zeros(64 * self.cfg.levels, np.float32)
+        pc = c64(pc)
+        self.lib.ref_vio_get_image_patch(self.h, img.ctypes.data, pc.ctypes.data, level, out.ctypes.data)
+        return out[64 * level: 64 * level + 64].copy()
+
+    def warp_affine(self, img_ref, A_cur_ref, px_ref, search_level):
+        img_ref = np.ascontiguousarray(img_ref, dtype=np.uint8)
+        out = np.zeros(64 * self.cfg.levels, np.float32)
+        A, px = c64(A_cur_ref), c64(px_ref)
+        for lvl in range(self.cfg.levels):  # retrieveFromVisualSparseMap loops the pyramid levels (vio.cpp:739-742)
+            self.lib.ref_vio_warp_affine(self.h, img_ref.ctypes.data, img_ref.shape[1], img_ref.shape[0], A.ctypes.data, px.ctypes.data, int(search_level), lvl, out.ctypes.data)
+        return out
+
+    def warp_matrix(self, px_ref, pos_w, normal_w, T_ref, T_cur):
+        A = np.zeros(4)
+        args = [c64(px_ref), c64(pos_w), c64(normal_w), c64(T_ref[0]), c64(T_ref[1]), c64(T_cur[0]), c64(T_cur[1])]
+        sl = self.lib.ref_vio_warp_matrix(self.h, *[x.ctypes.data for x in args], A.ctypes.data)
+        return A.reshape(2, 2), sl

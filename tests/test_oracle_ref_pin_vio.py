@@ -1,0 +1,114 @@
+"""Pins the VIO oracle (oracle/orc_vio.cpp, a restatement) against the REFERENCE'S OWN SOURCE: /root/reference/src/vio.cpp (+
+frame.cpp, visual_point.cpp) compiled from where it lies against stand-in headers (oracle/ref_shim/: matrix library, cv::Mat,
+Sophus::SE3, boost::noncopyable, PCL / ROS shells; oracle/ref_vio.cpp -> oracle/_ref/libfl2_ref_vio.so).
+
+What this pins: everything VIOManager::computeJacobianAndUpdateEKF -> updateState (projection, bilinear weights, taps, the
+Jacobian chain, H^T H, the gain, boxplus, the error-gated accept / rollback, P -= G P), the inverse-compositional variant
+(precomputeReferencePatches, updateStateInverse), getImagePatch, warpAffine, getWarpMatrixAffineHomography / getBestSearchLevel
+compute — the reference's own arithmetic. What it cannot pin: vikit (un-vendored, no version pin): the pinhole model and
+vk::interpolateMat_8u inside the stand-in are restatements of the published algorithm, shared by both sides (pinhole only).
+
+Runs where the library exists (the build container; the GPU box through the snapshot); tests/golden/ref_vio_golden.npz carries
+the reference's outputs elsewhere (tests/golden/make_ref_golden.py regenerates it)."""
+import dataclasses
+import os
+
+import numpy as np
+import pytest
+
+import oracle_bind as O
+from conftest import get_frame
+from fast_livo2_b200 import synthetic as S
+from parity_util import assert_state_close
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_vio_golden.npz")
+needs_ref = pytest.mark.skipif(not O.ref_vio_available(), reason="oracle/_ref/libfl2_ref_vio.so is built only where /root/reference exists")
+
+CASES = {
+    "small": dict(seed=2, n_pts=2000, n_map=120_000, n_patches=150, scene_scale=0.5),
+    "exposure": dict(seed=6, n_pts=1000, n_map=120_000, n_patches=200, scene_scale=0.5, vio=S.VioCfg(exposure_estimate_en=True)),
+    "three_levels": dict(seed=8, n_pts=1000, n_map=120_000, n_patches=300, scene_scale=0.5, vio=S.VioCfg(levels=3, img_point_cov=400.0)),
+    "distorted_pinhole": dict(seed=9, n_pts=1000, n_map=120_000, n_patches=200, scene_scale=0.5,
+                              cam=S.CamCfg(d=(-0.05, 0.02, 0.001, -0.0005, 0.0))),
+}
+
+
+def _prior(fr, seed=3):
+    rng = np.random.default_rng(seed)
+    t = S.unpack_state(fr["state_true"])
+    return S.pack_state(t["R"] @ S.so3_exp(rng.normal(0, np.deg2rad(0.15), 3)), t["p"] + rng.normal(0, 0.01, 3), 1.0 + rng.normal(0, 0.01), t["v"], g=t["g"],
+                        cov=S.random_prior_cov(rng, scale=0.2))
+
+
+def _inputs(name):
+    fr = get_frame(**CASES[name])
+    prior = _prior(fr)
+    w = O.oracle_warp_patches(fr, prior)
+    return fr, prior, w
+
+
+@needs_ref
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_vio_update_reproduces_the_reference_source(name):
+    fr, prior, w = _inputs(name)
+    args = (fr["img"], fr["vis_pos"], w["warp_patch"], w["search_levels"], fr["inv_ref_expo"], prior, prior)
+    ref = O.RefVIO(fr["cam_cfg"], fr["ext"], fr["vio_cfg"]).update(*args)
+    orc = O.OracleVIO(fr["cam_cfg"], fr["ext"], fr["vio_cfg"]).update(*args)
+    assert orc["total_iters"] >= 4
+    # same decisions (accept / rollback / stop) or the states would differ grossly; the sums differ only in association order
+    assert_state_close(orc["state"], ref["state"], rot_tol=1e-11, pos_tol=1e-11, cov_tol=1e-9, rest_tol=1e-11)
+    # per-patch photometric error: float accumulation in both, same order (one thread)
+    np.testing.assert_allclose(orc["errors"], ref["errors"], rtol=1e-6, atol=1e-4)
+    # the H_T_H member (vio.h:121) holds the normal matrix of the last ACCEPTED iteration: one of the oracle's per-iteration blocks
+    blocks = orc["HTH"].reshape(-1, 7, 7)
+    blocks = blocks[np.abs(blocks).max(axis=(1, 2)) > 0]
+    want = ref["H_T_H"][:7, :7]
+    rel = [np.abs(b - want).max() / np.abs(want).max() for b in blocks]
+    assert min(rel) < 1e-10, min(rel)
+
+
+@needs_ref
+def test_oracle_inverse_compositional_variant_reproduces_the_reference_source():
+    fr, prior, w = _inputs("small")
+    refs = O.inverse_refs_from_frame(fr)
+    n = len(fr["vis_pos"])
+    args = (fr["img"], fr["vis_pos"], w["warp_patch"], w["search_levels"], np.ones(n))
+    ref = O.RefVIO(fr["cam_cfg"], fr["ext"], fr["vio_cfg"]).update_inverse(*args, refs, prior, prior)
+    vio = O.OracleVIO(fr["cam_cfg"], fr["ext"], dataclasses.replace(fr["vio_cfg"], inverse_composition_en=True))
+    vio.set_inverse_refs(**refs)
+    vio.set_inverse(True)
+    orc = vio.update(*args, prior, prior)
+    assert_state_close(orc["state"], ref["state"], rot_tol=1e-11, pos_tol=1e-11, cov_tol=1e-9, rest_tol=1e-11)
+    np.testing.assert_allclose(orc["errors"], ref["errors"], rtol=1e-6, atol=1e-4)
+
+
+@needs_ref
+def test_oracle_patch_producers_reproduce_the_reference_source():
+    """getImagePatch, getWarpMatrixAffineHomography + getBestSearchLevel, warpAffine (vio.cpp:203-331)."""
+    fr, prior, w = _inputs("distorted_pinhole")
+    ref, orc = O.RefVIO(fr["cam_cfg"], fr["ext"], fr["vio_cfg"]), O.OracleVIO(fr["cam_cfg"], fr["ext"], fr["vio_cfg"])
+    st = S.unpack_state(prior)
+    T_cur = S.camera_pose(fr["ext"], st["R"], st["p"])
+    rng = np.random.default_rng(1)
+    for i in range(0, len(fr["vis_pos"]), 7):
+        Ar, sr = ref.warp_matrix(fr["px_ref"][i], fr["vis_pos"][i], fr["vis_normal"][i], fr["T_ref"], T_cur)
+        Ao, so = orc.warp_matrix(fr["px_ref"][i], fr["vis_pos"][i], fr["vis_normal"][i], fr["T_ref"], T_cur)
+        assert sr == so
+        np.testing.assert_allclose(Ao, Ar, rtol=1e-11, atol=1e-13)
+        np.testing.assert_array_equal(orc.warp_affine(fr["img_ref"], Ar, fr["px_ref"][i], sr), ref.warp_affine(fr["img_ref"], Ar, fr["px_ref"][i], sr))
+        pc = np.array([rng.uniform(40, fr["cam_cfg"].width - 40), rng.uniform(40, fr["cam_cfg"].height - 40)])
+        for lvl in range(fr["vio_cfg"].levels):
+            np.testing.assert_array_equal(orc.get_image_patch(fr["img"], pc, lvl), ref.get_image_patch(fr["img"], pc, lvl))
+
+
+def test_oracle_matches_reference_vio_golden():
+    """The reference library's own outputs, committed: the pin survives where the library cannot be built."""
+    if not os.path.exists(GOLDEN):
+        pytest.skip("tests/golden/ref_vio_golden.npz not generated")
+    g = np.load(GOLDEN, allow_pickle=False)
+    for name in ("small", "exposure"):
+        fr, prior, w = _inputs(name)
+        np.testing.assert_array_equal(w["warp_patch"], g[f"{name}_warp_patch"])  # same inputs as when the vectors were made
+        orc = O.OracleVIO(fr["cam_cfg"], fr["ext"], fr["vio_cfg"]).update(fr["img"], fr["vis_pos"], w["warp_patch"], w["search_levels"], fr["inv_ref_expo"], prior, prior)
+        assert_state_close(orc["state"], g[f"{name}_state"], rot_tol=1e-11, pos_tol=1e-11, cov_tol=1e-9, rest_tol=1e-11)
+        np.testing.assert_allclose(orc["errors"], g[f"{name}_errors"], rtol=1e-6, atol=1e-4)
