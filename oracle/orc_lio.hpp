@@ -1,4 +1,8 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header). PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header). PINNED to the reference source: oracle/_ref/libfl2_ref_lio.so is
+// the reference's own src/voxel_map.cpp compiled against stand-in headers (oracle/ref_voxel_map.cpp) and
+// tests/test_oracle_ref_pin.py holds StateEstimation of this restatement to it bit for bit (associations) / to 1e-12 (states).
+// The map-construction part (BuildVoxelMap / UpdateVoxelMap / init_plane) is compiled into that library too but is exercised by
+// the pin only through the maps it is handed; it is cross-checked against the numpy builder of the generator instead.
 //
 // CPU restatement of the reference's LIO ESIKF measurement update and of the voxel-map
 // construction that manufactures its input. Every function cites the reference lines it

@@ -1,9 +1,12 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header). PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header). PINNED to the reference source: oracle/_ref/libfl2_ref_vio.so is
+// the reference's own src/vio.cpp compiled against stand-in headers (oracle/ref_vio.cpp) and tests/test_oracle_ref_pin_vio.py
+// holds this restatement to it (update, inverse-compositional variant, patch producers). PARITY UNPINNED remains true for the
+// one dependency restated on BOTH sides of that comparison:
 //
 // CPU restatement of the reference's VIO ESIKF measurement update (src/vio.cpp) and of the
 // third-party camera arithmetic it calls (vikit, xuankuzcr/rpg_vikit, NO version pin in the
 // reference: README.md:80-84). The vikit parts are restated from its published algorithm
-// (pinhole + radtan, equidistant fisheye, interpolateMat_8u) and are doubly unpinned.
+// (pinhole + radtan, equidistant fisheye, interpolateMat_8u); the fisheye model has no pin at all.
 #pragma once
 #include "orc_math.hpp"
 

@@ -148,6 +148,77 @@ int ref_lio_state_estimation(const int64_t *keys, const int32_t *first, const in
   return rc;
 }
 
+// ---- the reference's own map construction (pins the oracle's BuildVoxelMap / UpdateVoxelMap / init_plane restatement, and through
+// it what the device-resident map is held to): a persistent VoxelMapManager fed with caller-supplied (point_w, var) lists.
+struct RefMap {
+  VoxelMapConfig config;
+  std::unordered_map<VOXEL_LOCATION, VoxelOctoTree *> map;
+  VoxelMapManager *mgr = nullptr;
+  ~RefMap() {
+    if (mgr)
+      for (auto &kv : mgr->voxel_map_) delete kv.second;  // the manager holds its own copy of the handle map (voxel_map.h:194, 221)
+    delete mgr;
+  }
+};
+// cfg: voxel_size, max_layer, min_eigen_value (planner_threshold_), max_points_num, layer_init_num[0..4]
+void *ref_map_create(const double *cfg) {
+  RefMap *r = new RefMap;
+  VoxelMapConfig &c = r->config;
+  c.max_voxel_size_ = cfg[0], c.max_layer_ = (int)cfg[1], c.planner_threshold_ = cfg[2], c.max_points_num_ = (int)cfg[3];
+  c.layer_init_num_ = std::vector<int>{(int)cfg[4], (int)cfg[5], (int)cfg[6], (int)cfg[7], (int)cfg[8]};
+  c.max_iterations_ = 5, c.sigma_num_ = 3, c.dept_err_ = 0.02, c.beam_err_ = 0.05, c.is_pub_plane_map_ = false;
+  c.sliding_thresh = 8, c.map_sliding_en = false, c.half_map_size = 100;
+  r->mgr = new VoxelMapManager(c, r->map);
+  return r;
+}
+void ref_map_destroy(void *h) { delete static_cast<RefMap *>(h); }
+// VoxelMapManager::UpdateVoxelMap (voxel_map.cpp:609-641) on the manager's own voxel_map_ (a by-value member, voxel_map.h:194).
+void ref_map_update(void *h, const double *pts_world, const double *var9, int n) {
+  RefMap *r = static_cast<RefMap *>(h);
+  std::vector<pointWithVar> pts(n);
+  for (int i = 0; i < n; i++) {
+    pts[i].point_w << pts_world[3 * i], pts_world[3 * i + 1], pts_world[3 * i + 2];
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) pts[i].var(a, b) = var9[9 * (size_t)i + 3 * a + b];
+  }
+  r->mgr->UpdateVoxelMap(pts);
+}
+static void ref_flatten_node(const VoxelOctoTree *node, int layer, int max_layer, int path, std::vector<FlatPlane> *out, int *count) {
+  if (node->plane_ptr_->is_plane_) {  // the order build_single_residual visits (voxel_map.cpp:721, 771-784)
+    if (out) {
+      const VoxelPlane &p = *node->plane_ptr_;
+      FlatPlane f;
+      memset(&f, 0, sizeof(f));
+      for (int k = 0; k < 3; k++) f.center[k] = p.center_(k), f.normal[k] = p.normal_(k);
+      int t = 0;
+      for (int i = 0; i < 6; i++)
+        for (int j = i; j < 6; j++) f.plane_var[t++] = p.plane_var_(i, j);
+      f.d = p.d_, f.radius = p.radius_, f.layer = layer, f.path = path;
+      out->push_back(f);
+    }
+    (*count)++;
+    return;
+  }
+  if (layer < max_layer)
+    for (int l = 0; l < 8; l++)
+      if (node->leaves_[l] != nullptr) ref_flatten_node(node->leaves_[l], layer + 1, max_layer, path | (l << (3 * layer)), out, count);
+}
+// two-call: planes == NULL returns the sizes
+void ref_map_flatten(void *h, int *n_roots, int *n_planes, int64_t *keys, int32_t *first, int32_t *count, void *planes_v) {
+  RefMap *r = static_cast<RefMap *>(h);
+  const auto &vm = r->mgr->voxel_map_;
+  std::vector<FlatPlane> planes;
+  int nr = 0, np = 0;
+  for (const auto &kv : vm) {
+    int c = 0;
+    ref_flatten_node(kv.second, 0, r->config.max_layer_, 0, planes_v ? &planes : nullptr, &c);
+    if (planes_v) keys[3 * nr] = kv.first.x, keys[3 * nr + 1] = kv.first.y, keys[3 * nr + 2] = kv.first.z, first[nr] = np, count[nr] = c;
+    nr++, np += c;
+  }
+  *n_roots = nr, *n_planes = np;
+  if (planes_v) memcpy(planes_v, planes.data(), planes.size() * sizeof(FlatPlane));
+}
+
 // calcBodyCov of the reference (voxel_map.cpp:15-34) for one point.
 void ref_calc_body_cov(const double *pb, float range_inc, float degree_inc, double *cov9) {
   Eigen::Vector3d p(pb[0], pb[1], pb[2]);

@@ -326,6 +326,42 @@ def ref_lio_state_estimation(fr, state_in=None, state_prop=None, cfg=None, pts=N
     return dict(state=out, iters=iters.value, M=M[:iters.value].copy(), normals=normals, ptpl_center=centers[:kk], ptpl_dis=dis[:kk], ptpl_point_b=pb[:kk], secs=secs.value)
 
 
+class RefMap:
+    """The REFERENCE SOURCE's map construction (VoxelMapManager::UpdateVoxelMap / UpdateOctoTree / init_plane of
+    oracle/_ref/libfl2_ref_lio.so) fed with caller-supplied (point_w, var) lists, flattened like OracleLIO.flatten."""
+
+    def __init__(self, cfg):
+        self.lib = C.CDLL(REF_LIO_SO)
+        self.lib.ref_map_create.restype = C.c_void_p
+        self.lib.ref_map_create.argtypes = [C.c_void_p]
+        self.lib.ref_map_destroy.argtypes = [C.c_void_p]
+        self.lib.ref_map_update.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        self.lib.ref_map_flatten.argtypes = [C.c_void_p] * 7
+        lin = list(cfg.layer_init_num) + [cfg.layer_init_num[-1]] * 5
+        a = c64([cfg.voxel_size, cfg.max_layer, cfg.min_eigen_value, cfg.max_points_num] + lin[:5])
+        self.h = self.lib.ref_map_create(a.ctypes.data)
+
+    def __del__(self):
+        try:
+            self.lib.ref_map_destroy(self.h)
+        except Exception:
+            pass
+
+    def update(self, pw, var):
+        pw, var = c64(np.asarray(pw).reshape(-1, 3)), c64(np.asarray(var).reshape(-1, 9))
+        self.lib.ref_map_update(self.h, pw.ctypes.data, var.ctypes.data, len(pw))
+
+    def flatten(self):
+        from fast_livo2_b200.synthetic import PLANE_DTYPE
+
+        nr, npl = C.c_int(0), C.c_int(0)
+        self.lib.ref_map_flatten(self.h, C.addressof(nr), C.addressof(npl), None, None, None, None)
+        keys, first, count = np.zeros((nr.value, 3), np.int64), np.zeros(nr.value, np.int32), np.zeros(nr.value, np.int32)
+        planes = np.zeros(npl.value, PLANE_DTYPE)
+        self.lib.ref_map_flatten(self.h, C.addressof(nr), C.addressof(npl), keys.ctypes.data, first.ctypes.data, count.ctypes.data, planes.ctypes.data)
+        return dict(keys=keys, first=first, count=count, planes=planes)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # oracle/_ref/libfl2_ref_vio.so: the reference's own src/vio.cpp (+ frame.cpp, visual_point.cpp) compiled against stand-in
 # headers (oracle/ref_vio.cpp). vikit's pinhole model and interpolateMat_8u are restatements (un-vendored dependency).

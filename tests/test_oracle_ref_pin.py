@@ -136,3 +136,28 @@ def test_oracle_matches_reference_golden(name):
     r = dict(iters=int(g[f"{name}_iters"]), M=g[f"{name}_M"], ptpl_center=g[f"{name}_ptpl_center"], ptpl_dis=g[f"{name}_ptpl_dis"], normals=g[f"{name}_normals"],
              state=g[f"{name}_state"])
     _check(o, r, fr["map"]["planes"])
+
+
+@pytest.mark.skipif(not O.ref_lio_available(), reason="oracle/_ref/libfl2_ref_lio.so is built only where /root/reference exists")
+@pytest.mark.parametrize("cfg", [S.LioCfg(), S.LioCfg(voxel_size=0.4, max_layer=3, max_points_num=20)], ids=["avia_defaults", "voxel0.4_layer3_max20"])
+def test_oracle_update_voxel_map_reproduces_the_reference_source(cfg):
+    """The map construction (f1's oracle): VoxelMapManager::UpdateVoxelMap / UpdateOctoTree / init_octo_tree / cut_octo_tree /
+    init_plane of the REFERENCE SOURCE against the oracle's restatement, tick by tick on the same (point_w, var) lists: the same
+    root voxels, the same octree shape (candidate planes per root in DFS order, layer / path), every plane's centre, normal,
+    plane_var, d and radius. Tolerance, not bits: the reference calls Eigen::EigenSolver, which here is the stand-in's Jacobi
+    and in the oracle another Jacobi — a genuine Eigen would differ in the last bits just the same."""
+    import map_bind as MB
+    from test_map_host import _oracle_update, _tick_points
+
+    rng = np.random.default_rng(5)
+    rects = S.make_scene("room", 0.5)
+    orc, ref = O.OracleLIO(cfg, S.avia_extrinsics()), O.RefMap(cfg)
+    n = 0
+    for tick in range(8):
+        lo = np.array([-10.0 + 1.5 * tick, -8.0, -2.0])
+        pw, var = _tick_points(rng, rects, 6000, lo, lo + np.array([8.0, 16.0, 6.0]))
+        _oracle_update(orc, pw, var)
+        ref.update(pw, var)
+        n = MB.compare_flat_maps(orc.flatten(), ref.flatten(), rtol=1e-9, what=("oracle", "reference source"))
+    f = ref.flatten()
+    assert n > 1500 and f["count"].max() > 1 and (f["planes"]["layer"] > 0).any()
