@@ -647,7 +647,7 @@ def b200_arm(args, rank, world, local_rank):
         cam = fr["cam_cfg"]
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
-            "ms_per_step_median": med_ms, "ms_per_step_max": max_ms,
+            "ms_per_step_median": med_ms, "ms_per_step_max": max_ms, "ms_per_step_all_rank0": [round(float(x), 4) for x in step_ms],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": fr["workload"], "name": args.config, "n_pts": n, "n_patches": npatch, "image": f"{cam.width}x{cam.height}" if has_vio else None,
                        "levels": L, "iters_per_step": iters_per_step,
