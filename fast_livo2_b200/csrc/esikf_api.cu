@@ -1191,6 +1191,7 @@ int esikf_vio_set_ref_images(esikf_ctx *ctx, const uint8_t *const *imgs, int32_t
   CK(cudaStreamSynchronize(ctx->stream));
   for (uint8_t *p : ctx->ref_imgs) cudaFree(p);
   ctx->ref_imgs.clear();
+  ctx->n_inv_refs = 0;  // the inverse-compositional reference indices pointed into the images just released
   for (int i = 0; i < n_imgs; i++) {
     uint8_t *d = nullptr;
     CK(cudaMalloc(&d, (size_t)width * height + 64));

@@ -11,10 +11,11 @@
 
 namespace fl2b200 {
 
-// Host-side packing of the per-tick inputs into the page-locked staging buffers runs on 4 threads (the reference's own
-// MP_PROC_NUM, CMakeLists.txt:46-58; a num_threads clause, so nothing leaks into the process like the reference's
-// omp_set_num_threads calls do): at 100 k points + 2 k patches the single-threaded copies were 0.29 ms of a 0.82 ms tick pair.
-#define FL2_PACK_THREADS 4
+// Host-side packing of the per-tick inputs into the page-locked staging buffers runs on a few threads (a num_threads clause, so
+// nothing leaks into the process like the reference's omp_set_num_threads calls do): at 100 k points + 2 k patches the
+// single-threaded copies were 0.29 ms of a 0.82 ms tick pair; 4 threads (the reference's MP_PROC_NUM) brought the pair to
+// 0.71 ms, 8 are used since the copies are memory-bound and the GPU hosts have the cores.
+#define FL2_PACK_THREADS 8
 static void par_memcpy(void *dst, const void *src, size_t bytes) {
   const size_t chunk = 64 * 1024;
   const long n_chunks = (long)((bytes + chunk - 1) / chunk);
@@ -398,6 +399,7 @@ void VIOManager::computeJacobianAndUpdateEKF(const GrayImage &img) {
   state->pack(sin);
   state_propagat->pack(sprop);
   esikf_vio_stats stats;
+  patch_img_ = nullptr;  // the update installs its own current image
   last_status_ = esikf_vio_update(ctx_, im, img.cols, img.rows, pos, wp, sl, ie, n, sin, sprop, sout, &stats, err);
   if (last_status_) {
     last_error_ = esikf_last_error(ctx_);
@@ -411,7 +413,11 @@ void VIOManager::computeJacobianAndUpdateEKF(const GrayImage &img) {
 // include/vio.h:151 / src/vio.cpp:203-225: writes patch_tmp[patch_size_total * level + row * patch_size + col]
 void VIOManager::getImagePatch(const GrayImage &img, const double pc[2], float *patch_tmp, int level) {
   if (!ctx_ || !img.data || !pc || !patch_tmp) return;
-  last_status_ = esikf_vio_set_image(ctx_, img.data, img.cols, img.rows);
+  last_status_ = 0;
+  if (img.data != patch_img_ || img.cols != patch_img_w_ || img.rows != patch_img_h_) {
+    last_status_ = esikf_vio_set_image(ctx_, img.data, img.cols, img.rows);
+    patch_img_ = last_status_ ? nullptr : img.data, patch_img_w_ = img.cols, patch_img_h_ = img.rows;
+  }
   float out[64];
   if (!last_status_) last_status_ = esikf_vio_get_image_patch(ctx_, pc, 1, level, out);
   if (last_status_) {
@@ -432,8 +438,12 @@ void VIOManager::warpAffine(const double A_cur_ref[4], const GrayImage &img_ref,
     last_error_ = "warpAffine: halfpatch_size must be 4 and pyramid_level inside the pyramid";
     return;
   }
-  const uint8_t *imgs[1] = {img_ref.data};
-  last_status_ = esikf_vio_set_ref_images(ctx_, imgs, 1, img_ref.cols, img_ref.rows);
+  last_status_ = 0;
+  if (img_ref.data != patch_ref_img_ || img_ref.cols != patch_ref_w_ || img_ref.rows != patch_ref_h_) {
+    const uint8_t *imgs[1] = {img_ref.data};
+    last_status_ = esikf_vio_set_ref_images(ctx_, imgs, 1, img_ref.cols, img_ref.rows);
+    patch_ref_img_ = last_status_ ? nullptr : img_ref.data, patch_ref_w_ = img_ref.cols, patch_ref_h_ = img_ref.rows;
+  }
   std::vector<float> all((size_t)64 * patch_pyrimid_level);
   const int32_t idx = 0, sl = search_level;
   if (!last_status_) last_status_ = esikf_vio_warp_affine(ctx_, 1, &idx, px_ref, A_cur_ref, &sl, all.data());

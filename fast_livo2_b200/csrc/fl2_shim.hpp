@@ -230,18 +230,25 @@ class VIOManager {
   V3D extT;
   int last_status_ = 0;
   int last_total_iters_ = 0;  // iterations executed by the last computeJacobianAndUpdateEKF
+  // The per-patch mirrors below are called once per point and level by the reference's retrieval code: the image they are
+  // handed is uploaded only when it is not the one of the previous call (same pixel pointer and size). A caller that rewrites
+  // the pixels in place calls InvalidatePatchImages().
+  void InvalidatePatchImages() { patch_img_ = patch_ref_img_ = nullptr; }
   std::string last_error_;
 
   explicit VIOManager(esikf_ctx *shared_ctx);  // shares the device context (and stream) of the VoxelMapManager
   void initializeVIO();                         // src/vio.cpp:41-160 (the parts the update needs)
   void computeJacobianAndUpdateEKF(const GrayImage &img);  // include/vio.h:153
-  // Per-patch helpers with the reference's signatures (include/vio.h:151, 161-162; V2D / Matrix2d as plain arrays). They
-  // upload the image on every call: use the batched esikf_vio_get_image_patch / esikf_vio_warp_patches on the frame path.
+  // Per-patch helpers with the reference's signatures (include/vio.h:151, 161-162; V2D / Matrix2d as plain arrays). One
+  // launch and one small read-back per call: the frame path should use the batched esikf_vio_get_image_patch /
+  // esikf_vio_warp_patches.
   void getImagePatch(const GrayImage &img, const double pc[2], float *patch_tmp, int level);
   void warpAffine(const double A_cur_ref[4] /* row-major 2x2 */, const GrayImage &img_ref, const double px_ref[2], int level_ref, int search_level,
                   int pyramid_level, int halfpatch_size, float *patch);
 
  private:
+  const uint8_t *patch_img_ = nullptr, *patch_ref_img_ = nullptr;  // what the per-patch helpers uploaded last
+  int patch_img_w_ = 0, patch_img_h_ = 0, patch_ref_w_ = 0, patch_ref_h_ = 0;
   esikf_ctx *ctx_ = nullptr;
   PinnedBuf<double> st_pos_, st_ie_, st_state_;
   PinnedBuf<float> st_wp_, st_err_;
