@@ -183,6 +183,32 @@ void ref_map_update(void *h, const double *pts_world, const double *var9, int n)
   }
   r->mgr->UpdateVoxelMap(pts);
 }
+// First LiDAR frame (LIVMapper.cpp:356-366): feats_down_world_ = TransformLidar(state, feats_down_body_) (the manager's own
+// TransformLidar, the same expression as LIVMapper::transformLidar :645), then VoxelMapManager::BuildVoxelMap (voxel_map.cpp:532-591).
+void ref_map_build(void *h, const float *pts_body, int n, const double *state, const double *extR, const double *extT, double dept_err, double beam_err) {
+  RefMap *r = static_cast<RefMap *>(h);
+  VoxelMapManager &m = *r->mgr;
+  m.config_setting_.dept_err_ = dept_err, m.config_setting_.beam_err_ = beam_err;
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) m.extR_(i, j) = extR[3 * i + j];
+    m.extT_(i) = extT[i];
+  }
+  m.feats_down_body_->points.resize(n);
+  for (int i = 0; i < n; i++) {
+    PointType &p = m.feats_down_body_->points[i];
+    p.x = pts_body[3 * i], p.y = pts_body[3 * i + 1], p.z = pts_body[3 * i + 2];
+  }
+  m.feats_down_size_ = n;
+  unpack_state(state, m.state_);
+  pcl::PointCloud<pcl::PointXYZI>::Ptr world(new pcl::PointCloud<pcl::PointXYZI>());
+  m.TransformLidar(m.state_.rot_end, m.state_.pos_end, m.feats_down_body_, world);
+  m.feats_down_world_->points.resize(n);
+  for (int i = 0; i < n; i++) {  // LIVMapper keeps the world cloud as PointXYZINormal: the float coordinates carry over unchanged
+    PointType &p = m.feats_down_world_->points[i];
+    p.x = world->points[i].x, p.y = world->points[i].y, p.z = world->points[i].z;
+  }
+  m.BuildVoxelMap();
+}
 static void ref_flatten_node(const VoxelOctoTree *node, int layer, int max_layer, int path, std::vector<FlatPlane> *out, int *count) {
   if (node->plane_ptr_->is_plane_) {  // the order build_single_residual visits (voxel_map.cpp:721, 771-784)
     if (out) {

@@ -351,6 +351,12 @@ class RefMap:
         pw, var = c64(np.asarray(pw).reshape(-1, 3)), c64(np.asarray(var).reshape(-1, 9))
         self.lib.ref_map_update(self.h, pw.ctypes.data, var.ctypes.data, len(pw))
 
+    def build(self, pts_body_f32, state, ext, cfg):
+        """First LiDAR frame: TransformLidar + BuildVoxelMap of the reference source (LIVMapper.cpp:356-366)."""
+        self.lib.ref_map_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double]
+        pb, st, R, t = np.ascontiguousarray(pts_body_f32, dtype=np.float32), c64(state), c64(ext.extR), c64(ext.extT)
+        self.lib.ref_map_build(self.h, pb.ctypes.data, len(pb), st.ctypes.data, R.ctypes.data, t.ctypes.data, float(cfg.dept_err), float(cfg.beam_err))
+
     def flatten(self):
         from fast_livo2_b200.synthetic import PLANE_DTYPE
 

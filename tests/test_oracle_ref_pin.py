@@ -161,3 +161,24 @@ def test_oracle_update_voxel_map_reproduces_the_reference_source(cfg):
         n = MB.compare_flat_maps(orc.flatten(), ref.flatten(), rtol=1e-9, what=("oracle", "reference source"))
     f = ref.flatten()
     assert n > 1500 and f["count"].max() > 1 and (f["planes"]["layer"] > 0).any()
+
+
+@pytest.mark.skipif(not O.ref_lio_available(), reason="oracle/_ref/libfl2_ref_lio.so is built only where /root/reference exists")
+def test_oracle_build_voxel_map_reproduces_the_reference_source():
+    """First LiDAR frame (LIVMapper.cpp:356-366): TransformLidar + BuildVoxelMap (per-point covariance with the raw body point's
+    cross matrix and calcBodyCov's own z fix, all points pushed, then init_octo_tree with the recursive cut) of the REFERENCE
+    SOURCE against the oracle's tick_build_map on a 60 k-point scan with non-identity extrinsics — the form the device map's
+    esikf_map_device_build is held to."""
+    import map_bind as MB
+
+    cfg, ext = S.LioCfg(), S.hilti_extrinsics()
+    rng = np.random.default_rng(21)
+    rects = S.make_scene("room", 0.5)
+    R0, p0 = S.so3_exp(np.array([0.01, -0.02, 0.3])), np.array([-2.0, 0.5, 0.3])
+    st0 = S.pack_state(R0, p0, cov=S.random_prior_cov(np.random.default_rng(3), scale=0.05), g=np.array([0, 0, -9.81]))
+    scan = S.scan_at(rects, ext, R0, p0, 60000, cfg, rng)
+    orc, ref = O.OracleLIO(cfg, ext), O.RefMap(cfg)
+    orc.tick_build_map(scan, st0)
+    ref.build(scan, st0, ext, cfg)
+    n = MB.compare_flat_maps(orc.flatten(), ref.flatten(), rtol=1e-9, what=("oracle BuildVoxelMap", "reference source"))
+    assert n > 1500
