@@ -209,6 +209,14 @@ void ref_map_build(void *h, const float *pts_body, int n, const double *state, c
   }
   m.BuildVoxelMap();
 }
+// VoxelMapManager::clearMemOutOfMap (voxel_map.cpp:950-971); its console line is swallowed
+void ref_map_clear_out_of_map(void *h, int x_max, int x_min, int y_max, int y_min, int z_max, int z_min) {
+  RefMap *r = static_cast<RefMap *>(h);
+  std::ostringstream captured;
+  std::streambuf *old = std::cout.rdbuf(captured.rdbuf());
+  r->mgr->clearMemOutOfMap(x_max, x_min, y_max, y_min, z_max, z_min);
+  std::cout.rdbuf(old);
+}
 static void ref_flatten_node(const VoxelOctoTree *node, int layer, int max_layer, int path, std::vector<FlatPlane> *out, int *count) {
   if (node->plane_ptr_->is_plane_) {  // the order build_single_residual visits (voxel_map.cpp:721, 771-784)
     if (out) {

@@ -9,6 +9,7 @@ the final ptpl_list_ (matched plane centres and signed distances, in order), pv.
 and the posterior state / covariance to 1e-12 (the two differ only in the summation order of small fixed-size products).
 tests/golden/ref_lio_golden.npz holds the reference's outputs for two of the cases, so that the pin survives on machines
 without the library (test_oracle_matches_reference_golden) — tests/golden/make_ref_golden.py regenerates it."""
+import ctypes as C
 import os
 
 import numpy as np
@@ -159,8 +160,17 @@ def test_oracle_update_voxel_map_reproduces_the_reference_source(cfg):
         _oracle_update(orc, pw, var)
         ref.update(pw, var)
         n = MB.compare_flat_maps(orc.flatten(), ref.flatten(), rtol=1e-9, what=("oracle", "reference source"))
-    f = ref.flatten()
-    assert n > 1500 and f["count"].max() > 1 and (f["planes"]["layer"] > 0).any()
+        if tick == 5:
+            f = ref.flatten()
+            assert f["count"].max() > 1 and (f["planes"]["layer"] > 0).any()  # octrees were cut: several candidates per root
+            # mapSliding's clearMemOutOfMap (:950-971) in between, then more ticks on the pruned maps
+            c, half = np.array([4, -2, 1]), 14
+            b = [int(c[0] + half), int(c[0] - half), int(c[1] + half), int(c[1] - half), int(c[2] + half), int(c[2] - half)]
+            deleted = orc.lib.orc_lio_clear_out_of_map(orc.h, *b)
+            ref.lib.ref_map_clear_out_of_map(C.c_void_p(ref.h), *b)
+            assert deleted > 0
+            MB.compare_flat_maps(orc.flatten(), ref.flatten(), rtol=1e-9, what=("oracle after clearMemOutOfMap", "reference source"))
+    assert n > 1500
 
 
 @pytest.mark.skipif(not O.ref_lio_available(), reason="oracle/_ref/libfl2_ref_lio.so is built only where /root/reference exists")
