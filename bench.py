@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"], help="BASELINE.json workload (cfg2 = configs[1], the metric's own)")
-    ap.add_argument("--cpu-baseline-frames", type=int, default=8)
+    ap.add_argument("--cpu-baseline-frames", type=int, default=30)  # bounded by 30 s of wall time
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-shim", action="store_true", help="skip the e2e_shim leg")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"], help="N>1: in-kernel NVLink peer-memory exchange (default) or NCCL per iteration")
