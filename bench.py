@@ -234,6 +234,45 @@ def parity_block(fr, r0, v0, world):
     return out
 
 
+def reference_source_timing(fr, restatement, budget_s=20.0):
+    """The reference's OWN translation units (oracle/_ref/*_timing.so: src/voxel_map.cpp and src/vio.cpp compiled against the
+    stand-in headers with -O3 -funroll-loops -fopenmp, MP_PROC_NUM=4; built where /root/reference exists, shipped with the
+    snapshot) timed on the same frame, next to the restatement that the arm's `value` comes from. Their linear algebra is the
+    stand-in matrix library (plain loops), not Eigen: a cross-check of the restatement's figure, not a replacement for it."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_bind as O
+
+        lio_so = os.path.join(ROOT, "oracle", "_ref", "libfl2_ref_lio_timing.so")
+        vio_so = os.path.join(ROOT, "oracle", "_ref", "libfl2_ref_vio_timing.so")
+        if not os.path.exists(lio_so):
+            return {"unavailable": "oracle/_ref/*_timing.so not in this checkout (built only where /root/reference exists)"}
+        has_vio = len(fr.get("vis_pos", [])) > 0 and os.path.exists(vio_so) and fr["cam_cfg"].model == 0
+        t_l = t_v = 0.0
+        it_l = it_v = frames = 0
+        t0 = time.time()
+        rv = O.RefVIO(fr["cam_cfg"], fr["ext"], fr["vio_cfg"], so=vio_so) if has_vio else None
+        w = restatement.get("warp")
+        while frames < 8 and time.time() - t0 < budget_s:
+            r = O.ref_lio_state_estimation(fr, so=lio_so)
+            if frames > 0 or budget_s < 1:
+                t_l += r["secs"]
+                it_l += r["iters"]
+            if has_vio:
+                v = rv.update(fr["img"], fr["vis_pos"], w["warp_patch"], w["search_levels"], fr["inv_ref_expo"], r["state"], r["state"])
+                if frames > 0:
+                    t_v += v["secs"]
+                    it_v += int(restatement["vio"]["total_iters"])  # the reference does not export its count; the restatement's is the same (pinned)
+            frames += 1
+        if it_l == 0:
+            return {"unavailable": "no timed frame inside the budget"}
+        return {"value": (it_l + it_v) / (t_l + t_v), "unit": UNIT, "lio_iters_per_s": it_l / t_l, "vio_iters_per_s": (it_v / t_v) if t_v else None,
+                "frames": frames - 1, "threads": 4,
+                "note": "reference source (voxel_map.cpp / vio.cpp) against stand-in headers, -O3 -funroll-loops -fopenmp, no -march=native (built on another host)"}
+    except Exception as e:  # a cross-check: never lose the arm's line over it
+        return {"error": repr(e)}
+
+
 def reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -250,6 +289,7 @@ def reference_arm(args, rank, world):
     best, cores = (res4, 4)
     if probe is not None and probe["value"] > res4["value"]:
         best, cores = run_cpu_reference(fr, ncpu, args.steps, warm=args.warmup, budget_s=150), ncpu
+    ref_src = reference_source_timing(fr, best)
     out = {
         "impl": "reference", "metric": METRIC, "value": best["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": best["frames"], "warmup": args.warmup,
         "ms_per_step": best["ms_per_frame"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -261,6 +301,7 @@ def reference_arm(args, rank, world):
                                    f"(-O3 -march=native -funroll-loops -fopenmp); 4 threads (reference cap): {res4['value']:.2f} it/s"
                                    + (f", {ncpu} threads (short sample): {probe['value']:.2f} it/s" if probe else "") + f"; host: {ncpu} logical cores"},
         "e2e": {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reference_source": ref_src,
     }
     print(json.dumps(out), flush=True)
 

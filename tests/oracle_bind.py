@@ -298,9 +298,9 @@ def ref_lio_available():
     return os.path.exists(REF_LIO_SO)
 
 
-def ref_lio_state_estimation(fr, state_in=None, state_prop=None, cfg=None, pts=None):
+def ref_lio_state_estimation(fr, state_in=None, state_prop=None, cfg=None, pts=None, so=None):
     """VoxelMapManager::StateEstimation of the REFERENCE SOURCE on a synthetic frame's flat map / scan."""
-    lib = C.CDLL(REF_LIO_SO)
+    lib = C.CDLL(so or REF_LIO_SO)
     cfg = cfg or fr["lio_cfg"]
     m = fr["map"]
     k, f, c, p = (np.ascontiguousarray(m["keys"], dtype=np.int64), np.ascontiguousarray(m["first"], dtype=np.int32), np.ascontiguousarray(m["count"], dtype=np.int32),
@@ -381,8 +381,8 @@ def ref_vio_available():
 class RefVIO:
     """VIOManager of the REFERENCE SOURCE (pinhole camera only)."""
 
-    def __init__(self, cam_cfg, ext, vio_cfg):
-        self.lib = C.CDLL(REF_VIO_SO)
+    def __init__(self, cam_cfg, ext, vio_cfg, so=None):
+        self.lib = C.CDLL(so or REF_VIO_SO)
         L = self.lib
         L.ref_vio_create.restype = C.c_void_p
         L.ref_vio_create.argtypes = [C.c_void_p] * 6
