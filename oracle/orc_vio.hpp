@@ -6,7 +6,7 @@
 // CPU restatement of the reference's VIO ESIKF measurement update (src/vio.cpp) and of the
 // third-party camera arithmetic it calls (vikit, xuankuzcr/rpg_vikit, NO version pin in the
 // reference: README.md:80-84). The vikit parts are restated from its published algorithm
-// (pinhole + radtan, equidistant fisheye, interpolateMat_8u); the fisheye model has no pin at all.
+// (pinhole + radtan, equidistant fisheye, interpolateMat_8u).
 #pragma once
 #include "orc_math.hpp"
 

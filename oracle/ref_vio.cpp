@@ -17,6 +17,7 @@
 #include <unordered_map>
 using namespace std;
 typedef unsigned char uchar;
+#include <vikit/equidistant_camera.h>
 #include "/root/reference/src/voxel_map.cpp"  // VoxelOctoTree::find_correspond etc., referenced by the retrieval code of vio.cpp
 #include "/root/reference/src/frame.cpp"
 #include "/root/reference/src/visual_point.cpp"
@@ -52,12 +53,15 @@ struct RefVio {
 
 extern "C" {
 
-// cam = [model (0 pinhole only), width, height, fx, fy, cx, cy, d0..d4]; cfg = [patch_pyrimid_level, max_iterations, img_point_cov, exposure_estimate_en]
+// cam = [model (0 pinhole / radtan, 1 equidistant), width, height, fx, fy, cx, cy, d0..d4]; cfg = [patch_pyrimid_level, max_iterations, img_point_cov, exposure_estimate_en]
 void *ref_vio_create(const double *cam, const double *extR, const double *extT, const double *Rcl, const double *Pcl, const double *cfg) {
-  if ((int)cam[0] != 0) return nullptr;  // vk::EquidistantCamera is not restated in ref_shim
+  if ((int)cam[0] != 0 && (int)cam[0] != 1) return nullptr;
   RefVio *r = new RefVio;
   VIOManager &v = r->v;
-  v.cam = new vk::PinholeCamera(cam[1], cam[2], 1.0, cam[3], cam[4], cam[5], cam[6], cam[7], cam[8], cam[9], cam[10], cam[11]);
+  if ((int)cam[0] == 0)
+    v.cam = new vk::PinholeCamera(cam[1], cam[2], 1.0, cam[3], cam[4], cam[5], cam[6], cam[7], cam[8], cam[9], cam[10], cam[11]);
+  else
+    v.cam = new vk::EquidistantCamera(cam[1], cam[2], 1.0, cam[3], cam[4], cam[5], cam[6], cam[7], cam[8], cam[9], cam[10]);
   M3D R;
   V3D t;
   for (int i = 0; i < 3; i++) {

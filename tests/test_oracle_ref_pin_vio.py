@@ -6,7 +6,7 @@ What this pins: everything VIOManager::computeJacobianAndUpdateEKF -> updateStat
 Jacobian chain, H^T H, the gain, boxplus, the error-gated accept / rollback, P -= G P), the inverse-compositional variant
 (precomputeReferencePatches, updateStateInverse), getImagePatch, warpAffine, getWarpMatrixAffineHomography / getBestSearchLevel
 compute — the reference's own arithmetic. What it cannot pin: vikit (un-vendored, no version pin): the pinhole model and
-vk::interpolateMat_8u inside the stand-in are restatements of the published algorithm, shared by both sides (pinhole only).
+vk::interpolateMat_8u inside the stand-in are restatements of the published algorithm, shared by both sides.
 
 Runs where the library exists (the build container; the GPU box through the snapshot); tests/golden/ref_vio_golden.npz carries
 the reference's outputs elsewhere (tests/golden/make_ref_golden.py regenerates it)."""
@@ -30,6 +30,10 @@ CASES = {
     "three_levels": dict(seed=8, n_pts=1000, n_map=120_000, n_patches=300, scene_scale=0.5, vio=S.VioCfg(levels=3, img_point_cov=400.0)),
     "distorted_pinhole": dict(seed=9, n_pts=1000, n_map=120_000, n_patches=200, scene_scale=0.5,
                               cam=S.CamCfg(d=(-0.05, 0.02, 0.001, -0.0005, 0.0))),
+    # config 3's camera (HILTI22 fisheye, vk::EquidistantCamera) behind the same abstract interface
+    "fisheye": dict(seed=10, n_pts=1000, n_map=120_000, n_patches=200, scene_scale=0.5, vio=S.VioCfg(img_point_cov=1000.0),
+                    cam=S.CamCfg(model=1, width=720, height=540, fx=351.31400364193297, fy=351.4911744656785, cx=367.8522793375995, cy=253.8402144980996,
+                                 d=(-0.03696737352869157, -0.008917880497032812, 0.008912969593422046, -0.0037685977496087313, 0.0))),
 }
 
 
