@@ -135,3 +135,23 @@ def test_capacity_errors_are_reported_not_ignored():
     far = pw.copy()
     far[0] = [3e6, 0, 0]
     assert MB.HostMap(cfg).apply(far, var) & 16                  # MAP_ERR_KEY: outside the +-2^20 key range
+
+
+@pytest.mark.parametrize("voxel_size", [0.5, 0.4, 2.0])
+def test_root_voxel_keys_on_voxel_faces_and_negative_coordinates(voxel_size):
+    """The key of UpdateVoxelMap (src/voxel_map.cpp:620-625): (float)(p / (double)(float)voxel_size), "-1 if negative", truncation.
+    World points (float-rounded, like TransformLidar's output) exactly on voxel faces, one ulp either side, around zero and at
+    negative integers of the quotient: the device code must open exactly the root voxels the oracle opens."""
+    cfg = S.LioCfg(voxel_size=voxel_size)
+    ks = np.arange(-6, 7, dtype=np.float64)
+    face = (ks * np.float64(np.float32(voxel_size))).astype(np.float32)
+    vals = np.concatenate([face, np.nextafter(face, np.float32(np.inf)), np.nextafter(face, np.float32(-np.inf)), np.float32([0.0, -0.0, 1e-30, -1e-30])])
+    grid = np.stack(np.meshgrid(vals, vals[::5], vals[::7], indexing="ij"), -1).reshape(-1, 3).astype(np.float64)
+    var = np.tile(np.eye(3) * 1e-4, (len(grid), 1, 1))
+    orc, hm = _oracle(cfg), MB.HostMap(cfg)
+    _oracle_update(orc, grid, var)
+    assert hm.apply(grid, var) == 0
+    a, b = hm.flatten(), orc.flatten()
+    assert len(a["keys"]) == len(b["keys"]) > 50
+    assert set(map(tuple, a["keys"].tolist())) == set(map(tuple, b["keys"].tolist()))
+    assert (a["keys"] < 0).any()
