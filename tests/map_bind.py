@@ -22,7 +22,7 @@ def build():
 
 
 class HostMap:
-    def __init__(self, cfg, hash_cap=1 << 16, node_cap=1 << 18, pool_cap=1 << 22, rec_cap=1 << 18):
+    def __init__(self, cfg, hash_cap=1 << 16, node_cap=1 << 16, pool_cap=1 << 19, rec_cap=1 << 16):
         build()
         self.lib = C.CDLL(SO)
         self.lib.maph_create.restype = C.c_void_p
